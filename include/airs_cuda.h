@@ -1,0 +1,156 @@
+/*
+ * airs_cuda.h - C-ABI of the B200 (sm_100a) backend of the AIRSPACE compressor.
+ *
+ * Plain C: pointers, sizes, fixed-width integers; no C++ or torch types.  This
+ * is what the host shim (lib/host/cmp_shim.c, the cmp.h API) calls, and what a
+ * foreign-function binding (ctypes, cgo, JNI ...) would bind.  Every entry point
+ * below names the reference interface it stands in for.
+ *
+ * The batched driver has no counterpart function in the reference; its
+ * semantics are DEFINED by the reference's API: running a batch is
+ * byte-identical to this loop over the reference library (lib/cmp.h:154-344),
+ * with a timestamp callback that returns a counter:
+ *
+ *   for each job j:
+ *       counter = j.identifier_base              (48-bit counter: coarse<<16|fine)
+ *       init_results[j] = cmp_initialise(&ctx, &j.params, work + j.work_offset, j.work_size)
+ *       for f in 0 .. j.n_frames-1:
+ *           results[j.first_result + f] =
+ *               cmp_compress_<dtype>(&ctx, dst_f, j.dst_capacity,
+ *                                    src + j.src_offset + f*j.src_frame_stride, j.src_size)
+ *   every timestamp request returns counter++ (cmp.c:27-34 is the same counter,
+ *   shared between contexts; here each job owns one so that jobs are independent).
+ *
+ * dst_f is dst + j.dst_offset + f*j.dst_frame_stride in the SLOTS layout.  In
+ * the CONCAT layout the streams of all frames are written back to back, in
+ * result-index order, starting at dst (what `airspace -c --stdout f1 f2 ...`
+ * produces, programs/airspacecli.c:131-202): out_offsets[k] is where stream k
+ * starts, out_offsets[n_results] the total; a frame that failed contributes 0
+ * bytes; dst_capacity still bounds each stream.
+ */
+#ifndef AIRS_CUDA_H
+#define AIRS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "cmp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* sample containers; values equal the reference's private enum cmp_type
+ * (lib/common/sample_reader.h:9) */
+#define AIRS_DTYPE_I16        0u
+#define AIRS_DTYPE_I16_IN_I32 1u
+#define AIRS_DTYPE_U16        2u
+
+#define AIRS_LAYOUT_SLOTS  0u /* every frame has its own dst slot */
+#define AIRS_LAYOUT_CONCAT 1u /* streams laid out back to back by a device-wide scan */
+
+/* result value of a frame that was not attempted because its job failed to
+ * initialise: the reference returns CMP_ERR_CONTEXT_INVALID there (cmp.c:353) */
+
+/*
+ * One compression context and the frames pushed through it, in order.
+ * Independent chunks are jobs with n_frames == 1.  120 bytes.
+ */
+struct airs_job {
+	uint64_t src_offset;       /* frame 0, bytes from the source base */
+	uint64_t src_frame_stride; /* bytes between consecutive frames */
+	uint64_t dst_offset;       /* SLOTS: slot of frame 0, bytes from the dst base */
+	uint64_t dst_frame_stride; /* SLOTS: bytes between consecutive slots */
+	uint64_t work_offset;      /* this context's work buffer, bytes from the work base */
+	uint64_t identifier_base;  /* timestamp counter when the job starts */
+	uint32_t src_size;         /* bytes per frame, in the source container type */
+	uint32_t dst_capacity;     /* bytes available per stream */
+	uint32_t work_size;        /* bytes of work buffer (0: none) */
+	uint32_t n_frames;
+	uint32_t dtype;            /* AIRS_DTYPE_* */
+	uint32_t first_result;     /* index of frame 0 in results[] / out_offsets[] */
+	struct cmp_params params;  /* as passed to cmp_initialise() */
+	uint32_t reserved;         /* must be 0 */
+};
+
+/* Device-resident batch: every pointer is a device pointer. */
+struct airs_batch {
+	const void *src;             /* source base */
+	void *dst;                   /* destination base, 16-byte aligned */
+	void *work;                  /* work-buffer base (models, IWT scratch) or NULL */
+	const struct airs_job *jobs; /* n_jobs descriptors */
+	uint32_t *results;           /* n_results: stream size or (uint32_t)-cmp_error */
+	uint32_t *init_results;      /* n_jobs: result of cmp_initialise, or NULL */
+	uint64_t *out_offsets;       /* CONCAT: n_results + 1 entries; else NULL */
+	void *scratch;               /* airs_cuda_batch_scratch_size() bytes */
+	uint64_t dst_size;           /* bytes available behind dst */
+	uint32_t n_jobs;
+	uint32_t n_results;          /* total number of frames */
+	uint32_t layout;             /* AIRS_LAYOUT_* */
+	uint32_t reserved;
+};
+
+/* 0 on success, else a negative value; airs_cuda_last_error() explains. */
+#define AIRS_OK              0
+#define AIRS_E_NO_DEVICE    -1 /* no CUDA device / driver: there is NO CPU fallback */
+#define AIRS_E_CUDA         -2 /* a CUDA runtime call failed */
+#define AIRS_E_ARGUMENT     -3
+#define AIRS_E_NOMEM        -4
+
+/* Number of usable sm_100 devices (0: none).  No reference counterpart. */
+int airs_cuda_device_count(void);
+
+/* Text of the last failure on this thread. */
+const char *airs_cuda_last_error(void);
+
+/* Bytes of device scratch a batch needs (look-back state, ticket counters). */
+size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results);
+
+/*
+ * Compress a device-resident batch on `stream` (a cudaStream_t passed as
+ * void *, NULL = default stream).  Asynchronous: results are valid once the
+ * stream has been synchronised.  Replaces, for a whole batch, the call chain
+ * cmp_initialise -> cmp_compress_{u16,i16,i16_in_i32} (lib/compress/cmp.c:152-209,
+ * 396-435) including compress_engine (cmp.c:213-338), the preprocessing methods
+ * (lib/compress/preprocess.c:268-411), the encoder (lib/compress/encoder.c:185-378),
+ * the bitstream writer (lib/common/bitstream_writer.h:124-227), the header
+ * (lib/common/header.c:24-67) and the checksum (header.c:137-163).
+ */
+int airs_cuda_compress_batch(const struct airs_batch *batch, void *stream);
+
+/* Number of kernels the last airs_cuda_compress_batch() on this thread launched. */
+int airs_cuda_last_launch_count(void);
+
+/*
+ * Host-buffer batch: src/dst/jobs/results/out_offsets are HOST pointers (pinned
+ * or pageable; work may be NULL, models then live in device memory owned by the
+ * call).  Copies the inputs to the device, runs airs_cuda_compress_batch,
+ * copies streams and results back, synchronises.  This is the end-to-end path
+ * a host caller of the reference library is switched to.
+ */
+struct airs_host_batch {
+	const void *src;
+	uint64_t src_size;           /* bytes behind src */
+	void *dst;
+	uint64_t dst_size;
+	void *work;                  /* host models in/out, or NULL */
+	uint64_t work_size;
+	const struct airs_job *jobs;
+	uint32_t *results;
+	uint32_t *init_results;      /* may be NULL */
+	uint64_t *out_offsets;       /* CONCAT only */
+	uint32_t n_jobs;
+	uint32_t n_results;
+	uint32_t layout;
+	uint32_t reserved;
+};
+int airs_cuda_compress_batch_host(const struct airs_host_batch *batch);
+
+/* Release cached device staging buffers of this thread (optional). */
+void airs_cuda_release_cache(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* AIRS_CUDA_H */
