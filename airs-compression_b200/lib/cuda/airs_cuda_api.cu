@@ -1,0 +1,372 @@
+/*
+ * airs_cuda_api.cu - the extern "C" boundary of the sm_100a backend
+ * (include/airs_cuda.h) and the staging helper of the host shim.
+ *
+ * No CPU fallback lives here or anywhere else in this library: when no CUDA
+ * device is usable every entry point fails with AIRS_E_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "airs_device.cuh"
+#include "airs_launch.h"
+#include "airs_private.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU(call)                                                                              \
+	do {                                                                                  \
+		cudaError_t e_ = (call);                                                      \
+		if (e_ != cudaSuccess)                                                        \
+			return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? \
+					    AIRS_E_NO_DEVICE : AIRS_E_CUDA,                   \
+				    "%s: %s", #call, cudaGetErrorString(e_));                 \
+	} while (0)
+
+constexpr size_t kScratchHeader = 256; /* ticket counter and friends */
+
+/* CTAs that fit the device at once for the persistent job loop */
+int resident_ctas(int *out)
+{
+	static thread_local int cached_dev = -1, cached = 0;
+	int dev;
+
+	CU(cudaGetDevice(&dev));
+	if (dev != cached_dev) {
+		cudaDeviceProp prop;
+		CU(cudaGetDeviceProperties(&prop, dev));
+		if (prop.major < 10)
+			return fail(AIRS_E_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only",
+				    dev, prop.major, prop.minor);
+		/* 3 CTAs of 256 threads per SM (launch bounds of airs_encode_kernel); grid sized in
+		 * multiples of the SM count */
+		cached = prop.multiProcessorCount * 3;
+		cached_dev = dev;
+	}
+	*out = cached;
+	return AIRS_OK;
+}
+
+/* grow-only device buffer owned by the calling thread */
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t n)
+	{
+		if (n <= cap)
+			return AIRS_OK;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 4 + 4096;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess)
+			return fail(AIRS_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+		cap = want;
+		return AIRS_OK;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct Cache {
+	DevBuf src, dst, work, jobs, results, init, offs, scratch, state;
+	cudaStream_t stream = nullptr;
+	int stream_dev = -1;
+};
+thread_local Cache g_cache;
+
+int cache_stream(cudaStream_t *s)
+{
+	int dev;
+	CU(cudaGetDevice(&dev));
+	if (!g_cache.stream || g_cache.stream_dev != dev) {
+		CU(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
+		g_cache.stream_dev = dev;
+	}
+	*s = g_cache.stream;
+	return AIRS_OK;
+}
+
+bool on_device(const void *p)
+{
+	cudaPointerAttributes at;
+	if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+} /* namespace */
+
+extern "C" const char *airs_cuda_last_error(void)
+{
+	return g_err;
+}
+
+extern "C" int airs_cuda_last_launch_count(void)
+{
+	return g_launches;
+}
+
+extern "C" int airs_cuda_device_count(void)
+{
+	int n = 0, usable = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+
+	if (e != cudaSuccess) {
+		fail(AIRS_E_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+		cudaGetLastError();
+		return 0;
+	}
+	for (int d = 0; d < n; d++) {
+		int major = 0;
+		if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major >= 10)
+			usable++;
+	}
+	if (!usable)
+		fail(AIRS_E_NO_DEVICE, "no sm_100 device among %d CUDA devices", n);
+	return usable;
+}
+
+extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)
+{
+	(void)n_results;
+	return kScratchHeader + 8 * ((size_t)n_jobs + 1);
+}
+
+static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
+{
+	g_launches = 0;
+	if (!b || !b->jobs || !b->results || !b->scratch)
+		return fail(AIRS_E_ARGUMENT, "batch, jobs, results and scratch must be non-NULL");
+	if (b->layout != AIRS_LAYOUT_SLOTS && b->layout != AIRS_LAYOUT_CONCAT)
+		return fail(AIRS_E_ARGUMENT, "unknown layout %u", b->layout);
+	if (b->layout == AIRS_LAYOUT_CONCAT && !b->out_offsets)
+		return fail(AIRS_E_ARGUMENT, "the CONCAT layout needs out_offsets");
+	if (b->n_jobs == 0)
+		return AIRS_OK;
+
+	int resident = 0;
+	int rc = resident_ctas(&resident);
+	if (rc != AIRS_OK)
+		return rc;
+
+	size_t scratch = airs_cuda_batch_scratch_size(b->n_jobs, b->n_results);
+	CU(cudaMemsetAsync(b->scratch, 0, scratch, stream));
+
+	AirsLaunch l;
+	memset(&l, 0, sizeof(l));
+	l.src = (const uint8_t *)b->src;
+	l.dst = (uint8_t *)b->dst;
+	l.work = (uint8_t *)b->work;
+	l.jobs = b->jobs;
+	l.results = b->results;
+	l.init_results = b->init_results;
+	l.out_offsets = b->out_offsets;
+	l.ticket = (uint32_t *)b->scratch;
+	l.lookback = (uint64_t *)((uint8_t *)b->scratch + kScratchHeader);
+	l.ctx_io = ctx_io;
+	l.n_jobs = b->n_jobs;
+	l.layout = b->layout;
+
+	unsigned int grid = b->n_jobs < (uint32_t)resident ? b->n_jobs : (unsigned int)resident;
+	CU(airs_launch_encode(&l, grid, stream));
+	g_launches = 1;
+	return AIRS_OK;
+}
+
+extern "C" int airs_cuda_compress_batch(const struct airs_batch *b, void *stream)
+{
+	return launch_batch(b, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
+{
+	if (!hb || !hb->jobs || !hb->results || !hb->src || !hb->dst)
+		return fail(AIRS_E_ARGUMENT, "host batch: src, dst, jobs and results must be non-NULL");
+	Cache &c = g_cache;
+	cudaStream_t s;
+	int rc = cache_stream(&s);
+	if (rc)
+		return rc;
+	size_t jobs_bytes = (size_t)hb->n_jobs * sizeof(struct airs_job);
+	size_t scratch = airs_cuda_batch_scratch_size(hb->n_jobs, hb->n_results);
+	if ((rc = c.src.reserve(hb->src_size + 64)) || (rc = c.dst.reserve(hb->dst_size + 64)) ||
+	    (rc = c.work.reserve(hb->work_size + 64)) || (rc = c.jobs.reserve(jobs_bytes + 64)) ||
+	    (rc = c.results.reserve((size_t)hb->n_results * 4 + 64)) ||
+	    (rc = c.init.reserve((size_t)hb->n_jobs * 4 + 64)) ||
+	    (rc = c.offs.reserve(((size_t)hb->n_results + 1) * 8 + 64)) || (rc = c.scratch.reserve(scratch)))
+		return rc;
+
+	CU(cudaMemcpyAsync(c.src.p, hb->src, hb->src_size, cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(c.jobs.p, hb->jobs, jobs_bytes, cudaMemcpyHostToDevice, s));
+	if (hb->work && hb->work_size)
+		CU(cudaMemcpyAsync(c.work.p, hb->work, hb->work_size, cudaMemcpyHostToDevice, s));
+
+	struct airs_batch b;
+	memset(&b, 0, sizeof(b));
+	b.src = c.src.p;
+	b.dst = c.dst.p;
+	b.work = hb->work_size ? c.work.p : nullptr;
+	b.jobs = (const struct airs_job *)c.jobs.p;
+	b.results = (uint32_t *)c.results.p;
+	b.init_results = (uint32_t *)c.init.p;
+	b.out_offsets = hb->layout == AIRS_LAYOUT_CONCAT ? (uint64_t *)c.offs.p : nullptr;
+	b.scratch = c.scratch.p;
+	b.dst_size = hb->dst_size;
+	b.n_jobs = hb->n_jobs;
+	b.n_results = hb->n_results;
+	b.layout = hb->layout;
+	rc = launch_batch(&b, nullptr, s);
+	if (rc)
+		return rc;
+
+	CU(cudaMemcpyAsync(hb->results, c.results.p, (size_t)hb->n_results * 4, cudaMemcpyDeviceToHost, s));
+	if (hb->init_results)
+		CU(cudaMemcpyAsync(hb->init_results, c.init.p, (size_t)hb->n_jobs * 4, cudaMemcpyDeviceToHost, s));
+	if (hb->layout == AIRS_LAYOUT_CONCAT) {
+		/* only the bytes the scan laid out travel back */
+		CU(cudaMemcpyAsync(hb->out_offsets, c.offs.p, ((size_t)hb->n_results + 1) * 8,
+				   cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		uint64_t total = hb->out_offsets[hb->n_results];
+		if (total > hb->dst_size)
+			return fail(AIRS_E_ARGUMENT, "dst_size %llu < concatenated size %llu",
+				    (unsigned long long)hb->dst_size, (unsigned long long)total);
+		CU(cudaMemcpyAsync(hb->dst, c.dst.p, total, cudaMemcpyDeviceToHost, s));
+	} else {
+		CU(cudaMemcpyAsync(hb->dst, c.dst.p, hb->dst_size, cudaMemcpyDeviceToHost, s));
+	}
+	if (hb->work && hb->work_size)
+		CU(cudaMemcpyAsync(hb->work, c.work.p, hb->work_size, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	return AIRS_OK;
+}
+
+extern "C" void airs_cuda_release_cache(void)
+{
+	Cache &c = g_cache;
+	c.src.release();
+	c.dst.release();
+	c.work.release();
+	c.jobs.release();
+	c.results.release();
+	c.init.release();
+	c.offs.release();
+	c.scratch.release();
+	c.state.release();
+	if (c.stream)
+		cudaStreamDestroy(c.stream);
+	c.stream = nullptr;
+	c.stream_dev = -1;
+}
+
+/* ------------------------------------------------------------------------ */
+/* single-call path used by the cmp.h shim                                   */
+
+extern "C" int airs_cuda_compress_resume(const struct airs_job *job, struct airs_ctx_state *state,
+					 const void *src, void *dst, void *work, int work_is_state,
+					 uint32_t *result)
+{
+	if (!job || !state || !result || job->n_frames != 1)
+		return fail(AIRS_E_ARGUMENT, "resume: bad arguments");
+	Cache &c = g_cache;
+	cudaStream_t s;
+	int rc = cache_stream(&s);
+	if (rc)
+		return rc;
+
+	const bool src_dev = on_device(src), dst_dev = on_device(dst), work_dev = on_device(work);
+	const uint32_t mis = (uint32_t)((uintptr_t)dst & 7u);
+	struct airs_job j = *job;
+
+	if ((rc = c.jobs.reserve(sizeof(j))) || (rc = c.results.reserve(64)) || (rc = c.state.reserve(sizeof(*state))) ||
+	    (rc = c.scratch.reserve(airs_cuda_batch_scratch_size(1, 1))))
+		return rc;
+
+	struct airs_batch b;
+	memset(&b, 0, sizeof(b));
+	j.src_offset = 0;
+	j.dst_offset = 0;
+	j.work_offset = 0;
+	j.first_result = 0;
+	if (src && !src_dev) {
+		if ((rc = c.src.reserve((size_t)j.src_size + 64)))
+			return rc;
+		CU(cudaMemcpyAsync(c.src.p, src, j.src_size, cudaMemcpyHostToDevice, s));
+		b.src = c.src.p;
+	} else {
+		b.src = src;
+	}
+	if (dst && !dst_dev) {
+		if ((rc = c.dst.reserve((size_t)j.dst_capacity + 64)))
+			return rc;
+		b.dst = c.dst.p; /* cudaMalloc memory is 256-byte aligned: reproduce the caller's alignment */
+		j.dst_offset = mis;
+	} else {
+		b.dst = dst;
+	}
+	if (work && j.work_size && !work_dev) {
+		if ((rc = c.work.reserve((size_t)j.work_size + 64)))
+			return rc;
+		if (work_is_state)
+			CU(cudaMemcpyAsync(c.work.p, work, j.work_size, cudaMemcpyHostToDevice, s));
+		b.work = c.work.p;
+	} else {
+		b.work = j.work_size ? work : nullptr;
+	}
+	CU(cudaMemcpyAsync(c.jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice, s));
+	CU(cudaMemcpyAsync(c.state.p, state, sizeof(*state), cudaMemcpyHostToDevice, s));
+	b.jobs = (const struct airs_job *)c.jobs.p;
+	b.results = (uint32_t *)c.results.p;
+	b.scratch = c.scratch.p;
+	b.dst_size = j.dst_capacity;
+	b.n_jobs = 1;
+	b.n_results = 1;
+	b.layout = AIRS_LAYOUT_SLOTS;
+	rc = launch_batch(&b, (struct airs_ctx_state *)c.state.p, s);
+	if (rc)
+		return rc;
+	CU(cudaMemcpyAsync(result, c.results.p, 4, cudaMemcpyDeviceToHost, s));
+	CU(cudaMemcpyAsync(state, c.state.p, sizeof(*state), cudaMemcpyDeviceToHost, s));
+	if (work && j.work_size && !work_dev && work_is_state)
+		CU(cudaMemcpyAsync(work, c.work.p, j.work_size, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	if (dst && !dst_dev && !airs_failed(*result)) {
+		CU(cudaMemcpyAsync(dst, (uint8_t *)c.dst.p + mis, *result, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+	}
+	return AIRS_OK;
+}
+
+extern "C" int airs_cuda_patch_bytes(void *dst, const uint8_t *bytes, uint32_t offset, uint32_t count)
+{
+	if (!on_device(dst)) {
+		memcpy((uint8_t *)dst + offset, bytes, count);
+		return AIRS_OK;
+	}
+	CU(cudaMemcpy((uint8_t *)dst + offset, bytes, count, cudaMemcpyHostToDevice));
+	return AIRS_OK;
+}

@@ -1,0 +1,37 @@
+/* airs_launch.h - what the C-ABI layer (airs_cuda_api.cu) hands to the kernels. */
+#ifndef AIRS_LAUNCH_H
+#define AIRS_LAUNCH_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/airs_cuda.h"
+
+struct airs_ctx_state;
+
+#define AIRS_THREADS 256
+
+struct AirsLaunch {
+	const uint8_t *src;
+	uint8_t *dst;
+	uint8_t *work;
+	const struct airs_job *jobs;
+	uint32_t *results;
+	uint32_t *init_results;
+	uint64_t *out_offsets;
+	uint32_t *ticket;      /* zeroed before the launch: next job to hand out */
+	uint64_t *lookback;    /* CONCAT: one status word per job, zeroed before the launch */
+	struct airs_ctx_state *ctx_io; /* host-shim path: context state in/out per job, else NULL */
+	uint32_t n_jobs;
+	uint32_t layout;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
+#ifdef __cplusplus
+}
+#endif
+
+#endif
