@@ -152,8 +152,8 @@ extern "C" int airs_cuda_device_count(void)
 
 extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)
 {
-	(void)n_results;
-	return kScratchHeader + 8 * ((size_t)n_jobs + 1);
+	(void)n_jobs;
+	return kScratchHeader + 8 * ((size_t)n_results + 1);
 }
 
 static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
@@ -188,7 +188,9 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.ticket = (uint32_t *)b->scratch;
 	l.lookback = (uint64_t *)((uint8_t *)b->scratch + kScratchHeader);
 	l.ctx_io = ctx_io;
+	l.dst_size = b->dst_size;
 	l.n_jobs = b->n_jobs;
+	l.n_results = b->n_results;
 	l.layout = b->layout;
 
 	unsigned int grid = b->n_jobs < (uint32_t)resident ? b->n_jobs : (unsigned int)resident;

@@ -494,6 +494,7 @@ struct Shared {
 	PassPlan plan;
 	uint32_t job;
 	uint32_t checksum;
+	uint64_t offset; /* CONCAT: where the current frame's stream starts */
 };
 
 /* byte-granular window of the destination a pass may write: [lo, hi) in the
@@ -518,7 +519,8 @@ __device__ __forceinline__ void store_word(const OutWin &o, uint32_t gword, uint
 }
 
 template <int ENC, int PRE>
-__device__ __noinline__ void encode_tiles(Shared &sh, const OutWin &o, uint32_t a, uint32_t &gw0, uint32_t &sbits)
+__device__ __noinline__ void encode_tiles(Shared &sh, const OutWin &o, uint32_t a, uint32_t &gw0, uint32_t &sbits,
+					  bool size_only)
 {
 	const PassPlan &P = sh.plan;
 	const EncConst e = P.enc;
@@ -586,6 +588,14 @@ __device__ __noinline__ void encode_tiles(Shared &sh, const OutWin &o, uint32_t 
 		uint32_t tile_bits = __reduce_add_sync(0xFFFFFFFFu, ws);
 		uint32_t wpre = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? ws : 0u);
 		uint32_t excl = wpre + incl - tb;
+
+		if (size_only) { /* CONCAT sizing pass: only the bit count is wanted */
+			const uint32_t staged0 = sbits + tile_bits;
+			gw0 += staged0 >> 5;
+			sbits = staged0 & 31u;
+			__syncthreads();
+			continue;
+		}
 
 		/* bit packing: this thread's codewords start at staging bit `pos` */
 		uint32_t pos = sbits + excl;
@@ -679,7 +689,7 @@ __device__ __noinline__ void encode_tiles(Shared &sh, const OutWin &o, uint32_t 
 
 /* one pass over one frame; returns the stream size or an error (uniform over the CTA).
  * ref compress_engine, cmp.c:213-338 */
-__device__ uint32_t encode_pass(Shared &sh)
+__device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 {
 	const PassPlan &P = sh.plan;
 	const uint32_t tid = threadIdx.x;
@@ -691,20 +701,24 @@ __device__ uint32_t encode_pass(Shared &sh)
 	OutWin o;
 	o.base4 = P.dst - a;
 	o.lo = a + P.hdr_len;
-	o.hi = a + P.cap_eff;
+	o.hi = suppress ? o.lo : a + P.cap_eff; /* suppress: run for the model side effects only */
 	/* position of stg[0] in 32-bit words of the aligned space, and bits already in it */
 	uint32_t gw0 = (8u * (a + P.hdr_len)) >> 5;
 	uint32_t sbits = (8u * (a + P.hdr_len)) & 31u;
 
 	if (P.pre == CMP_PREPROCESS_IWT)
 		iwt_global(P);
+	if (size_only) {
+		const uint32_t fb = gw0 * 32u + sbits - 8u * a;
+		(void)fb;
+	}
 
 #define AIRS_DISPATCH_PRE(ENC)                                                              \
 	switch (P.pre) {                                                                    \
-	case CMP_PREPROCESS_NONE:  encode_tiles<ENC, CMP_PREPROCESS_NONE>(sh, o, a, gw0, sbits); break;  \
-	case CMP_PREPROCESS_DIFF:  encode_tiles<ENC, CMP_PREPROCESS_DIFF>(sh, o, a, gw0, sbits); break;  \
-	case CMP_PREPROCESS_IWT:   encode_tiles<ENC, CMP_PREPROCESS_IWT>(sh, o, a, gw0, sbits); break;   \
-	default:                   encode_tiles<ENC, CMP_PREPROCESS_MODEL>(sh, o, a, gw0, sbits); break; \
+	case CMP_PREPROCESS_NONE:  encode_tiles<ENC, CMP_PREPROCESS_NONE>(sh, o, a, gw0, sbits, size_only); break;  \
+	case CMP_PREPROCESS_DIFF:  encode_tiles<ENC, CMP_PREPROCESS_DIFF>(sh, o, a, gw0, sbits, size_only); break;  \
+	case CMP_PREPROCESS_IWT:   encode_tiles<ENC, CMP_PREPROCESS_IWT>(sh, o, a, gw0, sbits, size_only); break;   \
+	default:                   encode_tiles<ENC, CMP_PREPROCESS_MODEL>(sh, o, a, gw0, sbits, size_only); break; \
 	}
 	switch (P.enc.type) {
 	case CMP_ENCODER_UNCOMPRESSED: AIRS_DISPATCH_PRE(CMP_ENCODER_UNCOMPRESSED) break;
@@ -713,8 +727,18 @@ __device__ uint32_t encode_pass(Shared &sh)
 	}
 #undef AIRS_DISPATCH_PRE
 
+	if (size_only) { /* the size is all the CONCAT look-back needs */
+		const uint32_t bits = gw0 * 32u + sbits - 8u * a;
+		const uint32_t sz = ((bits + 7u) >> 3) + (P.checksum ? 4u : 0u);
+		if (sz > P.cap_eff)
+			return AIRS_ERR(DST_TOO_SMALL);
+		if (sz > CMP_HDR_MAX_COMPRESSED_SIZE)
+			return AIRS_ERR(HDR_CMP_SIZE_TOO_LARGE);
+		return sz;
+	}
+
 	/* checksum of the samples while the tail is flushed */
-	if (P.checksum && tid < 32) {
+	if (P.checksum && !suppress && tid < 32) {
 		uint32_t h = frame_checksum(P);
 		if (tid == 0)
 			sh.checksum = h;
@@ -744,18 +768,57 @@ __device__ uint32_t encode_pass(Shared &sh)
 	else
 		result = size;
 
-	if (P.checksum && tid < 4) { /* trailer, big endian (ref cmp.c:314-319) */
+	if (P.checksum && !suppress && tid < 4) { /* trailer, big endian (ref cmp.c:314-319) */
 		uint64_t b = (uint64_t)a + payload_end + tid;
 		if (b < o.hi)
 			o.base4[b] = (uint8_t)(sh.checksum >> (24 - 8 * tid));
 	}
-	if (!airs_failed(result) && tid < P.hdr_len) { /* header with the final size (ref cmp.c:329-334) */
+	if (!airs_failed(result) && !suppress && tid < P.hdr_len) { /* header with the final size (ref cmp.c:329-334) */
 		uint8_t v = P.hdr[tid];
 		if (tid >= 2 && tid <= 4)
 			v = (uint8_t)(size >> (8 * (4 - tid)));
 		P.dst[tid] = v;
 	}
 	return result;
+}
+
+/* -------------------------------------------------------------------------
+ * CONCAT layout: single-pass device-wide scan over stream sizes (decoupled
+ * look-back over one 64-bit status word per frame: 2 flag bits | 62 value bits;
+ * flag 1 = this frame's size, flag 2 = inclusive prefix).  Called by warp 0;
+ * returns the byte offset of frame k.  Frames are published in result-index
+ * order by CTAs that took their jobs from the ticket counter in order, so every
+ * predecessor is running or done.
+ * ---------------------------------------------------------------------- */
+__device__ uint64_t lookback_offset(volatile uint64_t *st, uint32_t k, uint32_t my_size)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint64_t kValue = (1ull << 62) - 1;
+	uint64_t excl = 0;
+
+	if (lane == 0)
+		st[k] = (1ull << 62) | my_size;
+	for (int64_t idx = (int64_t)k - 1; idx >= 0; idx -= 32) {
+		const int64_t j = idx - lane;
+		uint64_t v;
+		do {
+			v = j >= 0 ? st[j] : (2ull << 62);
+		} while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0));
+		const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+		if (incl) {
+			const int first = __ffs((int)incl) - 1; /* nearest predecessor holding a prefix */
+			excl += __reduce_add_sync(0xFFFFFFFFu, (int)lane < first ? (uint32_t)(v & kValue) : 0u);
+			const uint64_t pv = v & kValue;
+			const uint32_t plo = __shfl_sync(0xFFFFFFFFu, (uint32_t)pv, first);
+			const uint32_t phi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(pv >> 32), first);
+			excl += ((uint64_t)phi << 32) | plo;
+			break;
+		}
+		excl += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(v & kValue));
+	}
+	if (lane == 0)
+		st[k] = (2ull << 62) | (excl + my_size);
+	return excl;
 }
 
 } /* namespace */
@@ -793,16 +856,50 @@ __global__ void __launch_bounds__(AIRS_THREADS, 3) airs_encode_kernel(AirsLaunch
 			if (tid == 0)
 				plan_frame(sh.js, sh.plan, b, f);
 			__syncthreads();
-			uint32_t r = encode_pass(sh);
-			if (sh.plan.fallback_ok && r == AIRS_ERR(DST_TOO_SMALL)) {
-				/* store the frame raw as a fresh primary pass (ref cmp.c:380-392) */
-				__syncthreads();
-				if (tid == 0) {
-					ctx_reset(sh.js);
-					plan_pass(sh.js, sh.plan, true);
+			uint32_t r;
+			if (b.layout == AIRS_LAYOUT_CONCAT) {
+				/* size first (exact, no output), then the offset from the scan, then one
+				 * pass that writes; a frame that fails contributes no bytes */
+				r = encode_pass(sh, true, false);
+				if (sh.plan.fallback_ok && r == AIRS_ERR(DST_TOO_SMALL)) {
+					__syncthreads();
+					if (tid == 0) {
+						ctx_reset(sh.js);
+						plan_pass(sh.js, sh.plan, true);
+					}
+					__syncthreads();
+					r = sh.plan.err ? sh.plan.err : sh.plan.cap_eff;
+				}
+				const uint32_t k = first + f;
+				if (tid < 32) {
+					uint64_t off = lookback_offset(b.lookback, k, airs_failed(r) ? 0u : r);
+					if (tid == 0) {
+						sh.offset = off;
+						b.out_offsets[k] = off;
+						if (k + 1 == b.n_results)
+							b.out_offsets[k + 1] = off + (airs_failed(r) ? 0u : r);
+						sh.plan.dst = b.dst + off;
+					}
 				}
 				__syncthreads();
-				r = encode_pass(sh);
+				const bool fits = !airs_failed(r) && sh.offset + r <= b.dst_size;
+				if (!sh.plan.err) {
+					uint32_t r2 = encode_pass(sh, false, !fits);
+					if (!airs_failed(r))
+						r = fits ? r2 : AIRS_ERR(DST_TOO_SMALL);
+				}
+			} else {
+				r = encode_pass(sh, false, false);
+				if (sh.plan.fallback_ok && r == AIRS_ERR(DST_TOO_SMALL)) {
+					/* store the frame raw as a fresh primary pass (ref cmp.c:380-392) */
+					__syncthreads();
+					if (tid == 0) {
+						ctx_reset(sh.js);
+						plan_pass(sh.js, sh.plan, true);
+					}
+					__syncthreads();
+					r = encode_pass(sh, false, false);
+				}
 			}
 			__syncthreads();
 			if (tid == 0) {

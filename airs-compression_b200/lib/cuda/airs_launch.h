@@ -22,7 +22,9 @@ struct AirsLaunch {
 	uint32_t *ticket;      /* zeroed before the launch: next job to hand out */
 	uint64_t *lookback;    /* CONCAT: one status word per job, zeroed before the launch */
 	struct airs_ctx_state *ctx_io; /* host-shim path: context state in/out per job, else NULL */
+	uint64_t dst_size;
 	uint32_t n_jobs;
+	uint32_t n_results;
 	uint32_t layout;
 };
 

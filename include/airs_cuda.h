@@ -126,7 +126,9 @@ int airs_cuda_last_launch_count(void);
  * or pageable; work may be NULL, models then live in device memory owned by the
  * call).  Copies the inputs to the device, runs airs_cuda_compress_batch,
  * copies streams and results back, synchronises.  This is the end-to-end path
- * a host caller of the reference library is switched to.
+ * a host caller of the reference library is switched to.  SLOTS: the whole dst
+ * range is copied back, so slot bytes behind a stream are unspecified; CONCAT:
+ * exactly out_offsets[n_results] bytes are copied back.
  */
 struct airs_host_batch {
 	const void *src;

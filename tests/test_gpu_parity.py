@@ -26,3 +26,107 @@ def test_random_jobs_multi_tile(gpu, oracle, seed):
     want = jobgen.run_cpu(oracle, js)
     got = gpu.run_jobs_device(js)
     jobgen.compare(want, got, js, "gpu-vs-oracle")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_concat_layout(gpu, oracle, seed):
+    """Streams laid out back to back by the device-wide scan == the oracle loop's concatenation."""
+    rng = np.random.default_rng(300 + seed)
+    js = jobgen.build_jobs(rng, 250, sizes=SMALL + [2048, 2049, 4099], max_frames=4,
+                           allow_invalid=True, layout=1)
+    want = jobgen.run_cpu(oracle, js)
+    got = gpu.run_jobs_device(js)
+    jobgen.compare(want, got, js, "gpu-concat")
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_host_batch(gpu, oracle, layout):
+    """airs_cuda_compress_batch_host: host buffers in, host buffers out."""
+    rng = np.random.default_rng(400 + layout)
+    js = jobgen.build_jobs(rng, 120, sizes=SMALL + [2048, 4099], max_frames=3, layout=layout)
+    want = jobgen.run_cpu(oracle, js)
+    got = gpu.run_jobs_host(js)
+    # slot bytes behind a stream are unspecified on the host path (the whole dst range is copied back)
+    jobgen.compare(want, got, js, "gpu-host-batch", check_tail=False)
+
+
+def _uniform_jobs(pkg, n_jobs, n, n_frames, params, dtype=2, cap=None):
+    abi = pkg.abi
+    jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
+    stride = 4 if dtype == 1 else 2
+    fb = n * stride
+    cap = cap or abi.compress_bound(2 * n)
+    slot = (cap + 15) // 16 * 16
+    idx = np.arange(n_jobs, dtype=np.uint64)
+    jobs["src_offset"] = idx * np.uint64(fb * n_frames)
+    jobs["src_frame_stride"] = fb
+    jobs["dst_offset"] = idx * np.uint64(slot * n_frames)
+    jobs["dst_frame_stride"] = slot
+    jobs["work_offset"] = idx * np.uint64(2 * n)
+    jobs["identifier_base"] = idx * np.uint64(100000) + np.uint64(7)
+    jobs["src_size"] = fb
+    jobs["dst_capacity"] = cap
+    jobs["work_size"] = 2 * n
+    jobs["n_frames"] = n_frames
+    jobs["dtype"] = dtype
+    jobs["first_result"] = (idx * np.uint64(n_frames)).astype(np.uint32)
+    jobs["params"] = params
+    return dict(jobs=jobs, dst_size=int(slot * n_frames * n_jobs + 64), work_size=int(2 * n * n_jobs + 64),
+                n_results=n_jobs * n_frames, layout=0)
+
+
+def test_config1_one_mebisample_buffer(gpu, oracle, pkg):
+    """BASELINE config 1: one 1 Mi-sample u16 buffer, diff + Golomb (zero and multi escape)."""
+    abi, synth = pkg.abi, pkg.synth
+    x = synth.chunks(1, 0, 1, 1 << 20)
+    for enc, g, outl, cs in [(1, 16, 0, 0), (1, 8, 0, 1), (2, 16, 200, 0)]:
+        p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=enc,
+                            primary_encoder_param=g, primary_encoder_outlier=outl, checksum_enabled=cs)
+        js = _uniform_jobs(pkg, 1, 1 << 20, 1, p)
+        js["src"] = x.view(np.uint8).reshape(-1)
+        jobgen.compare(jobgen.run_cpu(oracle, js), gpu.run_jobs_device(js), js, "config1")
+
+
+@pytest.mark.parametrize("dtype", [2, 0])
+def test_config2_model_frames(gpu, oracle, pkg, dtype):
+    """BASELINE config 2: model-based preprocessing with model update over 256 consecutive 64 KiB frames."""
+    abi, synth = pkg.abi, pkg.synth
+    for rate in (8, 11):
+        p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16,
+                            secondary_iterations=255, secondary_preprocessing=abi.PRE_MODEL,
+                            secondary_encoder_type=1, secondary_encoder_param=8, model_rate=rate)
+        x = np.stack([synth.frames(1, c, 256, 32768) for c in range(2)])
+        js = _uniform_jobs(pkg, 2, 32768, 256, p, dtype=dtype)
+        js["src"] = x.view(np.uint8).reshape(-1)
+        jobgen.compare(jobgen.run_cpu(oracle, js), gpu.run_jobs_device(js), js, "config2")
+
+
+def test_config3_many_small_chunks(gpu, oracle, pkg):
+    """BASELINE config 3 (reduced count): independent 4 KiB chunks, mixed Golomb parameters, escape heavy."""
+    abi, synth = pkg.abi, pkg.synth
+    n_chunks, n = 8192, 2048
+    x = synth.chunks(1, 0, n_chunks, n, esc=32)
+    js = _uniform_jobs(pkg, n_chunks, n, 1, abi.make_params())
+    idx = np.arange(n_chunks, dtype=np.uint64)
+    h = synth.mix(np.uint64(1) ^ idx)
+    gtab = np.array([1, 2, 4, 7, 16, 60, 255, 1055], dtype=np.uint32)
+    otab = np.array([5, 42, 107, 200], dtype=np.uint32)
+    P = js["jobs"]["params"]
+    P["primary_preprocessing"] = abi.PRE_DIFF
+    P["primary_encoder_type"] = 1 + (idx & np.uint64(1)).astype(np.uint32)
+    P["primary_encoder_param"] = gtab[(h & np.uint64(7)).astype(np.int64)]
+    P["primary_encoder_outlier"] = otab[((h >> np.uint64(3)) & np.uint64(3)).astype(np.int64)]
+    js["src"] = x.view(np.uint8).reshape(-1)
+    for layout in (0, 1):
+        js["layout"] = layout
+        jobgen.compare(jobgen.run_cpu(oracle, js, threads=8), gpu.run_jobs_device(js), js, "config3")
+
+
+def test_synth_torch_matches_numpy(gpu, pkg):
+    import torch
+    a = pkg.synth.chunks(3, 5, 7, 1000, esc=32)
+    b = pkg.synth.chunks_torch(3, 5, 7, 1000, esc=32, device="cuda").cpu().numpy().view(np.uint16)
+    assert np.array_equal(a, b)
+    a = np.stack([pkg.synth.frames(2, c, 5, 513) for c in range(3, 5)])
+    b = pkg.synth.frames_torch(2, 3, 2, 5, 513, device="cuda").cpu().numpy().view(np.uint16)
+    assert np.array_equal(a, b)

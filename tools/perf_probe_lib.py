@@ -1,0 +1,86 @@
+"""Quick device-timed throughput probe (development tool, not the bench contract)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from __graft_entry__ import load_package
+pkg = load_package(); abi = pkg.abi; synth = pkg.synth
+
+def make_uniform_jobs(n_jobs, n_samples, n_frames, params_fn, cap=None, model=False):
+    jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
+    fb = n_samples * 2
+    cap = cap or abi.compress_bound(fb)
+    slot = (cap + 15) // 16 * 16
+    idx = np.arange(n_jobs, dtype=np.uint64)
+    jobs["src_offset"] = idx * np.uint64(fb * n_frames)
+    jobs["src_frame_stride"] = fb
+    jobs["dst_offset"] = idx * np.uint64(slot * n_frames)
+    jobs["dst_frame_stride"] = slot
+    jobs["work_offset"] = idx * np.uint64(fb) if model else 0
+    jobs["identifier_base"] = idx * np.uint64(1000)
+    jobs["src_size"] = fb
+    jobs["dst_capacity"] = cap
+    jobs["work_size"] = fb if model else 0
+    jobs["n_frames"] = n_frames
+    jobs["dtype"] = abi.DT_U16
+    jobs["first_result"] = (idx * np.uint64(n_frames)).astype(np.uint32)
+    params_fn(jobs["params"], idx)
+    return jobs, slot * n_frames * n_jobs, (fb * n_jobs if model else 0)
+
+def time_batch(name, data, jobs, dst_size, work_size, n_results, steps=5, warmup=2):
+    db = pkg.batch.DeviceBatch(data.view(torch.uint8).reshape(-1), jobs, dst_size, work_size, n_results)
+    for _ in range(warmup):
+        db.run()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        a.record(); db.run(); b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    res = db.results.cpu().numpy().view(np.uint32)
+    bad = int((res > 0xFFFFFF80).sum())
+    out_bytes = int(res[res <= 0xFFFFFF80].astype(np.int64).sum())
+    in_bytes = data.numel() * 2
+    med = ms[len(ms) // 2]
+    B = in_bytes + out_bytes
+    print(f"{name}: {med:.3f} ms (min {ms[0]:.3f}) in {in_bytes/2**30:.2f} GiB ratio {in_bytes/max(out_bytes,1):.2f} "
+          f"input {in_bytes/med/1e6:.1f} GB/s  algorithmic {B/med/1e6:.1f} GB/s = {B/med/1e6/6531.6*100:.1f}% of 6531.6  errors {bad}", flush=True)
+    return med
+
+
+def run_case(case, steps=5, warmup=2, dev="cuda"):
+    gtab = np.array([1, 2, 4, 7, 16, 60, 255, 1055], dtype=np.uint32)
+    otab = np.array([5, 42, 107, 200], dtype=np.uint32)
+    def p_plain(p, idx):
+        p["primary_preprocessing"] = abi.PRE_DIFF; p["primary_encoder_type"] = 1; p["primary_encoder_param"] = 16
+    def p_multi(p, idx):
+        p["primary_preprocessing"] = abi.PRE_DIFF; p["primary_encoder_type"] = 2; p["primary_encoder_param"] = 16; p["primary_encoder_outlier"] = 200
+    def p_cs(p, idx):
+        p_plain(p, idx); p["checksum_enabled"] = 1
+    def p_mixed(p, idx):
+        h = synth.mix(np.uint64(1) ^ idx)
+        p["primary_preprocessing"] = abi.PRE_DIFF
+        p["primary_encoder_type"] = 1 + (idx & np.uint64(1)).astype(np.uint32)
+        p["primary_encoder_param"] = gtab[(h & np.uint64(7)).astype(np.int64)]
+        p["primary_encoder_outlier"] = otab[((h >> np.uint64(3)) & np.uint64(3)).astype(np.int64)]
+    def p_model(p, idx):
+        p_plain(p, idx)
+        p["secondary_iterations"] = 255; p["secondary_preprocessing"] = abi.PRE_MODEL
+        p["secondary_encoder_type"] = 1; p["secondary_encoder_param"] = 8; p["model_rate"] = 8
+    if case in ("c3", "c3plain", "c3cs", "c3multi"):
+        n_chunks, n = 1 << 18, 2048
+        data = synth.chunks_torch(1, 0, n_chunks, n, esc=32 if case == "c3" else 0, device=dev)
+        pf = {"c3": p_mixed, "c3plain": p_plain, "c3cs": p_cs, "c3multi": p_multi}[case]
+        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, pf)
+        return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
+    if case in ("c4", "c1"):
+        n_chunks, n = (512 if case == "c4" else 1), 1 << 20
+        data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
+        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_plain)
+        return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
+    if case in ("c2", "c2one"):
+        R, F, n = (148 if case == "c2" else 1), 256, 32768
+        data = synth.frames_torch(1, 0, R, F, n, device=dev)
+        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, model=True)
+        return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
+    raise SystemExit("unknown case " + case)
