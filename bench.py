@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the compression hot path on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference ...                     (the reference's CPU library, rank 0 only)
+
+Metric (BASELINE.json): input GB/s compressed, device-timed; one JSON line on rank 0.
+A "step" is one pass of the batched driver (airs_cuda_compress_batch) over the whole
+workload of this rank, inputs resident in HBM.  Default workload = BASELINE config 2,
+batched: R independent contexts x 256 consecutive 64 KiB frames, DIFF+Golomb primary
+pass, MODEL+Golomb secondary passes with model update (inputs far larger than L2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+METRIC = "input GB/s compressed (device-timed)"
+FRAMES, FRAME_SAMPLES = 256, 32768
+CHUNK_SAMPLES = 2048
+
+
+# --------------------------------------------------------------------------- workloads
+
+def c2_params(abi):
+    return abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=abi.ENC_GOLOMB_ZERO,
+                           primary_encoder_param=16, secondary_iterations=255,
+                           secondary_preprocessing=abi.PRE_MODEL, secondary_encoder_type=abi.ENC_GOLOMB_ZERO,
+                           secondary_encoder_param=8, model_rate=8)
+
+
+def uniform_jobs(abi, n_jobs, n, n_frames, cap, first_job=0, model=True):
+    jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
+    fb = 2 * n
+    slot = (cap + 15) // 16 * 16
+    idx = np.arange(n_jobs, dtype=np.uint64)
+    jobs["src_offset"] = idx * np.uint64(fb * n_frames)
+    jobs["src_frame_stride"] = fb
+    jobs["dst_offset"] = idx * np.uint64(slot * n_frames)
+    jobs["dst_frame_stride"] = slot
+    jobs["work_offset"] = idx * np.uint64(fb)
+    jobs["identifier_base"] = (idx + np.uint64(first_job)) * np.uint64(1 << 16)
+    jobs["src_size"] = fb
+    jobs["dst_capacity"] = cap
+    jobs["work_size"] = fb if model else 0
+    jobs["n_frames"] = n_frames
+    jobs["dtype"] = abi.DT_U16
+    jobs["first_result"] = (idx * np.uint64(n_frames)).astype(np.uint32)
+    return jobs, int(slot) * n_frames * n_jobs, (fb * n_jobs if model else 16)
+
+
+def build_workload(pkg, name, units, first_unit, device=None):
+    """Returns dict(data=int16 tensor or numpy, jobs, dst_size, work_size, n_results, desc)."""
+    abi, synth = pkg.abi, pkg.synth
+    if name == "c2":
+        n, nf = FRAME_SAMPLES, FRAMES
+        cap = 2 * n + 64
+        jobs, dsz, wsz = uniform_jobs(abi, units, n, nf, cap, first_unit)
+        jobs["params"] = c2_params(abi)
+        if device is None:
+            data = np.stack([synth.frames(1, first_unit + c, nf, n) for c in range(units)])
+        else:
+            data = synth.frames_torch(1, first_unit, units, nf, n, device=device)
+        desc = "config2 batched: %d contexts x %d frames x 64 KiB u16, DIFF+GOLOMB_ZERO g16 -> MODEL+GOLOMB_ZERO g8, " \
+               "255 secondary iterations, model_rate 8" % (units, nf)
+    elif name == "c3":
+        n, nf = CHUNK_SAMPLES, 1
+        cap = abi.compress_bound(2 * n)
+        jobs, dsz, wsz = uniform_jobs(abi, units, n, nf, cap, first_unit, model=False)
+        idx = np.arange(first_unit, first_unit + units, dtype=np.uint64)
+        h = synth.mix(np.uint64(1) ^ idx)
+        gtab = np.array([1, 2, 4, 7, 16, 60, 255, 1055], dtype=np.uint32)
+        otab = np.array([5, 42, 107, 200], dtype=np.uint32)
+        P = jobs["params"]
+        P["primary_preprocessing"] = abi.PRE_DIFF
+        P["primary_encoder_type"] = 1 + (idx & np.uint64(1)).astype(np.uint32)
+        P["primary_encoder_param"] = gtab[(h & np.uint64(7)).astype(np.int64)]
+        P["primary_encoder_outlier"] = otab[((h >> np.uint64(3)) & np.uint64(3)).astype(np.int64)]
+        if device is None:
+            data = synth.chunks(1, first_unit, units, n, esc=32)
+        else:
+            data = synth.chunks_torch(1, first_unit, units, n, esc=32, device=device)
+        desc = "config3: %d independent 4 KiB chunks, DIFF, mixed Golomb zero/multi parameters, escape heavy" % units
+    else:
+        raise SystemExit("unknown workload " + name)
+    return dict(data=data, jobs=jobs, dst_size=dsz, work_size=wsz, n_results=units * nf, desc=desc,
+                n_samples_total=units * nf * n, model_bytes=(2 * 2 * n * units if name == "c2" else 0))
+
+
+# --------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+            "clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < 5.0:   # nvidia-smi needs ~1 s to come up
+            time.sleep(0.05)
+
+    def mark(self):
+        self.first = len(self.rows)
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        time.sleep(0.06)
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        self.rows = rows
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------- CPU arm
+
+def cpu_reference_run(pkg, workload, steps, warmup, target_s):
+    """Times the reference's own CPU library (oracle/_ref, else the oracle port) on a bounded
+    sample of the workload with every host core.  Returns (GB/s, info dict, sample job set, outputs)."""
+    from oracle import oracle_py  # the one place bench.py executes oracle/: the CPU baseline
+    if oracle_py.have_ref():
+        lib, kind = oracle_py.load_ref(), "reference"
+    else:
+        lib, kind = oracle_py.load_oracle(), "port"
+    cores = os.cpu_count() or 1
+    abi = pkg.abi
+    # pilot: one unit per core to size the sample
+    unit_bytes = (FRAMES * FRAME_SAMPLES * 2) if workload == "c2" else CHUNK_SAMPLES * 2
+    per_core = 1 if workload == "c2" else 256
+    units = cores * per_core
+    w = build_workload(pkg, workload, units, 0)
+    src = np.ascontiguousarray(w["data"]).view(np.uint8).reshape(-1)
+    js = dict(src=src, jobs=w["jobs"], dst_size=w["dst_size"], work_size=w["work_size"], n_results=w["n_results"], layout=0)
+    dst = np.zeros(js["dst_size"], dtype=np.uint8)
+    work = np.zeros(js["work_size"], dtype=np.uint8)
+
+    def once():
+        t0 = time.perf_counter()
+        res, init, _ = lib.run_jobs(src, dst, work, js["jobs"], 0, threads=cores)
+        return time.perf_counter() - t0, res
+    t_pilot, res = once()
+    reps = max(1, int(target_s / max(t_pilot, 1e-3)))   # repeat the sample so a step lasts ~target_s
+    times = []
+    for s in range(warmup + steps):
+        t = 0.0
+        for _ in range(reps):
+            dt, res = once()
+            t += dt
+        if s >= warmup:
+            times.append(t)
+    in_bytes = units * unit_bytes * reps
+    gbs = in_bytes * len(times) / sum(times) / 1e9
+    info = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind,
+            "sample": "%d x (%s) per step, %.1f s per step, %d threads" % (reps, w["desc"], sum(times) / len(times), cores)}
+    return gbs, info, js, (dst, res), sum(times) / len(times) * 1e3
+
+
+# --------------------------------------------------------------------------- main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--units", type=int, default=0, help="contexts (c2) or chunks (c3) per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    pkg = load_package()
+    abi = pkg.abi
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        gbs, info, _, _, ms = cpu_reference_run(pkg, args.workload, args.steps, args.warmup, target_s=3.0)
+        print(json.dumps({
+            "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic", "impl": "reference",
+            "config": {"workload": info["sample"], "timing": "host wall clock around the compress calls only"},
+            "cpu_baseline": info,
+            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this backend has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = pkg.load_library()
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+
+    units = args.units or (3 * sms if args.workload == "c2" else 1 << 20)
+    first_unit = rank * units                                   # weak scaling: fixed work per GPU
+    w = build_workload(pkg, args.workload, units, first_unit, device=device)
+    data = w["data"].view(torch.uint8).reshape(-1)
+    db = pkg.batch.DeviceBatch(data, w["jobs"], w["dst_size"], w["work_size"], w["n_results"],
+                               layout=abi.LAYOUT_SLOTS, device=device)
+    in_bytes = w["n_samples_total"] * 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        db.run()
+    barrier()
+    sampler.mark()
+    stream = torch.cuda.current_stream(device)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record(stream)
+    launches = 0
+    for s in range(args.steps):
+        db.run(stream)
+        launches += db.launches()
+        evs[s + 1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    res = db.results.cpu().numpy().view(np.uint32)
+    n_err = int((res > 0xFFFFFF80).sum())
+    out_bytes = int(res[res <= 0xFFFFFF80].astype(np.int64).sum())
+
+    t = torch.tensor([total_ms, float(in_bytes), float(out_bytes), float(n_err)], dtype=torch.float64, device=device)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_ms = float(tmax[0])
+    all_in, all_out, all_err = float(t[1]), float(t[2]), int(t[3])
+    value = all_in * args.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- end to end through the C-ABI with HOST buffers (copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e_units = max(1, min(units, (sms // 4) if args.workload == "c2" else 1 << 17))
+        we = build_workload(pkg, args.workload, e_units, first_unit, device=device)
+        src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
+        src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
+        cap_total = we["dst_size"]
+        dst_h = torch.empty(cap_total, dtype=torch.uint8).pin_memory()
+        jobs_h = np.ascontiguousarray(we["jobs"])
+        results_h = np.zeros(we["n_results"], dtype=np.uint32)
+        init_h = np.zeros(e_units, dtype=np.uint32)
+        offs_h = np.zeros(we["n_results"] + 1, dtype=np.uint64)
+        import ctypes as C
+        hb = abi.AirsHostBatch()
+        hb.src, hb.src_size = src_h.data_ptr(), src_h.numel()
+        hb.dst, hb.dst_size = dst_h.data_ptr(), dst_h.numel()
+        hb.work, hb.work_size = None, we["work_size"]
+        hb.jobs, hb.results, hb.init_results = jobs_h.ctypes.data, results_h.ctypes.data, init_h.ctypes.data
+        hb.out_offsets = offs_h.ctypes.data
+        # independent chunks: CONCAT (only the streams travel back); multi-frame contexts: SLOTS
+        e_layout = abi.LAYOUT_CONCAT if args.workload == "c3" else abi.LAYOUT_SLOTS
+        hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], e_layout
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        e_in = we["n_samples_total"] * 2
+        e2e = {"value": e_in * world * e_steps / float(td[0]) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(src_h.numel() + jobs_h.nbytes),
+               "d2h_bytes_per_step": (int(offs_h[-1]) + offs_h.nbytes if e_layout == abi.LAYOUT_CONCAT
+                                      else dst_h.numel()) + results_h.nbytes + init_h.nbytes,
+               "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, %s layout)" % ("CONCAT" if e_layout else "SLOTS"),
+               "timing": "host wall clock, max over ranks, %d steps" % e_steps}
+        lib.airs_cuda_release_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = in_bytes + out_bytes + w["model_bytes"]         # per launch, this rank
+    launch_ms = float(np.mean(step_ms))
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath)).get(args.workload)
+        if tr and tr.get("units") == units:
+            traffic = tr["dram_bytes_per_launch"]
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": w["desc"], "per_gpu_input_bytes": in_bytes, "layout": "SLOTS",
+                   "l2": "inputs (%.1f GiB per GPU) larger than the 126 MB L2; no flush needed" % (in_bytes / 2**30),
+                   "compression_ratio": all_in / max(all_out, 1), "frames_with_errors": all_err},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "airs_encode_kernel",
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                     "bytes_per_sample": alg_bytes / w["n_samples_total"]},
+        "clocks": clocks, "gpu_launches": launches,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        gbs, info, js, (cdst, cres), _ = cpu_reference_run(pkg, args.workload, 1, 0, target_s=args.cpu_seconds)
+        line["cpu_baseline"] = info
+        # parity spot check: the CPU sample is a prefix of this rank's workload
+        k = len(cres)
+        gres = res[:k]
+        same = bool(np.array_equal(gres, cres))
+        if same:
+            jobs = js["jobs"]
+            gdst = db.dst
+            for j in (0, len(jobs) // 2, len(jobs) - 1):
+                for f in (0, int(jobs[j]["n_frames"]) - 1):
+                    r = int(cres[int(jobs[j]["first_result"]) + f])
+                    o = int(jobs[j]["dst_offset"]) + f * int(jobs[j]["dst_frame_stride"])
+                    og = int(w["jobs"][j]["dst_offset"]) + f * int(w["jobs"][j]["dst_frame_stride"])
+                    same &= bool(np.array_equal(cdst[o:o + r], gdst[og:og + r].cpu().numpy()))
+        line["config"]["parity_vs_cpu_reference_sample"] = same
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

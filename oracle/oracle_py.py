@@ -49,7 +49,8 @@ class _Lib:
                 jobs.ctypes.data)
         tail = (results.ctypes.data, init_results.ctypes.data,
                 offs.ctypes.data if offs is not None else None)
-        if threads <= 1 or layout == 1 or n_jobs < 2 * threads:
+        threads = min(threads, n_jobs)
+        if threads <= 1 or layout == 1:
             rc = self.run(*args, 0, n_jobs, layout, *tail)
             assert rc == 0
         else:
