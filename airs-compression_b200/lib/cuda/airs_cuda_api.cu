@@ -39,6 +39,11 @@ int fail(int code, const char *fmt, ...)
 
 constexpr size_t kScratchHeader = 256; /* ticket counter and friends */
 
+size_t lookback_bytes(uint32_t n_results)
+{
+	return (8 * ((size_t)n_results + 1) + 127) & ~(size_t)127;
+}
+
 /* CTAs that fit the device at once for the persistent job loop */
 int resident_ctas(int *out)
 {
@@ -52,9 +57,9 @@ int resident_ctas(int *out)
 		if (prop.major < 10)
 			return fail(AIRS_E_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only",
 				    dev, prop.major, prop.minor);
-		/* 3 CTAs of 256 threads per SM (launch bounds of airs_encode_kernel); grid sized in
+		/* 6 CTAs of 128 threads per SM (launch bounds of airs_encode_kernel); grid sized in
 		 * multiples of the SM count */
-		cached = prop.multiProcessorCount * 3;
+		cached = prop.multiProcessorCount * 6;
 		cached_dev = dev;
 	}
 	*out = cached;
@@ -152,8 +157,8 @@ extern "C" int airs_cuda_device_count(void)
 
 extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)
 {
-	(void)n_jobs;
-	return kScratchHeader + 8 * ((size_t)n_results + 1);
+	/* header | one look-back word per frame (+1) | one 128-byte plan per job */
+	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs;
 }
 
 static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
@@ -173,8 +178,9 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	if (rc != AIRS_OK)
 		return rc;
 
-	size_t scratch = airs_cuda_batch_scratch_size(b->n_jobs, b->n_results);
-	CU(cudaMemsetAsync(b->scratch, 0, scratch, stream));
+	if ((uintptr_t)b->scratch & 127u)
+		return fail(AIRS_E_ARGUMENT, "scratch must be 128-byte aligned");
+	CU(cudaMemsetAsync(b->scratch, 0, kScratchHeader + lookback_bytes(b->n_results), stream));
 
 	AirsLaunch l;
 	memset(&l, 0, sizeof(l));
@@ -187,6 +193,7 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.out_offsets = b->out_offsets;
 	l.ticket = (uint32_t *)b->scratch;
 	l.lookback = (uint64_t *)((uint8_t *)b->scratch + kScratchHeader);
+	l.plans = (struct JobPlan *)((uint8_t *)b->scratch + kScratchHeader + lookback_bytes(b->n_results));
 	l.ctx_io = ctx_io;
 	l.dst_size = b->dst_size;
 	l.n_jobs = b->n_jobs;
@@ -194,8 +201,9 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.layout = b->layout;
 
 	unsigned int grid = b->n_jobs < (uint32_t)resident ? b->n_jobs : (unsigned int)resident;
+	CU(airs_launch_plan(&l, stream));
 	CU(airs_launch_encode(&l, grid, stream));
-	g_launches = 1;
+	g_launches = 2;
 	return AIRS_OK;
 }
 

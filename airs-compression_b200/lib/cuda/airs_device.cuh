@@ -127,10 +127,32 @@ __device__ __forceinline__ void airs_golomb(const EncConst &e, uint32_t v, uint3
 }
 
 /*
- * One residual -> up to two bit strings: (cw, cwlen) then (raw, rawlen).
- * ref cmp_encoder_encode_s16, encoder.c:327-378.  ENC is a compile-time copy
- * of e.type so each pass runs straight-line code.
+ * One zig-zag mapped residual m -> up to two bit strings: (cw, cwlen) then (raw, rawlen).
+ * ref cmp_encoder_encode_s16, encoder.c:335-376.  ENC is a compile-time copy of e.type.
  */
+template <int ENC>
+__device__ __forceinline__ void airs_encode_mapped(const EncConst &e, uint32_t m, uint32_t &cw, uint32_t &cwlen,
+						   uint32_t &raw, uint32_t &rawlen)
+{
+	if (ENC == CMP_ENCODER_GOLOMB_ZERO) {
+		uint32_t c, l;
+		airs_golomb(e, m + 1u, c, l);
+		bool esc = m >= e.outlier;
+		cw = esc ? m : c; /* escape: codeword 0 (L+1 zero bits) then m raw in 16 bits */
+		cwlen = esc ? e.L + 17u : l;
+		raw = 0;
+		rawlen = 0;
+	} else {
+		bool esc = m >= e.outlier;
+		uint32_t d = m - e.outlier;
+		uint32_t level = d < 4u ? 0u : (31u - (uint32_t)__clz((int)d)) >> 1;
+		airs_golomb(e, esc ? e.outlier + level : m, cw, cwlen);
+		raw = esc ? d : 0u;
+		rawlen = esc ? 2u * level + 2u : 0u;
+	}
+}
+
+/* one residual (low 16 bits of r16): ref cmp_encoder_encode_s16, encoder.c:327-378 */
 template <int ENC>
 __device__ __forceinline__ void airs_encode(const EncConst &e, uint32_t r16, uint32_t &cw, uint32_t &cwlen,
 					    uint32_t &raw, uint32_t &rawlen)
@@ -140,23 +162,8 @@ __device__ __forceinline__ void airs_encode(const EncConst &e, uint32_t r16, uin
 		cwlen = 16;
 		raw = 0;
 		rawlen = 0;
-	} else if (ENC == CMP_ENCODER_GOLOMB_ZERO) {
-		uint32_t m = airs_zigzag16(r16);
-		uint32_t c, l;
-		airs_golomb(e, m + 1u, c, l);
-		bool esc = m >= e.outlier;
-		cw = esc ? m : c; /* escape: codeword 0 (L+1 zero bits) then m raw in 16 bits */
-		cwlen = esc ? e.L + 17u : l;
-		raw = 0;
-		rawlen = 0;
 	} else {
-		uint32_t m = airs_zigzag16(r16);
-		bool esc = m >= e.outlier;
-		uint32_t d = m - e.outlier;
-		uint32_t level = d < 4u ? 0u : (31u - (uint32_t)__clz((int)d)) >> 1;
-		airs_golomb(e, esc ? e.outlier + level : m, cw, cwlen);
-		raw = esc ? d : 0u;
-		rawlen = esc ? 2u * level + 2u : 0u;
+		airs_encode_mapped<ENC>(e, airs_zigzag16(r16), cw, cwlen, raw, rawlen);
 	}
 }
 

@@ -8,8 +8,9 @@
 #include "../../../include/airs_cuda.h"
 
 struct airs_ctx_state;
+struct JobPlan;
 
-#define AIRS_THREADS 256
+#define AIRS_THREADS 128
 
 struct AirsLaunch {
 	const uint8_t *src;
@@ -20,6 +21,7 @@ struct AirsLaunch {
 	uint32_t *init_results;
 	uint64_t *out_offsets;
 	uint32_t *ticket;      /* zeroed before the launch: next job to hand out */
+	struct JobPlan *plans; /* n_jobs plans written by airs_plan_kernel */
 	uint64_t *lookback;    /* CONCAT: one status word per job, zeroed before the launch */
 	struct airs_ctx_state *ctx_io; /* host-shim path: context state in/out per job, else NULL */
 	uint64_t dst_size;
@@ -31,6 +33,7 @@ struct AirsLaunch {
 #ifdef __cplusplus
 extern "C" {
 #endif
+cudaError_t airs_launch_plan(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 #ifdef __cplusplus
 }

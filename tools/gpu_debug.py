@@ -32,7 +32,10 @@ def first_diff(js, want, got):
 seeds = [int(x) for x in sys.argv[1:]] or [100]
 for seed in seeds:
     rng = np.random.default_rng(seed)
-    js = jobgen.build_jobs(rng, 300, sizes=[1, 2, 3, 5, 7, 8, 63, 64, 65, 255, 256, 257, 2049, 4099], max_frames=5, allow_invalid=True)
+    if seed >= 200:
+        js = jobgen.build_jobs(rng, 120, sizes=[1000, 2047, 2048, 2049, 4099, 6000, 10000], max_frames=4, allow_invalid=False)
+    else:
+        js = jobgen.build_jobs(rng, 300, sizes=[1, 2, 3, 5, 7, 8, 63, 64, 65, 255, 256, 257, 2049, 4099], max_frames=5, allow_invalid=True)
     want = jobgen.run_cpu(O, js)
     got = pkg.batch.run_jobs_device(js)
     nbad = 0
