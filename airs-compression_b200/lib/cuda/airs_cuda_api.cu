@@ -57,9 +57,9 @@ int resident_ctas(int *out)
 		if (prop.major < 10)
 			return fail(AIRS_E_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only",
 				    dev, prop.major, prop.minor);
-		/* 6 CTAs of 128 threads per SM (launch bounds of airs_encode_kernel); grid sized in
-		 * multiples of the SM count */
-		cached = prop.multiProcessorCount * 6;
+		/* resident CTAs per SM as promised by the launch bounds of airs_encode_kernel; the
+		 * grid is a multiple of the SM count */
+		cached = prop.multiProcessorCount * AIRS_CTAS_PER_SM;
 		cached_dev = dev;
 	}
 	*out = cached;

@@ -31,11 +31,23 @@
 #include "airs_plan.cuh"
 #include "airs_private.h"
 
+#ifdef AIRS_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define PHASE_T(var) const long long var = clock64()
+#define PHASE_ADD(i, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_clk[i], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define PHASE_T(var)
+#define PHASE_ADD(i, a, b)
+#endif
+
 namespace {
 
 constexpr uint32_t kThreads = AIRS_THREADS; /* 128 */
-constexpr uint32_t kSpt = 16;               /* samples per thread and tile */
+constexpr uint32_t kSpt = AIRS_SPT;         /* samples per thread and tile */
+constexpr uint32_t kPairs = kSpt / 2;       /* packed 16x2 words per thread */
+constexpr uint32_t kVec = kSpt / 8;         /* 16-byte vectors per thread */
 constexpr uint32_t kTile = kThreads * kSpt; /* 2048 samples = 4 KiB of u16 */
+static_assert(kTile == 2048 && (kSpt == 8 || kSpt == 16), "tile geometry");
 constexpr uint32_t kWarps = kThreads / 32;
 constexpr uint32_t kStgWords = kTile * 48 / 32 + 16;
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
@@ -60,6 +72,8 @@ struct Pass {
 	uint32_t checksum;
 	uint32_t seq;
 	uint32_t err;
+	uint32_t lut_sel;   /* which table of Shared::lut this pass uses */
+	uint32_t lut_range; /* its half range R, 0: none */
 };
 
 /* context state between frames: the mutable part of struct cmp_context */
@@ -73,6 +87,10 @@ struct CtxState {
 struct Shared {
 	uint32_t stg[kStgWords]; /* MSB-first 32-bit words of the stream being assembled (all zero when idle) */
 	uint32_t wsum[kWarps];
+	uint4 in[2][kThreads * (kVec + 1)]; /* cp.async ring: per thread its samples + the word before them */
+	uint4 min[2][kThreads * kVec];      /* cp.async ring: per thread its slice of the model */
+	uint32_t lut[2][256]; /* codeword tables of the primary / secondary encoder (build_lut) */
+	uint32_t lut_range[2];
 	JobPlan plan;
 	airs_job job;
 	Pass pass;
@@ -128,6 +146,8 @@ __device__ __noinline__ void plan_pass(Shared &sh, bool forced_raw, bool align_c
 	}
 	P.enc = pl.enc[sel];
 	P.pre = pl.pre[sel];
+	P.lut_sel = sel;
+	P.lut_range = sh.lut_range[sel];
 	if (forced_raw) { /* ref cmp.c:383-386 */
 		P.pre = CMP_PREPROCESS_NONE;
 		P.enc.type = CMP_ENCODER_UNCOMPRESSED;
@@ -336,41 +356,46 @@ __device__ __noinline__ uint32_t frame_checksum(const Pass &P)
  * building blocks shared by the fast and the generic tile
  * ---------------------------------------------------------------------- */
 
-/* per-thread bit writer into the staging words: up to 32 bits per push */
+/* per-thread bit writer into the staging words: up to 32 bits per push.  Branch
+ * free: the word store is a predicated shared-memory reduction, so a push is a
+ * short dependency chain (two funnel shifts, an OR, an add) whatever the data. */
 struct Packer {
 	uint32_t lo;   /* pending bits, right aligned (bits above `fill` are stale) */
 	uint32_t fill; /* number of pending bits, < 32 between pushes */
-	uint32_t wp;   /* staging word the pending bits belong to */
+	uint32_t wp;   /* shared-memory byte address of the word the pending bits belong to */
 };
 
-__device__ __forceinline__ void packer_open(Packer &p, uint32_t bitpos)
+__device__ __forceinline__ void packer_open(Packer &p, const uint32_t *stg, uint32_t bitpos)
 {
 	p.lo = 0;
 	p.fill = bitpos & 31u;
-	p.wp = bitpos >> 5;
+	p.wp = (uint32_t)__cvta_generic_to_shared(stg) + ((bitpos >> 5) << 2);
 }
 
-__device__ __forceinline__ void packer_push(Packer &p, uint32_t *stg, uint32_t code, uint32_t len)
+__device__ __forceinline__ void packer_push(Packer &p, uint32_t code, uint32_t len)
 {
 	/* (hi:lo) = (lo << len) | code; ref bitstream_add_bits32, bitstream_writer.h:124-158 */
 	const uint32_t hi = __funnelshift_lc(p.lo, 0u, len);
 	p.lo = __funnelshift_lc(0u, p.lo, len) | code;
 	p.fill += len;
-	if (p.fill >= 32u) {
-		atomicOr(&stg[p.wp], __funnelshift_r(p.lo, hi, p.fill));
-		p.wp++;
-		p.fill -= 32u;
-	}
+	/* the completed word if fill >= 32, else 0: OR-ing 0 is harmless and keeps the push free
+	 * of branches (ptxas turns a predicated ATOMS into a branch) */
+	const uint32_t word = p.fill >= 32u ? __funnelshift_r(p.lo, hi, p.fill) : 0u;
+	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(p.wp), "r"(word) : "memory");
+	p.wp += (p.fill >> 5) << 2;
+	p.fill &= 31u;
 }
 
-__device__ __forceinline__ void packer_close(Packer &p, uint32_t *stg)
+__device__ __forceinline__ void packer_close(Packer &p)
 {
-	if (p.fill)
-		atomicOr(&stg[p.wp], p.lo << (32u - p.fill));
+	const uint32_t word = p.fill ? p.lo << (32u - p.fill) : 0u;
+	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(p.wp), "r"(word) : "memory");
 }
 
-/* exclusive scan of per-thread bit counts over the CTA; one barrier */
-__device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t &total)
+/* exclusive scan of per-thread bit counts over the CTA; one barrier.  `flag` (warp
+ * uniform, 0/1) is OR-reduced over the CTA on the way (bit 31 of the warp sums). */
+__device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t &total, uint32_t flag = 0,
+					       uint32_t *any = nullptr)
 {
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	uint32_t incl = tb;
@@ -382,9 +407,12 @@ __device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t
 			incl += t;
 	}
 	if (lane == 31)
-		sh.wsum[warp] = incl;
+		sh.wsum[warp] = incl | (flag << 31);
 	__syncthreads();
 	uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
+	if (any)
+		*any = __reduce_or_sync(kFull, ws) >> 31;
+	ws &= 0x7FFFFFFFu;
 	total = __reduce_add_sync(kFull, ws);
 	uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
 	return wpre + incl - tb;
@@ -414,10 +442,20 @@ __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, Cursor &c,
 	const uint32_t staged = c.sbits + tile_bits;
 	const uint32_t wfull = staged >> 5;
 
-	for (uint32_t w = tid; w < wfull; w += kThreads) {
-		uint32_t v = sh.stg[w];
-		sh.stg[w] = 0;
-		store_word(o, c.gw0 + w, v);
+	if ((uint64_t)c.gw0 * 4 >= o.lo && ((uint64_t)c.gw0 + wfull) * 4 <= o.hi) {
+		/* every word lies inside the window (the usual case): plain coalesced stores */
+		uint32_t *out = (uint32_t *)o.base4 + c.gw0;
+		for (uint32_t w = tid; w < wfull; w += kThreads) {
+			uint32_t v = sh.stg[w];
+			sh.stg[w] = 0;
+			out[w] = airs_bswap32(v);
+		}
+	} else {
+		for (uint32_t w = tid; w < wfull; w += kThreads) {
+			uint32_t v = sh.stg[w];
+			sh.stg[w] = 0;
+			store_word(o, c.gw0 + w, v);
+		}
 	}
 	if (tid == 0 && wfull) { /* thread 0 zeroed stg[0] itself; stg[wfull] is nobody else's */
 		uint32_t carry = sh.stg[wfull];
@@ -491,16 +529,15 @@ __device__ __noinline__ void tile_generic(Shared &sh, const OutWin &o, uint32_t 
 		return;
 	}
 	Packer pk;
-	packer_open(pk, c.sbits + excl);
+	packer_open(pk, sh.stg, c.sbits + excl);
 	uint32_t cum = c.gw0 * 32u + c.sbits + excl - 8u * a; /* stream bits before this thread's samples */
 	for (uint32_t i = i0; i < i1; i++) {
 		uint32_t x = need_x ? sample_at(P.src, P.dtype, i) : 0u;
 		uint32_t m = (P.pre == CMP_PREPROCESS_MODEL || P.model_mode == 2) ? (uint32_t)P.work[i] : 0u;
 		uint32_t cw, cl, rw, rl;
 		encode_any(e, residual_at(P, i, x), cw, cl, rw, rl);
-		packer_push(pk, sh.stg, cw, cl);
-		if (rl)
-			packer_push(pk, sh.stg, rw, rl);
+		packer_push(pk, cw, cl);
+		packer_push(pk, rw, rl);
 		cum += cl + rl;
 		/* model := samples, or model update, while the reference's writer has not
 		 * given up (ref cmp.c:300-311) */
@@ -508,14 +545,23 @@ __device__ __noinline__ void tile_generic(Shared &sh, const OutWin &o, uint32_t 
 			P.work[i] = (uint16_t)(P.model_mode == 1 ? x : airs_model_update(x, m, P.rate, P.is_signed));
 	}
 	if (tb)
-		packer_close(pk, sh.stg);
+		packer_close(pk);
 	__syncthreads();
 	copy_out(sh, o, c, tile_bits);
 }
 
 /* -------------------------------------------------------------------------
- * fast tile: 2048 samples, 16-bit container, 16-byte aligned source (and work
- * buffer when used).  Everything lives in registers; all loops are unrolled.
+ * fast path: full 2048-sample tiles of a 16-bit container, 16-byte aligned
+ * source (and work buffer when used).  One loop over the tiles of a frame;
+ * the loads of tile t+1 are issued before tile t is encoded; everything lives
+ * in registers and all inner loops are unrolled.
+ *
+ * Codewords come from a 256-entry table in shared memory indexed by the
+ * residual itself (r + R, |r| < R <= 128): entry = length << 26 | code bits,
+ * built per job for both passes (build_lut).  This covers escapes as well, as
+ * long as the whole code of the sample fits 25 bits.  A warp whose 512 samples
+ * do not all hit the table computes its codewords arithmetically instead
+ * (airs_golomb).
  * ---------------------------------------------------------------------- */
 
 /* packed 16x2 zig-zag: ref map_to_unsigned, encoder.c:274-286 */
@@ -526,190 +572,318 @@ __device__ __forceinline__ uint32_t zigzag2(uint32_t d)
 	return ((d << 1) & 0xFFFEFFFEu) ^ sign;
 }
 
-__device__ __forceinline__ void load8(const uint16_t *p, uint32_t w[8], bool ro)
+/* Ampere-style asynchronous copies global -> shared (LDGSTS): the loads of the next
+ * tile are in flight while this one is encoded, without holding registers */
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void *g)
 {
-	const uint4 *q = (const uint4 *)p;
-	uint4 a = ro ? __ldg(q) : q[0], b = ro ? __ldg(q + 1) : q[1];
-	w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-	w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
 }
 
-template <int ENC, int PRE, int MODEL>
-__device__ __noinline__ void tile_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
-				       bool size_only)
+__device__ __forceinline__ void cp_async4(uint32_t smem, const void *g)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(g) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit()
+{
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+	asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr uint32_t kLutLenShift = 26;
+constexpr uint32_t kLutCodeMask = (1u << kLutLenShift) - 1;
+
+/* table of one encoder; returns the usable half range R (0: table unusable).
+ * All threads call it; contains one barrier. */
+__device__ __noinline__ uint32_t build_lut(const EncConst &e, uint32_t *lut)
+{
+	uint32_t bad = 0; /* bit i: an entry with |r| < 8 << i does not fit */
+
+	if (e.type == CMP_ENCODER_UNCOMPRESSED)
+		return 0; /* uniform */
+	for (uint32_t idx = threadIdx.x; idx < 256; idx += kThreads) {
+		const uint32_t r = (idx - 128u) & 0xFFFFu;
+		uint32_t cw, cl, rw, rl;
+		if (e.type == CMP_ENCODER_GOLOMB_ZERO)
+			airs_encode<CMP_ENCODER_GOLOMB_ZERO>(e, r, cw, cl, rw, rl);
+		else
+			airs_encode<CMP_ENCODER_GOLOMB_MULTI>(e, r, cw, cl, rw, rl);
+		const uint32_t len = cl + rl;
+		const bool ok = len <= 25u;
+		lut[idx] = ok ? (len << kLutLenShift) | (cw << rl) | rw : 0u;
+		if (!ok) {
+			const uint32_t dist = idx >= 128u ? idx - 127u : 128u - idx; /* r in [-R, R) <=> dist <= R */
+			bad |= dist <= 8u ? 0x1Fu : dist <= 16u ? 0x1Eu : dist <= 32u ? 0x1Cu : dist <= 64u ? 0x18u : 0x10u;
+		}
+	}
+	bad = __syncthreads_or(bad);
+	return 128u >> __popc(bad); /* 128, 64, 32, 16, 8 or (all bad) 4 */
+}
+
+/* the arithmetic encoders on a packed pair of zig-zag mapped samples; only
+ * called by warps that missed the table */
+__device__ __forceinline__ void encode_pair_compute(const EncConst &e, uint32_t z, uint32_t &pc, uint32_t &ph,
+						    uint32_t &pl)
+{
+	if (e.type == CMP_ENCODER_GOLOMB_ZERO) {
+		uint32_t c0, l0, c1, l1, r, q;
+		airs_encode_mapped<CMP_ENCODER_GOLOMB_ZERO>(e, z & 0xFFFFu, c0, l0, r, q);
+		airs_encode_mapped<CMP_ENCODER_GOLOMB_ZERO>(e, z >> 16, c1, l1, r, q);
+		pc = __funnelshift_lc(0u, c0, l1) | c1;
+		ph = __funnelshift_lc(c0, 0u, l1);
+		pl = l0 + l1;
+	} else {
+		/* escapes carry a raw part: samples are 64-bit strings, the pair fits 64 bits
+		 * or is flagged through pl > 64 */
+		uint32_t c0, l0, r0, q0, c1, l1, r1, q1;
+		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, z & 0xFFFFu, c0, l0, r0, q0);
+		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, z >> 16, c1, l1, r1, q1);
+		const uint64_t s0 = ((uint64_t)c0 << q0) | r0, s1 = ((uint64_t)c1 << q1) | r1;
+		const uint32_t sl0 = l0 + q0, sl1 = l1 + q1;
+		const uint64_t s = sl1 < 64u ? (s0 << sl1) | s1 : 0;
+		pc = (uint32_t)s;
+		ph = (uint32_t)(s >> 32);
+		pl = sl0 + sl1;
+	}
+}
+
+__device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_tiles,
+					bool size_only)
 {
 	const Pass &P = sh.pass;
 	const EncConst e = P.enc;
 	const uint32_t tid = threadIdx.x;
-	const uint32_t i0 = base + tid * kSpt;
-	const uint16_t *src = (const uint16_t *)P.src;
-	uint32_t w[8], mw[8], d[8];
+	const uint32_t pre = P.pre, model_mode = P.model_mode, enc = e.type;
+	const uint16_t *src = (const uint16_t *)P.src + tid * kSpt;
+	uint16_t *work = P.work + tid * kSpt;
+	const bool need_x = pre != CMP_PREPROCESS_IWT || model_mode;
+	const bool need_m = pre == CMP_PREPROCESS_MODEL || model_mode == 2;
+	/* table lookup constants: u = r + R per lane, hit <=> u < 2R */
+	const uint32_t R = P.lut_range;
+	const uint32_t rp = R * 0x00010001u, notmask = ~((2u * R - 1u) * 0x00010001u), imask = (2u * R - 1u) << 2;
+	const char *lut = (const char *)(sh.lut[P.lut_sel] + (128u - R));
+	/* per-thread slots of the two cp.async rings; a thread only ever reads what it copied
+	 * itself, so no barrier is involved in the input staging */
+	const uint32_t in_sm[2] = { (uint32_t)__cvta_generic_to_shared(&sh.in[0][tid * (kVec + 1)]),
+				    (uint32_t)__cvta_generic_to_shared(&sh.in[1][tid * (kVec + 1)]) };
+	const uint32_t m_sm[2] = { (uint32_t)__cvta_generic_to_shared(&sh.min[0][tid * kVec]),
+				   (uint32_t)__cvta_generic_to_shared(&sh.min[1][tid * kVec]) };
+	const bool diff = pre == CMP_PREPROCESS_DIFF;
 
-	if (PRE != CMP_PREPROCESS_IWT || MODEL)
-		load8(src + i0, w, true);
-	if (PRE == CMP_PREPROCESS_MODEL || MODEL == 2)
-		load8(P.work + i0, mw, false);
+#define AIRS_STAGE_TILE(t_)                                                                          \
+	do {                                                                                         \
+		const uint32_t st_ = (t_) & 1u, b_ = (t_) * kTile;                                   \
+		if (need_x) {                                                                        \
+			for (uint32_t v_ = 0; v_ < kVec; v_++)                                       \
+				cp_async16(in_sm[st_] + 16 * v_, src + b_ + 8 * v_);                 \
+			if (diff && (b_ | tid))                                                      \
+				cp_async4(in_sm[st_] + 16 * kVec, src + b_ - 2); /* [x(i0-2), x(i0-1)] */ \
+		}                                                                                    \
+		if (need_m) {                                                                        \
+			for (uint32_t v_ = 0; v_ < kVec; v_++)                                       \
+				cp_async16(m_sm[st_] + 16 * v_, work + b_ + 8 * v_);                 \
+		}                                                                                    \
+		cp_async_commit();                                                                   \
+	} while (0)
 
-	/* packed residuals: ref preprocess.c:268-290,348-353,406-411 */
-	if (PRE == CMP_PREPROCESS_NONE) {
-#pragma unroll
-		for (int k = 0; k < 8; k++)
-			d[k] = w[k];
-	} else if (PRE == CMP_PREPROCESS_DIFF) {
-		uint32_t pw = i0 ? __ldg((const uint32_t *)(src + i0 - 2)) : 0u; /* [x(i0-2), x(i0-1)] */
-#pragma unroll
-		for (int k = 0; k < 8; k++) {
-			uint32_t prev = __funnelshift_l(k ? w[k - 1] : pw, w[k], 16); /* [x(2k-1), x(2k)] */
-			d[k] = __vsub2(w[k], prev);
-		}
-	} else if (PRE == CMP_PREPROCESS_IWT) {
-		load8(P.work + i0, d, false);
-	} else {
-#pragma unroll
-		for (int k = 0; k < 8; k++)
-			d[k] = __vsub2(w[k], mw[k]);
-	}
+	AIRS_STAGE_TILE(0u);
 
-	/* codewords; the two samples of a word are merged into one string of pl bits:
-	 * (ph:pc) = code_lo << len_hi | code_hi */
-	uint32_t pc[8], ph[8], pl[8], tb = 0, mx = 0;
-#pragma unroll
-	for (int k = 0; k < 8; k++) {
-		if (ENC == CMP_ENCODER_UNCOMPRESSED) {
-			pc[k] = __byte_perm(d[k], 0, 0x1032); /* first sample in the upper half */
-			ph[k] = 0;
-			pl[k] = 32;
-		} else if (ENC == CMP_ENCODER_GOLOMB_ZERO) {
-			const uint32_t z = zigzag2(d[k]);
-			const uint32_t m0 = z & 0xFFFFu, m1 = z >> 16;
-			uint32_t g0, g1, gl0, gl1;
-			airs_golomb(e, m0 + 1u, g0, gl0);
-			airs_golomb(e, m1 + 1u, g1, gl1);
-			const bool e0 = m0 >= e.outlier, e1 = m1 >= e.outlier;
-			const uint32_t c0 = e0 ? m0 : g0, l0 = e0 ? e.L + 17u : gl0;
-			const uint32_t c1 = e1 ? m1 : g1, l1 = e1 ? e.L + 17u : gl1;
-			pc[k] = __funnelshift_lc(0u, c0, l1) | c1;
-			ph[k] = __funnelshift_lc(c0, 0u, l1);
-			pl[k] = l0 + l1;
+	for (uint32_t t = 0; t < n_tiles; t++) {
+		const uint32_t base = t * kTile, st = t & 1u;
+		uint32_t w[kPairs], mw[kPairs], d[kPairs];
+
+		PHASE_T(t0);
+		/* next tile's copies go out before this tile is encoded */
+		if (t + 1 < n_tiles) {
+			AIRS_STAGE_TILE(t + 1);
+			cp_async_wait<1>();
 		} else {
-			/* escapes carry a raw part: samples are 64-bit strings, the pair fits
-			 * 64 bits or is flagged through mx */
-			const uint32_t z = zigzag2(d[k]);
-			uint32_t c0, l0, r0, q0, c1, l1, r1, q1;
-			airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, z & 0xFFFFu, c0, l0, r0, q0);
-			airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, z >> 16, c1, l1, r1, q1);
-			const uint64_t s0 = ((uint64_t)c0 << q0) | r0, s1 = ((uint64_t)c1 << q1) | r1;
-			const uint32_t sl0 = l0 + q0, sl1 = l1 + q1;
-			const uint64_t s = sl1 < 64u ? (s0 << sl1) | s1 : 0;
-			pc[k] = (uint32_t)s;
-			ph[k] = (uint32_t)(s >> 32);
-			pl[k] = sl0 + sl1;
+			cp_async_wait<0>();
 		}
-		tb += pl[k];
-		mx = max(mx, pl[k]);
-	}
-	/* 0: every pair of the warp fits 32 bits, 1: 64 bits, 2: not even that (rare) */
-	const uint32_t wide = __reduce_max_sync(kFull, mx > 64u ? 2u : (mx > 32u ? 1u : 0u));
-
-	uint32_t tile_bits;
-	const uint32_t excl = block_scan(sh, tb, tile_bits);
-	if (size_only) {
-		const uint32_t staged = c.sbits + tile_bits;
-		c.gw0 += staged >> 5;
-		c.sbits = staged & 31u;
-		__syncthreads();
-		return;
-	}
-	const uint32_t tile_end = c.gw0 * 32u + c.sbits + tile_bits - 8u * a; /* stream bits after this tile */
-
-	if (__syncthreads_or(wide == 2u)) {
-		/* a pair longer than 64 bits (multi-escape pile-up): redo the tile the slow way.
-		 * Nothing has been staged yet. */
-		tile_generic(sh, o, a, c, base, false);
-		return;
-	}
-
-	Packer pk;
-	packer_open(pk, c.sbits + excl);
-	if (wide == 0u) {
+		if (need_x) {
 #pragma unroll
-		for (int k = 0; k < 8; k++)
-			packer_push(pk, sh.stg, pc[k], pl[k]);
-	} else {
-#pragma unroll
-		for (int k = 0; k < 8; k++) {
-			const uint32_t hl = pl[k] > 32u ? pl[k] - 32u : 0u;
-			packer_push(pk, sh.stg, ph[k], hl);
-			packer_push(pk, sh.stg, pc[k], pl[k] - hl);
+			for (uint32_t v = 0; v < kVec; v++) {
+				const uint4 q = sh.in[st][tid * (kVec + 1) + v];
+				w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+			}
 		}
-	}
-	packer_close(pk, sh.stg);
-
-	/* model := samples, or model update (ref cmp.c:304-311) */
-	if (MODEL) {
-		if (tile_end < P.trip) {
-			uint32_t nm[8];
+		if (need_m) {
 #pragma unroll
-			for (int k = 0; k < 8; k++) {
-				if (MODEL == 1) {
-					nm[k] = w[k];
-				} else {
-					uint32_t lo = airs_model_update(w[k] & 0xFFFFu, mw[k] & 0xFFFFu, P.rate, P.is_signed);
-					uint32_t hi = airs_model_update(w[k] >> 16, mw[k] >> 16, P.rate, P.is_signed);
-					nm[k] = lo | (hi << 16);
+			for (uint32_t v = 0; v < kVec; v++) {
+				const uint4 q = sh.min[st][tid * kVec + v];
+				mw[4 * v] = q.x; mw[4 * v + 1] = q.y; mw[4 * v + 2] = q.z; mw[4 * v + 3] = q.w;
+			}
+		}
+		PHASE_T(t1);
+		PHASE_ADD(0, t0, t1);
+
+		/* packed residuals: ref preprocess.c:268-290,348-353,406-411 */
+		if (pre == CMP_PREPROCESS_DIFF) {
+			const uint32_t pw = (base | tid) ? sh.in[st][tid * (kVec + 1) + kVec].x : 0u; /* [x(i0-2), x(i0-1)] */
+#pragma unroll
+			for (int k = 0; k < (int)kPairs; k++)
+				d[k] = __vsub2(w[k], __funnelshift_l(k ? w[k - 1] : pw, w[k], 16));
+		} else if (pre == CMP_PREPROCESS_MODEL) {
+#pragma unroll
+			for (int k = 0; k < (int)kPairs; k++)
+				d[k] = __vsub2(w[k], mw[k]);
+		} else if (pre == CMP_PREPROCESS_IWT) {
+			{
+#pragma unroll
+				for (uint32_t v = 0; v < kVec; v++) {
+					const uint4 q = ((const uint4 *)(work + base))[v];
+					d[4 * v] = q.x; d[4 * v + 1] = q.y; d[4 * v + 2] = q.z; d[4 * v + 3] = q.w;
 				}
 			}
-			uint4 *q = (uint4 *)(P.work + i0);
-			q[0] = make_uint4(nm[0], nm[1], nm[2], nm[3]);
-			q[1] = make_uint4(nm[4], nm[5], nm[6], nm[7]);
 		} else {
-			/* the stream overflows its capacity inside this tile: per-sample gate */
-			uint32_t cum = c.gw0 * 32u + c.sbits + excl - 8u * a;
-			for (uint32_t i = i0; i < i0 + kSpt; i++) {
-				uint32_t x = sample_at(P.src, P.dtype, i);
-				uint32_t m = P.work[i];
-				uint32_t cw, cl, rw, rl;
-				encode_any(e, residual_at(P, i, x), cw, cl, rw, rl);
-				cum += cl + rl;
-				if (cum < P.trip)
-					P.work[i] = (uint16_t)(MODEL == 1 ? x : airs_model_update(x, m, P.rate, P.is_signed));
+#pragma unroll
+			for (int k = 0; k < (int)kPairs; k++)
+				d[k] = w[k];
+		}
+
+		/* codewords; the two samples of a word are merged into one string of pl bits:
+		 * (ph:pc) = code_lo << len_hi | code_hi */
+		uint32_t pc[kPairs], ph[kPairs], pl[kPairs], tb = 0, mx = 0;
+		if (enc == CMP_ENCODER_UNCOMPRESSED) {
+#pragma unroll
+			for (int k = 0; k < (int)kPairs; k++) {
+				pc[k] = __byte_perm(d[k], 0, 0x1032); /* first sample in the upper half */
+				ph[k] = 0;
+				pl[k] = 32;
+			}
+			tb = 32 * kPairs;
+			mx = 32;
+		} else {
+			uint32_t u[kPairs], chk = 0;
+#pragma unroll
+			for (int k = 0; k < (int)kPairs; k++) {
+				asm("add.u16x2 %0, %1, %2;" : "=r"(u[k]) : "r"(d[k]), "r"(rp));
+				chk |= u[k];
+			}
+			if (__all_sync(kFull, R >= 8u && (chk & notmask) == 0u)) {
+#pragma unroll
+				for (int k = 0; k < (int)kPairs; k++) {
+					const uint32_t e0 = *(const uint32_t *)(lut + ((u[k] << 2) & imask));
+					const uint32_t e1 = *(const uint32_t *)(lut + ((u[k] >> 14) & imask));
+					const uint32_t l1 = e1 >> kLutLenShift, c0 = e0 & kLutCodeMask;
+					pc[k] = __funnelshift_lc(0u, c0, l1) | (e1 & kLutCodeMask);
+					ph[k] = __funnelshift_lc(c0, 0u, l1);
+					pl[k] = (e0 >> kLutLenShift) + l1;
+					tb += pl[k];
+					mx = max(mx, pl[k]);
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < (int)kPairs; k++) {
+					encode_pair_compute(e, zigzag2(d[k]), pc[k], ph[k], pl[k]);
+					tb += pl[k];
+					mx = max(mx, pl[k]);
+				}
 			}
 		}
-	}
-	__syncthreads();
-	copy_out(sh, o, c, tile_bits);
-}
+		/* 0: every pair of the warp fits 32 bits, 1: 64 bits, 2: not even that (rare) */
+		const uint32_t wide = __reduce_max_sync(kFull, mx > 64u ? 2u : (mx > 32u ? 1u : 0u));
+		PHASE_T(t2);
+		PHASE_ADD(1, t1, t2);
 
-template <int ENC, int PRE>
-__device__ __forceinline__ void tile_fast_model(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
-						bool size_only, uint32_t model_mode)
-{
-	if (model_mode == 0)
-		tile_fast<ENC, PRE, 0>(sh, o, a, c, base, size_only);
-	else if (model_mode == 1)
-		tile_fast<ENC, PRE, 1>(sh, o, a, c, base, size_only);
-	else
-		tile_fast<ENC, PRE, 2>(sh, o, a, c, base, size_only);
-}
+		uint32_t tile_bits, overlong;
+		const uint32_t excl = block_scan(sh, tb, tile_bits, wide == 2u, &overlong);
+		PHASE_T(t3);
+		PHASE_ADD(2, t2, t3);
+		if (size_only) {
+			const uint32_t staged = c.sbits + tile_bits;
+			c.gw0 += staged >> 5;
+			c.sbits = staged & 31u;
+			__syncthreads();
+		} else if (overlong) {
+			__syncthreads(); /* the scan's warp sums are reused by tile_generic */
+			/* a pair longer than 64 bits (multi-escape pile-up): the slow way.  Nothing
+			 * has been staged yet. */
+			tile_generic(sh, o, a, c, base, false);
+		} else {
+			const uint32_t tile_end = c.gw0 * 32u + c.sbits + tile_bits - 8u * a; /* stream bits after this tile */
+			/* two independent writers (pairs 0-3 and 4-7) double the instruction level
+			 * parallelism of the packing chain */
+			Packer pa, pb;
+			const uint32_t pos = c.sbits + excl;
+			packer_open(pa, sh.stg, pos);
+			uint32_t half = 0;
+#pragma unroll
+			for (int k = 0; k < (int)kPairs / 2; k++)
+				half += pl[k];
+			packer_open(pb, sh.stg, pos + half);
+			if (wide == 0u) {
+#pragma unroll
+				for (int k = 0; k < (int)kPairs / 2; k++) {
+					packer_push(pa, pc[k], pl[k]);
+					packer_push(pb, pc[k + kPairs / 2], pl[k + kPairs / 2]);
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < (int)kPairs / 2; k++) {
+					const uint32_t ha = pl[k] > 32u ? pl[k] - 32u : 0u;
+					const uint32_t hb = pl[k + kPairs / 2] > 32u ? pl[k + kPairs / 2] - 32u : 0u;
+					packer_push(pa, ph[k], ha);
+					packer_push(pb, ph[k + kPairs / 2], hb);
+					packer_push(pa, pc[k], pl[k] - ha);
+					packer_push(pb, pc[k + kPairs / 2], pl[k + kPairs / 2] - hb);
+				}
+			}
+			packer_close(pa);
+			packer_close(pb);
+			PHASE_T(t4);
+			PHASE_ADD(3, t3, t4);
 
-template <int ENC>
-__device__ __forceinline__ void tile_fast_pre(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
-					      bool size_only, uint32_t pre, uint32_t model_mode)
-{
-	switch (pre) {
-	case CMP_PREPROCESS_NONE:
-		tile_fast_model<ENC, CMP_PREPROCESS_NONE>(sh, o, a, c, base, size_only, model_mode);
-		break;
-	case CMP_PREPROCESS_DIFF:
-		tile_fast_model<ENC, CMP_PREPROCESS_DIFF>(sh, o, a, c, base, size_only, model_mode);
-		break;
-	case CMP_PREPROCESS_IWT:
-		tile_fast_model<ENC, CMP_PREPROCESS_IWT>(sh, o, a, c, base, size_only, model_mode);
-		break;
-	default: /* MODEL preprocessing only happens in secondary passes: model_mode == 2 */
-		tile_fast<ENC, CMP_PREPROCESS_MODEL, 2>(sh, o, a, c, base, size_only);
-		break;
+			/* model := samples, or model update (ref cmp.c:304-311) */
+			if (model_mode) {
+				if (tile_end < P.trip) {
+					uint32_t nm[kPairs];
+#pragma unroll
+					for (int k = 0; k < (int)kPairs; k++) {
+						if (model_mode == 1) {
+							nm[k] = w[k];
+						} else {
+							uint32_t lo = airs_model_update(w[k] & 0xFFFFu, mw[k] & 0xFFFFu, P.rate, P.is_signed);
+							uint32_t hi = airs_model_update(w[k] >> 16, mw[k] >> 16, P.rate, P.is_signed);
+							nm[k] = lo | (hi << 16);
+						}
+					}
+					uint4 *q = (uint4 *)(work + base);
+#pragma unroll
+					for (uint32_t v = 0; v < kVec; v++)
+						q[v] = make_uint4(nm[4 * v], nm[4 * v + 1], nm[4 * v + 2], nm[4 * v + 3]);
+				} else {
+					/* the stream overflows its capacity inside this tile: per-sample gate */
+					uint32_t cum = c.gw0 * 32u + c.sbits + excl - 8u * a;
+					const uint32_t i0 = base + tid * kSpt;
+					for (uint32_t i = i0; i < i0 + kSpt; i++) {
+						uint32_t x = sample_at(P.src, P.dtype, i);
+						uint32_t m = P.work[i];
+						uint32_t cw, cl, rw, rl;
+						encode_any(e, residual_at(P, i, x), cw, cl, rw, rl);
+						cum += cl + rl;
+						if (cum < P.trip)
+							P.work[i] = (uint16_t)(model_mode == 1 ? x : airs_model_update(x, m, P.rate, P.is_signed));
+					}
+				}
+			}
+			PHASE_T(t5);
+			__syncthreads();
+			PHASE_T(t6);
+			copy_out(sh, o, c, tile_bits);
+			PHASE_T(t7);
+			PHASE_ADD(4, t4, t5);
+			PHASE_ADD(5, t5, t6);
+			PHASE_ADD(6, t6, t7);
+			PHASE_ADD(7, t0, t7);
+		}
 	}
+#undef AIRS_STAGE_TILE
 }
 
 /* one pass over one frame; returns the stream size or an error (uniform over the CTA).
@@ -734,21 +908,14 @@ __device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 	if (P.pre == CMP_PREPROCESS_IWT)
 		iwt_global(P);
 
-	const uint32_t n = P.n, pre = P.pre, enc = P.enc.type, model_mode = P.model_mode;
+	const uint32_t n = P.n, pre = P.pre, model_mode = P.model_mode;
 	const bool fast_ok = P.dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)P.src & 15u) == 0 &&
 			     (((uintptr_t)P.work & 15u) == 0 || (pre < CMP_PREPROCESS_IWT && !model_mode));
-	for (uint32_t base = 0; base < n; base += kTile) {
-		if (fast_ok && base + kTile <= n) {
-			if (enc == CMP_ENCODER_UNCOMPRESSED)
-				tile_fast_pre<CMP_ENCODER_UNCOMPRESSED>(sh, o, a, c, base, size_only, pre, model_mode);
-			else if (enc == CMP_ENCODER_GOLOMB_ZERO)
-				tile_fast_pre<CMP_ENCODER_GOLOMB_ZERO>(sh, o, a, c, base, size_only, pre, model_mode);
-			else
-				tile_fast_pre<CMP_ENCODER_GOLOMB_MULTI>(sh, o, a, c, base, size_only, pre, model_mode);
-		} else {
-			tile_generic(sh, o, a, c, base, size_only);
-		}
-	}
+	const uint32_t n_fast = fast_ok ? n / kTile : 0u;
+	if (n_fast)
+		frame_fast(sh, o, a, c, n_fast, size_only);
+	for (uint32_t base = n_fast * kTile; base < n; base += kTile)
+		tile_generic(sh, o, a, c, base, size_only);
 	__syncthreads();
 
 	const uint32_t frame_bits = c.gw0 * 32u + c.sbits - 8u * a;
@@ -846,7 +1013,7 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 		b.init_results[j] = pl.init_result;
 }
 
-__global__ void __launch_bounds__(AIRS_THREADS, 6) airs_encode_kernel(AirsLaunch b)
+__global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_kernel(AirsLaunch b)
 {
 	__shared__ Shared sh;
 	const uint32_t tid = threadIdx.x;
@@ -857,6 +1024,7 @@ __global__ void __launch_bounds__(AIRS_THREADS, 6) airs_encode_kernel(AirsLaunch
 		sh.ticket = atomicAdd(b.ticket, 1u);
 
 	for (;;) {
+		PHASE_T(j0);
 		__syncthreads();
 		const uint32_t job = sh.ticket;
 		if (job >= b.n_jobs)
@@ -867,6 +1035,16 @@ __global__ void __launch_bounds__(AIRS_THREADS, 6) airs_encode_kernel(AirsLaunch
 		else if (tid < 62)
 			((uint32_t *)&sh.job)[tid - 32] = ((const uint32_t *)&b.jobs[job])[tid - 32];
 		__syncthreads();
+		PHASE_T(j1);
+		PHASE_ADD(8, j0, j1);
+		if (!sh.plan.frame_err) { /* codeword tables of this job's encoders (uniform branch) */
+			uint32_t r0 = build_lut(sh.plan.enc[0], sh.lut[0]);
+			uint32_t r1 = sh.plan.sec_iter ? build_lut(sh.plan.enc[1], sh.lut[1]) : 0u;
+			if (tid == 0) {
+				sh.lut_range[0] = r0;
+				sh.lut_range[1] = r1;
+			}
+		}
 		if (tid == 0) {
 			sh.ticket = atomicAdd(b.ticket, 1u); /* next job, fetched while this one runs */
 			CtxState &c = sh.ctx;
@@ -883,11 +1061,16 @@ __global__ void __launch_bounds__(AIRS_THREADS, 6) airs_encode_kernel(AirsLaunch
 		}
 		const uint32_t n_frames = sh.job.n_frames;
 		const uint32_t first = sh.job.first_result;
+		PHASE_T(j2);
+		PHASE_ADD(9, j1, j2);
 
 		for (uint32_t f = 0; f < n_frames; f++) {
+			PHASE_T(f0);
 			if (tid == 0)
 				plan_frame(sh, b, f);
 			__syncthreads();
+			PHASE_T(f1);
+			PHASE_ADD(10, f0, f1);
 			uint32_t r;
 			if (b.layout == AIRS_LAYOUT_CONCAT) {
 				/* size first (exact, no output), then the offset from the scan, then one
@@ -939,6 +1122,8 @@ __global__ void __launch_bounds__(AIRS_THREADS, 6) airs_encode_kernel(AirsLaunch
 					sh.ctx.seq = (sh.ctx.seq + 1u) & 0xFFu;
 				b.results[first + f] = r;
 			}
+			PHASE_T(f2);
+			PHASE_ADD(11, f1, f2);
 		}
 		if (tid == 0 && b.ctx_io) {
 			airs_ctx_state &st = b.ctx_io[job];
@@ -949,6 +1134,17 @@ __global__ void __launch_bounds__(AIRS_THREADS, 6) airs_encode_kernel(AirsLaunch
 		}
 	}
 }
+
+#ifdef AIRS_PHASE_CLOCKS
+extern "C" void airs_phase_clocks(unsigned long long *out, int reset)
+{
+	cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(g_phase_clk));
+	if (reset) {
+		unsigned long long z[16] = { 0 };
+		cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+	}
+}
+#endif
 
 extern "C" cudaError_t airs_launch_plan(const AirsLaunch *b, cudaStream_t stream)
 {

@@ -10,7 +10,11 @@
 struct airs_ctx_state;
 struct JobPlan;
 
-#define AIRS_THREADS 128
+#ifndef AIRS_SPT
+#define AIRS_SPT 8 /* samples per thread and tile: 8 (256 threads) or 16 (128 threads) */
+#endif
+#define AIRS_THREADS (2048 / AIRS_SPT)
+#define AIRS_CTAS_PER_SM (AIRS_SPT == 8 ? 4 : 6)
 
 struct AirsLaunch {
 	const uint8_t *src;

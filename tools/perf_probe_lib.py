@@ -73,8 +73,8 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         pf = {"c3": p_mixed, "c3plain": p_plain, "c3cs": p_cs, "c3multi": p_multi}[case]
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, pf)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
-    if case in ("c4", "c1"):
-        n_chunks, n = (512 if case == "c4" else 1), 1 << 20
+    if case in ("c4", "c1", "c4b"):
+        n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17)}[case]
         data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_plain)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
