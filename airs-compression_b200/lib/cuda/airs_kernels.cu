@@ -3,22 +3,27 @@
  *
  * airs_plan_kernel    one thread per job: cmp_initialise validation and every
  *                     constant that follows from the parameters (airs_plan.cuh).
- * airs_encode_kernel  persistent CTAs of 128 threads; a CTA takes one job (one
+ * airs_encode_kernel  persistent CTAs of 256 threads; a CTA takes one job (one
  *                     compression context, lib/cmp.h:129-137) at a time from a
  *                     ticket counter and pushes its frames through in order.
  *
- * Per 2048-sample tile, 16 consecutive samples per thread:
- *   2 x 128-bit loads -> packed 16x2 residuals (VIADD.16x2: none / diff / IWT
- *   coefficient / model) -> packed zig-zag (PRMT sign replicate) -> Golomb /
- *   escape codeword and length per sample, branch-free, in registers -> the two
- *   codewords of a sample pair merged into one bit string -> warp-shuffle +
- *   REDUX block scan over bit counts -> every thread shifts its strings into
- *   place with funnel shifts and ORs 32-bit words of the MSB-first stream into
- *   shared memory (shared-memory atomicOr: 2.3 cycles per warp instruction,
- *   tools/micro/atoms.cu) -> coalesced byte-swapped stores.  Two block barriers
- *   per tile.  Header, padding and XXH32 trailer are written when the size is
- *   known.  Ragged, unaligned or i32-container tiles take tile_generic (same
- *   results, rolled loops).
+ * Fast path (frame_fast), per 4096-sample tile.  A warp owns 512 consecutive
+ * samples as 64 pieces of 8; lane l holds piece l ("A") and piece 32 + l ("B"),
+ * so both 128-bit loads of a warp are fully coalesced:
+ *   2 x LDG.128 (next tile's loads in flight while this one is encoded) ->
+ *   packed 16x2 biased residuals u = r + R (VIADD.16x2; none / diff / IWT
+ *   coefficient / model) -> if every residual of the warp lies in [-R, R): one
+ *   64-bit shared-memory load per PAIR of samples from a 4096-entry table that
+ *   holds the merged codeword and length of both (build_pair_lut) -> two pairs
+ *   merged into a "quad" of at most 64 bits -> one shuffle scan over packed
+ *   (A, B) bit counts + REDUX over the 8 warp sums -> every quad is shifted into
+ *   place with three funnel shifts and OR-ed into the MSB-first staging words
+ *   in shared memory (RED.OR) -> 128-bit byte-swapped coalesced stores.
+ * Two block barriers per tile.  A warp with a residual outside the table range
+ * (escapes, wide data) computes its codewords arithmetically instead, sample by
+ * sample, into the same staging words.  Tiles that could overflow the staging
+ * area or the destination capacity, ragged tails, unaligned frames and the
+ * i16-in-i32 container go through tile_generic (rolled loops, same results).
  *
  * Reference being replaced: compress_engine and cmp_compress_generic
  * (lib/compress/cmp.c:213-393), preprocess.c:268-411, encoder.c:274-378,
@@ -31,25 +36,22 @@
 #include "airs_plan.cuh"
 #include "airs_private.h"
 
-#ifdef AIRS_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clk[16];
-#define PHASE_T(var) const long long var = clock64()
-#define PHASE_ADD(i, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_phase_clk[i], (unsigned long long)((b) - (a))); } while (0)
-#else
-#define PHASE_T(var)
-#define PHASE_ADD(i, a, b)
-#endif
-
 namespace {
 
-constexpr uint32_t kThreads = AIRS_THREADS; /* 128 */
-constexpr uint32_t kSpt = AIRS_SPT;         /* samples per thread and tile */
-constexpr uint32_t kPairs = kSpt / 2;       /* packed 16x2 words per thread */
-constexpr uint32_t kVec = kSpt / 8;         /* 16-byte vectors per thread */
-constexpr uint32_t kTile = kThreads * kSpt; /* 2048 samples = 4 KiB of u16 */
-static_assert(kTile == 2048 && (kSpt == 8 || kSpt == 16), "tile geometry");
+constexpr uint32_t kThreads = AIRS_THREADS; /* 256 */
 constexpr uint32_t kWarps = kThreads / 32;
-constexpr uint32_t kStgWords = kTile * 48 / 32 + 16;
+constexpr uint32_t kSpt = 16;               /* fast path: samples per thread and tile */
+constexpr uint32_t kTile = kThreads * kSpt; /* 4096 samples = 8 KiB of u16 */
+constexpr uint32_t kGenSpt = 4;             /* generic path: samples per thread and tile */
+constexpr uint32_t kGenTile = kThreads * kGenSpt;
+/* staging area: one fast tile at <= 16 bits per sample, or one generic tile at
+ * 48 bits per sample, plus the < 128 bits carried over from the tile before */
+constexpr uint32_t kStgBits = kTile * 16 + 128;
+constexpr uint32_t kStgWords = kStgBits / 32 + 4;
+static_assert(kGenTile * 48 + 128 <= kStgBits, "a generic tile must fit the staging area");
+constexpr uint32_t kLutR = 32;              /* pair table covers residuals in [-32, 32) */
+constexpr uint32_t kLutStride = 2 * kLutR;
+constexpr uint32_t kLutMinSamples = 4 * kTile; /* frames shorter than this do not pay for a table build */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -72,8 +74,6 @@ struct Pass {
 	uint32_t checksum;
 	uint32_t seq;
 	uint32_t err;
-	uint32_t lut_sel;   /* which table of Shared::lut this pass uses */
-	uint32_t lut_range; /* its half range R, 0: none */
 };
 
 /* context state between frames: the mutable part of struct cmp_context */
@@ -85,12 +85,13 @@ struct CtxState {
 };
 
 struct Shared {
-	uint32_t stg[kStgWords]; /* MSB-first 32-bit words of the stream being assembled (all zero when idle) */
+	uint2 plut[kLutStride * kLutStride]; /* pair table: {merged codeword, length} at [u_hi * 64 + u_lo] */
+	alignas(16) uint32_t stg_pad[4];     /* quads ending in word 0 or 1 OR zeros below the staging area */
+	uint32_t stg[kStgWords];             /* MSB-first 32-bit words of the stream being assembled (all zero when idle) */
+	uint2 slut[kLutStride];              /* single-sample table the pair table is built from */
 	uint32_t wsum[kWarps];
-	uint4 in[2][kThreads * (kVec + 1)]; /* cp.async ring: per thread its samples + the word before them */
-	uint4 min[2][kThreads * kVec];      /* cp.async ring: per thread its slice of the model */
-	uint32_t lut[2][256]; /* codeword tables of the primary / secondary encoder (build_lut) */
-	uint32_t lut_range[2];
+	uint32_t plut_key[3];                /* encoder the pair table was built for: type, g, outlier */
+	uint32_t plut_R;                     /* its usable half range: 32, 16, 8 or 0 (none) */
 	JobPlan plan;
 	airs_job job;
 	Pass pass;
@@ -100,18 +101,25 @@ struct Shared {
 	uint32_t checksum;
 };
 
-/* byte window of the destination a pass may write, in the 4-byte aligned space
- * that starts at dst - (dst & 3) */
+/* byte window of the destination a pass may write, in the 16-byte aligned
+ * space that starts at dst - (dst & 15) */
 struct OutWin {
-	uint8_t *base4;
+	uint8_t *base;
 	uint32_t lo, hi;
 };
 
-/* position of the stream under construction: stg[0] is word gw0 of the aligned
- * space and already holds sbits bits */
+/* position of the stream under construction: stg[0] is word gw0 (a multiple of
+ * 4) of the aligned space and already holds sbits (< 128) bits */
 struct Cursor {
 	uint32_t gw0, sbits;
 };
+
+__device__ __forceinline__ void cursor_advance(Cursor &c, uint32_t bits)
+{
+	const uint32_t staged = c.sbits + bits;
+	c.gw0 += (staged >> 7) << 2;
+	c.sbits = staged & 127u;
+}
 
 /* -------------------------------------------------------------------------
  * thread-0 logic per frame (ref cmp.c:228-294); all heavy lifting is in the plan
@@ -146,8 +154,6 @@ __device__ __noinline__ void plan_pass(Shared &sh, bool forced_raw, bool align_c
 	}
 	P.enc = pl.enc[sel];
 	P.pre = pl.pre[sel];
-	P.lut_sel = sel;
-	P.lut_range = sh.lut_range[sel];
 	if (forced_raw) { /* ref cmp.c:383-386 */
 		P.pre = CMP_PREPROCESS_NONE;
 		P.enc.type = CMP_ENCODER_UNCOMPRESSED;
@@ -357,8 +363,8 @@ __device__ __noinline__ uint32_t frame_checksum(const Pass &P)
  * ---------------------------------------------------------------------- */
 
 /* per-thread bit writer into the staging words: up to 32 bits per push.  Branch
- * free: the word store is a predicated shared-memory reduction, so a push is a
- * short dependency chain (two funnel shifts, an OR, an add) whatever the data. */
+ * free: the word store is a shared-memory reduction, so a push is a short
+ * dependency chain (two funnel shifts, an OR, an add) whatever the data. */
 struct Packer {
 	uint32_t lo;   /* pending bits, right aligned (bits above `fill` are stale) */
 	uint32_t fill; /* number of pending bits, < 32 between pushes */
@@ -392,10 +398,8 @@ __device__ __forceinline__ void packer_close(Packer &p)
 	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(p.wp), "r"(word) : "memory");
 }
 
-/* exclusive scan of per-thread bit counts over the CTA; one barrier.  `flag` (warp
- * uniform, 0/1) is OR-reduced over the CTA on the way (bit 31 of the warp sums). */
-__device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t &total, uint32_t flag = 0,
-					       uint32_t *any = nullptr)
+/* exclusive scan of per-thread bit counts over the CTA; one barrier */
+__device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t &total)
 {
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	uint32_t incl = tb;
@@ -407,63 +411,60 @@ __device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t
 			incl += t;
 	}
 	if (lane == 31)
-		sh.wsum[warp] = incl | (flag << 31);
+		sh.wsum[warp] = incl;
 	__syncthreads();
-	uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
-	if (any)
-		*any = __reduce_or_sync(kFull, ws) >> 31;
-	ws &= 0x7FFFFFFFu;
+	const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
 	total = __reduce_add_sync(kFull, ws);
-	uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
+	const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
 	return wpre + incl - tb;
 }
 
-__device__ __forceinline__ void store_word(const OutWin &o, uint32_t gword, uint32_t v)
+__device__ __forceinline__ void store_word(const OutWin &o, uint64_t b, uint32_t v)
 {
-	uint64_t b = (uint64_t)gword * 4;
-
 	if (b >= o.lo && b + 4 <= o.hi) {
-		*(uint32_t *)(o.base4 + b) = airs_bswap32(v);
+		*(uint32_t *)(o.base + b) = airs_bswap32(v);
 	} else {
 #pragma unroll
 		for (int k = 0; k < 4; k++)
 			if (b + k >= o.lo && b + k < o.hi)
-				o.base4[b + k] = (uint8_t)(v >> (24 - 8 * k));
+				o.base[b + k] = (uint8_t)(v >> (24 - 8 * k));
 	}
 }
 
-/* after the packing barrier: full staged words leave as coalesced stores, the
- * staging area is zeroed behind them, the trailing partial word moves to
- * stg[0].  No barrier afterwards: the next tile touches the staging words only
- * after its own scan barrier, which every thread reaches after its copy-out. */
+/* after the packing barrier: complete 16-byte groups of staged words leave as
+ * coalesced 128-bit stores, the staging area is zeroed behind them, the
+ * trailing partial group moves to stg[0..3].  No barrier afterwards: the next
+ * tile touches the staging words only after its own scan barrier, which every
+ * thread reaches after its copy-out. */
 __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, Cursor &c, uint32_t tile_bits)
 {
 	const uint32_t tid = threadIdx.x;
 	const uint32_t staged = c.sbits + tile_bits;
-	const uint32_t wfull = staged >> 5;
+	const uint32_t nvec = staged >> 7;
+	uint4 *stg4 = reinterpret_cast<uint4 *>(sh.stg);
+	const uint64_t b0 = (uint64_t)c.gw0 * 4;
 
-	if ((uint64_t)c.gw0 * 4 >= o.lo && ((uint64_t)c.gw0 + wfull) * 4 <= o.hi) {
-		/* every word lies inside the window (the usual case): plain coalesced stores */
-		uint32_t *out = (uint32_t *)o.base4 + c.gw0;
-		for (uint32_t w = tid; w < wfull; w += kThreads) {
-			uint32_t v = sh.stg[w];
-			sh.stg[w] = 0;
-			out[w] = airs_bswap32(v);
-		}
-	} else {
-		for (uint32_t w = tid; w < wfull; w += kThreads) {
-			uint32_t v = sh.stg[w];
-			sh.stg[w] = 0;
-			store_word(o, c.gw0 + w, v);
+	for (uint32_t v = tid; v < nvec; v += kThreads) {
+		const uint4 q = stg4[v];
+		const uint64_t b = b0 + 16ull * v;
+		stg4[v] = make_uint4(0, 0, 0, 0);
+		if (b >= o.lo && b + 16 <= o.hi) {
+			*reinterpret_cast<uint4 *>(o.base + b) =
+				make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
+		} else { /* edge of the window: header in front, capacity or a neighbour stream behind */
+			store_word(o, b, q.x);
+			store_word(o, b + 4, q.y);
+			store_word(o, b + 8, q.z);
+			store_word(o, b + 12, q.w);
 		}
 	}
-	if (tid == 0 && wfull) { /* thread 0 zeroed stg[0] itself; stg[wfull] is nobody else's */
-		uint32_t carry = sh.stg[wfull];
-		sh.stg[wfull] = 0;
-		sh.stg[0] = carry;
+	if (tid == 0 && nvec) { /* thread 0 zeroed group 0 itself; group nvec is nobody else's */
+		const uint4 carry = stg4[nvec];
+		stg4[nvec] = make_uint4(0, 0, 0, 0);
+		stg4[0] = carry;
 	}
-	c.gw0 += wfull;
-	c.sbits = staged & 31u;
+	c.gw0 += nvec << 2;
+	c.sbits = staged & 127u;
 }
 
 /* -------------------------------------------------------------------------
@@ -501,15 +502,15 @@ __device__ __forceinline__ void encode_any(const EncConst &e, uint32_t r, uint32
 	}
 }
 
-__device__ __noinline__ void tile_generic(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
-					  bool size_only)
+/* samples [base, min(base + kGenTile, end)) */
+__device__ __noinline__ void tile_generic_range(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
+						uint32_t end, bool size_only)
 {
 	const Pass &P = sh.pass;
 	const EncConst e = P.enc;
 	const uint32_t tid = threadIdx.x;
-	const uint32_t n = P.n;
-	const uint32_t i0 = min(base + tid * kSpt, n);
-	const uint32_t i1 = min(i0 + kSpt, n);
+	const uint32_t i0 = min(base + tid * kGenSpt, end);
+	const uint32_t i1 = min(i0 + kGenSpt, end);
 	const bool need_x = P.pre != CMP_PREPROCESS_IWT || P.model_mode;
 	uint32_t tb = 0;
 
@@ -522,9 +523,7 @@ __device__ __noinline__ void tile_generic(Shared &sh, const OutWin &o, uint32_t 
 	uint32_t tile_bits;
 	const uint32_t excl = block_scan(sh, tb, tile_bits);
 	if (size_only) {
-		const uint32_t staged = c.sbits + tile_bits;
-		c.gw0 += staged >> 5;
-		c.sbits = staged & 31u;
+		cursor_advance(c, tile_bits);
 		__syncthreads();
 		return;
 	}
@@ -551,17 +550,54 @@ __device__ __noinline__ void tile_generic(Shared &sh, const OutWin &o, uint32_t 
 }
 
 /* -------------------------------------------------------------------------
- * fast path: full 2048-sample tiles of a 16-bit container, 16-byte aligned
- * source (and work buffer when used).  One loop over the tiles of a frame;
- * the loads of tile t+1 are issued before tile t is encoded; everything lives
- * in registers and all inner loops are unrolled.
- *
- * Codewords come from a 256-entry table in shared memory indexed by the
- * residual itself (r + R, |r| < R <= 128): entry = length << 26 | code bits,
- * built per job for both passes (build_lut).  This covers escapes as well, as
- * long as the whole code of the sample fits 25 bits.  A warp whose 512 samples
- * do not all hit the table computes its codewords arithmetically instead
- * (airs_golomb).
+ * pair table.  Entry [u1 * 64 + u0], u = r + R, holds the codewords of two
+ * consecutive residuals r0 (first in the stream), r1 merged into one string,
+ * and its length.  Only residuals whose codeword (escape part included) is at
+ * most 16 bits long qualify, so that a pair fits 32 and a quad 64 bits; R
+ * shrinks (32, 16, 8) until that holds, 0 = no table for this encoder.
+ * All threads call it; two barriers.
+ * ---------------------------------------------------------------------- */
+__device__ __noinline__ void build_pair_lut(Shared &sh, const EncConst &e)
+{
+	const uint32_t tid = threadIdx.x;
+	uint32_t bad = 0; /* bit i: a residual with |r| <= 8 << i does not qualify */
+
+	if (tid < kLutStride) {
+		const uint32_t r = (tid - kLutR) & 0xFFFFu;
+		uint32_t cw, cl, rw, rl;
+		if (e.type == CMP_ENCODER_GOLOMB_ZERO)
+			airs_encode<CMP_ENCODER_GOLOMB_ZERO>(e, r, cw, cl, rw, rl);
+		else
+			airs_encode<CMP_ENCODER_GOLOMB_MULTI>(e, r, cw, cl, rw, rl);
+		const uint32_t len = cl + rl;
+		sh.slut[tid] = make_uint2((cw << rl) | rw, len);
+		if (len > 16u) {
+			const uint32_t dist = tid >= kLutR ? tid - kLutR + 1u : kLutR - tid; /* r in [-R, R) <=> dist <= R */
+			bad = dist <= 8u ? 7u : dist <= 16u ? 6u : 4u;
+		}
+	}
+	bad = __syncthreads_or(bad);
+	const uint32_t R = (bad & 1u) ? 0u : kLutR >> __popc(bad);
+	if (R) {
+		for (uint32_t idx = tid; idx < kLutStride * kLutStride; idx += kThreads) {
+			const uint32_t u0 = idx % kLutStride, u1 = idx / kLutStride;
+			if (u0 < 2u * R && u1 < 2u * R) {
+				const uint2 e0 = sh.slut[u0 + kLutR - R], e1 = sh.slut[u1 + kLutR - R];
+				sh.plut[idx] = make_uint2((e0.x << e1.y) | e1.x, e0.y + e1.y);
+			}
+		}
+	}
+	if (tid == 0) {
+		sh.plut_key[0] = e.type;
+		sh.plut_key[1] = e.g;
+		sh.plut_key[2] = e.outlier;
+		sh.plut_R = R;
+	}
+	__syncthreads();
+}
+
+/* -------------------------------------------------------------------------
+ * fast path
  * ---------------------------------------------------------------------- */
 
 /* packed 16x2 zig-zag: ref map_to_unsigned, encoder.c:274-286 */
@@ -572,318 +608,339 @@ __device__ __forceinline__ uint32_t zigzag2(uint32_t d)
 	return ((d << 1) & 0xFFFEFFFEu) ^ sign;
 }
 
-/* Ampere-style asynchronous copies global -> shared (LDGSTS): the loads of the next
- * tile are in flight while this one is encoded, without holding registers */
-__device__ __forceinline__ void cp_async16(uint32_t smem, const void *g)
+/* OR a bit string of len <= 64 bits (hi:lo, right aligned) into the staging
+ * words so that it ends where the running cursor says: ne = -(end bit) before
+ * the call's own subtraction, i.e. the caller keeps ne = -(start bit).
+ * Three funnel shifts and three reductions whatever the length; words the
+ * string does not reach receive zeros (stg_pad absorbs those below word 0). */
+__device__ __forceinline__ void put_unit(uint32_t stg_sa, int32_t &ne, uint32_t hi, uint32_t lo, uint32_t len)
 {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
+	ne -= (int32_t)len;
+	const uint32_t s = (uint32_t)ne; /* funnel shifts in wrap mode use s & 31 = bits free behind the string's last bit */
+	const uint32_t v0 = __funnelshift_l(0u, lo, s);
+	const uint32_t v1 = __funnelshift_l(lo, hi, s);
+	const uint32_t v2 = __funnelshift_l(hi, 0u, s);
+	/* byte address of the word holding the last bit: ((end - 1) >> 5) * 4, end - 1 = ~ne */
+	const uint32_t addr = stg_sa + (uint32_t)((~ne >> 3) & ~3);
+	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v0) : "memory");
+	asm volatile("red.shared.or.b32 [%0+-4], %1;" ::"r"(addr), "r"(v1) : "memory");
+	asm volatile("red.shared.or.b32 [%0+-8], %1;" ::"r"(addr), "r"(v2) : "memory");
 }
 
-__device__ __forceinline__ void cp_async4(uint32_t smem, const void *g)
+/* PRMT with the full selector (the __byte_perm intrinsic drops the sign-replicate bit) */
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(g) : "memory");
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+	return r;
 }
 
-__device__ __forceinline__ void cp_async_commit()
+/* packed model update of two samples (ref update_model_16, cmp.c:120-142):
+ * (m * rate + x * (16 - rate)) >> 4 truncated to 16 bits.  The weights come
+ * pre-multiplied by 16 so that the result sits in bytes 1-2 of each product sum
+ * and one PRMT packs both lanes.  ext_lo/ext_hi are the PRMT selectors that
+ * widen a lane (zero extension for u16, sign extension for i16 containers). */
+__device__ __forceinline__ uint32_t model_update2(uint32_t x, uint32_t m, uint32_t wx16, uint32_t wm16,
+						  uint32_t ext_lo, uint32_t ext_hi)
 {
-	asm volatile("cp.async.commit_group;" ::: "memory");
+	const uint32_t xl = prmt(x, 0u, ext_lo), xh = prmt(x, 0u, ext_hi);
+	const uint32_t ml = prmt(m, 0u, ext_lo), mh = prmt(m, 0u, ext_hi);
+	const uint32_t tl = ml * wm16 + xl * wx16;
+	const uint32_t th = mh * wm16 + xh * wx16;
+	return __byte_perm(tl, th, 0x6521);
 }
 
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
+/* bit count of the 8 residuals in d[0..3] (arithmetic encoders) */
+template <int ENC>
+__device__ __forceinline__ uint32_t seg_bits(const EncConst &e, const uint32_t *d)
 {
-	asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-constexpr uint32_t kLutLenShift = 26;
-constexpr uint32_t kLutCodeMask = (1u << kLutLenShift) - 1;
-
-/* table of one encoder; returns the usable half range R (0: table unusable).
- * All threads call it; contains one barrier. */
-__device__ __noinline__ uint32_t build_lut(const EncConst &e, uint32_t *lut)
-{
-	uint32_t bad = 0; /* bit i: an entry with |r| < 8 << i does not fit */
-
-	if (e.type == CMP_ENCODER_UNCOMPRESSED)
-		return 0; /* uniform */
-	for (uint32_t idx = threadIdx.x; idx < 256; idx += kThreads) {
-		const uint32_t r = (idx - 128u) & 0xFFFFu;
+	uint32_t bits = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t z = zigzag2(d[k]);
 		uint32_t cw, cl, rw, rl;
-		if (e.type == CMP_ENCODER_GOLOMB_ZERO)
-			airs_encode<CMP_ENCODER_GOLOMB_ZERO>(e, r, cw, cl, rw, rl);
-		else
-			airs_encode<CMP_ENCODER_GOLOMB_MULTI>(e, r, cw, cl, rw, rl);
-		const uint32_t len = cl + rl;
-		const bool ok = len <= 25u;
-		lut[idx] = ok ? (len << kLutLenShift) | (cw << rl) | rw : 0u;
-		if (!ok) {
-			const uint32_t dist = idx >= 128u ? idx - 127u : 128u - idx; /* r in [-R, R) <=> dist <= R */
-			bad |= dist <= 8u ? 0x1Fu : dist <= 16u ? 0x1Eu : dist <= 32u ? 0x1Cu : dist <= 64u ? 0x18u : 0x10u;
+		airs_encode_mapped<ENC>(e, z & 0xFFFFu, cw, cl, rw, rl);
+		bits += cl + rl;
+		airs_encode_mapped<ENC>(e, z >> 16, cw, cl, rw, rl);
+		bits += cl + rl;
+	}
+	return bits;
+}
+
+template <int ENC>
+__device__ __forceinline__ void seg_put(const EncConst &e, const uint32_t *d, uint32_t stg_sa, int32_t ne)
+{
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t z = zigzag2(d[k]);
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			uint32_t cw, cl, rw, rl;
+			airs_encode_mapped<ENC>(e, h ? z >> 16 : z & 0xFFFFu, cw, cl, rw, rl);
+			if (ENC == CMP_ENCODER_GOLOMB_ZERO) /* one string of at most 32 bits */
+				put_unit(stg_sa, ne, 0u, cw, cl);
+			else /* codeword then raw escape bits: at most 48 */
+				put_unit(stg_sa, ne, __funnelshift_lc(cw, 0u, rl), __funnelshift_lc(0u, cw, rl) | rw, cl + rl);
 		}
 	}
-	bad = __syncthreads_or(bad);
-	return 128u >> __popc(bad); /* 128, 64, 32, 16, 8 or (all bad) 4 */
 }
 
-/* the arithmetic encoders on a packed pair of zig-zag mapped samples; only
- * called by warps that missed the table */
-__device__ __forceinline__ void encode_pair_compute(const EncConst &e, uint32_t z, uint32_t &pc, uint32_t &ph,
-						    uint32_t &pl)
-{
-	if (e.type == CMP_ENCODER_GOLOMB_ZERO) {
-		uint32_t c0, l0, c1, l1, r, q;
-		airs_encode_mapped<CMP_ENCODER_GOLOMB_ZERO>(e, z & 0xFFFFu, c0, l0, r, q);
-		airs_encode_mapped<CMP_ENCODER_GOLOMB_ZERO>(e, z >> 16, c1, l1, r, q);
-		pc = __funnelshift_lc(0u, c0, l1) | c1;
-		ph = __funnelshift_lc(c0, 0u, l1);
-		pl = l0 + l1;
-	} else {
-		/* escapes carry a raw part: samples are 64-bit strings, the pair fits 64 bits
-		 * or is flagged through pl > 64 */
-		uint32_t c0, l0, r0, q0, c1, l1, r1, q1;
-		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, z & 0xFFFFu, c0, l0, r0, q0);
-		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, z >> 16, c1, l1, r1, q1);
-		const uint64_t s0 = ((uint64_t)c0 << q0) | r0, s1 = ((uint64_t)c1 << q1) | r1;
-		const uint32_t sl0 = l0 + q0, sl1 = l1 + q1;
-		const uint64_t s = sl1 < 64u ? (s0 << sl1) | s1 : 0;
-		pc = (uint32_t)s;
-		ph = (uint32_t)(s >> 32);
-		pl = sl0 + sl1;
-	}
-}
-
-__device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_tiles,
+/*
+ * Pieces [0, n_pieces) of a frame (8 samples each) whose source (and work
+ * buffer when used) is 16-byte aligned, 16-bit container.
+ */
+__device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_pieces,
 					bool size_only)
 {
 	const Pass &P = sh.pass;
 	const EncConst e = P.enc;
-	const uint32_t tid = threadIdx.x;
-	const uint32_t pre = P.pre, model_mode = P.model_mode, enc = e.type;
-	const uint16_t *src = (const uint16_t *)P.src + tid * kSpt;
-	uint16_t *work = P.work + tid * kSpt;
-	const bool need_x = pre != CMP_PREPROCESS_IWT || model_mode;
-	const bool need_m = pre == CMP_PREPROCESS_MODEL || model_mode == 2;
-	/* table lookup constants: u = r + R per lane, hit <=> u < 2R */
-	const uint32_t R = P.lut_range;
-	const uint32_t rp = R * 0x00010001u, notmask = ~((2u * R - 1u) * 0x00010001u), imask = (2u * R - 1u) << 2;
-	const char *lut = (const char *)(sh.lut[P.lut_sel] + (128u - R));
-	/* per-thread slots of the two cp.async rings; a thread only ever reads what it copied
-	 * itself, so no barrier is involved in the input staging */
-	const uint32_t in_sm[2] = { (uint32_t)__cvta_generic_to_shared(&sh.in[0][tid * (kVec + 1)]),
-				    (uint32_t)__cvta_generic_to_shared(&sh.in[1][tid * (kVec + 1)]) };
-	const uint32_t m_sm[2] = { (uint32_t)__cvta_generic_to_shared(&sh.min[0][tid * kVec]),
-				   (uint32_t)__cvta_generic_to_shared(&sh.min[1][tid * kVec]) };
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const uint32_t pre = P.pre, enc = e.type;
+	const uint32_t mm = size_only ? 0u : P.model_mode;
+	const bool unc = enc == CMP_ENCODER_UNCOMPRESSED;
+	/* table of this pass: built for this encoder and long enough a frame */
+	const bool have_lut = !unc && sh.plut_key[0] == enc && sh.plut_key[1] == e.g && sh.plut_key[2] == e.outlier;
+	const uint32_t R = have_lut ? sh.plut_R : 0u;
+	const uint32_t Rb = R * 0x00010001u;        /* + R per lane */
+	const uint32_t B1 = (R + 1u) * 0x00010001u; /* ~v + B1 = R - v per lane */
+	const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
+	const uint32_t notmask = ~((2u * R - 1u) * 0x00010001u);
+	const bool need_x = pre != CMP_PREPROCESS_IWT || mm;
+	const bool need_m = pre == CMP_PREPROCESS_MODEL || pre == CMP_PREPROCESS_IWT || mm == 2u;
 	const bool diff = pre == CMP_PREPROCESS_DIFF;
+	/* a small frame spreads over all warps as A pieces only */
+	const bool small = n_pieces <= kThreads;
+	const uint32_t pa_idx = small ? tid : warp * 64u + lane; /* piece of this thread in a tile: A; B = A + 32 */
+	const uint32_t tile_pieces = small ? kThreads : 2u * kThreads;
+	const uint32_t n_tiles = (n_pieces + tile_pieces - 1u) / tile_pieces;
+	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
+	uint4 *work4 = reinterpret_cast<uint4 *>(P.work);
+	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
+	const uint32_t stg_sa = (uint32_t)__cvta_generic_to_shared(sh.stg);
+	/* model update weights, see model_update2 */
+	const uint32_t wm16 = P.rate << 4, wx16 = (16u - P.rate) << 4;
+	const uint32_t ext_lo = P.is_signed ? 0x9910u : 0x4410u, ext_hi = P.is_signed ? 0xBB32u : 0x4432u;
+	const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
-#define AIRS_STAGE_TILE(t_)                                                                          \
+	uint4 nxa = zero4, nxb = zero4, nma = zero4, nmb = zero4;
+	uint32_t nps = 0;
+
+	/* loads of tile t_ into the n* registers; pieces beyond the frame read nothing */
+#define AIRS_LOAD_TILE(t_)                                                                           \
 	do {                                                                                         \
-		const uint32_t st_ = (t_) & 1u, b_ = (t_) * kTile;                                   \
+		const uint32_t pa_ = (t_) * tile_pieces + pa_idx, pb_ = pa_ + 32u;                   \
+		const bool va_ = pa_ < n_pieces, vb_ = !small && pb_ < n_pieces;                     \
 		if (need_x) {                                                                        \
-			for (uint32_t v_ = 0; v_ < kVec; v_++)                                       \
-				cp_async16(in_sm[st_] + 16 * v_, src + b_ + 8 * v_);                 \
-			if (diff && (b_ | tid))                                                      \
-				cp_async4(in_sm[st_] + 16 * kVec, src + b_ - 2); /* [x(i0-2), x(i0-1)] */ \
+			nxa = va_ ? __ldg(src4 + pa_) : zero4;                                       \
+			nxb = vb_ ? __ldg(src4 + pb_) : zero4;                                       \
+			/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */ \
+			nps = (diff && lane == 0 && pa_ != 0 && va_) ? (uint32_t)__ldg(src16 + 8u * pa_ - 1u) : 0u; \
 		}                                                                                    \
 		if (need_m) {                                                                        \
-			for (uint32_t v_ = 0; v_ < kVec; v_++)                                       \
-				cp_async16(m_sm[st_] + 16 * v_, work + b_ + 8 * v_);                 \
+			nma = va_ ? work4[pa_] : zero4;                                              \
+			nmb = vb_ ? work4[pb_] : zero4;                                              \
 		}                                                                                    \
-		cp_async_commit();                                                                   \
 	} while (0)
 
-	AIRS_STAGE_TILE(0u);
+	AIRS_LOAD_TILE(0u);
 
 	for (uint32_t t = 0; t < n_tiles; t++) {
-		const uint32_t base = t * kTile, st = t & 1u;
-		uint32_t w[kPairs], mw[kPairs], d[kPairs];
+		const uint32_t pa = t * tile_pieces + pa_idx, pb = pa + 32u;
+		const bool va = pa < n_pieces, vb = !small && pb < n_pieces;
+		const bool partial = (t + 1u) * tile_pieces > n_pieces || small;
+		uint32_t w[8] = { nxa.x, nxa.y, nxa.z, nxa.w, nxb.x, nxb.y, nxb.z, nxb.w };
+		uint32_t m[8] = { nma.x, nma.y, nma.z, nma.w, nmb.x, nmb.y, nmb.z, nmb.w };
+		const uint32_t ps = nps;
 
-		PHASE_T(t0);
-		/* next tile's copies go out before this tile is encoded */
-		if (t + 1 < n_tiles) {
-			AIRS_STAGE_TILE(t + 1);
-			cp_async_wait<1>();
-		} else {
-			cp_async_wait<0>();
+		/* a tile that might cross the point where the reference's writer gives up keeps
+		 * the model exact sample by sample: generic path (ref cmp.c:300-311) */
+		const uint32_t cur = c.gw0 * 32u + c.sbits - 8u * a;
+		if (mm && cur + kTile * 48u >= P.trip) {
+			const uint32_t s0 = t * tile_pieces * 8u, s1 = min(s0 + tile_pieces * 8u, n_pieces * 8u);
+			if (t + 1u < n_tiles)
+				AIRS_LOAD_TILE(t + 1u);
+			for (uint32_t base = s0; base < s1; base += kGenTile)
+				tile_generic_range(sh, o, a, c, base, s1, size_only);
+			continue;
 		}
-		if (need_x) {
-#pragma unroll
-			for (uint32_t v = 0; v < kVec; v++) {
-				const uint4 q = sh.in[st][tid * (kVec + 1) + v];
-				w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
-			}
-		}
-		if (need_m) {
-#pragma unroll
-			for (uint32_t v = 0; v < kVec; v++) {
-				const uint4 q = sh.min[st][tid * kVec + v];
-				mw[4 * v] = q.x; mw[4 * v + 1] = q.y; mw[4 * v + 2] = q.z; mw[4 * v + 3] = q.w;
-			}
-		}
-		PHASE_T(t1);
-		PHASE_ADD(0, t0, t1);
+		if (t + 1u < n_tiles)
+			AIRS_LOAD_TILE(t + 1u);
 
-		/* packed residuals: ref preprocess.c:268-290,348-353,406-411 */
-		if (pre == CMP_PREPROCESS_DIFF) {
-			const uint32_t pw = (base | tid) ? sh.in[st][tid * (kVec + 1) + kVec].x : 0u; /* [x(i0-2), x(i0-1)] */
+		/* biased packed residuals u = r + R: ref preprocess.c:268-290,348-353,406-411 */
+		uint32_t u[8];
+		if (diff) {
+			const uint32_t src_lane = (lane - 1u) & 31u;
+			const uint32_t t1 = __shfl_sync(kFull, w[3], src_lane);
+			const uint32_t t2 = __shfl_sync(kFull, w[7], src_lane);
+			const uint32_t t3 = __shfl_sync(kFull, w[3], 31);
+			uint32_t nbp = __vadd2(~(lane ? t1 : ps << 16), B1);
 #pragma unroll
-			for (int k = 0; k < (int)kPairs; k++)
-				d[k] = __vsub2(w[k], __funnelshift_l(k ? w[k - 1] : pw, w[k], 16));
+			for (int k = 0; k < 4; k++) {
+				const uint32_t nb = __vadd2(~w[k], B1);
+				u[k] = __vadd2(w[k], __byte_perm(nbp, nb, 0x5432));
+				nbp = nb;
+			}
+			nbp = __vadd2(~(lane ? t2 : t3), B1);
+#pragma unroll
+			for (int k = 4; k < 8; k++) {
+				const uint32_t nb = __vadd2(~w[k], B1);
+				u[k] = __vadd2(w[k], __byte_perm(nbp, nb, 0x5432));
+				nbp = nb;
+			}
 		} else if (pre == CMP_PREPROCESS_MODEL) {
 #pragma unroll
-			for (int k = 0; k < (int)kPairs; k++)
-				d[k] = __vsub2(w[k], mw[k]);
+			for (int k = 0; k < 8; k++)
+				u[k] = __vadd2(w[k], __vadd2(~m[k], B1));
 		} else if (pre == CMP_PREPROCESS_IWT) {
-			{
 #pragma unroll
-				for (uint32_t v = 0; v < kVec; v++) {
-					const uint4 q = ((const uint4 *)(work + base))[v];
-					d[4 * v] = q.x; d[4 * v + 1] = q.y; d[4 * v + 2] = q.z; d[4 * v + 3] = q.w;
-				}
-			}
+			for (int k = 0; k < 8; k++)
+				u[k] = __vadd2(m[k], Rb);
 		} else {
 #pragma unroll
-			for (int k = 0; k < (int)kPairs; k++)
-				d[k] = w[k];
+			for (int k = 0; k < 8; k++)
+				u[k] = __vadd2(w[k], Rb);
 		}
 
-		/* codewords; the two samples of a word are merged into one string of pl bits:
-		 * (ph:pc) = code_lo << len_hi | code_hi */
-		uint32_t pc[kPairs], ph[kPairs], pl[kPairs], tb = 0, mx = 0;
-		if (enc == CMP_ENCODER_UNCOMPRESSED) {
+		/* the new model takes the place of the old one (ref cmp.c:304-311) */
+		if (mm == 2u) {
 #pragma unroll
-			for (int k = 0; k < (int)kPairs; k++) {
-				pc[k] = __byte_perm(d[k], 0, 0x1032); /* first sample in the upper half */
-				ph[k] = 0;
-				pl[k] = 32;
+			for (int k = 0; k < 8; k++)
+				m[k] = model_update2(w[k], m[k], wx16, wm16, ext_lo, ext_hi);
+		} else if (mm == 1u) {
+#pragma unroll
+			for (int k = 0; k < 8; k++)
+				m[k] = w[k];
+		}
+
+		if (partial) { /* pieces beyond the frame: residual 0, so that they do not spoil the table check */
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				u[k] = va ? u[k] : Rb;
+				u[k + 4] = vb ? u[k + 4] : Rb;
 			}
-			tb = 32 * kPairs;
-			mx = 32;
-		} else {
-			uint32_t u[kPairs], chk = 0;
+		}
+		uint32_t chk = 0;
 #pragma unroll
-			for (int k = 0; k < (int)kPairs; k++) {
-				asm("add.u16x2 %0, %1, %2;" : "=r"(u[k]) : "r"(d[k]), "r"(rp));
-				chk |= u[k];
-			}
-			if (__all_sync(kFull, R >= 8u && (chk & notmask) == 0u)) {
+		for (int k = 0; k < 8; k++)
+			chk |= u[k];
+		const bool fast = unc || (R != 0u && __all_sync(kFull, (chk & notmask) == 0u));
+
+		/* fast: four quads (hi:lo, length); slow: the plain residuals stay in u[] */
+		uint32_t qh[4], ql[4], qn[4];
+		uint32_t bits_a, bits_b;
+		if (fast) {
+			uint32_t pc[8], pl[8];
+			if (unc) {
 #pragma unroll
-				for (int k = 0; k < (int)kPairs; k++) {
-					const uint32_t e0 = *(const uint32_t *)(lut + ((u[k] << 2) & imask));
-					const uint32_t e1 = *(const uint32_t *)(lut + ((u[k] >> 14) & imask));
-					const uint32_t l1 = e1 >> kLutLenShift, c0 = e0 & kLutCodeMask;
-					pc[k] = __funnelshift_lc(0u, c0, l1) | (e1 & kLutCodeMask);
-					ph[k] = __funnelshift_lc(c0, 0u, l1);
-					pl[k] = (e0 >> kLutLenShift) + l1;
-					tb += pl[k];
-					mx = max(mx, pl[k]);
+				for (int k = 0; k < 8; k++) {
+					pc[k] = __byte_perm(u[k], 0u, 0x1032); /* first sample in the upper half */
+					pl[k] = 32u;
 				}
 			} else {
+				const char *lut = reinterpret_cast<const char *>(sh.plut);
 #pragma unroll
-				for (int k = 0; k < (int)kPairs; k++) {
-					encode_pair_compute(e, zigzag2(d[k]), pc[k], ph[k], pl[k]);
-					tb += pl[k];
-					mx = max(mx, pl[k]);
+				for (int k = 0; k < 8; k++) {
+					const uint32_t off = ((u[k] << 3) & (8u * (kLutStride - 1u))) | (u[k] >> 7);
+					const uint2 ent = *reinterpret_cast<const uint2 *>(lut + off);
+					pc[k] = ent.x;
+					pl[k] = ent.y;
 				}
 			}
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				ql[q] = __funnelshift_lc(0u, pc[2 * q], pl[2 * q + 1]) | pc[2 * q + 1];
+				qh[q] = __funnelshift_lc(pc[2 * q], 0u, pl[2 * q + 1]);
+				qn[q] = pl[2 * q] + pl[2 * q + 1];
+			}
+			if (partial) {
+				if (!va)
+					qn[0] = qn[1] = ql[0] = ql[1] = qh[0] = qh[1] = 0u;
+				if (!vb)
+					qn[2] = qn[3] = ql[2] = ql[3] = qh[2] = qh[3] = 0u;
+			}
+			bits_a = qn[0] + qn[1];
+			bits_b = qn[2] + qn[3];
+		} else {
+#pragma unroll
+			for (int k = 0; k < 8; k++)
+				u[k] = __vadd2(u[k], negRb);
+			if (enc == CMP_ENCODER_GOLOMB_ZERO) {
+				bits_a = seg_bits<CMP_ENCODER_GOLOMB_ZERO>(e, u);
+				bits_b = seg_bits<CMP_ENCODER_GOLOMB_ZERO>(e, u + 4);
+			} else {
+				bits_a = seg_bits<CMP_ENCODER_GOLOMB_MULTI>(e, u);
+				bits_b = seg_bits<CMP_ENCODER_GOLOMB_MULTI>(e, u + 4);
+			}
+			if (!va)
+				bits_a = 0u;
+			if (!vb)
+				bits_b = 0u;
 		}
-		/* 0: every pair of the warp fits 32 bits, 1: 64 bits, 2: not even that (rare) */
-		const uint32_t wide = __reduce_max_sync(kFull, mx > 64u ? 2u : (mx > 32u ? 1u : 0u));
-		PHASE_T(t2);
-		PHASE_ADD(1, t1, t2);
 
-		uint32_t tile_bits, overlong;
-		const uint32_t excl = block_scan(sh, tb, tile_bits, wide == 2u, &overlong);
-		PHASE_T(t3);
-		PHASE_ADD(2, t2, t3);
+		/* one scan for both segments: A counts in the low, B counts in the high half.
+		 * Stream order inside a warp: all A pieces, then all B pieces. */
+		uint32_t incl = bits_a | (bits_b << 16);
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t v = __shfl_up_sync(kFull, incl, d);
+			if (lane >= (uint32_t)d)
+				incl += v;
+		}
+		const uint32_t wtot = __shfl_sync(kFull, incl, 31);
+		const uint32_t tot_a = wtot & 0xFFFFu;
+		if (lane == 31)
+			sh.wsum[warp] = tot_a + (wtot >> 16);
+		__syncthreads();
+		const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
+		const uint32_t tile_bits = __reduce_add_sync(kFull, ws);
+		const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
+		const uint32_t pos_a = wpre + (incl & 0xFFFFu) - bits_a;
+		const uint32_t pos_b = wpre + tot_a + (incl >> 16) - bits_b;
+
 		if (size_only) {
-			const uint32_t staged = c.sbits + tile_bits;
-			c.gw0 += staged >> 5;
-			c.sbits = staged & 31u;
+			cursor_advance(c, tile_bits);
 			__syncthreads();
-		} else if (overlong) {
-			__syncthreads(); /* the scan's warp sums are reused by tile_generic */
-			/* a pair longer than 64 bits (multi-escape pile-up): the slow way.  Nothing
-			 * has been staged yet. */
-			tile_generic(sh, o, a, c, base, false);
-		} else {
-			const uint32_t tile_end = c.gw0 * 32u + c.sbits + tile_bits - 8u * a; /* stream bits after this tile */
-			/* two independent writers (pairs 0-3 and 4-7) double the instruction level
-			 * parallelism of the packing chain */
-			Packer pa, pb;
-			const uint32_t pos = c.sbits + excl;
-			packer_open(pa, sh.stg, pos);
-			uint32_t half = 0;
-#pragma unroll
-			for (int k = 0; k < (int)kPairs / 2; k++)
-				half += pl[k];
-			packer_open(pb, sh.stg, pos + half);
-			if (wide == 0u) {
-#pragma unroll
-				for (int k = 0; k < (int)kPairs / 2; k++) {
-					packer_push(pa, pc[k], pl[k]);
-					packer_push(pb, pc[k + kPairs / 2], pl[k + kPairs / 2]);
-				}
-			} else {
-#pragma unroll
-				for (int k = 0; k < (int)kPairs / 2; k++) {
-					const uint32_t ha = pl[k] > 32u ? pl[k] - 32u : 0u;
-					const uint32_t hb = pl[k + kPairs / 2] > 32u ? pl[k + kPairs / 2] - 32u : 0u;
-					packer_push(pa, ph[k], ha);
-					packer_push(pb, ph[k + kPairs / 2], hb);
-					packer_push(pa, pc[k], pl[k] - ha);
-					packer_push(pb, pc[k + kPairs / 2], pl[k + kPairs / 2] - hb);
-				}
-			}
-			packer_close(pa);
-			packer_close(pb);
-			PHASE_T(t4);
-			PHASE_ADD(3, t3, t4);
-
-			/* model := samples, or model update (ref cmp.c:304-311) */
-			if (model_mode) {
-				if (tile_end < P.trip) {
-					uint32_t nm[kPairs];
-#pragma unroll
-					for (int k = 0; k < (int)kPairs; k++) {
-						if (model_mode == 1) {
-							nm[k] = w[k];
-						} else {
-							uint32_t lo = airs_model_update(w[k] & 0xFFFFu, mw[k] & 0xFFFFu, P.rate, P.is_signed);
-							uint32_t hi = airs_model_update(w[k] >> 16, mw[k] >> 16, P.rate, P.is_signed);
-							nm[k] = lo | (hi << 16);
-						}
-					}
-					uint4 *q = (uint4 *)(work + base);
-#pragma unroll
-					for (uint32_t v = 0; v < kVec; v++)
-						q[v] = make_uint4(nm[4 * v], nm[4 * v + 1], nm[4 * v + 2], nm[4 * v + 3]);
-				} else {
-					/* the stream overflows its capacity inside this tile: per-sample gate */
-					uint32_t cum = c.gw0 * 32u + c.sbits + excl - 8u * a;
-					const uint32_t i0 = base + tid * kSpt;
-					for (uint32_t i = i0; i < i0 + kSpt; i++) {
-						uint32_t x = sample_at(P.src, P.dtype, i);
-						uint32_t m = P.work[i];
-						uint32_t cw, cl, rw, rl;
-						encode_any(e, residual_at(P, i, x), cw, cl, rw, rl);
-						cum += cl + rl;
-						if (cum < P.trip)
-							P.work[i] = (uint16_t)(model_mode == 1 ? x : airs_model_update(x, m, P.rate, P.is_signed));
-					}
-				}
-			}
-			PHASE_T(t5);
-			__syncthreads();
-			PHASE_T(t6);
-			copy_out(sh, o, c, tile_bits);
-			PHASE_T(t7);
-			PHASE_ADD(4, t4, t5);
-			PHASE_ADD(5, t5, t6);
-			PHASE_ADD(6, t6, t7);
-			PHASE_ADD(7, t0, t7);
+			continue;
 		}
+		if (c.sbits + tile_bits > kStgBits) {
+			/* too many bits for the staging area (only warps on the arithmetic path can
+			 * cause this): nothing has been staged or stored yet, do the tile again the slow way */
+			__syncthreads();
+			const uint32_t s0 = t * tile_pieces * 8u, s1 = min(s0 + tile_pieces * 8u, n_pieces * 8u);
+			for (uint32_t base = s0; base < s1; base += kGenTile)
+				tile_generic_range(sh, o, a, c, base, s1, false);
+			continue;
+		}
+
+		if (mm) {
+			if (va)
+				work4[pa] = make_uint4(m[0], m[1], m[2], m[3]);
+			if (vb)
+				work4[pb] = make_uint4(m[4], m[5], m[6], m[7]);
+		}
+
+		int32_t ne = -(int32_t)(c.sbits + pos_a);
+		if (fast) {
+			put_unit(stg_sa, ne, qh[0], ql[0], qn[0]);
+			put_unit(stg_sa, ne, qh[1], ql[1], qn[1]);
+			ne = -(int32_t)(c.sbits + pos_b);
+			put_unit(stg_sa, ne, qh[2], ql[2], qn[2]);
+			put_unit(stg_sa, ne, qh[3], ql[3], qn[3]);
+		} else if (enc == CMP_ENCODER_GOLOMB_ZERO) {
+			if (va)
+				seg_put<CMP_ENCODER_GOLOMB_ZERO>(e, u, stg_sa, ne);
+			if (vb)
+				seg_put<CMP_ENCODER_GOLOMB_ZERO>(e, u + 4, stg_sa, -(int32_t)(c.sbits + pos_b));
+		} else {
+			if (va)
+				seg_put<CMP_ENCODER_GOLOMB_MULTI>(e, u, stg_sa, ne);
+			if (vb)
+				seg_put<CMP_ENCODER_GOLOMB_MULTI>(e, u + 4, stg_sa, -(int32_t)(c.sbits + pos_b));
+		}
+		__syncthreads();
+		copy_out(sh, o, c, tile_bits);
 	}
-#undef AIRS_STAGE_TILE
+#undef AIRS_LOAD_TILE
 }
 
 /* one pass over one frame; returns the stream size or an error (uniform over the CTA).
@@ -896,14 +953,14 @@ __device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 	if (P.err)
 		return P.err;
 
-	const uint32_t a = (uint32_t)((uintptr_t)P.dst & 3u);
+	const uint32_t a = (uint32_t)((uintptr_t)P.dst & 15u);
 	OutWin o;
-	o.base4 = P.dst - a;
+	o.base = P.dst - a;
 	o.lo = a + P.hdr_len;
 	o.hi = suppress ? o.lo : a + P.cap_eff; /* suppress: run for the model side effects only */
 	Cursor c;
-	c.gw0 = (8u * (a + P.hdr_len)) >> 5;
-	c.sbits = (8u * (a + P.hdr_len)) & 31u;
+	c.gw0 = ((8u * (a + P.hdr_len)) >> 7) << 2;
+	c.sbits = (8u * (a + P.hdr_len)) & 127u;
 
 	if (P.pre == CMP_PREPROCESS_IWT)
 		iwt_global(P);
@@ -911,11 +968,17 @@ __device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 	const uint32_t n = P.n, pre = P.pre, model_mode = P.model_mode;
 	const bool fast_ok = P.dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)P.src & 15u) == 0 &&
 			     (((uintptr_t)P.work & 15u) == 0 || (pre < CMP_PREPROCESS_IWT && !model_mode));
-	const uint32_t n_fast = fast_ok ? n / kTile : 0u;
-	if (n_fast)
-		frame_fast(sh, o, a, c, n_fast, size_only);
-	for (uint32_t base = n_fast * kTile; base < n; base += kTile)
-		tile_generic(sh, o, a, c, base, size_only);
+	const uint32_t n_pieces = fast_ok ? n / 8u : 0u;
+	if (n_pieces) {
+		/* pair table of this pass's encoder, kept across frames and jobs while the encoder stays */
+		const EncConst &e = P.enc;
+		if (e.type != CMP_ENCODER_UNCOMPRESSED && n >= kLutMinSamples &&
+		    (sh.plut_key[0] != e.type || sh.plut_key[1] != e.g || sh.plut_key[2] != e.outlier))
+			build_pair_lut(sh, e);
+		frame_fast(sh, o, a, c, n_pieces, size_only);
+	}
+	for (uint32_t base = n_pieces * 8u; base < n; base += kGenTile)
+		tile_generic_range(sh, o, a, c, base, n, size_only);
 	__syncthreads();
 
 	const uint32_t frame_bits = c.gw0 * 32u + c.sbits - 8u * a;
@@ -937,22 +1000,21 @@ __device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 		if (tid == 0)
 			sh.checksum = h;
 	}
-	if (tid == 32) { /* last partial word, zero padded (ref bitstream_writer.h:205-227) */
-		uint32_t v = sh.stg[0];
-		uint32_t nb = (c.sbits + 7u) >> 3;
+	if (tid == 32) { /* last partial group, zero padded (ref bitstream_writer.h:205-227) */
+		const uint32_t nb = (c.sbits + 7u) >> 3;
 		for (uint32_t k = 0; k < nb; k++) {
-			uint64_t b = (uint64_t)c.gw0 * 4 + k;
+			const uint64_t b = (uint64_t)c.gw0 * 4 + k;
 			if (b >= o.lo && b < o.hi)
-				o.base4[b] = (uint8_t)(v >> (24 - 8 * k));
+				o.base[b] = (uint8_t)(sh.stg[k >> 2] >> (24 - 8 * (k & 3)));
 		}
-		sh.stg[0] = 0;
+		sh.stg[0] = sh.stg[1] = sh.stg[2] = sh.stg[3] = 0;
 	}
 	__syncthreads();
 
 	if (P.checksum && !suppress && tid < 4) { /* trailer, big endian (ref cmp.c:314-319) */
 		uint64_t b = (uint64_t)a + payload_end + tid;
 		if (b < o.hi)
-			o.base4[b] = (uint8_t)(sh.checksum >> (24 - 8 * tid));
+			o.base[b] = (uint8_t)(sh.checksum >> (24 - 8 * tid));
 	}
 	if (!airs_failed(result) && !suppress && tid < P.hdr_len) /* header with the final size (ref cmp.c:329-334) */
 		P.dst[tid] = (uint8_t)header_byte(P, tid, size);
@@ -1020,11 +1082,15 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 
 	for (uint32_t w = tid; w < kStgWords; w += kThreads)
 		sh.stg[w] = 0;
-	if (tid == 0)
+	if (tid < 4)
+		sh.stg_pad[tid] = 0;
+	if (tid == 0) {
+		sh.plut_key[0] = 0xFFFFFFFFu; /* no table yet */
+		sh.plut_R = 0;
 		sh.ticket = atomicAdd(b.ticket, 1u);
+	}
 
 	for (;;) {
-		PHASE_T(j0);
 		__syncthreads();
 		const uint32_t job = sh.ticket;
 		if (job >= b.n_jobs)
@@ -1035,16 +1101,6 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 		else if (tid < 62)
 			((uint32_t *)&sh.job)[tid - 32] = ((const uint32_t *)&b.jobs[job])[tid - 32];
 		__syncthreads();
-		PHASE_T(j1);
-		PHASE_ADD(8, j0, j1);
-		if (!sh.plan.frame_err) { /* codeword tables of this job's encoders (uniform branch) */
-			uint32_t r0 = build_lut(sh.plan.enc[0], sh.lut[0]);
-			uint32_t r1 = sh.plan.sec_iter ? build_lut(sh.plan.enc[1], sh.lut[1]) : 0u;
-			if (tid == 0) {
-				sh.lut_range[0] = r0;
-				sh.lut_range[1] = r1;
-			}
-		}
 		if (tid == 0) {
 			sh.ticket = atomicAdd(b.ticket, 1u); /* next job, fetched while this one runs */
 			CtxState &c = sh.ctx;
@@ -1061,16 +1117,11 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 		}
 		const uint32_t n_frames = sh.job.n_frames;
 		const uint32_t first = sh.job.first_result;
-		PHASE_T(j2);
-		PHASE_ADD(9, j1, j2);
 
 		for (uint32_t f = 0; f < n_frames; f++) {
-			PHASE_T(f0);
 			if (tid == 0)
 				plan_frame(sh, b, f);
 			__syncthreads();
-			PHASE_T(f1);
-			PHASE_ADD(10, f0, f1);
 			uint32_t r;
 			if (b.layout == AIRS_LAYOUT_CONCAT) {
 				/* size first (exact, no output), then the offset from the scan, then one
@@ -1122,8 +1173,6 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 					sh.ctx.seq = (sh.ctx.seq + 1u) & 0xFFu;
 				b.results[first + f] = r;
 			}
-			PHASE_T(f2);
-			PHASE_ADD(11, f1, f2);
 		}
 		if (tid == 0 && b.ctx_io) {
 			airs_ctx_state &st = b.ctx_io[job];
@@ -1134,17 +1183,6 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 		}
 	}
 }
-
-#ifdef AIRS_PHASE_CLOCKS
-extern "C" void airs_phase_clocks(unsigned long long *out, int reset)
-{
-	cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(g_phase_clk));
-	if (reset) {
-		unsigned long long z[16] = { 0 };
-		cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
-	}
-}
-#endif
 
 extern "C" cudaError_t airs_launch_plan(const AirsLaunch *b, cudaStream_t stream)
 {

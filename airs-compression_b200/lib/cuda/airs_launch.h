@@ -10,11 +10,10 @@
 struct airs_ctx_state;
 struct JobPlan;
 
-#ifndef AIRS_SPT
-#define AIRS_SPT 8 /* samples per thread and tile: 8 (256 threads) or 16 (128 threads) */
+#define AIRS_THREADS 256
+#ifndef AIRS_CTAS_PER_SM
+#define AIRS_CTAS_PER_SM 3 /* resident CTAs per SM the encode kernel is compiled for */
 #endif
-#define AIRS_THREADS (2048 / AIRS_SPT)
-#define AIRS_CTAS_PER_SM (AIRS_SPT == 8 ? 4 : 6)
 
 struct AirsLaunch {
 	const uint8_t *src;
