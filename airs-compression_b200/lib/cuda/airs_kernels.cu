@@ -419,7 +419,7 @@ __device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t
 	return wpre + incl - tb;
 }
 
-__device__ __forceinline__ void store_word(const OutWin &o, uint64_t b, uint32_t v)
+__device__ __forceinline__ void store_word(const OutWin &o, uint32_t b, uint32_t v)
 {
 	if (b >= o.lo && b + 4 <= o.hi) {
 		*(uint32_t *)(o.base + b) = airs_bswap32(v);
@@ -442,21 +442,22 @@ __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, Cursor &c,
 	const uint32_t staged = c.sbits + tile_bits;
 	const uint32_t nvec = staged >> 7;
 	uint4 *stg4 = reinterpret_cast<uint4 *>(sh.stg);
-	const uint64_t b0 = (uint64_t)c.gw0 * 4;
+	const uint32_t b0 = c.gw0 * 4u; /* streams are shorter than 2^24 bytes */
 
 	for (uint32_t v = tid; v < nvec; v += kThreads) {
-		const uint4 q = stg4[v];
-		const uint64_t b = b0 + 16ull * v;
-		stg4[v] = make_uint4(0, 0, 0, 0);
-		if (b >= o.lo && b + 16 <= o.hi) {
+		const uint32_t b = b0 + 16u * v;
+		if (b >= o.lo && b + 16u <= o.hi) {
+			const uint4 q = stg4[v];
 			*reinterpret_cast<uint4 *>(o.base + b) =
 				make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
 		} else { /* edge of the window: header in front, capacity or a neighbour stream behind */
-			store_word(o, b, q.x);
-			store_word(o, b + 4, q.y);
-			store_word(o, b + 8, q.z);
-			store_word(o, b + 12, q.w);
+			const uint8_t *s8 = reinterpret_cast<const uint8_t *>(stg4 + v);
+#pragma unroll 1
+			for (uint32_t k = 0; k < 16u; k++)
+				if (b + k >= o.lo && b + k < o.hi)
+					o.base[b + k] = s8[k ^ 3u]; /* stream byte k sits in the MSB-first word k / 4 */
 		}
+		stg4[v] = make_uint4(0, 0, 0, 0);
 	}
 	if (tid == 0 && nvec) { /* thread 0 zeroed group 0 itself; group nvec is nobody else's */
 		const uint4 carry = stg4[nvec];
@@ -503,8 +504,8 @@ __device__ __forceinline__ void encode_any(const EncConst &e, uint32_t r, uint32
 }
 
 /* samples [base, min(base + kGenTile, end)) */
-__device__ __noinline__ void tile_generic_range(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
-						uint32_t end, bool size_only)
+__device__ __forceinline__ void tile_generic_range(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t base,
+						    uint32_t end, bool size_only)
 {
 	const Pass &P = sh.pass;
 	const EncConst e = P.enc;
@@ -547,6 +548,16 @@ __device__ __noinline__ void tile_generic_range(Shared &sh, const OutWin &o, uin
 		packer_close(pk);
 	__syncthreads();
 	copy_out(sh, o, c, tile_bits);
+}
+
+/* samples [s0, s1) through the generic path; the cursor travels by value so that the
+ * caller's copy can stay in registers */
+__device__ __noinline__ Cursor generic_span(Shared &sh, const OutWin o, uint32_t a, Cursor c, uint32_t s0, uint32_t s1,
+					    bool size_only)
+{
+	for (uint32_t base = s0; base < s1; base += kGenTile)
+		tile_generic_range(sh, o, a, c, base, s1, size_only);
+	return c;
 }
 
 /* -------------------------------------------------------------------------
@@ -609,22 +620,18 @@ __device__ __forceinline__ uint32_t zigzag2(uint32_t d)
 }
 
 /* OR a bit string of len <= 64 bits (hi:lo, right aligned) into the staging
- * words so that it ends where the running cursor says: ne = -(end bit) before
- * the call's own subtraction, i.e. the caller keeps ne = -(start bit).
- * Three funnel shifts and three reductions whatever the length; words the
- * string does not reach receive zeros (stg_pad absorbs those below word 0). */
-__device__ __forceinline__ void put_unit(uint32_t stg_sa, int32_t &ne, uint32_t hi, uint32_t lo, uint32_t len)
+ * words.  ne = -(bit position where the string starts), updated to the start of
+ * the next one.  Three funnel shifts and three reductions whatever the length;
+ * words the string does not reach receive zeros (stg_pad absorbs those below
+ * word 0). */
+__device__ __forceinline__ void put_unit(uint32_t *stg, int32_t &ne, uint32_t hi, uint32_t lo, uint32_t len)
 {
-	ne -= (int32_t)len;
-	const uint32_t s = (uint32_t)ne; /* funnel shifts in wrap mode use s & 31 = bits free behind the string's last bit */
-	const uint32_t v0 = __funnelshift_l(0u, lo, s);
-	const uint32_t v1 = __funnelshift_l(lo, hi, s);
-	const uint32_t v2 = __funnelshift_l(hi, 0u, s);
-	/* byte address of the word holding the last bit: ((end - 1) >> 5) * 4, end - 1 = ~ne */
-	const uint32_t addr = stg_sa + (uint32_t)((~ne >> 3) & ~3);
-	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v0) : "memory");
-	asm volatile("red.shared.or.b32 [%0+-4], %1;" ::"r"(addr), "r"(v1) : "memory");
-	asm volatile("red.shared.or.b32 [%0+-8], %1;" ::"r"(addr), "r"(v2) : "memory");
+	ne -= (int32_t)len;              /* -(end bit) */
+	const uint32_t s = (uint32_t)ne; /* wrap-mode funnel shifts use s & 31: the bits free behind the string's last bit */
+	uint32_t *p = stg + (~ne >> 5);  /* word of the last bit: (end - 1) >> 5, end - 1 = ~ne */
+	atomicOr(p, __funnelshift_l(0u, lo, s));
+	atomicOr(p - 1, __funnelshift_l(lo, hi, s));
+	atomicOr(p - 2, __funnelshift_l(hi, 0u, s));
 }
 
 /* PRMT with the full selector (the __byte_perm intrinsic drops the sign-replicate bit) */
@@ -650,125 +657,137 @@ __device__ __forceinline__ uint32_t model_update2(uint32_t x, uint32_t m, uint32
 	return __byte_perm(tl, th, 0x6521);
 }
 
-/* bit count of the 8 residuals in d[0..3] (arithmetic encoders) */
-template <int ENC>
-__device__ __forceinline__ uint32_t seg_bits(const EncConst &e, const uint32_t *d)
+/* arithmetic encoders for a warp that missed the table.  Rolled loops over the
+ * packed residuals d[0..7] (local memory): small code, no calls, so that the
+ * table path around them keeps its registers. */
+__device__ __forceinline__ void encode_mapped_rt(const EncConst &e, uint32_t m, uint32_t &cw, uint32_t &cl,
+						 uint32_t &rw, uint32_t &rl)
+{
+	if (e.type == CMP_ENCODER_GOLOMB_ZERO)
+		airs_encode_mapped<CMP_ENCODER_GOLOMB_ZERO>(e, m, cw, cl, rw, rl);
+	else
+		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, m, cw, cl, rw, rl);
+}
+
+/* bit counts of the segments d[0..3] and d[4..7]: A | B << 16 */
+__device__ __forceinline__ uint32_t slow_bits(const EncConst &e, const uint32_t *d)
 {
 	uint32_t bits = 0;
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
+#pragma unroll 1
+	for (uint32_t k = 0; k < 8u; k++) {
 		const uint32_t z = zigzag2(d[k]);
-		uint32_t cw, cl, rw, rl;
-		airs_encode_mapped<ENC>(e, z & 0xFFFFu, cw, cl, rw, rl);
-		bits += cl + rl;
-		airs_encode_mapped<ENC>(e, z >> 16, cw, cl, rw, rl);
-		bits += cl + rl;
+		uint32_t cw, cl, rw, rl, n;
+		encode_mapped_rt(e, z & 0xFFFFu, cw, cl, rw, rl);
+		n = cl + rl;
+		encode_mapped_rt(e, z >> 16, cw, cl, rw, rl);
+		n += cl + rl;
+		bits += k < 4u ? n : n << 16;
 	}
 	return bits;
 }
 
-template <int ENC>
-__device__ __forceinline__ void seg_put(const EncConst &e, const uint32_t *d, uint32_t stg_sa, int32_t ne)
+/* the 8 samples of d[0..3] into the staging words from bit `start` on */
+__device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, uint32_t *stg, uint32_t start)
 {
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
+	int32_t ne = -(int32_t)start;
+#pragma unroll 1
+	for (uint32_t k = 0; k < 4u; k++) {
 		const uint32_t z = zigzag2(d[k]);
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+		for (uint32_t h = 0; h < 2u; h++) {
 			uint32_t cw, cl, rw, rl;
-			airs_encode_mapped<ENC>(e, h ? z >> 16 : z & 0xFFFFu, cw, cl, rw, rl);
-			if (ENC == CMP_ENCODER_GOLOMB_ZERO) /* one string of at most 32 bits */
-				put_unit(stg_sa, ne, 0u, cw, cl);
-			else /* codeword then raw escape bits: at most 48 */
-				put_unit(stg_sa, ne, __funnelshift_lc(cw, 0u, rl), __funnelshift_lc(0u, cw, rl) | rw, cl + rl);
+			encode_mapped_rt(e, h ? z >> 16 : z & 0xFFFFu, cw, cl, rw, rl);
+			/* codeword then raw escape bits: at most 48 */
+			put_unit(stg, ne, __funnelshift_lc(cw, 0u, rl), __funnelshift_lc(0u, cw, rl) | rw, cl + rl);
 		}
 	}
 }
 
 /*
- * Pieces [0, n_pieces) of a frame (8 samples each) whose source (and work
- * buffer when used) is 16-byte aligned, 16-bit container.
+ * Tiles of pieces (8 samples each) of a frame whose source (and work buffer
+ * when used) is 16-byte aligned, 16-bit container.
+ *
+ * PRE / MM / UNC >= 0 fix the preprocessing, the model mode and "uncompressed
+ * encoder" at compile time (the hot instantiations); -1 reads them from the
+ * pass at run time (one catch-all instantiation).
+ * PARTIAL = false: the full tiles t0 .. n_tiles-1 (tile t starts at piece
+ * p0 + 512 t), next tile's loads in flight while one is encoded.
+ * PARTIAL = true: the single tile that starts at piece p0 and ends with the
+ * frame (n_pieces); a small one spreads over all warps as A pieces.
+ * Returns n_tiles, or the index of a tile it left untouched because it has to
+ * go through the generic path.  Inlined into the kernel and free of calls: a
+ * called function only gets the registers its caller leaves over.
  */
-__device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_pieces,
-					bool size_only)
+template <int PRE, int MM, int UNC, bool PARTIAL>
+__device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c_io, uint32_t t0,
+					    uint32_t n_tiles, uint32_t p0, uint32_t n_pieces, bool size_only)
 {
 	const Pass &P = sh.pass;
-	const EncConst e = P.enc;
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	const uint32_t pre = P.pre, enc = e.type;
-	const uint32_t mm = size_only ? 0u : P.model_mode;
-	const bool unc = enc == CMP_ENCODER_UNCOMPRESSED;
-	/* table of this pass: built for this encoder and long enough a frame */
-	const bool have_lut = !unc && sh.plut_key[0] == enc && sh.plut_key[1] == e.g && sh.plut_key[2] == e.outlier;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t pre = PRE >= 0 ? (uint32_t)PRE : P.pre;
+	const uint32_t mm = MM >= 0 ? (uint32_t)MM : (size_only ? 0u : P.model_mode);
+	const bool unc = UNC >= 0 ? UNC != 0 : P.enc.type == CMP_ENCODER_UNCOMPRESSED;
+	/* table of this pass: built for this encoder (encode_pass) */
+	const bool have_lut = !unc && sh.plut_key[0] == P.enc.type && sh.plut_key[1] == P.enc.g &&
+			      sh.plut_key[2] == P.enc.outlier;
 	const uint32_t R = have_lut ? sh.plut_R : 0u;
 	const uint32_t Rb = R * 0x00010001u;        /* + R per lane */
 	const uint32_t B1 = (R + 1u) * 0x00010001u; /* ~v + B1 = R - v per lane */
-	const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
 	const uint32_t notmask = ~((2u * R - 1u) * 0x00010001u);
-	const bool need_x = pre != CMP_PREPROCESS_IWT || mm;
-	const bool need_m = pre == CMP_PREPROCESS_MODEL || pre == CMP_PREPROCESS_IWT || mm == 2u;
 	const bool diff = pre == CMP_PREPROCESS_DIFF;
-	/* a small frame spreads over all warps as A pieces only */
-	const bool small = n_pieces <= kThreads;
-	const uint32_t pa_idx = small ? tid : warp * 64u + lane; /* piece of this thread in a tile: A; B = A + 32 */
-	const uint32_t tile_pieces = small ? kThreads : 2u * kThreads;
-	const uint32_t n_tiles = (n_pieces + tile_pieces - 1u) / tile_pieces;
+	const bool use_m = pre == CMP_PREPROCESS_MODEL || pre == CMP_PREPROCESS_IWT; /* residuals read the work buffer */
+	const bool need_x = pre != CMP_PREPROCESS_IWT || mm;
+	const bool small = PARTIAL && n_pieces - p0 <= kThreads;
+	const uint32_t pa0 = p0 + (small ? threadIdx.x : warp * 64u + lane); /* piece A of this thread in tile 0; B = A + 32 */
 	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
 	uint4 *work4 = reinterpret_cast<uint4 *>(P.work);
 	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
-	const uint32_t stg_sa = (uint32_t)__cvta_generic_to_shared(sh.stg);
-	/* model update weights, see model_update2 */
-	const uint32_t wm16 = P.rate << 4, wx16 = (16u - P.rate) << 4;
-	const uint32_t ext_lo = P.is_signed ? 0x9910u : 0x4410u, ext_hi = P.is_signed ? 0xBB32u : 0x4432u;
+	uint32_t *stg = sh.stg;
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
+	Cursor c = c_io;
 
 	uint4 nxa = zero4, nxb = zero4, nma = zero4, nmb = zero4;
 	uint32_t nps = 0;
 
-	/* loads of tile t_ into the n* registers; pieces beyond the frame read nothing */
-#define AIRS_LOAD_TILE(t_)                                                                           \
+	/* loads of the tile whose piece A is pa_ into the n* registers; pieces beyond the frame read nothing */
+#define AIRS_LOAD_TILE(pa_)                                                                          \
 	do {                                                                                         \
-		const uint32_t pa_ = (t_) * tile_pieces + pa_idx, pb_ = pa_ + 32u;                   \
-		const bool va_ = pa_ < n_pieces, vb_ = !small && pb_ < n_pieces;                     \
+		const bool va_ = !PARTIAL || (pa_) < n_pieces;                                       \
+		const bool vb_ = !PARTIAL || (!small && (pa_) + 32u < n_pieces);                     \
 		if (need_x) {                                                                        \
-			nxa = va_ ? __ldg(src4 + pa_) : zero4;                                       \
-			nxb = vb_ ? __ldg(src4 + pb_) : zero4;                                       \
+			nxa = va_ ? __ldg(src4 + (pa_)) : zero4;                                     \
+			nxb = vb_ ? __ldg(src4 + (pa_) + 32u) : zero4;                               \
 			/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */ \
-			nps = (diff && lane == 0 && pa_ != 0 && va_) ? (uint32_t)__ldg(src16 + 8u * pa_ - 1u) : 0u; \
+			if (diff)                                                                    \
+				nps = (lane == 0 && (pa_) != 0 && va_) ? (uint32_t)__ldg(src16 + 8u * (pa_) - 1u) : 0u; \
 		}                                                                                    \
-		if (need_m) {                                                                        \
-			nma = va_ ? work4[pa_] : zero4;                                              \
-			nmb = vb_ ? work4[pb_] : zero4;                                              \
+		if (use_m || mm == 2u) {                                                             \
+			nma = va_ ? work4[(pa_)] : zero4;                                            \
+			nmb = vb_ ? work4[(pa_) + 32u] : zero4;                                      \
 		}                                                                                    \
 	} while (0)
 
-	AIRS_LOAD_TILE(0u);
+	AIRS_LOAD_TILE(pa0 + t0 * (2u * kThreads));
 
-	for (uint32_t t = 0; t < n_tiles; t++) {
-		const uint32_t pa = t * tile_pieces + pa_idx, pb = pa + 32u;
-		const bool va = pa < n_pieces, vb = !small && pb < n_pieces;
-		const bool partial = (t + 1u) * tile_pieces > n_pieces || small;
+	uint32_t t = t0;
+	for (; t < n_tiles; t++) {
+		const uint32_t pa = pa0 + t * (2u * kThreads), pb = pa + 32u;
+		const bool va = !PARTIAL || pa < n_pieces, vb = !PARTIAL || (!small && pb < n_pieces);
 		uint32_t w[8] = { nxa.x, nxa.y, nxa.z, nxa.w, nxb.x, nxb.y, nxb.z, nxb.w };
 		uint32_t m[8] = { nma.x, nma.y, nma.z, nma.w, nmb.x, nmb.y, nmb.z, nmb.w };
 		const uint32_t ps = nps;
 
+		if (!PARTIAL && t + 1u < n_tiles)
+			AIRS_LOAD_TILE(pa + 2u * kThreads);
+
 		/* a tile that might cross the point where the reference's writer gives up keeps
 		 * the model exact sample by sample: generic path (ref cmp.c:300-311) */
-		const uint32_t cur = c.gw0 * 32u + c.sbits - 8u * a;
-		if (mm && cur + kTile * 48u >= P.trip) {
-			const uint32_t s0 = t * tile_pieces * 8u, s1 = min(s0 + tile_pieces * 8u, n_pieces * 8u);
-			if (t + 1u < n_tiles)
-				AIRS_LOAD_TILE(t + 1u);
-			for (uint32_t base = s0; base < s1; base += kGenTile)
-				tile_generic_range(sh, o, a, c, base, s1, size_only);
-			continue;
-		}
-		if (t + 1u < n_tiles)
-			AIRS_LOAD_TILE(t + 1u);
+		if (mm && c.gw0 * 32u + c.sbits - 8u * a + kTile * 48u >= P.trip)
+			break;
 
 		/* biased packed residuals u = r + R: ref preprocess.c:268-290,348-353,406-411 */
 		uint32_t u[8];
-		if (diff) {
+		if (pre == CMP_PREPROCESS_DIFF) {
 			const uint32_t src_lane = (lane - 1u) & 31u;
 			const uint32_t t1 = __shfl_sync(kFull, w[3], src_lane);
 			const uint32_t t2 = __shfl_sync(kFull, w[7], src_lane);
@@ -803,6 +822,8 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 
 		/* the new model takes the place of the old one (ref cmp.c:304-311) */
 		if (mm == 2u) {
+			const uint32_t wm16 = P.rate << 4, wx16 = (16u - P.rate) << 4;
+			const uint32_t ext_lo = P.is_signed ? 0x9910u : 0x4410u, ext_hi = P.is_signed ? 0xBB32u : 0x4432u;
 #pragma unroll
 			for (int k = 0; k < 8; k++)
 				m[k] = model_update2(w[k], m[k], wx16, wm16, ext_lo, ext_hi);
@@ -812,7 +833,7 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 				m[k] = w[k];
 		}
 
-		if (partial) { /* pieces beyond the frame: residual 0, so that they do not spoil the table check */
+		if (PARTIAL) { /* pieces beyond the frame: residual 0, so that they do not spoil the table check */
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				u[k] = va ? u[k] : Rb;
@@ -825,9 +846,10 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 			chk |= u[k];
 		const bool fast = unc || (R != 0u && __all_sync(kFull, (chk & notmask) == 0u));
 
-		/* fast: four quads (hi:lo, length); slow: the plain residuals stay in u[] */
+		/* fast: four quads (hi:lo, length); slow: plain residuals in d[] (local memory, they cross a call) */
 		uint32_t qh[4], ql[4], qn[4];
-		uint32_t bits_a, bits_b;
+		uint32_t d[8];
+		uint32_t bits_ab; /* A | B << 16 */
 		if (fast) {
 			uint32_t pc[8], pl[8];
 			if (unc) {
@@ -852,38 +874,30 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 				qh[q] = __funnelshift_lc(pc[2 * q], 0u, pl[2 * q + 1]);
 				qn[q] = pl[2 * q] + pl[2 * q + 1];
 			}
-			if (partial) {
+			if (PARTIAL) {
 				if (!va)
 					qn[0] = qn[1] = ql[0] = ql[1] = qh[0] = qh[1] = 0u;
 				if (!vb)
 					qn[2] = qn[3] = ql[2] = ql[3] = qh[2] = qh[3] = 0u;
 			}
-			bits_a = qn[0] + qn[1];
-			bits_b = qn[2] + qn[3];
+			bits_ab = (qn[0] + qn[1]) | ((qn[2] + qn[3]) << 16);
 		} else {
+			const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
 #pragma unroll
 			for (int k = 0; k < 8; k++)
-				u[k] = __vadd2(u[k], negRb);
-			if (enc == CMP_ENCODER_GOLOMB_ZERO) {
-				bits_a = seg_bits<CMP_ENCODER_GOLOMB_ZERO>(e, u);
-				bits_b = seg_bits<CMP_ENCODER_GOLOMB_ZERO>(e, u + 4);
-			} else {
-				bits_a = seg_bits<CMP_ENCODER_GOLOMB_MULTI>(e, u);
-				bits_b = seg_bits<CMP_ENCODER_GOLOMB_MULTI>(e, u + 4);
-			}
-			if (!va)
-				bits_a = 0u;
-			if (!vb)
-				bits_b = 0u;
+				d[k] = __vadd2(u[k], negRb);
+			bits_ab = slow_bits(P.enc, d);
+			if (PARTIAL)
+				bits_ab = (va ? bits_ab & 0xFFFFu : 0u) | (vb ? bits_ab & 0xFFFF0000u : 0u);
 		}
 
 		/* one scan for both segments: A counts in the low, B counts in the high half.
 		 * Stream order inside a warp: all A pieces, then all B pieces. */
-		uint32_t incl = bits_a | (bits_b << 16);
+		uint32_t incl = bits_ab;
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t v = __shfl_up_sync(kFull, incl, d);
-			if (lane >= (uint32_t)d)
+		for (int dd = 1; dd < 32; dd <<= 1) {
+			const uint32_t v = __shfl_up_sync(kFull, incl, dd);
+			if (lane >= (uint32_t)dd)
 				incl += v;
 		}
 		const uint32_t wtot = __shfl_sync(kFull, incl, 31);
@@ -894,8 +908,9 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 		const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
 		const uint32_t tile_bits = __reduce_add_sync(kFull, ws);
 		const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
-		const uint32_t pos_a = wpre + (incl & 0xFFFFu) - bits_a;
-		const uint32_t pos_b = wpre + tot_a + (incl >> 16) - bits_b;
+		const uint32_t excl = incl - bits_ab; /* exclusive, both halves */
+		const uint32_t pos_a = c.sbits + wpre + (excl & 0xFFFFu);
+		const uint32_t pos_b = c.sbits + wpre + tot_a + (excl >> 16);
 
 		if (size_only) {
 			cursor_advance(c, tile_bits);
@@ -906,10 +921,7 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 			/* too many bits for the staging area (only warps on the arithmetic path can
 			 * cause this): nothing has been staged or stored yet, do the tile again the slow way */
 			__syncthreads();
-			const uint32_t s0 = t * tile_pieces * 8u, s1 = min(s0 + tile_pieces * 8u, n_pieces * 8u);
-			for (uint32_t base = s0; base < s1; base += kGenTile)
-				tile_generic_range(sh, o, a, c, base, s1, false);
-			continue;
+			break;
 		}
 
 		if (mm) {
@@ -919,33 +931,71 @@ __device__ __noinline__ void frame_fast(Shared &sh, const OutWin &o, uint32_t a,
 				work4[pb] = make_uint4(m[4], m[5], m[6], m[7]);
 		}
 
-		int32_t ne = -(int32_t)(c.sbits + pos_a);
 		if (fast) {
-			put_unit(stg_sa, ne, qh[0], ql[0], qn[0]);
-			put_unit(stg_sa, ne, qh[1], ql[1], qn[1]);
-			ne = -(int32_t)(c.sbits + pos_b);
-			put_unit(stg_sa, ne, qh[2], ql[2], qn[2]);
-			put_unit(stg_sa, ne, qh[3], ql[3], qn[3]);
-		} else if (enc == CMP_ENCODER_GOLOMB_ZERO) {
-			if (va)
-				seg_put<CMP_ENCODER_GOLOMB_ZERO>(e, u, stg_sa, ne);
-			if (vb)
-				seg_put<CMP_ENCODER_GOLOMB_ZERO>(e, u + 4, stg_sa, -(int32_t)(c.sbits + pos_b));
+			int32_t ne = -(int32_t)pos_a;
+			put_unit(stg, ne, qh[0], ql[0], qn[0]);
+			put_unit(stg, ne, qh[1], ql[1], qn[1]);
+			ne = -(int32_t)pos_b;
+			put_unit(stg, ne, qh[2], ql[2], qn[2]);
+			put_unit(stg, ne, qh[3], ql[3], qn[3]);
 		} else {
 			if (va)
-				seg_put<CMP_ENCODER_GOLOMB_MULTI>(e, u, stg_sa, ne);
+				slow_put(P.enc, d, stg, pos_a);
 			if (vb)
-				seg_put<CMP_ENCODER_GOLOMB_MULTI>(e, u + 4, stg_sa, -(int32_t)(c.sbits + pos_b));
+				slow_put(P.enc, d + 4, stg, pos_b);
 		}
 		__syncthreads();
 		copy_out(sh, o, c, tile_bits);
 	}
 #undef AIRS_LOAD_TILE
+	c_io = c;
+	return t;
+}
+
+/* all pieces of a frame: full tiles through the instantiation specialised for
+ * this pass, the partial tile (and every uncompressed pass) through the
+ * catch-all; a tile the fast path hands back goes through the generic path */
+__device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_pieces,
+					       bool size_only)
+{
+	const Pass &P = sh.pass;
+	const uint32_t n_full = n_pieces / (2u * kThreads);
+	const uint32_t mm = size_only ? 0u : P.model_mode;
+	const uint32_t key = P.enc.type == CMP_ENCODER_UNCOMPRESSED ? 99u : P.pre * 3u + mm;
+
+	for (uint32_t t = 0; t < n_full;) {
+		switch (key) {
+#define AIRS_HOT(pre_, mm_)                                                                            \
+	case (pre_) * 3u + (mm_):                                                                      \
+		t = frame_fast<(pre_), (mm_), 0, false>(sh, o, a, c, t, n_full, 0u, n_pieces, size_only); \
+		break;
+		AIRS_HOT(CMP_PREPROCESS_NONE, 0)
+		AIRS_HOT(CMP_PREPROCESS_NONE, 1)
+		AIRS_HOT(CMP_PREPROCESS_DIFF, 0)
+		AIRS_HOT(CMP_PREPROCESS_DIFF, 1)
+		AIRS_HOT(CMP_PREPROCESS_IWT, 0)
+		AIRS_HOT(CMP_PREPROCESS_IWT, 1)
+		AIRS_HOT(CMP_PREPROCESS_MODEL, 0)
+		AIRS_HOT(CMP_PREPROCESS_MODEL, 2)
+#undef AIRS_HOT
+		default:
+			t = frame_fast<-1, -1, -1, false>(sh, o, a, c, t, n_full, 0u, n_pieces, size_only);
+			break;
+		}
+		if (t < n_full) {
+			c = generic_span(sh, o, a, c, t * kTile, (t + 1u) * kTile, size_only);
+			t++;
+		}
+	}
+	if (n_full * (2u * kThreads) < n_pieces) {
+		if (!frame_fast<-1, -1, -1, true>(sh, o, a, c, 0u, 1u, n_full * (2u * kThreads), n_pieces, size_only))
+			c = generic_span(sh, o, a, c, n_full * kTile, n_pieces * 8u, size_only);
+	}
 }
 
 /* one pass over one frame; returns the stream size or an error (uniform over the CTA).
  * ref compress_engine, cmp.c:213-338 */
-__device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
+__device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 {
 	const Pass &P = sh.pass;
 	const uint32_t tid = threadIdx.x;
@@ -975,10 +1025,10 @@ __device__ uint32_t encode_pass(Shared &sh, bool size_only, bool suppress)
 		if (e.type != CMP_ENCODER_UNCOMPRESSED && n >= kLutMinSamples &&
 		    (sh.plut_key[0] != e.type || sh.plut_key[1] != e.g || sh.plut_key[2] != e.outlier))
 			build_pair_lut(sh, e);
-		frame_fast(sh, o, a, c, n_pieces, size_only);
+		frame_fast_any(sh, o, a, c, n_pieces, size_only);
 	}
-	for (uint32_t base = n_pieces * 8u; base < n; base += kGenTile)
-		tile_generic_range(sh, o, a, c, base, n, size_only);
+	if (n_pieces * 8u < n)
+		c = generic_span(sh, o, a, c, n_pieces * 8u, n, size_only);
 	__syncthreads();
 
 	const uint32_t frame_bits = c.gw0 * 32u + c.sbits - 8u * a;
@@ -1118,24 +1168,42 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 		const uint32_t n_frames = sh.job.n_frames;
 		const uint32_t first = sh.job.first_result;
 
+		const bool concat = b.layout == AIRS_LAYOUT_CONCAT;
 		for (uint32_t f = 0; f < n_frames; f++) {
 			if (tid == 0)
 				plan_frame(sh, b, f);
 			__syncthreads();
-			uint32_t r;
-			if (b.layout == AIRS_LAYOUT_CONCAT) {
-				/* size first (exact, no output), then the offset from the scan, then one
-				 * pass that writes; a frame that fails contributes no bytes */
-				r = encode_pass(sh, true, false);
-				if ((sh.plan.flags & AIRS_PF_FALLBACK_OK) && r == AIRS_ERR(DST_TOO_SMALL)) {
+			/* One call site for encode_pass (it is inlined).  SLOTS: stage 0 encodes, stage 1 is
+			 * the raw retry of the fallback (ref cmp.c:380-392).  CONCAT: stage 0 sizes the
+			 * stream (exact, no output), the scan turns sizes into offsets, stage 1 writes;
+			 * a frame that fails contributes no bytes. */
+			uint32_t r = 0, stage = 0;
+			bool fits = true;
+			for (;;) {
+				const uint32_t rp = encode_pass(sh, concat && stage == 0, concat && stage == 1 && !fits);
+				const bool fall_back = stage == 0 && (sh.plan.flags & AIRS_PF_FALLBACK_OK) &&
+						       rp == AIRS_ERR(DST_TOO_SMALL);
+				if (fall_back) { /* the frame is stored raw as a fresh primary pass */
 					__syncthreads();
 					if (tid == 0) {
 						ctx_reset(sh.ctx);
-						plan_pass(sh, true, false);
+						plan_pass(sh, true, !concat);
 					}
 					__syncthreads();
-					r = sh.pass.err ? sh.pass.err : sh.plan.raw_size;
 				}
+				if (!concat) {
+					r = rp;
+					if (!fall_back)
+						break;
+					stage = 1;
+					continue;
+				}
+				if (stage == 1) {
+					if (!airs_failed(r))
+						r = fits ? rp : AIRS_ERR(DST_TOO_SMALL);
+					break;
+				}
+				r = fall_back ? (sh.pass.err ? sh.pass.err : sh.plan.raw_size) : rp;
 				const uint32_t k = first + f;
 				if (tid < 32) {
 					uint64_t off = lookback_offset(b.lookback, k, airs_failed(r) ? 0u : r);
@@ -1148,24 +1216,10 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 					}
 				}
 				__syncthreads();
-				const bool fits = !airs_failed(r) && sh.offset + r <= b.dst_size;
-				if (!sh.pass.err) {
-					uint32_t r2 = encode_pass(sh, false, !fits);
-					if (!airs_failed(r))
-						r = fits ? r2 : AIRS_ERR(DST_TOO_SMALL);
-				}
-			} else {
-				r = encode_pass(sh, false, false);
-				if ((sh.plan.flags & AIRS_PF_FALLBACK_OK) && r == AIRS_ERR(DST_TOO_SMALL)) {
-					/* store the frame raw as a fresh primary pass (ref cmp.c:380-392) */
-					__syncthreads();
-					if (tid == 0) {
-						ctx_reset(sh.ctx);
-						plan_pass(sh, true, true);
-					}
-					__syncthreads();
-					r = encode_pass(sh, false, false);
-				}
+				fits = !airs_failed(r) && sh.offset + r <= b.dst_size;
+				if (sh.pass.err)
+					break;
+				stage = 1;
 			}
 			__syncthreads();
 			if (tid == 0) {
