@@ -51,6 +51,8 @@ constexpr uint32_t kStgWords = kStgBits / 32 + 4;
 static_assert(kGenTile * 48 + 128 <= kStgBits, "a generic tile must fit the staging area");
 constexpr uint32_t kLutR = 32;              /* pair table covers residuals in [-32, 32) */
 constexpr uint32_t kLutStride = 2 * kLutR;
+constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair codeword */
+constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
 constexpr uint32_t kLutMinSamples = 4 * kTile; /* frames shorter than this do not pay for a table build */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -85,7 +87,7 @@ struct CtxState {
 };
 
 struct Shared {
-	uint2 plut[kLutStride * kLutStride]; /* pair table: {merged codeword, length} at [u_hi * 64 + u_lo] */
+	uint32_t plut[kLutStride * kLutStride]; /* pair table: length << 26 | merged codeword at [u_hi * 64 + u_lo] */
 	alignas(16) uint32_t stg_pad[4];     /* quads ending in word 0 or 1 OR zeros below the staging area */
 	uint32_t stg[kStgWords];             /* MSB-first 32-bit words of the stream being assembled (all zero when idle) */
 	uint2 slut[kLutStride];              /* single-sample table the pair table is built from */
@@ -444,20 +446,23 @@ __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, Cursor &c,
 	uint4 *stg4 = reinterpret_cast<uint4 *>(sh.stg);
 	const uint32_t b0 = c.gw0 * 4u; /* streams are shorter than 2^24 bytes */
 
-	for (uint32_t v = tid; v < nvec; v += kThreads) {
-		const uint32_t b = b0 + 16u * v;
-		if (b >= o.lo && b + 16u <= o.hi) {
+	if (b0 >= o.lo && b0 + 16u * nvec <= o.hi) { /* the usual case: all groups inside the window */
+		uint4 *out = reinterpret_cast<uint4 *>(o.base + b0);
+		for (uint32_t v = tid; v < nvec; v += kThreads) {
 			const uint4 q = stg4[v];
-			*reinterpret_cast<uint4 *>(o.base + b) =
-				make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
-		} else { /* edge of the window: header in front, capacity or a neighbour stream behind */
+			stg4[v] = make_uint4(0, 0, 0, 0);
+			out[v] = make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
+		}
+	} else { /* an edge of the window: header in front, capacity or a neighbour stream behind */
+		for (uint32_t v = tid; v < nvec; v += kThreads) {
+			const uint32_t b = b0 + 16u * v;
 			const uint8_t *s8 = reinterpret_cast<const uint8_t *>(stg4 + v);
 #pragma unroll 1
 			for (uint32_t k = 0; k < 16u; k++)
 				if (b + k >= o.lo && b + k < o.hi)
 					o.base[b + k] = s8[k ^ 3u]; /* stream byte k sits in the MSB-first word k / 4 */
+			stg4[v] = make_uint4(0, 0, 0, 0);
 		}
-		stg4[v] = make_uint4(0, 0, 0, 0);
 	}
 	if (tid == 0 && nvec) { /* thread 0 zeroed group 0 itself; group nvec is nobody else's */
 		const uint4 carry = stg4[nvec];
@@ -563,9 +568,10 @@ __device__ __noinline__ Cursor generic_span(Shared &sh, const OutWin o, uint32_t
 /* -------------------------------------------------------------------------
  * pair table.  Entry [u1 * 64 + u0], u = r + R, holds the codewords of two
  * consecutive residuals r0 (first in the stream), r1 merged into one string,
- * and its length.  Only residuals whose codeword (escape part included) is at
- * most 16 bits long qualify, so that a pair fits 32 and a quad 64 bits; R
- * shrinks (32, 16, 8) until that holds, 0 = no table for this encoder.
+ * and its length (length << 26 | codeword).  Only residuals whose codeword
+ * (escape part included) is at most 13 bits long qualify, so that a pair fits
+ * the 26 codeword bits of an entry and a quad 64 bits; R shrinks (32, 16, 8)
+ * until that holds, 0 = no table for this encoder.
  * All threads call it; two barriers.
  * ---------------------------------------------------------------------- */
 __device__ __noinline__ void build_pair_lut(Shared &sh, const EncConst &e)
@@ -582,7 +588,7 @@ __device__ __noinline__ void build_pair_lut(Shared &sh, const EncConst &e)
 			airs_encode<CMP_ENCODER_GOLOMB_MULTI>(e, r, cw, cl, rw, rl);
 		const uint32_t len = cl + rl;
 		sh.slut[tid] = make_uint2((cw << rl) | rw, len);
-		if (len > 16u) {
+		if (len > kLutMaxLen) {
 			const uint32_t dist = tid >= kLutR ? tid - kLutR + 1u : kLutR - tid; /* r in [-R, R) <=> dist <= R */
 			bad = dist <= 8u ? 7u : dist <= 16u ? 6u : 4u;
 		}
@@ -594,7 +600,7 @@ __device__ __noinline__ void build_pair_lut(Shared &sh, const EncConst &e)
 			const uint32_t u0 = idx % kLutStride, u1 = idx / kLutStride;
 			if (u0 < 2u * R && u1 < 2u * R) {
 				const uint2 e0 = sh.slut[u0 + kLutR - R], e1 = sh.slut[u1 + kLutR - R];
-				sh.plut[idx] = make_uint2((e0.x << e1.y) | e1.x, e0.y + e1.y);
+				sh.plut[idx] = ((e0.y + e1.y) << kLutLenShift) | (e0.x << e1.y) | e1.x;
 			}
 		}
 	}
@@ -628,7 +634,8 @@ __device__ __forceinline__ void put_unit(uint32_t *stg, int32_t &ne, uint32_t hi
 {
 	ne -= (int32_t)len;              /* -(end bit) */
 	const uint32_t s = (uint32_t)ne; /* wrap-mode funnel shifts use s & 31: the bits free behind the string's last bit */
-	uint32_t *p = stg + (~ne >> 5);  /* word of the last bit: (end - 1) >> 5, end - 1 = ~ne */
+	/* word of the last bit: (end - 1) >> 5 with end - 1 = ~ne; as a byte offset ~(ne >> 3) & ~3 (SHF + LOP3) */
+	uint32_t *p = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(stg) + (~(ne >> 3) & ~3));
 	atomicOr(p, __funnelshift_l(0u, lo, s));
 	atomicOr(p - 1, __funnelshift_l(lo, hi, s));
 	atomicOr(p - 2, __funnelshift_l(hi, 0u, s));
@@ -703,13 +710,43 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
 	}
 }
 
+/* One scan for both segments of every thread: A bit counts in the low, B counts
+ * in the high half of bits_ab.  Stream order inside a warp: all A pieces, then
+ * all B pieces.  Returns the bits of the whole tile and where this thread's
+ * segments start in the staging area (sbits bits are staged already).  One
+ * block barrier; warps may call it from different places. */
+__device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t lane, uint32_t warp, uint32_t bits_ab,
+					      uint32_t sbits, uint32_t &pos_a, uint32_t &pos_b)
+{
+	uint32_t incl = bits_ab;
+#pragma unroll
+	for (int dd = 1; dd < 32; dd <<= 1) {
+		const uint32_t v = __shfl_up_sync(kFull, incl, dd);
+		if (lane >= (uint32_t)dd)
+			incl += v;
+	}
+	const uint32_t wtot = __shfl_sync(kFull, incl, 31);
+	const uint32_t tot_a = wtot & 0xFFFFu;
+	if (lane == 31)
+		sh.wsum[warp] = tot_a + (wtot >> 16);
+	__syncthreads();
+	const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
+	const uint32_t tile_bits = __reduce_add_sync(kFull, ws);
+	const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
+	const uint32_t excl = incl - bits_ab; /* exclusive, both halves */
+	pos_a = sbits + wpre + (excl & 0xFFFFu);
+	pos_b = sbits + wpre + tot_a + (excl >> 16);
+	return tile_bits;
+}
+
 /*
  * Tiles of pieces (8 samples each) of a frame whose source (and work buffer
  * when used) is 16-byte aligned, 16-bit container.
  *
- * PRE / MM / UNC >= 0 fix the preprocessing, the model mode and "uncompressed
- * encoder" at compile time (the hot instantiations); -1 reads them from the
- * pass at run time (one catch-all instantiation).
+ * PRE / MM / UNC / SZ >= 0 fix the preprocessing, the model mode, "uncompressed
+ * encoder" and "size only" at compile time (the hot instantiations, inlined
+ * into the kernel); -1 reads them from the pass at run time (the catch-all
+ * instantiations, called).
  * PARTIAL = false: the full tiles t0 .. n_tiles-1 (tile t starts at piece
  * p0 + 512 t), next tile's loads in flight while one is encoded.
  * PARTIAL = true: the single tile that starts at piece p0 and ends with the
@@ -718,11 +755,12 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
  * go through the generic path.  Inlined into the kernel and free of calls: a
  * called function only gets the registers its caller leaves over.
  */
-template <int PRE, int MM, int UNC, bool PARTIAL>
+template <int PRE, int MM, int UNC, int SZ, bool PARTIAL>
 __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c_io, uint32_t t0,
-					    uint32_t n_tiles, uint32_t p0, uint32_t n_pieces, bool size_only)
+					    uint32_t n_tiles, uint32_t p0, uint32_t n_pieces, bool size_only_rt)
 {
 	const Pass &P = sh.pass;
+	const bool size_only = SZ >= 0 ? SZ != 0 : size_only_rt;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t pre = PRE >= 0 ? (uint32_t)PRE : P.pre;
 	const uint32_t mm = MM >= 0 ? (uint32_t)MM : (size_only ? 0u : P.model_mode);
@@ -846,11 +884,25 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			chk |= u[k];
 		const bool fast = unc || (R != 0u && __all_sync(kFull, (chk & notmask) == 0u));
 
-		/* fast: four quads (hi:lo, length); slow: plain residuals in d[] (local memory, they cross a call) */
-		uint32_t qh[4], ql[4], qn[4];
-		uint32_t d[8];
-		uint32_t bits_ab; /* A | B << 16 */
+		/* Table path and arithmetic path are two separate arms up to the staging of their
+		 * bits (each with its own scan and barrier), so that nothing of one is live in the other. */
+		uint32_t tile_bits;
+		uint32_t action; /* 0: bits staged, 1: size only, 2: too many bits for the staging area */
+#define AIRS_AFTER_SCAN(put_)                                                                        \
+	do {                                                                                         \
+		action = size_only ? 1u : (c.sbits + tile_bits > kStgBits ? 2u : 0u);                \
+		if (action == 0u) {                                                                  \
+			if (mm) {                                                                    \
+				if (va)                                                              \
+					work4[pa] = make_uint4(m[0], m[1], m[2], m[3]);              \
+				if (vb)                                                              \
+					work4[pb] = make_uint4(m[4], m[5], m[6], m[7]);              \
+			}                                                                            \
+			put_                                                                         \
+		}                                                                                    \
+	} while (0)
 		if (fast) {
+			uint32_t qh[4], ql[4], qn[4];
 			uint32_t pc[8], pl[8];
 			if (unc) {
 #pragma unroll
@@ -862,10 +914,10 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				const char *lut = reinterpret_cast<const char *>(sh.plut);
 #pragma unroll
 				for (int k = 0; k < 8; k++) {
-					const uint32_t off = ((u[k] << 3) & (8u * (kLutStride - 1u))) | (u[k] >> 7);
-					const uint2 ent = *reinterpret_cast<const uint2 *>(lut + off);
-					pc[k] = ent.x;
-					pl[k] = ent.y;
+					const uint32_t off = ((u[k] << 2) & (4u * (kLutStride - 1u))) | (u[k] >> 8);
+					const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
+					pc[k] = ent & ((1u << kLutLenShift) - 1u);
+					pl[k] = ent >> kLutLenShift;
 				}
 			}
 #pragma unroll
@@ -880,8 +932,19 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				if (!vb)
 					qn[2] = qn[3] = ql[2] = ql[3] = qh[2] = qh[3] = 0u;
 			}
-			bits_ab = (qn[0] + qn[1]) | ((qn[2] + qn[3]) << 16);
+			uint32_t pos_a, pos_b;
+			tile_bits = tile_scan(sh, lane, warp, (qn[0] + qn[1]) | ((qn[2] + qn[3]) << 16), c.sbits, pos_a, pos_b);
+			AIRS_AFTER_SCAN({
+				int32_t ne = -(int32_t)pos_a;
+				put_unit(stg, ne, qh[0], ql[0], qn[0]);
+				put_unit(stg, ne, qh[1], ql[1], qn[1]);
+				ne = -(int32_t)pos_b;
+				put_unit(stg, ne, qh[2], ql[2], qn[2]);
+				put_unit(stg, ne, qh[3], ql[3], qn[3]);
+			});
 		} else {
+			uint32_t d[8]; /* plain residuals, local memory (indexed by rolled loops) */
+			uint32_t bits_ab;
 			const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
 #pragma unroll
 			for (int k = 0; k < 8; k++)
@@ -889,60 +952,26 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			bits_ab = slow_bits(P.enc, d);
 			if (PARTIAL)
 				bits_ab = (va ? bits_ab & 0xFFFFu : 0u) | (vb ? bits_ab & 0xFFFF0000u : 0u);
+			uint32_t pos_a, pos_b;
+			tile_bits = tile_scan(sh, lane, warp, bits_ab, c.sbits, pos_a, pos_b);
+			AIRS_AFTER_SCAN({
+				if (va)
+					slow_put(P.enc, d, stg, pos_a);
+				if (vb)
+					slow_put(P.enc, d + 4, stg, pos_b);
+			});
 		}
-
-		/* one scan for both segments: A counts in the low, B counts in the high half.
-		 * Stream order inside a warp: all A pieces, then all B pieces. */
-		uint32_t incl = bits_ab;
-#pragma unroll
-		for (int dd = 1; dd < 32; dd <<= 1) {
-			const uint32_t v = __shfl_up_sync(kFull, incl, dd);
-			if (lane >= (uint32_t)dd)
-				incl += v;
-		}
-		const uint32_t wtot = __shfl_sync(kFull, incl, 31);
-		const uint32_t tot_a = wtot & 0xFFFFu;
-		if (lane == 31)
-			sh.wsum[warp] = tot_a + (wtot >> 16);
-		__syncthreads();
-		const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
-		const uint32_t tile_bits = __reduce_add_sync(kFull, ws);
-		const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
-		const uint32_t excl = incl - bits_ab; /* exclusive, both halves */
-		const uint32_t pos_a = c.sbits + wpre + (excl & 0xFFFFu);
-		const uint32_t pos_b = c.sbits + wpre + tot_a + (excl >> 16);
-
-		if (size_only) {
+#undef AIRS_AFTER_SCAN
+		if (action == 1u) {
 			cursor_advance(c, tile_bits);
 			__syncthreads();
 			continue;
 		}
-		if (c.sbits + tile_bits > kStgBits) {
-			/* too many bits for the staging area (only warps on the arithmetic path can
-			 * cause this): nothing has been staged or stored yet, do the tile again the slow way */
+		if (action == 2u) {
+			/* (only warps on the arithmetic path can cause this) nothing has been staged or
+			 * stored yet: the tile goes back to the caller and through the generic path */
 			__syncthreads();
 			break;
-		}
-
-		if (mm) {
-			if (va)
-				work4[pa] = make_uint4(m[0], m[1], m[2], m[3]);
-			if (vb)
-				work4[pb] = make_uint4(m[4], m[5], m[6], m[7]);
-		}
-
-		if (fast) {
-			int32_t ne = -(int32_t)pos_a;
-			put_unit(stg, ne, qh[0], ql[0], qn[0]);
-			put_unit(stg, ne, qh[1], ql[1], qn[1]);
-			ne = -(int32_t)pos_b;
-			put_unit(stg, ne, qh[2], ql[2], qn[2]);
-			put_unit(stg, ne, qh[3], ql[3], qn[3]);
-		} else {
-			if (va)
-				slow_put(P.enc, d, stg, pos_a);
-			if (vb)
-				slow_put(P.enc, d + 4, stg, pos_b);
 		}
 		__syncthreads();
 		copy_out(sh, o, c, tile_bits);
@@ -952,34 +981,42 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	return t;
 }
 
+/* the catch-all instantiations: any preprocessing / model mode / encoder, sizing passes */
+__device__ __noinline__ uint32_t frame_fast_full_rt(Shared &sh, const OutWin o, uint32_t a, Cursor &c, uint32_t t0,
+						    uint32_t n_tiles, uint32_t n_pieces, bool size_only)
+{
+	return frame_fast<-1, -1, -1, -1, false>(sh, o, a, c, t0, n_tiles, 0u, n_pieces, size_only);
+}
+
+__device__ __noinline__ uint32_t frame_fast_tail_rt(Shared &sh, const OutWin o, uint32_t a, Cursor &c, uint32_t p0,
+						    uint32_t n_pieces, bool size_only)
+{
+	return frame_fast<-1, -1, -1, -1, true>(sh, o, a, c, 0u, 1u, p0, n_pieces, size_only);
+}
+
 /* all pieces of a frame: full tiles through the instantiation specialised for
- * this pass, the partial tile (and every uncompressed pass) through the
- * catch-all; a tile the fast path hands back goes through the generic path */
+ * this pass when there is one, else through the catch-all, like the partial
+ * tile; a tile the fast path hands back goes through the generic path */
 __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_pieces,
 					       bool size_only)
 {
 	const Pass &P = sh.pass;
 	const uint32_t n_full = n_pieces / (2u * kThreads);
-	const uint32_t mm = size_only ? 0u : P.model_mode;
-	const uint32_t key = P.enc.type == CMP_ENCODER_UNCOMPRESSED ? 99u : P.pre * 3u + mm;
+	const uint32_t key = (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only) ? 99u : P.pre * 3u + P.model_mode;
 
 	for (uint32_t t = 0; t < n_full;) {
 		switch (key) {
-#define AIRS_HOT(pre_, mm_)                                                                            \
-	case (pre_) * 3u + (mm_):                                                                      \
-		t = frame_fast<(pre_), (mm_), 0, false>(sh, o, a, c, t, n_full, 0u, n_pieces, size_only); \
+#define AIRS_HOT(pre_, mm_)                                                                             \
+	case (pre_) * 3u + (mm_):                                                                       \
+		t = frame_fast<(pre_), (mm_), 0, 0, false>(sh, o, a, c, t, n_full, 0u, n_pieces, false); \
 		break;
 		AIRS_HOT(CMP_PREPROCESS_NONE, 0)
-		AIRS_HOT(CMP_PREPROCESS_NONE, 1)
 		AIRS_HOT(CMP_PREPROCESS_DIFF, 0)
 		AIRS_HOT(CMP_PREPROCESS_DIFF, 1)
-		AIRS_HOT(CMP_PREPROCESS_IWT, 0)
-		AIRS_HOT(CMP_PREPROCESS_IWT, 1)
-		AIRS_HOT(CMP_PREPROCESS_MODEL, 0)
 		AIRS_HOT(CMP_PREPROCESS_MODEL, 2)
 #undef AIRS_HOT
 		default:
-			t = frame_fast<-1, -1, -1, false>(sh, o, a, c, t, n_full, 0u, n_pieces, size_only);
+			t = frame_fast_full_rt(sh, o, a, c, t, n_full, n_pieces, size_only);
 			break;
 		}
 		if (t < n_full) {
@@ -988,7 +1025,7 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 		}
 	}
 	if (n_full * (2u * kThreads) < n_pieces) {
-		if (!frame_fast<-1, -1, -1, true>(sh, o, a, c, 0u, 1u, n_full * (2u * kThreads), n_pieces, size_only))
+		if (!frame_fast_tail_rt(sh, o, a, c, n_full * (2u * kThreads), n_pieces, size_only))
 			c = generic_span(sh, o, a, c, n_full * kTile, n_pieces * 8u, size_only);
 	}
 }

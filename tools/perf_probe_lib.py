@@ -5,6 +5,8 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 from __graft_entry__ import load_package
 pkg = load_package(); abi = pkg.abi; synth = pkg.synth
+if os.environ.get("AIRS_PROBE_LIB"):  # development builds with other launch bounds
+    pkg.loader.library_path = lambda: os.path.join(ROOT, "airs-compression_b200", os.environ["AIRS_PROBE_LIB"])
 
 def make_uniform_jobs(n_jobs, n_samples, n_frames, params_fn, cap=None, model=False):
     jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
@@ -79,8 +81,8 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_plain)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     if case in ("c2", "c2one"):
-        R, F, n = (148 if case == "c2" else 1), 256, 32768
+        R, F, n = (592 if case == "c2" else 1), 256, 32768
         data = synth.frames_torch(1, 0, R, F, n, device=dev)
-        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, model=True)
+        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, cap=2 * n + 64, model=True)
         return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
     raise SystemExit("unknown case " + case)
