@@ -88,10 +88,12 @@ struct CtxState {
 
 struct Shared {
 	uint32_t plut[kLutStride * kLutStride]; /* pair table: length << 26 | merged codeword at [u_hi * 64 + u_lo] */
-	alignas(16) uint32_t stg_pad[4];     /* quads ending in word 0 or 1 OR zeros below the staging area */
-	uint32_t stg[kStgWords];             /* MSB-first 32-bit words of the stream being assembled (all zero when idle) */
+	/* two staging areas (the fast path fills one while the other one drains): MSB-first
+	 * 32-bit words of the stream being assembled, all zero when idle; the 4 pad words in
+	 * front absorb the zeros that strings ending in word 0 or 1 OR below the area */
+	alignas(16) uint32_t stg_mem[2][4 + kStgWords];
 	uint2 slut[kLutStride];              /* single-sample table the pair table is built from */
-	uint32_t wsum[kWarps];
+	uint32_t wsum[2][kWarps];            /* warp totals of the tile scan, alternating between tiles */
 	uint32_t plut_key[3];                /* encoder the pair table was built for: type, g, outlier */
 	uint32_t plut_R;                     /* its usable half range: 32, 16, 8 or 0 (none) */
 	JobPlan plan;
@@ -110,11 +112,17 @@ struct OutWin {
 	uint32_t lo, hi;
 };
 
-/* position of the stream under construction: stg[0] is word gw0 (a multiple of
- * 4) of the aligned space and already holds sbits (< 128) bits */
+/* position of the stream under construction: word 0 of staging area `buf` is
+ * word gw0 (a multiple of 4) of the aligned space and already holds sbits
+ * (< 128) bits */
 struct Cursor {
-	uint32_t gw0, sbits;
+	uint32_t gw0, sbits, buf;
 };
+
+__device__ __forceinline__ uint32_t *stg_of(Shared &sh, uint32_t buf)
+{
+	return sh.stg_mem[buf] + 4;
+}
 
 __device__ __forceinline__ void cursor_advance(Cursor &c, uint32_t bits)
 {
@@ -413,9 +421,9 @@ __device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t
 			incl += t;
 	}
 	if (lane == 31)
-		sh.wsum[warp] = incl;
+		sh.wsum[0][warp] = incl;
 	__syncthreads();
-	const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
+	const uint32_t ws = lane < kWarps ? sh.wsum[0][lane] : 0u;
 	total = __reduce_add_sync(kFull, ws);
 	const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
 	return wpre + incl - tb;
@@ -433,18 +441,21 @@ __device__ __forceinline__ void store_word(const OutWin &o, uint32_t b, uint32_t
 	}
 }
 
-/* after the packing barrier: complete 16-byte groups of staged words leave as
- * coalesced 128-bit stores, the staging area is zeroed behind them, the
- * trailing partial group moves to stg[0..3].  No barrier afterwards: the next
- * tile touches the staging words only after its own scan barrier, which every
- * thread reaches after its copy-out. */
-__device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, Cursor &c, uint32_t tile_bits)
+/* Complete 16-byte groups of staged words leave as coalesced 128-bit stores and
+ * the staging area is zeroed behind them; call after a barrier that follows the
+ * staging.  `staged` = bits in area `buf` (word 0 = word gw0 of the aligned
+ * space).  The trailing partial group moves to the front of area `carry_to`:
+ * the same area (nobody else touches it until the next barrier), or the other
+ * one, where it is OR-ed in because the next tile is being staged there at the
+ * same time.  No barrier afterwards: the next staging into a drained area
+ * happens behind the next scan barrier. */
+__device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, uint32_t buf, uint32_t gw0, uint32_t staged,
+					 uint32_t carry_to)
 {
 	const uint32_t tid = threadIdx.x;
-	const uint32_t staged = c.sbits + tile_bits;
 	const uint32_t nvec = staged >> 7;
-	uint4 *stg4 = reinterpret_cast<uint4 *>(sh.stg);
-	const uint32_t b0 = c.gw0 * 4u; /* streams are shorter than 2^24 bytes */
+	uint4 *stg4 = reinterpret_cast<uint4 *>(stg_of(sh, buf));
+	const uint32_t b0 = gw0 * 4u; /* streams are shorter than 2^24 bytes */
 
 	if (b0 >= o.lo && b0 + 16u * nvec <= o.hi) { /* the usual case: all groups inside the window */
 		uint4 *out = reinterpret_cast<uint4 *>(o.base + b0);
@@ -456,21 +467,40 @@ __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, Cursor &c,
 	} else { /* an edge of the window: header in front, capacity or a neighbour stream behind */
 		for (uint32_t v = tid; v < nvec; v += kThreads) {
 			const uint32_t b = b0 + 16u * v;
-			const uint8_t *s8 = reinterpret_cast<const uint8_t *>(stg4 + v);
+			const uint4 q = stg4[v];
+			if (b >= o.lo && b + 16u <= o.hi) {
+				*reinterpret_cast<uint4 *>(o.base + b) =
+					make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
+			} else {
+				const uint8_t *s8 = reinterpret_cast<const uint8_t *>(stg4 + v);
 #pragma unroll 1
-			for (uint32_t k = 0; k < 16u; k++)
-				if (b + k >= o.lo && b + k < o.hi)
-					o.base[b + k] = s8[k ^ 3u]; /* stream byte k sits in the MSB-first word k / 4 */
+				for (uint32_t k = 0; k < 16u; k++)
+					if (b + k >= o.lo && b + k < o.hi)
+						o.base[b + k] = s8[k ^ 3u]; /* stream byte k sits in the MSB-first word k / 4 */
+			}
 			stg4[v] = make_uint4(0, 0, 0, 0);
 		}
 	}
-	if (tid == 0 && nvec) { /* thread 0 zeroed group 0 itself; group nvec is nobody else's */
+	if (tid == 0 && (nvec || carry_to != buf)) { /* thread 0 drained group 0 itself; group nvec is nobody else's */
 		const uint4 carry = stg4[nvec];
 		stg4[nvec] = make_uint4(0, 0, 0, 0);
-		stg4[0] = carry;
+		uint32_t *dst = stg_of(sh, carry_to);
+		if (carry_to == buf) {
+			*reinterpret_cast<uint4 *>(dst) = carry;
+		} else {
+			atomicOr(dst, carry.x);
+			atomicOr(dst + 1, carry.y);
+			atomicOr(dst + 2, carry.z);
+			atomicOr(dst + 3, carry.w);
+		}
 	}
-	c.gw0 += nvec << 2;
-	c.sbits = staged & 127u;
+}
+
+/* the synchronous form: drain into the stream, keep the rest in the same area */
+__device__ __forceinline__ void copy_out_sync(Shared &sh, const OutWin &o, Cursor &c, uint32_t tile_bits)
+{
+	copy_out(sh, o, c.buf, c.gw0, c.sbits + tile_bits, c.buf);
+	cursor_advance(c, tile_bits);
 }
 
 /* -------------------------------------------------------------------------
@@ -534,7 +564,7 @@ __device__ __forceinline__ void tile_generic_range(Shared &sh, const OutWin &o, 
 		return;
 	}
 	Packer pk;
-	packer_open(pk, sh.stg, c.sbits + excl);
+	packer_open(pk, stg_of(sh, c.buf), c.sbits + excl);
 	uint32_t cum = c.gw0 * 32u + c.sbits + excl - 8u * a; /* stream bits before this thread's samples */
 	for (uint32_t i = i0; i < i1; i++) {
 		uint32_t x = need_x ? sample_at(P.src, P.dtype, i) : 0u;
@@ -552,7 +582,7 @@ __device__ __forceinline__ void tile_generic_range(Shared &sh, const OutWin &o, 
 	if (tb)
 		packer_close(pk);
 	__syncthreads();
-	copy_out(sh, o, c, tile_bits);
+	copy_out_sync(sh, o, c, tile_bits);
 }
 
 /* samples [s0, s1) through the generic path; the cursor travels by value so that the
@@ -714,9 +744,11 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
  * in the high half of bits_ab.  Stream order inside a warp: all A pieces, then
  * all B pieces.  Returns the bits of the whole tile and where this thread's
  * segments start in the staging area (sbits bits are staged already).  One
- * block barrier; warps may call it from different places. */
-__device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t lane, uint32_t warp, uint32_t bits_ab,
-					      uint32_t sbits, uint32_t &pos_a, uint32_t &pos_b)
+ * block barrier; warps may call it from different places.  The warp totals
+ * alternate between two slots (parity), so that no second barrier is needed
+ * before the next tile's scan. */
+__device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t parity, uint32_t lane, uint32_t warp,
+					      uint32_t bits_ab, uint32_t sbits, uint32_t &pos_a, uint32_t &pos_b)
 {
 	uint32_t incl = bits_ab;
 #pragma unroll
@@ -728,9 +760,9 @@ __device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t lane, uint32_
 	const uint32_t wtot = __shfl_sync(kFull, incl, 31);
 	const uint32_t tot_a = wtot & 0xFFFFu;
 	if (lane == 31)
-		sh.wsum[warp] = tot_a + (wtot >> 16);
+		sh.wsum[parity][warp] = tot_a + (wtot >> 16);
 	__syncthreads();
-	const uint32_t ws = lane < kWarps ? sh.wsum[lane] : 0u;
+	const uint32_t ws = lane < kWarps ? sh.wsum[parity][lane] : 0u;
 	const uint32_t tile_bits = __reduce_add_sync(kFull, ws);
 	const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
 	const uint32_t excl = incl - bits_ab; /* exclusive, both halves */
@@ -780,9 +812,14 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
 	uint4 *work4 = reinterpret_cast<uint4 *>(P.work);
 	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
-	uint32_t *stg = sh.stg;
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
+	/* c: where the next tile's bits go (area c.buf).  While pend is set, the tile before is
+	 * still staged in the other area (pend_bits bits from word pend_gw0 on) and drains behind
+	 * the next scan barrier: one barrier per tile. */
+	const uint32_t trip_slack = kTile * 48u - 8u * a;
 	Cursor c = c_io;
+	bool pend = false;
+	uint32_t pend_gw0 = 0, pend_bits = 0;
 
 	uint4 nxa = zero4, nxb = zero4, nma = zero4, nmb = zero4;
 	uint32_t nps = 0;
@@ -820,7 +857,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 
 		/* a tile that might cross the point where the reference's writer gives up keeps
 		 * the model exact sample by sample: generic path (ref cmp.c:300-311) */
-		if (mm && c.gw0 * 32u + c.sbits - 8u * a + kTile * 48u >= P.trip)
+		if (mm && c.gw0 * 32u + c.sbits + trip_slack >= P.trip)
 			break;
 
 		/* biased packed residuals u = r + R: ref preprocess.c:268-290,348-353,406-411 */
@@ -892,12 +929,16 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	do {                                                                                         \
 		action = size_only ? 1u : (c.sbits + tile_bits > kStgBits ? 2u : 0u);                \
 		if (action == 0u) {                                                                  \
+			/* the scan barrier is behind us: the tile before is completely staged */   \
+			if (pend)                                                                    \
+				copy_out(sh, o, c.buf ^ 1u, pend_gw0, pend_bits, c.buf);             \
 			if (mm) {                                                                    \
 				if (va)                                                              \
 					work4[pa] = make_uint4(m[0], m[1], m[2], m[3]);              \
 				if (vb)                                                              \
 					work4[pb] = make_uint4(m[4], m[5], m[6], m[7]);              \
 			}                                                                            \
+			uint32_t *stg = stg_of(sh, c.buf);                                           \
 			put_                                                                         \
 		}                                                                                    \
 	} while (0)
@@ -933,7 +974,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 					qn[2] = qn[3] = ql[2] = ql[3] = qh[2] = qh[3] = 0u;
 			}
 			uint32_t pos_a, pos_b;
-			tile_bits = tile_scan(sh, lane, warp, (qn[0] + qn[1]) | ((qn[2] + qn[3]) << 16), c.sbits, pos_a, pos_b);
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, (qn[0] + qn[1]) | ((qn[2] + qn[3]) << 16), c.sbits, pos_a,
+					      pos_b);
 			AIRS_AFTER_SCAN({
 				int32_t ne = -(int32_t)pos_a;
 				put_unit(stg, ne, qh[0], ql[0], qn[0]);
@@ -953,7 +995,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			if (PARTIAL)
 				bits_ab = (va ? bits_ab & 0xFFFFu : 0u) | (vb ? bits_ab & 0xFFFF0000u : 0u);
 			uint32_t pos_a, pos_b;
-			tile_bits = tile_scan(sh, lane, warp, bits_ab, c.sbits, pos_a, pos_b);
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, bits_ab, c.sbits, pos_a, pos_b);
 			AIRS_AFTER_SCAN({
 				if (va)
 					slow_put(P.enc, d, stg, pos_a);
@@ -964,19 +1006,25 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 #undef AIRS_AFTER_SCAN
 		if (action == 1u) {
 			cursor_advance(c, tile_bits);
-			__syncthreads();
 			continue;
 		}
-		if (action == 2u) {
-			/* (only warps on the arithmetic path can cause this) nothing has been staged or
-			 * stored yet: the tile goes back to the caller and through the generic path */
-			__syncthreads();
+		if (action == 2u) /* (only warps on the arithmetic path can cause this) nothing of this tile has
+				   * been staged or stored: it goes back to the caller and through the generic path */
 			break;
-		}
-		__syncthreads();
-		copy_out(sh, o, c, tile_bits);
+		pend = true;
+		pend_gw0 = c.gw0;
+		pend_bits = c.sbits + tile_bits;
+		cursor_advance(c, tile_bits);
+		c.buf ^= 1u;
 	}
 #undef AIRS_LOAD_TILE
+	/* drain the tile still staged; what is left of it stays in its own area, which becomes
+	 * the current one again */
+	__syncthreads();
+	if (pend) {
+		c.buf ^= 1u;
+		copy_out(sh, o, c.buf, pend_gw0, pend_bits, c.buf);
+	}
 	c_io = c;
 	return t;
 }
@@ -1048,6 +1096,7 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 	Cursor c;
 	c.gw0 = ((8u * (a + P.hdr_len)) >> 7) << 2;
 	c.sbits = (8u * (a + P.hdr_len)) & 127u;
+	c.buf = 0;
 
 	if (P.pre == CMP_PREPROCESS_IWT)
 		iwt_global(P);
@@ -1089,12 +1138,13 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 	}
 	if (tid == 32) { /* last partial group, zero padded (ref bitstream_writer.h:205-227) */
 		const uint32_t nb = (c.sbits + 7u) >> 3;
+		uint32_t *stg = stg_of(sh, c.buf);
 		for (uint32_t k = 0; k < nb; k++) {
 			const uint64_t b = (uint64_t)c.gw0 * 4 + k;
 			if (b >= o.lo && b < o.hi)
-				o.base[b] = (uint8_t)(sh.stg[k >> 2] >> (24 - 8 * (k & 3)));
+				o.base[b] = (uint8_t)(stg[k >> 2] >> (24 - 8 * (k & 3)));
 		}
-		sh.stg[0] = sh.stg[1] = sh.stg[2] = sh.stg[3] = 0;
+		stg[0] = stg[1] = stg[2] = stg[3] = 0;
 	}
 	__syncthreads();
 
@@ -1167,10 +1217,8 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 	__shared__ Shared sh;
 	const uint32_t tid = threadIdx.x;
 
-	for (uint32_t w = tid; w < kStgWords; w += kThreads)
-		sh.stg[w] = 0;
-	if (tid < 4)
-		sh.stg_pad[tid] = 0;
+	for (uint32_t w = tid; w < 2u * (4u + kStgWords); w += kThreads)
+		(&sh.stg_mem[0][0])[w] = 0;
 	if (tid == 0) {
 		sh.plut_key[0] = 0xFFFFFFFFu; /* no table yet */
 		sh.plut_R = 0;
