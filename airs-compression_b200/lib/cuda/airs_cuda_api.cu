@@ -57,9 +57,13 @@ int resident_ctas(int *out)
 		if (prop.major < 10)
 			return fail(AIRS_E_NO_DEVICE, "device %d is sm_%d%d; this library holds sm_100a code only",
 				    dev, prop.major, prop.minor);
-		/* resident CTAs per SM as promised by the launch bounds of airs_encode_kernel; the
-		 * grid is a multiple of the SM count */
-		cached = prop.multiProcessorCount * AIRS_CTAS_PER_SM;
+		/* resident CTAs per SM as the occupancy calculator sees them (the launch bounds of
+		 * airs_encode_kernel promise AIRS_CTAS_PER_SM); the grid is a multiple of the SM count */
+		int per_sm = 0;
+		CU(airs_encode_ctas_per_sm(&per_sm));
+		if (per_sm < 1)
+			return fail(AIRS_E_CUDA, "the encode kernel does not fit an SM of device %d", dev);
+		cached = prop.multiProcessorCount * per_sm;
 		cached_dev = dev;
 	}
 	*out = cached;
@@ -153,6 +157,12 @@ extern "C" int airs_cuda_device_count(void)
 	if (!usable)
 		fail(AIRS_E_NO_DEVICE, "no sm_100 device among %d CUDA devices", n);
 	return usable;
+}
+
+extern "C" int airs_cuda_concurrent_jobs(void)
+{
+	int n = 0;
+	return resident_ctas(&n) == AIRS_OK ? n : 0;
 }
 
 extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)

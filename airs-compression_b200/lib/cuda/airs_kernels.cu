@@ -3,27 +3,29 @@
  *
  * airs_plan_kernel    one thread per job: cmp_initialise validation and every
  *                     constant that follows from the parameters (airs_plan.cuh).
- * airs_encode_kernel  persistent CTAs of 256 threads; a CTA takes one job (one
+ * airs_encode_kernel  persistent CTAs of 128 threads; a CTA takes one job (one
  *                     compression context, lib/cmp.h:129-137) at a time from a
  *                     ticket counter and pushes its frames through in order.
  *
- * Fast path (frame_fast), per 4096-sample tile.  A warp owns 512 consecutive
- * samples as 64 pieces of 8; lane l holds piece l ("A") and piece 32 + l ("B"),
- * so both 128-bit loads of a warp are fully coalesced:
- *   2 x LDG.128 (next tile's loads in flight while this one is encoded) ->
- *   packed 16x2 biased residuals u = r + R (VIADD.16x2; none / diff / IWT
- *   coefficient / model) -> if every residual of the warp lies in [-R, R): one
- *   64-bit shared-memory load per PAIR of samples from a 4096-entry table that
- *   holds the merged codeword and length of both (build_pair_lut) -> two pairs
- *   merged into a "quad" of at most 64 bits -> one shuffle scan over packed
- *   (A, B) bit counts + REDUX over the 8 warp sums -> every quad is shifted into
- *   place with three funnel shifts and OR-ed into the MSB-first staging words
- *   in shared memory (RED.OR) -> 128-bit byte-swapped coalesced stores.
- * Two block barriers per tile.  A warp with a residual outside the table range
- * (escapes, wide data) computes its codewords arithmetically instead, sample by
- * sample, into the same staging words.  Tiles that could overflow the staging
- * area or the destination capacity, ragged tails, unaligned frames and the
- * i16-in-i32 container go through tile_generic (rolled loops, same results).
+ * Fast path (frame_fast), per 4096-sample tile.  A warp owns 1024 consecutive
+ * samples as 128 pieces of 8; lane l holds pieces l, 32 + l, 64 + l, 96 + l
+ * ("segments"), so every 128-bit load of a warp is fully coalesced:
+ *   4 x LDG.128 (half of the next tile's loads in flight while this one is
+ *   encoded) -> packed 16x2 biased residuals u = r + R (VIADD.16x2; none / diff
+ *   / IWT coefficient / model) -> if every residual of the warp lies in [-R, R):
+ *   one shared-memory load per PAIR of samples from a 4096-entry table that
+ *   holds the merged codeword and length of both (build_pair_lut) -> pairs
+ *   merged into quads, quads into one string of at most 64 bits per segment ->
+ *   two shuffle scans over packed bit counts + REDUX over the 4 warp sums ->
+ *   every string is shifted into place with three funnel shifts and OR-ed into
+ *   the MSB-first staging words in shared memory (RED.OR) -> 128-bit
+ *   byte-swapped coalesced stores of the tile before, which drains from a second
+ *   staging area behind this tile's scan barrier: one block barrier per tile.
+ * A warp with a residual outside the table range (escapes, wide data) computes
+ * its codewords arithmetically instead, sample by sample, into the same staging
+ * words.  Tiles that could overflow the staging area or the destination
+ * capacity, ragged tails, unaligned frames and the i16-in-i32 container go
+ * through tile_generic (rolled loops, same results).
  *
  * Reference being replaced: compress_engine and cmp_compress_generic
  * (lib/compress/cmp.c:213-393), preprocess.c:268-411, encoder.c:274-378,
@@ -38,15 +40,17 @@
 
 namespace {
 
-constexpr uint32_t kThreads = AIRS_THREADS; /* 256 */
+constexpr uint32_t kThreads = AIRS_THREADS; /* 128 */
 constexpr uint32_t kWarps = kThreads / 32;
-constexpr uint32_t kSpt = 16;               /* fast path: samples per thread and tile */
-constexpr uint32_t kTile = kThreads * kSpt; /* 4096 samples = 8 KiB of u16 */
-constexpr uint32_t kGenSpt = 4;             /* generic path: samples per thread and tile */
+constexpr uint32_t kSeg = 4;                /* fast path: segments (pieces of 8 samples) per thread and tile */
+constexpr uint32_t kTilePieces = kThreads * kSeg;
+constexpr uint32_t kTile = kTilePieces * 8; /* 4096 samples = 8 KiB of u16 */
+constexpr uint32_t kGenSpt = 8;             /* generic path: samples per thread and tile */
 constexpr uint32_t kGenTile = kThreads * kGenSpt;
-/* staging area: one fast tile at <= 16 bits per sample, or one generic tile at
- * 48 bits per sample, plus the < 128 bits carried over from the tile before */
-constexpr uint32_t kStgBits = kTile * 16 + 128;
+/* staging area: one fast tile at <= 12 bits per sample (the table path needs at
+ * most 8; a tile with more goes through the generic path), or one generic tile
+ * at 48 bits per sample, plus the < 128 bits carried over from the tile before */
+constexpr uint32_t kStgBits = kTile * 12 + 128;
 constexpr uint32_t kStgWords = kStgBits / 32 + 4;
 static_assert(kGenTile * 48 + 128 <= kStgBits, "a generic tile must fit the staging area");
 constexpr uint32_t kLutR = 32;              /* pair table covers residuals in [-32, 32) */
@@ -429,18 +433,6 @@ __device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t
 	return wpre + incl - tb;
 }
 
-__device__ __forceinline__ void store_word(const OutWin &o, uint32_t b, uint32_t v)
-{
-	if (b >= o.lo && b + 4 <= o.hi) {
-		*(uint32_t *)(o.base + b) = airs_bswap32(v);
-	} else {
-#pragma unroll
-		for (int k = 0; k < 4; k++)
-			if (b + k >= o.lo && b + k < o.hi)
-				o.base[b + k] = (uint8_t)(v >> (24 - 8 * k));
-	}
-}
-
 /* Complete 16-byte groups of staged words leave as coalesced 128-bit stores and
  * the staging area is zeroed behind them; call after a barrier that follows the
  * staging.  `staged` = bits in area `buf` (word 0 = word gw0 of the aligned
@@ -706,21 +698,25 @@ __device__ __forceinline__ void encode_mapped_rt(const EncConst &e, uint32_t m, 
 		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, m, cw, cl, rw, rl);
 }
 
-/* bit counts of the segments d[0..3] and d[4..7]: A | B << 16 */
-__device__ __forceinline__ uint32_t slow_bits(const EncConst &e, const uint32_t *d)
+/* bit counts of the four segments d[0..3] .. d[12..15]: b01 = segment 0 | segment 1 << 16, b23 likewise */
+__device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t &b01, uint32_t &b23)
 {
-	uint32_t bits = 0;
+	b01 = 0;
+	b23 = 0;
 #pragma unroll 1
-	for (uint32_t k = 0; k < 8u; k++) {
+	for (uint32_t k = 0; k < 4u * kSeg; k++) {
 		const uint32_t z = zigzag2(d[k]);
 		uint32_t cw, cl, rw, rl, n;
 		encode_mapped_rt(e, z & 0xFFFFu, cw, cl, rw, rl);
 		n = cl + rl;
 		encode_mapped_rt(e, z >> 16, cw, cl, rw, rl);
 		n += cl + rl;
-		bits += k < 4u ? n : n << 16;
+		n = (k & 4u) ? n << 16 : n;
+		if (k < 8u)
+			b01 += n;
+		else
+			b23 += n;
 	}
-	return bits;
 }
 
 /* the 8 samples of d[0..3] into the staging words from bit `start` on */
@@ -740,56 +736,145 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
 	}
 }
 
-/* One scan for both segments of every thread: A bit counts in the low, B counts
- * in the high half of bits_ab.  Stream order inside a warp: all A pieces, then
- * all B pieces.  Returns the bits of the whole tile and where this thread's
- * segments start in the staging area (sbits bits are staged already).  One
- * block barrier; warps may call it from different places.  The warp totals
- * alternate between two slots (parity), so that no second barrier is needed
- * before the next tile's scan. */
-__device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t parity, uint32_t lane, uint32_t warp,
-					      uint32_t bits_ab, uint32_t sbits, uint32_t &pos_a, uint32_t &pos_b)
+/* One scan for the four segments of every thread: b01 = bits of segment 0 |
+ * segment 1 << 16, b23 likewise.  Stream order inside a warp: segment 0 of all
+ * lanes, then segment 1 of all lanes, ...  Returns the bits of the whole tile
+ * and where this thread's segments start in the staging area (sbits bits are
+ * staged already).  One block barrier; warps may call it from different
+ * places.  The warp totals alternate between two slots (parity), so that no
+ * second barrier is needed before the next tile's scan. */
+__device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t parity, uint32_t lane, uint32_t warp, uint32_t b01,
+					      uint32_t b23, uint32_t sbits, uint32_t (&pos)[kSeg])
 {
-	uint32_t incl = bits_ab;
-#pragma unroll
-	for (int dd = 1; dd < 32; dd <<= 1) {
-		const uint32_t v = __shfl_up_sync(kFull, incl, dd);
-		if (lane >= (uint32_t)dd)
-			incl += v;
-	}
-	const uint32_t wtot = __shfl_sync(kFull, incl, 31);
-	const uint32_t tot_a = wtot & 0xFFFFu;
+	uint32_t i01 = b01, i23 = b23;
+
+	/* shuffle with its "source lane exists" predicate feeding the adds directly */
+#define AIRS_SCAN_STEP(d_)                                                                           \
+	asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t0, t1;\n\t"                                   \
+		     "shfl.sync.up.b32 t0|p, %0, " #d_ ", 0, 0xffffffff;\n\t"                        \
+		     "shfl.sync.up.b32 t1, %1, " #d_ ", 0, 0xffffffff;\n\t"                          \
+		     "@p add.u32 %0, %0, t0;\n\t@p add.u32 %1, %1, t1;\n\t}"                         \
+		     : "+r"(i01), "+r"(i23))
+	AIRS_SCAN_STEP(1);
+	AIRS_SCAN_STEP(2);
+	AIRS_SCAN_STEP(4);
+	AIRS_SCAN_STEP(8);
+	AIRS_SCAN_STEP(16);
+#undef AIRS_SCAN_STEP
+	const uint32_t t01 = __shfl_sync(kFull, i01, 31), t23 = __shfl_sync(kFull, i23, 31);
+	const uint32_t tot0 = t01 & 0xFFFFu, tot01 = tot0 + (t01 >> 16), tot012 = tot01 + (t23 & 0xFFFFu);
 	if (lane == 31)
-		sh.wsum[parity][warp] = tot_a + (wtot >> 16);
+		sh.wsum[parity][warp] = tot012 + (t23 >> 16);
 	__syncthreads();
 	const uint32_t ws = lane < kWarps ? sh.wsum[parity][lane] : 0u;
 	const uint32_t tile_bits = __reduce_add_sync(kFull, ws);
-	const uint32_t wpre = __reduce_add_sync(kFull, lane < warp ? ws : 0u);
-	const uint32_t excl = incl - bits_ab; /* exclusive, both halves */
-	pos_a = sbits + wpre + (excl & 0xFFFFu);
-	pos_b = sbits + wpre + tot_a + (excl >> 16);
+	const uint32_t base = sbits + __reduce_add_sync(kFull, lane < warp ? ws : 0u);
+	const uint32_t e01 = i01 - b01, e23 = i23 - b23; /* exclusive, both halves */
+	pos[0] = base + (e01 & 0xFFFFu);
+	pos[1] = base + tot0 + (e01 >> 16);
+	pos[2] = base + tot01 + (e23 & 0xFFFFu);
+	pos[3] = base + tot012 + (e23 >> 16);
 	return tile_bits;
+}
+
+/* global memory accesses with L2 eviction hints (createpolicy descriptors): samples pass
+ * through once, models are read and rewritten once per frame and should stay in the L2 */
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+	uint64_t pol;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p, uint64_t pol)
+{
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+		     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+	return v;
+}
+
+__device__ __forceinline__ uint4 ld_keep(const uint4 *p, uint64_t pol)
+{
+	uint4 v;
+	asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+		     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void st_keep(uint4 *p, const uint4 v, uint64_t pol)
+{
+	asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+		     :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
+/* biased packed residuals u = r + R of one segment (4 words = 8 samples):
+ * ref preprocess.c:268-290,348-353,406-411.  w: samples, m: work buffer words
+ * (model or IWT coefficients), pw: the word in front of the segment (its upper
+ * half is the previous sample), Rb = R per lane, B1 = R + 1 per lane. */
+__device__ __forceinline__ void seg_residuals(uint32_t pre, const uint32_t (&w)[4], const uint32_t (&m)[4], uint32_t pw,
+					      uint32_t Rb, uint32_t B1, uint32_t (&u)[4])
+{
+	if (pre == CMP_PREPROCESS_DIFF) {
+		uint32_t nbp = __vadd2(~pw, B1); /* ~v + B1 = R - v per lane */
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t nb = __vadd2(~w[k], B1);
+			u[k] = __vadd2(w[k], __byte_perm(nbp, nb, 0x5432));
+			nbp = nb;
+		}
+	} else if (pre == CMP_PREPROCESS_MODEL) {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			u[k] = __vadd2(w[k], __vadd2(~m[k], B1));
+	} else if (pre == CMP_PREPROCESS_IWT) {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			u[k] = __vadd2(m[k], Rb);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			u[k] = __vadd2(w[k], Rb);
+	}
 }
 
 /*
  * Tiles of pieces (8 samples each) of a frame whose source (and work buffer
- * when used) is 16-byte aligned, 16-bit container.
+ * when used) is 16-byte aligned, 16-bit container.  A tile is 512 pieces; a
+ * warp owns 128 consecutive pieces, lane l holds pieces l, 32 + l, 64 + l and
+ * 96 + l of them ("segments" 0-3), so every 128-bit load of a warp is fully
+ * coalesced.
  *
  * PRE / MM / UNC / SZ >= 0 fix the preprocessing, the model mode, "uncompressed
  * encoder" and "size only" at compile time (the hot instantiations, inlined
  * into the kernel); -1 reads them from the pass at run time (the catch-all
  * instantiations, called).
  * PARTIAL = false: the full tiles t0 .. n_tiles-1 (tile t starts at piece
- * p0 + 512 t), next tile's loads in flight while one is encoded.
+ * p0 + 512 t); the loads of the next tile are in flight while one is encoded.
  * PARTIAL = true: the single tile that starts at piece p0 and ends with the
- * frame (n_pieces); a small one spreads over all warps as A pieces.
+ * frame (n_pieces); a warp then owns 32, 64, 96 or 128 pieces, whatever keeps
+ * all warps busy.
+ *
+ * Three arms per warp and tile: "table" - every residual hits the pair table and
+ * the eight codewords of every segment fit 64 bits: one string per segment, 3
+ * shared memory reductions each; "raw" - the uncompressed encoder, two 64-bit strings
+ * per segment; "arithmetic" - everything else, sample by sample from reloaded
+ * data (rolled loops).
+ *
  * Returns n_tiles, or the index of a tile it left untouched because it has to
  * go through the generic path.  Inlined into the kernel and free of calls: a
  * called function only gets the registers its caller leaves over.
  */
 template <int PRE, int MM, int UNC, int SZ, bool PARTIAL>
 __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c_io, uint32_t t0,
-					    uint32_t n_tiles, uint32_t p0, uint32_t n_pieces, bool size_only_rt)
+					       uint32_t n_tiles, uint32_t p0, uint32_t n_pieces, bool size_only_rt)
 {
 	const Pass &P = sh.pass;
 	const bool size_only = SZ >= 0 ? SZ != 0 : size_only_rt;
@@ -807,200 +892,209 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	const bool diff = pre == CMP_PREPROCESS_DIFF;
 	const bool use_m = pre == CMP_PREPROCESS_MODEL || pre == CMP_PREPROCESS_IWT; /* residuals read the work buffer */
 	const bool need_x = pre != CMP_PREPROCESS_IWT || mm;
-	const bool small = PARTIAL && n_pieces - p0 <= kThreads;
-	const uint32_t pa0 = p0 + (small ? threadIdx.x : warp * 64u + lane); /* piece A of this thread in tile 0; B = A + 32 */
+	const bool need_m = use_m || mm == 2u;
+	/* segments per warp in this tile */
+	const uint32_t nseg = PARTIAL ? min(kSeg, (n_pieces - p0 + kThreads - 1u) / kThreads) : kSeg;
+	const uint32_t pw0 = p0 + warp * 32u * nseg; /* first piece of the warp in tile 0 */
 	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
 	uint4 *work4 = reinterpret_cast<uint4 *>(P.work);
 	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
+	const char *lut = reinterpret_cast<const char *>(sh.plut);
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
+	const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+	/* stream bits at which the reference's writer gives up, in staging coordinates */
+	const uint32_t trip = mm ? P.trip + 8u * a : 0xFFFFFFFFu;
 	/* c: where the next tile's bits go (area c.buf).  While pend is set, the tile before is
 	 * still staged in the other area (pend_bits bits from word pend_gw0 on) and drains behind
 	 * the next scan barrier: one barrier per tile. */
-	const uint32_t trip_slack = kTile * 48u - 8u * a;
 	Cursor c = c_io;
 	bool pend = false;
 	uint32_t pend_gw0 = 0, pend_bits = 0;
 
-	uint4 nxa = zero4, nxb = zero4, nma = zero4, nmb = zero4;
-	uint32_t nps = 0;
+	/* samples / work words of segment j_ of the tile whose warp starts at piece pw_ (none beyond the frame) */
+#define AIRS_SEG_VALID(pw_, j_) (!PARTIAL || ((j_) < nseg && (pw_) + 32u * (j_) + lane < n_pieces))
+#define AIRS_LOAD_X(pw_, j_) ((need_x && AIRS_SEG_VALID(pw_, j_)) ? ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream) : zero4)
+#define AIRS_LOAD_M(pw_, j_) ((need_m && AIRS_SEG_VALID(pw_, j_)) ? ld_keep(work4 + (pw_) + 32u * (j_) + lane, pol_keep) : zero4)
+	/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */
+#define AIRS_LOAD_PS(pw_) ((diff && lane == 0 && (pw_) != 0 && AIRS_SEG_VALID(pw_, 0)) ? (uint32_t)__ldg(src16 + 8u * (pw_) - 1u) : 0u)
 
-	/* loads of the tile whose piece A is pa_ into the n* registers; pieces beyond the frame read nothing */
-#define AIRS_LOAD_TILE(pa_)                                                                          \
-	do {                                                                                         \
-		const bool va_ = !PARTIAL || (pa_) < n_pieces;                                       \
-		const bool vb_ = !PARTIAL || (!small && (pa_) + 32u < n_pieces);                     \
-		if (need_x) {                                                                        \
-			nxa = va_ ? __ldg(src4 + (pa_)) : zero4;                                     \
-			nxb = vb_ ? __ldg(src4 + (pa_) + 32u) : zero4;                               \
-			/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */ \
-			if (diff)                                                                    \
-				nps = (lane == 0 && (pa_) != 0 && va_) ? (uint32_t)__ldg(src16 + 8u * (pa_) - 1u) : 0u; \
-		}                                                                                    \
-		if (use_m || mm == 2u) {                                                             \
-			nma = va_ ? work4[(pa_)] : zero4;                                            \
-			nmb = vb_ ? work4[(pa_) + 32u] : zero4;                                      \
-		}                                                                                    \
-	} while (0)
-
-	AIRS_LOAD_TILE(pa0 + t0 * (2u * kThreads));
+	/* the whole next tile is loaded one tile ahead (the scheduler pulls the first consumers of
+	 * all four segments to the top of the loop body, so a later load would be waited for) */
+	uint4 nx0 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 0), nx1 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 1);
+	uint4 nx2 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 2), nx3 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 3);
+	uint32_t nps = AIRS_LOAD_PS(pw0 + t0 * kTilePieces);
 
 	uint32_t t = t0;
 	for (; t < n_tiles; t++) {
-		const uint32_t pa = pa0 + t * (2u * kThreads), pb = pa + 32u;
-		const bool va = !PARTIAL || pa < n_pieces, vb = !PARTIAL || (!small && pb < n_pieces);
-		uint32_t w[8] = { nxa.x, nxa.y, nxa.z, nxa.w, nxb.x, nxb.y, nxb.z, nxb.w };
-		uint32_t m[8] = { nma.x, nma.y, nma.z, nma.w, nmb.x, nmb.y, nmb.z, nmb.w };
+		const uint32_t pw = pw0 + t * kTilePieces;
+		bool v[kSeg];
+#pragma unroll
+		for (int j = 0; j < (int)kSeg; j++)
+			v[j] = AIRS_SEG_VALID(pw, j);
+
+		uint32_t w[kSeg][4], m[kSeg][4];
+		{
+			/* work buffer words (model, IWT coefficients) are not loaded ahead: they come from
+			 * the L2 and would double the registers held across a tile */
+			const uint4 nm0 = AIRS_LOAD_M(pw, 0), nm1 = AIRS_LOAD_M(pw, 1);
+			const uint4 x2 = nx2, x3 = nx3, m2 = AIRS_LOAD_M(pw, 2), m3 = AIRS_LOAD_M(pw, 3);
+			w[0][0] = nx0.x; w[0][1] = nx0.y; w[0][2] = nx0.z; w[0][3] = nx0.w;
+			w[1][0] = nx1.x; w[1][1] = nx1.y; w[1][2] = nx1.z; w[1][3] = nx1.w;
+			w[2][0] = x2.x; w[2][1] = x2.y; w[2][2] = x2.z; w[2][3] = x2.w;
+			w[3][0] = x3.x; w[3][1] = x3.y; w[3][2] = x3.z; w[3][3] = x3.w;
+			m[0][0] = nm0.x; m[0][1] = nm0.y; m[0][2] = nm0.z; m[0][3] = nm0.w;
+			m[1][0] = nm1.x; m[1][1] = nm1.y; m[1][2] = nm1.z; m[1][3] = nm1.w;
+			m[2][0] = m2.x; m[2][1] = m2.y; m[2][2] = m2.z; m[2][3] = m2.w;
+			m[3][0] = m3.x; m[3][1] = m3.y; m[3][2] = m3.z; m[3][3] = m3.w;
+		}
 		const uint32_t ps = nps;
-
-		if (!PARTIAL && t + 1u < n_tiles)
-			AIRS_LOAD_TILE(pa + 2u * kThreads);
-
-		/* a tile that might cross the point where the reference's writer gives up keeps
-		 * the model exact sample by sample: generic path (ref cmp.c:300-311) */
-		if (mm && c.gw0 * 32u + c.sbits + trip_slack >= P.trip)
-			break;
-
-		/* biased packed residuals u = r + R: ref preprocess.c:268-290,348-353,406-411 */
-		uint32_t u[8];
-		if (pre == CMP_PREPROCESS_DIFF) {
-			const uint32_t src_lane = (lane - 1u) & 31u;
-			const uint32_t t1 = __shfl_sync(kFull, w[3], src_lane);
-			const uint32_t t2 = __shfl_sync(kFull, w[7], src_lane);
-			const uint32_t t3 = __shfl_sync(kFull, w[3], 31);
-			uint32_t nbp = __vadd2(~(lane ? t1 : ps << 16), B1);
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const uint32_t nb = __vadd2(~w[k], B1);
-				u[k] = __vadd2(w[k], __byte_perm(nbp, nb, 0x5432));
-				nbp = nb;
-			}
-			nbp = __vadd2(~(lane ? t2 : t3), B1);
-#pragma unroll
-			for (int k = 4; k < 8; k++) {
-				const uint32_t nb = __vadd2(~w[k], B1);
-				u[k] = __vadd2(w[k], __byte_perm(nbp, nb, 0x5432));
-				nbp = nb;
-			}
-		} else if (pre == CMP_PREPROCESS_MODEL) {
-#pragma unroll
-			for (int k = 0; k < 8; k++)
-				u[k] = __vadd2(w[k], __vadd2(~m[k], B1));
-		} else if (pre == CMP_PREPROCESS_IWT) {
-#pragma unroll
-			for (int k = 0; k < 8; k++)
-				u[k] = __vadd2(m[k], Rb);
-		} else {
-#pragma unroll
-			for (int k = 0; k < 8; k++)
-				u[k] = __vadd2(w[k], Rb);
+		if (!PARTIAL && t + 1u < n_tiles) {
+			nx0 = AIRS_LOAD_X(pw + kTilePieces, 0);
+			nx1 = AIRS_LOAD_X(pw + kTilePieces, 1);
+			nx2 = AIRS_LOAD_X(pw + kTilePieces, 2);
+			nx3 = AIRS_LOAD_X(pw + kTilePieces, 3);
+			nps = AIRS_LOAD_PS(pw + kTilePieces);
 		}
 
-		/* the new model takes the place of the old one (ref cmp.c:304-311) */
-		if (mm == 2u) {
-			const uint32_t wm16 = P.rate << 4, wx16 = (16u - P.rate) << 4;
-			const uint32_t ext_lo = P.is_signed ? 0x9910u : 0x4410u, ext_hi = P.is_signed ? 0xBB32u : 0x4432u;
-#pragma unroll
-			for (int k = 0; k < 8; k++)
-				m[k] = model_update2(w[k], m[k], wx16, wm16, ext_lo, ext_hi);
-		} else if (mm == 1u) {
-#pragma unroll
-			for (int k = 0; k < 8; k++)
-				m[k] = w[k];
-		}
-
-		if (PARTIAL) { /* pieces beyond the frame: residual 0, so that they do not spoil the table check */
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				u[k] = va ? u[k] : Rb;
-				u[k + 4] = vb ? u[k + 4] : Rb;
-			}
-		}
+		/* residuals of the four segments; the new model takes the place of the old one
+		 * (ref cmp.c:304-311) */
+		uint32_t u[kSeg][4];
 		uint32_t chk = 0;
+		{
+			const uint32_t src_lane = (lane - 1u) & 31u;
+			uint32_t front0 = ps << 16; /* lane 0: the word in front of its segment j */
 #pragma unroll
-		for (int k = 0; k < 8; k++)
-			chk |= u[k];
-		const bool fast = unc || (R != 0u && __all_sync(kFull, (chk & notmask) == 0u));
+			for (int j = 0; j < (int)kSeg; j++) {
+				uint32_t pw_word = 0;
+				if (diff) {
+					/* lanes 1-31 receive their left neighbour's last word; lane 0 receives lane
+					 * 31's, which is in front of its segment j + 1 */
+					const uint32_t up = __shfl_sync(kFull, w[j][3], src_lane);
+					pw_word = lane ? up : front0;
+					front0 = up;
+				}
+				seg_residuals(pre, w[j], m[j], pw_word, Rb, B1, u[j]);
+				if (mm == 2u) {
+					const uint32_t wm16 = P.rate << 4, wx16 = (16u - P.rate) << 4;
+					const uint32_t ext_lo = P.is_signed ? 0x9910u : 0x4410u, ext_hi = P.is_signed ? 0xBB32u : 0x4432u;
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						m[j][k] = model_update2(w[j][k], m[j][k], wx16, wm16, ext_lo, ext_hi);
+				} else if (mm == 1u) {
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						m[j][k] = w[j][k];
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					if (PARTIAL) /* pieces beyond the frame: residual 0, so that they do not spoil the table check */
+						u[j][k] = v[j] ? u[j][k] : Rb;
+					chk |= u[j][k];
+				}
+			}
+		}
 
-		/* Table path and arithmetic path are two separate arms up to the staging of their
-		 * bits (each with its own scan and barrier), so that nothing of one is live in the other. */
 		uint32_t tile_bits;
-		uint32_t action; /* 0: bits staged, 1: size only, 2: too many bits for the staging area */
+		uint32_t action; /* 0: bits staged, 1: size only, 2: tile handed back */
+		uint32_t pos[kSeg];
 #define AIRS_AFTER_SCAN(put_)                                                                        \
 	do {                                                                                         \
-		action = size_only ? 1u : (c.sbits + tile_bits > kStgBits ? 2u : 0u);                \
+		/* a tile too big for the staging area, or one that crosses the point where the  \
+		 * reference's writer gives up (the model then has to stay exact sample by       \
+		 * sample, ref cmp.c:300-311), goes back untouched */                            \
+		action = size_only ? 1u : ((c.sbits + tile_bits > kStgBits ||                        \
+					    c.gw0 * 32u + c.sbits + tile_bits >= trip) ? 2u : 0u);   \
 		if (action == 0u) {                                                                  \
 			/* the scan barrier is behind us: the tile before is completely staged */   \
 			if (pend)                                                                    \
 				copy_out(sh, o, c.buf ^ 1u, pend_gw0, pend_bits, c.buf);             \
 			if (mm) {                                                                    \
-				if (va)                                                              \
-					work4[pa] = make_uint4(m[0], m[1], m[2], m[3]);              \
-				if (vb)                                                              \
-					work4[pb] = make_uint4(m[4], m[5], m[6], m[7]);              \
+				_Pragma("unroll") for (int j = 0; j < (int)kSeg; j++)                \
+					if (v[j])                                                    \
+						st_keep(work4 + pw + 32u * j + lane, make_uint4(m[j][0], m[j][1], m[j][2], m[j][3]), pol_keep); \
 			}                                                                            \
 			uint32_t *stg = stg_of(sh, c.buf);                                           \
 			put_                                                                         \
 		}                                                                                    \
 	} while (0)
-		if (fast) {
-			uint32_t qh[4], ql[4], qn[4];
-			uint32_t pc[8], pl[8];
-			if (unc) {
+
+		/* ---- table arm, first half: codewords of pairs, quads, segments */
+		bool table = !unc && R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
+		uint32_t sh_[kSeg], sl_[kSeg], sn_[kSeg]; /* one string per segment: hi, lo, length */
+		if (table) {
+			uint32_t qchk = 0;
 #pragma unroll
-				for (int k = 0; k < 8; k++) {
-					pc[k] = __byte_perm(u[k], 0u, 0x1032); /* first sample in the upper half */
-					pl[k] = 32u;
-				}
-			} else {
-				const char *lut = reinterpret_cast<const char *>(sh.plut);
+			for (int j = 0; j < (int)kSeg; j++) {
+				uint32_t pc[4], pl[4];
 #pragma unroll
-				for (int k = 0; k < 8; k++) {
-					const uint32_t off = ((u[k] << 2) & (4u * (kLutStride - 1u))) | (u[k] >> 8);
+				for (int k = 0; k < 4; k++) {
+					const uint32_t off = ((u[j][k] << 2) & (4u * (kLutStride - 1u))) | (u[j][k] >> 8);
 					const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
 					pc[k] = ent & ((1u << kLutLenShift) - 1u);
 					pl[k] = ent >> kLutLenShift;
 				}
-			}
+				/* the four pair strings appended one after the other: 64-bit shifts by < 32 */
+				uint32_t lo = pc[0], hi = 0u, n = pl[0];
 #pragma unroll
-			for (int q = 0; q < 4; q++) {
-				ql[q] = __funnelshift_lc(0u, pc[2 * q], pl[2 * q + 1]) | pc[2 * q + 1];
-				qh[q] = __funnelshift_lc(pc[2 * q], 0u, pl[2 * q + 1]);
-				qn[q] = pl[2 * q] + pl[2 * q + 1];
+				for (int k = 1; k < 4; k++) {
+					hi = __funnelshift_l(lo, hi, pl[k]);
+					lo = (lo << pl[k]) | pc[k];
+					n += pl[k];
+				}
+				qchk |= n + 63u; /* bit 7 set: a segment longer than 64 bits */
+				sl_[j] = (PARTIAL && !v[j]) ? 0u : lo;
+				sh_[j] = (PARTIAL && !v[j]) ? 0u : hi;
+				sn_[j] = (PARTIAL && !v[j]) ? 0u : n;
 			}
-			if (PARTIAL) {
-				if (!va)
-					qn[0] = qn[1] = ql[0] = ql[1] = qh[0] = qh[1] = 0u;
-				if (!vb)
-					qn[2] = qn[3] = ql[2] = ql[3] = qh[2] = qh[3] = 0u;
-			}
-			uint32_t pos_a, pos_b;
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, (qn[0] + qn[1]) | ((qn[2] + qn[3]) << 16), c.sbits, pos_a,
-					      pos_b);
+			table = __all_sync(kFull, (qchk & 128u) == 0u);
+		}
+
+		if (table) {
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, sn_[0] | (sn_[1] << 16), sn_[2] | (sn_[3] << 16), c.sbits, pos);
 			AIRS_AFTER_SCAN({
-				int32_t ne = -(int32_t)pos_a;
-				put_unit(stg, ne, qh[0], ql[0], qn[0]);
-				put_unit(stg, ne, qh[1], ql[1], qn[1]);
-				ne = -(int32_t)pos_b;
-				put_unit(stg, ne, qh[2], ql[2], qn[2]);
-				put_unit(stg, ne, qh[3], ql[3], qn[3]);
+				_Pragma("unroll") for (int j = 0; j < (int)kSeg; j++) {
+					int32_t ne = -(int32_t)pos[j];
+					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
+				}
+			});
+		} else if (unc) {
+			/* ---- raw arm: 16 bits per sample, two 64-bit strings per segment */
+			const uint32_t nb = 128u;
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, (v[0] ? nb : 0u) | ((v[1] ? nb : 0u) << 16),
+					      (v[2] ? nb : 0u) | ((v[3] ? nb : 0u) << 16), c.sbits, pos);
+			AIRS_AFTER_SCAN({
+				_Pragma("unroll") for (int j = 0; j < (int)kSeg; j++) {
+					if (v[j]) {
+						int32_t ne = -(int32_t)pos[j];
+						/* first sample of a word in the upper half */
+						put_unit(stg, ne, __byte_perm(u[j][0], 0u, 0x1032), __byte_perm(u[j][1], 0u, 0x1032), 64u);
+						put_unit(stg, ne, __byte_perm(u[j][2], 0u, 0x1032), __byte_perm(u[j][3], 0u, 0x1032), 64u);
+					}
+				}
 			});
 		} else {
-			uint32_t d[8]; /* plain residuals, local memory (indexed by rolled loops) */
-			uint32_t bits_ab;
-			const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
+			/* ---- arithmetic arm: plain residuals from reloaded data into local memory, then
+			 * rolled loops over them */
+			uint32_t d[kSeg * 4];
+			{
+				const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
 #pragma unroll
-			for (int k = 0; k < 8; k++)
-				d[k] = __vadd2(u[k], negRb);
-			bits_ab = slow_bits(P.enc, d);
-			if (PARTIAL)
-				bits_ab = (va ? bits_ab & 0xFFFFu : 0u) | (vb ? bits_ab & 0xFFFF0000u : 0u);
-			uint32_t pos_a, pos_b;
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, bits_ab, c.sbits, pos_a, pos_b);
+				for (int j = 0; j < (int)kSeg; j++)
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						d[4 * j + k] = __vadd2(u[j][k], negRb);
+			}
+			uint32_t b01, b23;
+			slow_bits(P.enc, d, b01, b23);
+			if (PARTIAL) {
+				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
+				b23 = (v[2] ? b23 & 0xFFFFu : 0u) | (v[3] ? b23 & 0xFFFF0000u : 0u);
+			}
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, b01, b23, c.sbits, pos);
 			AIRS_AFTER_SCAN({
-				if (va)
-					slow_put(P.enc, d, stg, pos_a);
-				if (vb)
-					slow_put(P.enc, d + 4, stg, pos_b);
+				_Pragma("unroll 1") for (uint32_t j = 0; j < kSeg; j++)
+					if (!PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces))
+						slow_put(P.enc, d + 4 * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
 			});
 		}
 #undef AIRS_AFTER_SCAN
@@ -1008,8 +1102,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			cursor_advance(c, tile_bits);
 			continue;
 		}
-		if (action == 2u) /* (only warps on the arithmetic path can cause this) nothing of this tile has
-				   * been staged or stored: it goes back to the caller and through the generic path */
+		if (action == 2u) /* nothing of this tile has been staged or stored: it goes back to the caller
+				   * and through the generic path */
 			break;
 		pend = true;
 		pend_gw0 = c.gw0;
@@ -1017,7 +1111,10 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 		cursor_advance(c, tile_bits);
 		c.buf ^= 1u;
 	}
-#undef AIRS_LOAD_TILE
+#undef AIRS_SEG_VALID
+#undef AIRS_LOAD_X
+#undef AIRS_LOAD_M
+#undef AIRS_LOAD_PS
 	/* drain the tile still staged; what is left of it stays in its own area, which becomes
 	 * the current one again */
 	__syncthreads();
@@ -1049,7 +1146,7 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 					       bool size_only)
 {
 	const Pass &P = sh.pass;
-	const uint32_t n_full = n_pieces / (2u * kThreads);
+	const uint32_t n_full = n_pieces / kTilePieces;
 	const uint32_t key = (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only) ? 99u : P.pre * 3u + P.model_mode;
 
 	for (uint32_t t = 0; t < n_full;) {
@@ -1072,8 +1169,8 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 			t++;
 		}
 	}
-	if (n_full * (2u * kThreads) < n_pieces) {
-		if (!frame_fast_tail_rt(sh, o, a, c, n_full * (2u * kThreads), n_pieces, size_only))
+	if (n_full * kTilePieces < n_pieces) {
+		if (!frame_fast_tail_rt(sh, o, a, c, n_full * kTilePieces, n_pieces, size_only))
 			c = generic_span(sh, o, a, c, n_full * kTile, n_pieces * 8u, size_only);
 	}
 }
@@ -1237,7 +1334,6 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 			((uint32_t *)&sh.job)[tid - 32] = ((const uint32_t *)&b.jobs[job])[tid - 32];
 		__syncthreads();
 		if (tid == 0) {
-			sh.ticket = atomicAdd(b.ticket, 1u); /* next job, fetched while this one runs */
 			CtxState &c = sh.ctx;
 			if (b.ctx_io) { /* host shim: continue the caller's context */
 				const airs_ctx_state &st = b.ctx_io[job];
@@ -1254,9 +1350,17 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 		const uint32_t first = sh.job.first_result;
 
 		const bool concat = b.layout == AIRS_LAYOUT_CONCAT;
+		if (tid == 0 && n_frames == 0)
+			sh.ticket = atomicAdd(b.ticket, 1u);
 		for (uint32_t f = 0; f < n_frames; f++) {
-			if (tid == 0)
+			if (tid == 0) {
+				/* the next job is drawn while the last frame of this one is encoded: early
+				 * enough to hide the atomic, late enough that a CTA does not sit on a second
+				 * long job while other CTAs run dry */
+				if (f + 1 == n_frames)
+					sh.ticket = atomicAdd(b.ticket, 1u);
 				plan_frame(sh, b, f);
+			}
 			__syncthreads();
 			/* One call site for encode_pass (it is inlined).  SLOTS: stage 0 encodes, stage 1 is
 			 * the raw retry of the fallback (ref cmp.c:380-392).  CONCAT: stage 0 sizes the
@@ -1327,6 +1431,23 @@ extern "C" cudaError_t airs_launch_plan(const AirsLaunch *b, cudaStream_t stream
 {
 	airs_plan_kernel<<<(b->n_jobs + 127) / 128, 128, 0, stream>>>(*b);
 	return cudaGetLastError();
+}
+
+/* resident CTAs per SM of the encode kernel on the current device */
+extern "C" cudaError_t airs_encode_ctas_per_sm(int *out)
+{
+	/* shared memory for AIRS_CTAS_PER_SM CTAs (1 KiB per CTA is reserved by the system), the
+	 * rest of the 228 KiB stays L1 */
+	cudaFuncAttributes fa;
+	cudaError_t e = cudaFuncGetAttributes(&fa, airs_encode_kernel);
+	if (e != cudaSuccess)
+		return e;
+	const size_t need = (size_t)AIRS_CTAS_PER_SM * (fa.sharedSizeBytes + 1024);
+	int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+	e = cudaFuncSetAttribute(airs_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+	if (e != cudaSuccess)
+		return e;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, airs_encode_kernel, AIRS_THREADS, 0);
 }
 
 extern "C" cudaError_t airs_launch_encode(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)

@@ -10,9 +10,11 @@
 struct airs_ctx_state;
 struct JobPlan;
 
-#define AIRS_THREADS 256
+#ifndef AIRS_THREADS
+#define AIRS_THREADS 128
+#endif
 #ifndef AIRS_CTAS_PER_SM
-#define AIRS_CTAS_PER_SM 3 /* resident CTAs per SM the encode kernel is compiled for */
+#define AIRS_CTAS_PER_SM 6 /* resident CTAs per SM the encode kernel is compiled for */
 #endif
 
 struct AirsLaunch {
@@ -38,6 +40,7 @@ extern "C" {
 #endif
 cudaError_t airs_launch_plan(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
+cudaError_t airs_encode_ctas_per_sm(int *out);
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ EXPORTS = [
     # include/cmp_errors.h
     "cmp_get_error_code", "cmp_get_error_message", "cmp_get_error_string",
     # include/airs_cuda.h
-    "airs_cuda_device_count", "airs_cuda_last_error", "airs_cuda_batch_scratch_size",
+    "airs_cuda_device_count", "airs_cuda_concurrent_jobs", "airs_cuda_last_error", "airs_cuda_batch_scratch_size",
     "airs_cuda_compress_batch", "airs_cuda_last_launch_count", "airs_cuda_compress_batch_host",
     "airs_cuda_release_cache",
 ]
@@ -63,6 +63,7 @@ def load_library():
     lib.cmp_get_error_string.argtypes = [C.c_int]
     lib.cmp_get_error_string.restype = C.c_char_p
     lib.airs_cuda_device_count.restype = C.c_int
+    lib.airs_cuda_concurrent_jobs.restype = C.c_int
     lib.airs_cuda_last_error.restype = C.c_char_p
     lib.airs_cuda_batch_scratch_size.argtypes = [u32, u32]
     lib.airs_cuda_batch_scratch_size.restype = C.c_size_t

@@ -230,7 +230,8 @@ def main():
     lib = pkg.load_library()
     sms = torch.cuda.get_device_properties(device).multi_processor_count
 
-    units = args.units or (3 * sms if args.workload == "c2" else 1 << 20)
+    # one context per resident CTA of the encode kernel: all contexts of a rank run side by side
+    units = args.units or (lib.airs_cuda_concurrent_jobs() if args.workload == "c2" else 1 << 20)
     first_unit = rank * units                                   # weak scaling: fixed work per GPU
     w = build_workload(pkg, args.workload, units, first_unit, device=device)
     data = w["data"].view(torch.uint8).reshape(-1)

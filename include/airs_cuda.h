@@ -100,6 +100,12 @@ struct airs_batch {
 /* Number of usable sm_100 devices (0: none).  No reference counterpart. */
 int airs_cuda_device_count(void);
 
+/* Number of jobs (compression contexts) the current device works on at the same
+ * time: one per resident CTA of the encode kernel.  A batch keeps the device busy
+ * when it holds at least this many jobs of similar length (0: no usable device).
+ * No reference counterpart. */
+int airs_cuda_concurrent_jobs(void);
+
 /* Text of the last failure on this thread. */
 const char *airs_cuda_last_error(void);
 

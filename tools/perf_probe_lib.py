@@ -81,7 +81,8 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_plain)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     if case in ("c2", "c2one"):
-        R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "444")) if case == "c2" else 1), 256, 32768
+        R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "0")) or pkg.load_library().airs_cuda_concurrent_jobs()) if case == "c2" else 1, 256, 32768
+        print("c2 contexts:", R)
         data = synth.frames_torch(1, 0, R, F, n, device=dev)
         jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, cap=2 * n + 64, model=True)
         return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
