@@ -98,9 +98,13 @@ struct DevBuf {
 	}
 };
 
+constexpr int kMaxGroups = 64; /* pipeline stages of one host batch */
+
 struct Cache {
 	DevBuf src, dst, work, jobs, results, init, offs, scratch, state;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;            /* compute (and everything of the unpipelined paths) */
+	cudaStream_t s_in = nullptr, s_out = nullptr; /* host-to-device / device-to-host copies of the pipelined path */
+	cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_start = nullptr;
 	int stream_dev = -1;
 };
 thread_local Cache g_cache;
@@ -111,6 +115,13 @@ int cache_stream(cudaStream_t *s)
 	CU(cudaGetDevice(&dev));
 	if (!g_cache.stream || g_cache.stream_dev != dev) {
 		CU(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&g_cache.s_in, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&g_cache.s_out, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&g_cache.ev_start, cudaEventDisableTiming));
+		for (int i = 0; i < kMaxGroups; i++) {
+			CU(cudaEventCreateWithFlags(&g_cache.ev_in[i], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&g_cache.ev_done[i], cudaEventDisableTiming));
+		}
 		g_cache.stream_dev = dev;
 	}
 	*s = g_cache.stream;
@@ -222,6 +233,108 @@ extern "C" int airs_cuda_compress_batch(const struct airs_batch *b, void *stream
 	return launch_batch(b, nullptr, (cudaStream_t)stream);
 }
 
+/*
+ * SLOTS layout, large batch: the jobs are cut into groups of consecutive jobs
+ * (about equal source bytes); group g's samples travel to the device while
+ * group g-1 is encoded and the slots of group g-2 travel back, on three streams.
+ * Each group is one airs_cuda_compress_batch launch over its slice of the job
+ * table.  The device buffers are reserved by the caller.
+ */
+static int host_batch_pipelined(const struct airs_host_batch *hb, cudaStream_t s_comp)
+{
+	Cache &c = g_cache;
+	const struct airs_job *jobs = hb->jobs;
+	const uint64_t total_src = hb->src_size;
+	int n_groups = (int)(total_src / (256u << 20)) + 1;
+	if (n_groups < 4)
+		n_groups = 4;
+	if (n_groups > kMaxGroups)
+		n_groups = kMaxGroups;
+	if ((uint32_t)n_groups > hb->n_jobs)
+		n_groups = (int)hb->n_jobs;
+
+	/* everything the groups share goes first: job table, host models */
+	CU(cudaMemcpyAsync(c.jobs.p, hb->jobs, (size_t)hb->n_jobs * sizeof(struct airs_job), cudaMemcpyHostToDevice, c.s_in));
+	if (hb->work && hb->work_size)
+		CU(cudaMemcpyAsync(c.work.p, hb->work, hb->work_size, cudaMemcpyHostToDevice, c.s_in));
+	CU(cudaEventRecord(c.ev_start, c.s_in));
+	CU(cudaStreamWaitEvent(s_comp, c.ev_start, 0));
+
+	uint64_t bytes_total = 0;
+	for (uint32_t j = 0; j < hb->n_jobs; j++)
+		bytes_total += (uint64_t)jobs[j].src_size * jobs[j].n_frames;
+	const uint64_t per_group = bytes_total / (uint64_t)n_groups + 1;
+
+	uint32_t j0 = 0;
+	int launches = 0;
+	for (int g = 0; g < n_groups && j0 < hb->n_jobs; g++) {
+		/* jobs of this group and the byte ranges they touch */
+		uint64_t acc = 0, s_lo = ~0ull, s_hi = 0, d_lo = ~0ull, d_hi = 0;
+		uint32_t j1 = j0;
+		while (j1 < hb->n_jobs && (acc < per_group || g == n_groups - 1)) {
+			const struct airs_job &jb = jobs[j1];
+			const uint64_t nf = jb.n_frames;
+			acc += (uint64_t)jb.src_size * nf;
+			if (nf) {
+				const uint64_t se = jb.src_offset + (nf - 1) * jb.src_frame_stride + jb.src_size;
+				const uint64_t de = jb.dst_offset + (nf - 1) * jb.dst_frame_stride + jb.dst_capacity;
+				if (jb.src_offset < s_lo)
+					s_lo = jb.src_offset;
+				if (se > s_hi)
+					s_hi = se;
+				if (jb.dst_offset < d_lo)
+					d_lo = jb.dst_offset;
+				if (de > d_hi)
+					d_hi = de;
+			}
+			j1++;
+		}
+		if (s_hi > hb->src_size)
+			s_hi = hb->src_size;
+		if (d_hi > hb->dst_size)
+			d_hi = hb->dst_size;
+		if (s_lo < s_hi)
+			CU(cudaMemcpyAsync((uint8_t *)c.src.p + s_lo, (const uint8_t *)hb->src + s_lo, s_hi - s_lo,
+					   cudaMemcpyHostToDevice, c.s_in));
+		CU(cudaEventRecord(c.ev_in[g], c.s_in));
+		CU(cudaStreamWaitEvent(s_comp, c.ev_in[g], 0));
+
+		struct airs_batch b;
+		memset(&b, 0, sizeof(b));
+		b.src = c.src.p;
+		b.dst = c.dst.p;
+		b.work = hb->work_size ? c.work.p : nullptr;
+		b.jobs = (const struct airs_job *)c.jobs.p + j0;
+		b.results = (uint32_t *)c.results.p;
+		b.init_results = (uint32_t *)c.init.p + j0;
+		b.scratch = c.scratch.p;
+		b.dst_size = hb->dst_size;
+		b.n_jobs = j1 - j0;
+		b.n_results = hb->n_results;
+		b.layout = AIRS_LAYOUT_SLOTS;
+		int rc = launch_batch(&b, nullptr, s_comp);
+		if (rc)
+			return rc;
+		launches += g_launches;
+		CU(cudaEventRecord(c.ev_done[g], s_comp));
+		CU(cudaStreamWaitEvent(c.s_out, c.ev_done[g], 0));
+		if (d_lo < d_hi)
+			CU(cudaMemcpyAsync((uint8_t *)hb->dst + d_lo, (const uint8_t *)c.dst.p + d_lo, d_hi - d_lo,
+					   cudaMemcpyDeviceToHost, c.s_out));
+		j0 = j1;
+	}
+	g_launches = launches;
+	/* results, init results and models once everything has been encoded (s_out is behind the last group) */
+	CU(cudaMemcpyAsync(hb->results, c.results.p, (size_t)hb->n_results * 4, cudaMemcpyDeviceToHost, c.s_out));
+	if (hb->init_results)
+		CU(cudaMemcpyAsync(hb->init_results, c.init.p, (size_t)hb->n_jobs * 4, cudaMemcpyDeviceToHost, c.s_out));
+	if (hb->work && hb->work_size)
+		CU(cudaMemcpyAsync(hb->work, c.work.p, hb->work_size, cudaMemcpyDeviceToHost, c.s_out));
+	CU(cudaStreamSynchronize(c.s_out));
+	CU(cudaStreamSynchronize(s_comp));
+	return AIRS_OK;
+}
+
 extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
 {
 	if (!hb || !hb->jobs || !hb->results || !hb->src || !hb->dst)
@@ -239,6 +352,9 @@ extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
 	    (rc = c.init.reserve((size_t)hb->n_jobs * 4 + 64)) ||
 	    (rc = c.offs.reserve(((size_t)hb->n_results + 1) * 8 + 64)) || (rc = c.scratch.reserve(scratch)))
 		return rc;
+
+	if (hb->layout == AIRS_LAYOUT_SLOTS && hb->n_jobs >= 8 && hb->src_size >= (64u << 20))
+		return host_batch_pipelined(hb, s);
 
 	CU(cudaMemcpyAsync(c.src.p, hb->src, hb->src_size, cudaMemcpyHostToDevice, s));
 	CU(cudaMemcpyAsync(c.jobs.p, hb->jobs, jobs_bytes, cudaMemcpyHostToDevice, s));
@@ -297,9 +413,17 @@ extern "C" void airs_cuda_release_cache(void)
 	c.offs.release();
 	c.scratch.release();
 	c.state.release();
-	if (c.stream)
+	if (c.stream) {
 		cudaStreamDestroy(c.stream);
-	c.stream = nullptr;
+		cudaStreamDestroy(c.s_in);
+		cudaStreamDestroy(c.s_out);
+		cudaEventDestroy(c.ev_start);
+		for (int i = 0; i < kMaxGroups; i++) {
+			cudaEventDestroy(c.ev_in[i]);
+			cudaEventDestroy(c.ev_done[i]);
+		}
+	}
+	c.stream = c.s_in = c.s_out = nullptr;
 	c.stream_dev = -1;
 }
 

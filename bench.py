@@ -279,7 +279,8 @@ def main():
     # ---- end to end through the C-ABI with HOST buffers (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
-        e_units = max(1, min(units, (sms // 4) if args.workload == "c2" else 1 << 17))
+        # a quarter of the device-resident workload (c2: 222 contexts = 3.7 GB of samples per step)
+        e_units = max(1, min(units, max(8, units // 4) if args.workload == "c2" else 1 << 17))
         we = build_workload(pkg, args.workload, e_units, first_unit, device=device)
         src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
         src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())

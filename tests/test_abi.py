@@ -112,6 +112,7 @@ def test_no_cpu_fallback(lib):
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
     assert lib.airs_cuda_device_count() == 0
+    assert lib.airs_cuda_concurrent_jobs() == 0
     ctx = abi.CmpContext()
     p = abi.params_to_ctypes(abi.make_params())
     assert lib.cmp_initialise(C.byref(ctx), C.byref(p), None, 0) == 0

@@ -50,6 +50,24 @@ def test_host_batch(gpu, oracle, layout):
     jobgen.compare(want, got, js, "gpu-host-batch", check_tail=False)
 
 
+def test_host_batch_pipelined(gpu, oracle, pkg):
+    """A host batch large enough (>= 64 MiB, >= 8 jobs, SLOTS) to take the pipelined path of
+    airs_cuda_compress_batch_host: groups of jobs copied in, encoded and copied back on three streams."""
+    abi, synth = pkg.abi, pkg.synth
+    n_jobs, n, nf = 48, 1 << 18, 3                      # 48 contexts x 3 frames x 512 KiB = 72 MiB
+    p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16,
+                        secondary_iterations=2, secondary_preprocessing=abi.PRE_MODEL,
+                        secondary_encoder_type=2, secondary_encoder_param=8, secondary_encoder_outlier=60,
+                        model_rate=11, checksum_enabled=1)
+    js = _uniform_jobs(pkg, n_jobs, n, nf, p, cap=2 * n + 64)
+    x = np.stack([synth.frames(3, c, nf, n) for c in range(n_jobs)])
+    js["src"] = x.view(np.uint8).reshape(-1)
+    assert js["src"].nbytes >= 64 << 20
+    want = jobgen.run_cpu(oracle, js, threads=8)
+    got = gpu.run_jobs_host(js)
+    jobgen.compare(want, got, js, "gpu-host-pipelined", check_tail=False)
+
+
 def _uniform_jobs(pkg, n_jobs, n, n_frames, params, dtype=2, cap=None):
     abi = pkg.abi
     jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
