@@ -43,6 +43,7 @@ namespace {
 constexpr uint32_t kThreads = AIRS_THREADS; /* 128 */
 constexpr uint32_t kWarps = kThreads / 32;
 constexpr uint32_t kSeg = 4;                /* fast path: segments (pieces of 8 samples) per thread and tile */
+constexpr uint32_t kSegModel = 2;           /* ... of the model pass (old and new model words next to the samples) */
 constexpr uint32_t kTilePieces = kThreads * kSeg;
 constexpr uint32_t kTile = kTilePieces * 8; /* 4096 samples = 8 KiB of u16 */
 constexpr uint32_t kGenSpt = 8;             /* generic path: samples per thread and tile */
@@ -698,13 +699,14 @@ __device__ __forceinline__ void encode_mapped_rt(const EncConst &e, uint32_t m, 
 		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, m, cw, cl, rw, rl);
 }
 
-/* bit counts of the four segments d[0..3] .. d[12..15]: b01 = segment 0 | segment 1 << 16, b23 likewise */
-__device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t &b01, uint32_t &b23)
+/* bit counts of the segments d[0..3], d[4..7], ..: b01 = segment 0 | segment 1 << 16, b23 likewise */
+__device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t &b01,
+					  uint32_t &b23)
 {
 	b01 = 0;
 	b23 = 0;
 #pragma unroll 1
-	for (uint32_t k = 0; k < 4u * kSeg; k++) {
+	for (uint32_t k = 0; k < n_words; k++) {
 		const uint32_t z = zigzag2(d[k]);
 		uint32_t cw, cl, rw, rl, n;
 		encode_mapped_rt(e, z & 0xFFFFu, cw, cl, rw, rl);
@@ -744,7 +746,7 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
  * places.  The warp totals alternate between two slots (parity), so that no
  * second barrier is needed before the next tile's scan. */
 __device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t parity, uint32_t lane, uint32_t warp, uint32_t b01,
-					      uint32_t b23, uint32_t sbits, uint32_t (&pos)[kSeg])
+					      uint32_t b23, uint32_t sbits, uint32_t (&pos)[4])
 {
 	uint32_t i01 = b01, i23 = b23;
 
@@ -872,7 +874,7 @@ __device__ __forceinline__ void seg_residuals(uint32_t pre, const uint32_t (&w)[
  * go through the generic path.  Inlined into the kernel and free of calls: a
  * called function only gets the registers its caller leaves over.
  */
-template <int PRE, int MM, int UNC, int SZ, bool PARTIAL>
+template <int PRE, int MM, int UNC, int SZ, bool PARTIAL, int SEG>
 __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint32_t a, Cursor &c_io, uint32_t t0,
 					       uint32_t n_tiles, uint32_t p0, uint32_t n_pieces, bool size_only_rt)
 {
@@ -894,7 +896,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	const bool need_x = pre != CMP_PREPROCESS_IWT || mm;
 	const bool need_m = use_m || mm == 2u;
 	/* segments per warp in this tile */
-	const uint32_t nseg = PARTIAL ? min(kSeg, (n_pieces - p0 + kThreads - 1u) / kThreads) : kSeg;
+	constexpr uint32_t kTP = kThreads * SEG; /* pieces per tile */
+	const uint32_t nseg = PARTIAL ? min((uint32_t)SEG, (n_pieces - p0 + kThreads - 1u) / kThreads) : (uint32_t)SEG;
 	const uint32_t pw0 = p0 + warp * 32u * nseg; /* first piece of the warp in tile 0 */
 	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
 	uint4 *work4 = reinterpret_cast<uint4 *>(P.work);
@@ -920,51 +923,52 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 
 	/* the whole next tile is loaded one tile ahead (the scheduler pulls the first consumers of
 	 * all four segments to the top of the loop body, so a later load would be waited for) */
-	uint4 nx0 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 0), nx1 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 1);
-	uint4 nx2 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 2), nx3 = AIRS_LOAD_X(pw0 + t0 * kTilePieces, 3);
-	uint32_t nps = AIRS_LOAD_PS(pw0 + t0 * kTilePieces);
+	/* work buffer words (model, IWT coefficients) are loaded ahead as well where a tile is
+	 * small enough for the registers (the model pass) */
+	constexpr bool kAheadM = SEG <= 2;
+	uint4 nx[SEG], nm[SEG];
+#pragma unroll
+	for (int j = 0; j < SEG; j++) {
+		nx[j] = AIRS_LOAD_X(pw0 + t0 * kTP, j);
+		nm[j] = kAheadM ? AIRS_LOAD_M(pw0 + t0 * kTP, j) : zero4;
+	}
+	uint32_t nps = AIRS_LOAD_PS(pw0 + t0 * kTP);
 
 	uint32_t t = t0;
 	for (; t < n_tiles; t++) {
-		const uint32_t pw = pw0 + t * kTilePieces;
-		bool v[kSeg];
+		const uint32_t pw = pw0 + t * kTP;
+		bool v[SEG];
 #pragma unroll
-		for (int j = 0; j < (int)kSeg; j++)
+		for (int j = 0; j < SEG; j++)
 			v[j] = AIRS_SEG_VALID(pw, j);
 
-		uint32_t w[kSeg][4], m[kSeg][4];
-		{
-			/* work buffer words (model, IWT coefficients) are not loaded ahead: they come from
-			 * the L2 and would double the registers held across a tile */
-			const uint4 nm0 = AIRS_LOAD_M(pw, 0), nm1 = AIRS_LOAD_M(pw, 1);
-			const uint4 x2 = nx2, x3 = nx3, m2 = AIRS_LOAD_M(pw, 2), m3 = AIRS_LOAD_M(pw, 3);
-			w[0][0] = nx0.x; w[0][1] = nx0.y; w[0][2] = nx0.z; w[0][3] = nx0.w;
-			w[1][0] = nx1.x; w[1][1] = nx1.y; w[1][2] = nx1.z; w[1][3] = nx1.w;
-			w[2][0] = x2.x; w[2][1] = x2.y; w[2][2] = x2.z; w[2][3] = x2.w;
-			w[3][0] = x3.x; w[3][1] = x3.y; w[3][2] = x3.z; w[3][3] = x3.w;
-			m[0][0] = nm0.x; m[0][1] = nm0.y; m[0][2] = nm0.z; m[0][3] = nm0.w;
-			m[1][0] = nm1.x; m[1][1] = nm1.y; m[1][2] = nm1.z; m[1][3] = nm1.w;
-			m[2][0] = m2.x; m[2][1] = m2.y; m[2][2] = m2.z; m[2][3] = m2.w;
-			m[3][0] = m3.x; m[3][1] = m3.y; m[3][2] = m3.z; m[3][3] = m3.w;
+		uint32_t w[SEG][4], m[SEG][4];
+#pragma unroll
+		for (int j = 0; j < SEG; j++) {
+			const uint4 mj = kAheadM ? nm[j] : AIRS_LOAD_M(pw, j);
+			w[j][0] = nx[j].x; w[j][1] = nx[j].y; w[j][2] = nx[j].z; w[j][3] = nx[j].w;
+			m[j][0] = mj.x; m[j][1] = mj.y; m[j][2] = mj.z; m[j][3] = mj.w;
 		}
 		const uint32_t ps = nps;
 		if (!PARTIAL && t + 1u < n_tiles) {
-			nx0 = AIRS_LOAD_X(pw + kTilePieces, 0);
-			nx1 = AIRS_LOAD_X(pw + kTilePieces, 1);
-			nx2 = AIRS_LOAD_X(pw + kTilePieces, 2);
-			nx3 = AIRS_LOAD_X(pw + kTilePieces, 3);
-			nps = AIRS_LOAD_PS(pw + kTilePieces);
+#pragma unroll
+			for (int j = 0; j < SEG; j++) {
+				nx[j] = AIRS_LOAD_X(pw + kTP, j);
+				if (kAheadM)
+					nm[j] = AIRS_LOAD_M(pw + kTP, j);
+			}
+			nps = AIRS_LOAD_PS(pw + kTP);
 		}
 
 		/* residuals of the four segments; the new model takes the place of the old one
 		 * (ref cmp.c:304-311) */
-		uint32_t u[kSeg][4];
+		uint32_t u[SEG][4];
 		uint32_t chk = 0;
 		{
 			const uint32_t src_lane = (lane - 1u) & 31u;
 			uint32_t front0 = ps << 16; /* lane 0: the word in front of its segment j */
 #pragma unroll
-			for (int j = 0; j < (int)kSeg; j++) {
+			for (int j = 0; j < SEG; j++) {
 				uint32_t pw_word = 0;
 				if (diff) {
 					/* lanes 1-31 receive their left neighbour's last word; lane 0 receives lane
@@ -996,7 +1000,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 
 		uint32_t tile_bits;
 		uint32_t action; /* 0: bits staged, 1: size only, 2: tile handed back */
-		uint32_t pos[kSeg];
+		uint32_t pos[4];
 #define AIRS_AFTER_SCAN(put_)                                                                        \
 	do {                                                                                         \
 		/* a tile too big for the staging area, or one that crosses the point where the  \
@@ -1009,7 +1013,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			if (pend)                                                                    \
 				copy_out(sh, o, c.buf ^ 1u, pend_gw0, pend_bits, c.buf);             \
 			if (mm) {                                                                    \
-				_Pragma("unroll") for (int j = 0; j < (int)kSeg; j++)                \
+				_Pragma("unroll") for (int j = 0; j < SEG; j++)                \
 					if (v[j])                                                    \
 						st_keep(work4 + pw + 32u * j + lane, make_uint4(m[j][0], m[j][1], m[j][2], m[j][3]), pol_keep); \
 			}                                                                            \
@@ -1020,11 +1024,11 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 
 		/* ---- table arm, first half: codewords of pairs, quads, segments */
 		bool table = !unc && R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
-		uint32_t sh_[kSeg], sl_[kSeg], sn_[kSeg]; /* one string per segment: hi, lo, length */
+		uint32_t sh_[SEG], sl_[SEG], sn_[SEG]; /* one string per segment: hi, lo, length */
 		if (table) {
 			uint32_t qchk = 0;
 #pragma unroll
-			for (int j = 0; j < (int)kSeg; j++) {
+			for (int j = 0; j < SEG; j++) {
 				uint32_t pc[4], pl[4];
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
@@ -1050,9 +1054,10 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 		}
 
 		if (table) {
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, sn_[0] | (sn_[1] << 16), sn_[2] | (sn_[3] << 16), c.sbits, pos);
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, sn_[0] | (sn_[1] << 16), SEG > 2 ? sn_[SEG - 2] | (sn_[SEG - 1] << 16) : 0u,
+					      c.sbits, pos);
 			AIRS_AFTER_SCAN({
-				_Pragma("unroll") for (int j = 0; j < (int)kSeg; j++) {
+				_Pragma("unroll") for (int j = 0; j < SEG; j++) {
 					int32_t ne = -(int32_t)pos[j];
 					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
 				}
@@ -1061,9 +1066,9 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			/* ---- raw arm: 16 bits per sample, two 64-bit strings per segment */
 			const uint32_t nb = 128u;
 			tile_bits = tile_scan(sh, t & 1u, lane, warp, (v[0] ? nb : 0u) | ((v[1] ? nb : 0u) << 16),
-					      (v[2] ? nb : 0u) | ((v[3] ? nb : 0u) << 16), c.sbits, pos);
+					      SEG > 2 ? (v[SEG - 2] ? nb : 0u) | ((v[SEG - 1] ? nb : 0u) << 16) : 0u, c.sbits, pos);
 			AIRS_AFTER_SCAN({
-				_Pragma("unroll") for (int j = 0; j < (int)kSeg; j++) {
+				_Pragma("unroll") for (int j = 0; j < SEG; j++) {
 					if (v[j]) {
 						int32_t ne = -(int32_t)pos[j];
 						/* first sample of a word in the upper half */
@@ -1075,24 +1080,25 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 		} else {
 			/* ---- arithmetic arm: plain residuals from reloaded data into local memory, then
 			 * rolled loops over them */
-			uint32_t d[kSeg * 4];
+			uint32_t d[SEG * 4];
 			{
 				const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
 #pragma unroll
-				for (int j = 0; j < (int)kSeg; j++)
+				for (int j = 0; j < SEG; j++)
 #pragma unroll
 					for (int k = 0; k < 4; k++)
 						d[4 * j + k] = __vadd2(u[j][k], negRb);
 			}
 			uint32_t b01, b23;
-			slow_bits(P.enc, d, b01, b23);
+			slow_bits(P.enc, d, 4u * SEG, b01, b23);
 			if (PARTIAL) {
 				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
-				b23 = (v[2] ? b23 & 0xFFFFu : 0u) | (v[3] ? b23 & 0xFFFF0000u : 0u);
+				if (SEG > 2)
+					b23 = (v[SEG - 2] ? b23 & 0xFFFFu : 0u) | (v[SEG - 1] ? b23 & 0xFFFF0000u : 0u);
 			}
 			tile_bits = tile_scan(sh, t & 1u, lane, warp, b01, b23, c.sbits, pos);
 			AIRS_AFTER_SCAN({
-				_Pragma("unroll 1") for (uint32_t j = 0; j < kSeg; j++)
+				_Pragma("unroll 1") for (uint32_t j = 0; j < (uint32_t)SEG; j++)
 					if (!PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces))
 						slow_put(P.enc, d + 4 * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
 			});
@@ -1130,48 +1136,51 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 __device__ __noinline__ uint32_t frame_fast_full_rt(Shared &sh, const OutWin o, uint32_t a, Cursor &c, uint32_t t0,
 						    uint32_t n_tiles, uint32_t n_pieces, bool size_only)
 {
-	return frame_fast<-1, -1, -1, -1, false>(sh, o, a, c, t0, n_tiles, 0u, n_pieces, size_only);
+	return frame_fast<-1, -1, -1, -1, false, kSeg>(sh, o, a, c, t0, n_tiles, 0u, n_pieces, size_only);
 }
 
 __device__ __noinline__ uint32_t frame_fast_tail_rt(Shared &sh, const OutWin o, uint32_t a, Cursor &c, uint32_t p0,
 						    uint32_t n_pieces, bool size_only)
 {
-	return frame_fast<-1, -1, -1, -1, true>(sh, o, a, c, 0u, 1u, p0, n_pieces, size_only);
+	return frame_fast<-1, -1, -1, -1, true, kSeg>(sh, o, a, c, 0u, 1u, p0, n_pieces, size_only);
 }
 
 /* all pieces of a frame: full tiles through the instantiation specialised for
  * this pass when there is one, else through the catch-all, like the partial
- * tile; a tile the fast path hands back goes through the generic path */
+ * tile; a tile the fast path hands back goes through the generic path.  The
+ * model pass works on half-size tiles (two segments per thread): it holds old
+ * and new model words next to the samples. */
 __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint32_t a, Cursor &c, uint32_t n_pieces,
 					       bool size_only)
 {
 	const Pass &P = sh.pass;
-	const uint32_t n_full = n_pieces / kTilePieces;
 	const uint32_t key = (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only) ? 99u : P.pre * 3u + P.model_mode;
+	const uint32_t tp = key == CMP_PREPROCESS_MODEL * 3u + 2u ? kThreads * kSegModel : kTilePieces; /* pieces per tile */
+	const uint32_t n_full = n_pieces / tp;
 
 	for (uint32_t t = 0; t < n_full;) {
 		switch (key) {
-#define AIRS_HOT(pre_, mm_)                                                                             \
-	case (pre_) * 3u + (mm_):                                                                       \
-		t = frame_fast<(pre_), (mm_), 0, 0, false>(sh, o, a, c, t, n_full, 0u, n_pieces, false); \
+#define AIRS_HOT(pre_, mm_, seg_)                                                                              \
+	case (pre_) * 3u + (mm_):                                                                              \
+		t = frame_fast<(pre_), (mm_), 0, 0, false, (seg_)>(sh, o, a, c, t, n_full, 0u, n_pieces, false); \
 		break;
-		AIRS_HOT(CMP_PREPROCESS_NONE, 0)
-		AIRS_HOT(CMP_PREPROCESS_DIFF, 0)
-		AIRS_HOT(CMP_PREPROCESS_DIFF, 1)
-		AIRS_HOT(CMP_PREPROCESS_MODEL, 2)
+		AIRS_HOT(CMP_PREPROCESS_NONE, 0, kSeg)
+		AIRS_HOT(CMP_PREPROCESS_DIFF, 0, kSeg)
+		AIRS_HOT(CMP_PREPROCESS_DIFF, 1, kSeg)
+		AIRS_HOT(CMP_PREPROCESS_MODEL, 2, kSegModel)
 #undef AIRS_HOT
 		default:
 			t = frame_fast_full_rt(sh, o, a, c, t, n_full, n_pieces, size_only);
 			break;
 		}
 		if (t < n_full) {
-			c = generic_span(sh, o, a, c, t * kTile, (t + 1u) * kTile, size_only);
+			c = generic_span(sh, o, a, c, t * tp * 8u, (t + 1u) * tp * 8u, size_only);
 			t++;
 		}
 	}
-	if (n_full * kTilePieces < n_pieces) {
-		if (!frame_fast_tail_rt(sh, o, a, c, n_full * kTilePieces, n_pieces, size_only))
-			c = generic_span(sh, o, a, c, n_full * kTile, n_pieces * 8u, size_only);
+	if (n_full * tp < n_pieces) {
+		if (!frame_fast_tail_rt(sh, o, a, c, n_full * tp, n_pieces, size_only))
+			c = generic_span(sh, o, a, c, n_full * tp * 8u, n_pieces * 8u, size_only);
 	}
 }
 
