@@ -664,26 +664,24 @@ __device__ __forceinline__ void put_unit(uint32_t *stg, int32_t &ne, uint32_t hi
 	atomicOr(p - 2, __funnelshift_l(hi, 0u, s));
 }
 
-/* PRMT with the full selector (the __byte_perm intrinsic drops the sign-replicate bit) */
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-	uint32_t r;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-	return r;
-}
-
 /* packed model update of two samples (ref update_model_16, cmp.c:120-142):
- * (m * rate + x * (16 - rate)) >> 4 truncated to 16 bits.  The weights come
- * pre-multiplied by 16 so that the result sits in bytes 1-2 of each product sum
- * and one PRMT packs both lanes.  ext_lo/ext_hi are the PRMT selectors that
- * widen a lane (zero extension for u16, sign extension for i16 containers). */
-__device__ __forceinline__ uint32_t model_update2(uint32_t x, uint32_t m, uint32_t wx16, uint32_t wm16,
-						  uint32_t ext_lo, uint32_t ext_hi)
+ * (m * rate + x * (16 - rate)) >> 4 truncated to 16 bits, for 1 <= rate <= 15.
+ * The pairs (m, x) of each lane go through one IDP.2A (two 16-bit x 8-bit
+ * products summed) with the weights pre-multiplied by 16, so that the result
+ * sits in bytes 1-2 of each sum and one PRMT packs both lanes.  wdp = 16 * rate |
+ * 16 * (16 - rate) << 8; SIGNED: i16 containers (operands sign-extended). */
+template <bool SIGNED>
+__device__ __forceinline__ uint32_t model_update2(uint32_t x, uint32_t m, uint32_t wdp)
 {
-	const uint32_t xl = prmt(x, 0u, ext_lo), xh = prmt(x, 0u, ext_hi);
-	const uint32_t ml = prmt(m, 0u, ext_lo), mh = prmt(m, 0u, ext_hi);
-	const uint32_t tl = ml * wm16 + xl * wx16;
-	const uint32_t th = mh * wm16 + xh * wx16;
+	const uint32_t lo = __byte_perm(m, x, 0x5410), hi = __byte_perm(m, x, 0x7632); /* (m, x) of the low / high lane */
+	uint32_t tl, th;
+	if (SIGNED) {
+		asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(tl) : "r"(lo), "r"(wdp), "r"(0u));
+		asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(th) : "r"(hi), "r"(wdp), "r"(0u));
+	} else {
+		asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(tl) : "r"(lo), "r"(wdp), "r"(0u));
+		asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(th) : "r"(hi), "r"(wdp), "r"(0u));
+	}
 	return __byte_perm(tl, th, 0x6521);
 }
 
@@ -979,11 +977,23 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				}
 				seg_residuals(pre, w[j], m[j], pw_word, Rb, B1, u[j]);
 				if (mm == 2u) {
-					const uint32_t wm16 = P.rate << 4, wx16 = (16u - P.rate) << 4;
-					const uint32_t ext_lo = P.is_signed ? 0x9910u : 0x4410u, ext_hi = P.is_signed ? 0xBB32u : 0x4432u;
+					/* rate 16 keeps the model as it is, rate 0 replaces it by the samples */
+					const uint32_t rate = P.rate, wdp = (rate << 4) | ((16u - rate) << 12);
+					if (rate == 0u) {
 #pragma unroll
-					for (int k = 0; k < 4; k++)
-						m[j][k] = model_update2(w[j][k], m[j][k], wx16, wm16, ext_lo, ext_hi);
+						for (int k = 0; k < 4; k++)
+							m[j][k] = w[j][k];
+					} else if (rate < 16u) {
+						if (P.is_signed) {
+#pragma unroll
+							for (int k = 0; k < 4; k++)
+								m[j][k] = model_update2<true>(w[j][k], m[j][k], wdp);
+						} else {
+#pragma unroll
+							for (int k = 0; k < 4; k++)
+								m[j][k] = model_update2<false>(w[j][k], m[j][k], wdp);
+						}
+					}
 				} else if (mm == 1u) {
 #pragma unroll
 					for (int k = 0; k < 4; k++)
