@@ -58,7 +58,7 @@ constexpr uint32_t kLutR = 32;              /* pair table covers residuals in [-
 constexpr uint32_t kLutStride = 2 * kLutR;
 constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair codeword */
 constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
-constexpr uint32_t kLutMinSamples = 4 * kTile; /* frames shorter than this do not pay for a table build */
+constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -101,6 +101,7 @@ struct Shared {
 	uint32_t wsum[2][kWarps];            /* warp totals of the tile scan, alternating between tiles */
 	uint32_t plut_key[3];                /* encoder the pair table was built for: type, g, outlier */
 	uint32_t plut_R;                     /* its usable half range: 32, 16, 8 or 0 (none) */
+	uint32_t first_code[3];              /* DIFF: codeword (hi, lo, bits) of the frame's first sample, used by thread 0 */
 	JobPlan plan;
 	airs_job job;
 	Pass pass;
@@ -697,6 +698,18 @@ __device__ __forceinline__ void encode_mapped_rt(const EncConst &e, uint32_t m, 
 		airs_encode_mapped<CMP_ENCODER_GOLOMB_MULTI>(e, m, cw, cl, rw, rl);
 }
 
+/* codeword (hi:lo, n <= 48 bits) of the first sample of a frame under DIFF preprocessing: its
+ * residual is the sample itself (ref preprocess.c:284-290) */
+__device__ __noinline__ void first_sample_code(const EncConst &e, uint32_t x0, uint32_t *out)
+{
+	uint32_t cw = 0, cl = 0, rw = 0, rl = 0;
+	if (e.type != CMP_ENCODER_UNCOMPRESSED)
+		encode_mapped_rt(e, airs_zigzag16(x0), cw, cl, rw, rl);
+	out[0] = __funnelshift_lc(cw, 0u, rl);
+	out[1] = __funnelshift_lc(0u, cw, rl) | rw;
+	out[2] = cl + rl;
+}
+
 /* bit counts of the segments d[0..3], d[4..7], ..: b01 = segment 0 | segment 1 << 16, b23 likewise */
 __device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t &b01,
 					  uint32_t &b23)
@@ -939,6 +952,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 #pragma unroll
 		for (int j = 0; j < SEG; j++)
 			v[j] = AIRS_SEG_VALID(pw, j);
+		/* this thread holds sample 0 of the frame and a table is there to be missed */
+		const bool first = diff && R != 0u && pw == 0u && lane == 0u;
 
 		uint32_t w[SEG][4], m[SEG][4];
 #pragma unroll
@@ -976,6 +991,11 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 					front0 = up;
 				}
 				seg_residuals(pre, w[j], m[j], pw_word, Rb, B1, u[j]);
+				/* the first sample of a frame has no predecessor: its "difference" is the
+				 * sample itself, far outside any table.  The thread that holds it encodes it
+				 * on its own (first_sample_*) and lets residual 0 stand in here. */
+				if (j == 0 && first)
+					u[0][0] = (u[0][0] & 0xFFFF0000u) | (Rb & 0xFFFFu);
 				if (mm == 2u) {
 					/* rate 16 keeps the model as it is, rate 0 replaces it by the samples */
 					const uint32_t rate = P.rate, wdp = (rate << 4) | ((16u - rate) << 12);
@@ -1047,6 +1067,10 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 					pc[k] = ent & ((1u << kLutLenShift) - 1u);
 					pl[k] = ent >> kLutLenShift;
 				}
+				if (j == 0 && first) { /* drop the stand-in's codeword from the head of pair 0 */
+					pl[0] -= sh.slut[kLutR].y;
+					pc[0] &= (1u << pl[0]) - 1u;
+				}
 				/* the four pair strings appended one after the other: 64-bit shifts by < 32 */
 				uint32_t lo = pc[0], hi = 0u, n = pl[0];
 #pragma unroll
@@ -1064,9 +1088,17 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 		}
 
 		if (table) {
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, sn_[0] | (sn_[1] << 16), SEG > 2 ? sn_[SEG - 2] | (sn_[SEG - 1] << 16) : 0u,
-					      c.sbits, pos);
+			/* bits of the frame's first sample, in front of this thread's segment 0 (thread 0
+			 * wrote them itself, encode_pass) */
+			const uint32_t n_first = first ? sh.first_code[2] : 0u;
+			tile_bits = tile_scan(sh, t & 1u, lane, warp, (sn_[0] + n_first) | (sn_[1] << 16),
+					      SEG > 2 ? sn_[SEG - 2] | (sn_[SEG - 1] << 16) : 0u, c.sbits, pos);
 			AIRS_AFTER_SCAN({
+				if (first) {
+					int32_t ne = -(int32_t)pos[0];
+					put_unit(stg, ne, sh.first_code[0], sh.first_code[1], n_first);
+					pos[0] += n_first;
+				}
 				_Pragma("unroll") for (int j = 0; j < SEG; j++) {
 					int32_t ne = -(int32_t)pos[j];
 					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
@@ -1098,6 +1130,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 #pragma unroll
 					for (int k = 0; k < 4; k++)
 						d[4 * j + k] = __vadd2(u[j][k], negRb);
+				if (first) /* the stand-in goes, the sample comes back */
+					d[0] = (d[0] & 0xFFFF0000u) | (uint32_t)__ldg(src16);
 			}
 			uint32_t b01, b23;
 			slow_bits(P.enc, d, 4u * SEG, b01, b23);
@@ -1227,6 +1261,8 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 		if (e.type != CMP_ENCODER_UNCOMPRESSED && n >= kLutMinSamples &&
 		    (sh.plut_key[0] != e.type || sh.plut_key[1] != e.g || sh.plut_key[2] != e.outlier))
 			build_pair_lut(sh, e);
+		if (tid == 0 && pre == CMP_PREPROCESS_DIFF)
+			first_sample_code(e, __ldg(reinterpret_cast<const uint16_t *>(P.src)), sh.first_code);
 		frame_fast_any(sh, o, a, c, n_pieces, size_only);
 	}
 	if (n_pieces * 8u < n)
