@@ -756,25 +756,35 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
  * staged already).  One block barrier; warps may call it from different
  * places.  The warp totals alternate between two slots (parity), so that no
  * second barrier is needed before the next tile's scan. */
+template <int SEG>
 __device__ __forceinline__ uint32_t tile_scan(Shared &sh, uint32_t parity, uint32_t lane, uint32_t warp, uint32_t b01,
 					      uint32_t b23, uint32_t sbits, uint32_t (&pos)[4])
 {
 	uint32_t i01 = b01, i23 = b23;
 
-	/* shuffle with its "source lane exists" predicate feeding the adds directly */
+	/* shuffle with its "source lane exists" predicate feeding the adds directly; two
+	 * segments per thread need one chain only */
 #define AIRS_SCAN_STEP(d_)                                                                           \
-	asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t0, t1;\n\t"                                   \
-		     "shfl.sync.up.b32 t0|p, %0, " #d_ ", 0, 0xffffffff;\n\t"                        \
-		     "shfl.sync.up.b32 t1, %1, " #d_ ", 0, 0xffffffff;\n\t"                          \
-		     "@p add.u32 %0, %0, t0;\n\t@p add.u32 %1, %1, t1;\n\t}"                         \
-		     : "+r"(i01), "+r"(i23))
+	do {                                                                                         \
+		if (SEG > 2)                                                                         \
+			asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t0, t1;\n\t"                       \
+				     "shfl.sync.up.b32 t0|p, %0, " #d_ ", 0, 0xffffffff;\n\t"            \
+				     "shfl.sync.up.b32 t1, %1, " #d_ ", 0, 0xffffffff;\n\t"              \
+				     "@p add.u32 %0, %0, t0;\n\t@p add.u32 %1, %1, t1;\n\t}"             \
+				     : "+r"(i01), "+r"(i23));                                        \
+		else                                                                                 \
+			asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t0;\n\t"                           \
+				     "shfl.sync.up.b32 t0|p, %0, " #d_ ", 0, 0xffffffff;\n\t"            \
+				     "@p add.u32 %0, %0, t0;\n\t}"                                      \
+				     : "+r"(i01));                                                   \
+	} while (0)
 	AIRS_SCAN_STEP(1);
 	AIRS_SCAN_STEP(2);
 	AIRS_SCAN_STEP(4);
 	AIRS_SCAN_STEP(8);
 	AIRS_SCAN_STEP(16);
 #undef AIRS_SCAN_STEP
-	const uint32_t t01 = __shfl_sync(kFull, i01, 31), t23 = __shfl_sync(kFull, i23, 31);
+	const uint32_t t01 = __shfl_sync(kFull, i01, 31), t23 = SEG > 2 ? __shfl_sync(kFull, i23, 31) : 0u;
 	const uint32_t tot0 = t01 & 0xFFFFu, tot01 = tot0 + (t01 >> 16), tot012 = tot01 + (t23 & 0xFFFFu);
 	if (lane == 31)
 		sh.wsum[parity][warp] = tot012 + (t23 >> 16);
@@ -1091,7 +1101,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			/* bits of the frame's first sample, in front of this thread's segment 0 (thread 0
 			 * wrote them itself, encode_pass) */
 			const uint32_t n_first = first ? sh.first_code[2] : 0u;
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, (sn_[0] + n_first) | (sn_[1] << 16),
+			tile_bits = tile_scan<SEG>(sh, t & 1u, lane, warp, (sn_[0] + n_first) | (sn_[1] << 16),
 					      SEG > 2 ? sn_[SEG - 2] | (sn_[SEG - 1] << 16) : 0u, c.sbits, pos);
 			AIRS_AFTER_SCAN({
 				if (first) {
@@ -1107,7 +1117,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 		} else if (unc) {
 			/* ---- raw arm: 16 bits per sample, two 64-bit strings per segment */
 			const uint32_t nb = 128u;
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, (v[0] ? nb : 0u) | ((v[1] ? nb : 0u) << 16),
+			tile_bits = tile_scan<SEG>(sh, t & 1u, lane, warp, (v[0] ? nb : 0u) | ((v[1] ? nb : 0u) << 16),
 					      SEG > 2 ? (v[SEG - 2] ? nb : 0u) | ((v[SEG - 1] ? nb : 0u) << 16) : 0u, c.sbits, pos);
 			AIRS_AFTER_SCAN({
 				_Pragma("unroll") for (int j = 0; j < SEG; j++) {
@@ -1140,7 +1150,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				if (SEG > 2)
 					b23 = (v[SEG - 2] ? b23 & 0xFFFFu : 0u) | (v[SEG - 1] ? b23 & 0xFFFF0000u : 0u);
 			}
-			tile_bits = tile_scan(sh, t & 1u, lane, warp, b01, b23, c.sbits, pos);
+			tile_bits = tile_scan<SEG>(sh, t & 1u, lane, warp, b01, b23, c.sbits, pos);
 			AIRS_AFTER_SCAN({
 				_Pragma("unroll 1") for (uint32_t j = 0; j < (uint32_t)SEG; j++)
 					if (!PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces))
