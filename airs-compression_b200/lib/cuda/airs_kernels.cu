@@ -903,7 +903,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	const bool size_only = SZ >= 0 ? SZ != 0 : size_only_rt;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t pre = PRE >= 0 ? (uint32_t)PRE : P.pre;
-	const uint32_t mm = MM >= 0 ? (uint32_t)MM : (size_only ? 0u : P.model_mode);
+	/* MM 2 / 3: model update with a rate of 1..15, zero- / sign-extended operands */
+	const uint32_t mm = MM >= 0 ? (MM >= 2 ? 2u : (uint32_t)MM) : (size_only ? 0u : P.model_mode);
 	const bool unc = UNC >= 0 ? UNC != 0 : P.enc.type == CMP_ENCODER_UNCOMPRESSED;
 	/* table of this pass: built for this encoder (encode_pass) */
 	const bool have_lut = !unc && sh.plut_key[0] == P.enc.type && sh.plut_key[1] == P.enc.g &&
@@ -973,14 +974,11 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			m[j][0] = mj.x; m[j][1] = mj.y; m[j][2] = mj.z; m[j][3] = mj.w;
 		}
 		const uint32_t ps = nps;
-		if (!PARTIAL && t + 1u < n_tiles) {
+		/* the model words of the next tile come from the L2: requested a whole tile ahead */
+		if (kAheadM && !PARTIAL && t + 1u < n_tiles) {
 #pragma unroll
-			for (int j = 0; j < SEG; j++) {
-				nx[j] = AIRS_LOAD_X(pw + kTP, j);
-				if (kAheadM)
-					nm[j] = AIRS_LOAD_M(pw + kTP, j);
-			}
-			nps = AIRS_LOAD_PS(pw + kTP);
+			for (int j = 0; j < SEG; j++)
+				nm[j] = AIRS_LOAD_M(pw + kTP, j);
 		}
 
 		/* residuals of the four segments; the new model takes the place of the old one
@@ -1009,7 +1007,12 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				if (mm == 2u) {
 					/* rate 16 keeps the model as it is, rate 0 replaces it by the samples */
 					const uint32_t rate = P.rate, wdp = (rate << 4) | ((16u - rate) << 12);
-					if (rate == 0u) {
+					if (MM == 2 || MM == 3) {
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							m[j][k] = MM == 3 ? model_update2<true>(w[j][k], m[j][k], wdp)
+									  : model_update2<false>(w[j][k], m[j][k], wdp);
+					} else if (rate == 0u) {
 #pragma unroll
 						for (int k = 0; k < 4; k++)
 							m[j][k] = w[j][k];
@@ -1036,6 +1039,15 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 					chk |= u[j][k];
 				}
 			}
+		}
+
+		/* the samples are used up: their registers take the next tile's (requested here, not
+		 * at the top of the tile, so that no second copy of a tile is alive) */
+		if (!PARTIAL && t + 1u < n_tiles) {
+#pragma unroll
+			for (int j = 0; j < SEG; j++)
+				nx[j] = AIRS_LOAD_X(pw + kTP, j);
+			nps = AIRS_LOAD_PS(pw + kTP);
 		}
 
 		uint32_t tile_bits;
@@ -1208,20 +1220,28 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 					       bool size_only)
 {
 	const Pass &P = sh.pass;
-	const uint32_t key = (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only) ? 99u : P.pre * 3u + P.model_mode;
-	const uint32_t tp = key == CMP_PREPROCESS_MODEL * 3u + 2u ? kThreads * kSegModel : kTilePieces; /* pieces per tile */
+	/* pass key: preprocessing * 4 + model mode, mode 2 -> 3 for sign-extended model updates;
+	 * passes without a specialised instantiation get 99 */
+	uint32_t key = P.pre * 4u + P.model_mode;
+	if (P.model_mode == 2u)
+		key = (P.rate >= 1u && P.rate <= 15u) ? key + P.is_signed : 99u;
+	if (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only)
+		key = 99u;
+	const bool model_pass = key == CMP_PREPROCESS_MODEL * 4u + 2u || key == CMP_PREPROCESS_MODEL * 4u + 3u;
+	const uint32_t tp = model_pass ? kThreads * kSegModel : kTilePieces; /* pieces per tile */
 	const uint32_t n_full = n_pieces / tp;
 
 	for (uint32_t t = 0; t < n_full;) {
 		switch (key) {
 #define AIRS_HOT(pre_, mm_, seg_)                                                                              \
-	case (pre_) * 3u + (mm_):                                                                              \
+	case (pre_) * 4u + (mm_):                                                                              \
 		t = frame_fast<(pre_), (mm_), 0, 0, false, (seg_)>(sh, o, a, c, t, n_full, 0u, n_pieces, false); \
 		break;
 		AIRS_HOT(CMP_PREPROCESS_NONE, 0, kSeg)
 		AIRS_HOT(CMP_PREPROCESS_DIFF, 0, kSeg)
 		AIRS_HOT(CMP_PREPROCESS_DIFF, 1, kSeg)
 		AIRS_HOT(CMP_PREPROCESS_MODEL, 2, kSegModel)
+		AIRS_HOT(CMP_PREPROCESS_MODEL, 3, kSegModel)
 #undef AIRS_HOT
 		default:
 			t = frame_fast_full_rt(sh, o, a, c, t, n_full, n_pieces, size_only);
