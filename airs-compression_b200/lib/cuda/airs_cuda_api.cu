@@ -178,8 +178,8 @@ extern "C" int airs_cuda_concurrent_jobs(void)
 
 extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)
 {
-	/* header | one look-back word per frame (+1) | one 128-byte plan per job */
-	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs;
+	/* header | one look-back word per frame (+1) | one 128-byte plan per job | two job lists */
+	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs + 64;
 }
 
 static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
@@ -215,6 +215,8 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.ticket = (uint32_t *)b->scratch;
 	l.lookback = (uint64_t *)((uint8_t *)b->scratch + kScratchHeader);
 	l.plans = (struct JobPlan *)((uint8_t *)b->scratch + kScratchHeader + lookback_bytes(b->n_results));
+	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
+	l.small_list = l.big_list + b->n_jobs;
 	l.ctx_io = ctx_io;
 	l.dst_size = b->dst_size;
 	l.n_jobs = b->n_jobs;
@@ -225,6 +227,10 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	CU(airs_launch_plan(&l, stream));
 	CU(airs_launch_encode(&l, grid, stream));
 	g_launches = 2;
+	if (b->layout == AIRS_LAYOUT_SLOTS && !ctx_io) { /* short single-frame jobs: one warp each */
+		CU(airs_launch_small(&l, (unsigned int)resident, stream));
+		g_launches = 3;
+	}
 	return AIRS_OK;
 }
 

@@ -59,6 +59,7 @@ constexpr uint32_t kLutStride = 2 * kLutR;
 constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair codeword */
 constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
 constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
+constexpr uint32_t kSmallMaxSamples = 8192; /* longest frame a single warp encodes (airs_small_kernel) */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 
@@ -1379,6 +1380,304 @@ __device__ uint64_t lookback_offset(volatile uint64_t *st, uint32_t k, uint32_t 
 	return excl;
 }
 
+/* -------------------------------------------------------------------------
+ * airs_small_kernel: one warp per short single-frame job (AIRS_PF_SMALL).
+ *
+ * The same stages as the fast path of airs_encode_kernel, but warp-synchronous:
+ * a warp owns its job, its staging area and its (single-sample) codeword table,
+ * so nothing waits at a block barrier and nothing runs on one thread while 127
+ * others idle.  Per warp tile of 1024 samples: 4 x LDG.128 per lane, packed
+ * residuals, table arm (8 lookups and one 64-bit string per segment) or
+ * arithmetic arm, shuffle scan, 3 reductions per string into the warp's staging
+ * words, 128-bit stores.  Fewer than 8 samples at the end of a frame are encoded
+ * by lane 0.  ref compress_engine / cmp_compress_generic, cmp.c:213-393.
+ * ---------------------------------------------------------------------- */
+
+constexpr uint32_t kWStgBits = 1024u * 48u + 128u; /* one warp tile at 48 bits per sample + the carried group */
+constexpr uint32_t kWStgWords = kWStgBits / 32u + 4u;
+
+struct WarpShared {
+	alignas(16) uint32_t stg_mem[4 + kWStgWords];
+	uint2 slut[kLutStride]; /* {codeword, length} of residual r at [r + 32] */
+	uint32_t key[3];        /* encoder the table was built for */
+	uint32_t R;             /* its usable half range: 32, 16, 8 or 0 */
+	JobPlan plan;
+	airs_job job;
+	Pass pass;
+	uint32_t checksum;
+};
+
+/* single-sample table of one warp; residuals qualify while their codeword is at most 16 bits long */
+__device__ __noinline__ void build_single_lut(WarpShared &ws, const EncConst &e)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t bad = 0;
+
+	for (uint32_t idx = lane; idx < kLutStride; idx += 32u) {
+		const uint32_t r = (idx - kLutR) & 0xFFFFu;
+		uint32_t cw, cl, rw, rl;
+		encode_mapped_rt(e, airs_zigzag16(r), cw, cl, rw, rl);
+		const uint32_t len = cl + rl;
+		ws.slut[idx] = make_uint2((cw << rl) | rw, len);
+		if (len > 16u) {
+			const uint32_t dist = idx >= kLutR ? idx - kLutR + 1u : kLutR - idx;
+			bad |= dist <= 8u ? 7u : dist <= 16u ? 6u : 4u;
+		}
+	}
+	bad = __reduce_or_sync(kFull, bad);
+	if (lane == 0) {
+		ws.key[0] = e.type;
+		ws.key[1] = e.g;
+		ws.key[2] = e.outlier;
+		ws.R = (bad & 1u) ? 0u : kLutR >> __popc(bad);
+	}
+	__syncwarp();
+}
+
+/* drain the warp's staging area (see copy_out); the partial group stays in front */
+__device__ __forceinline__ void warp_copy_out(WarpShared &ws, const OutWin &o, Cursor &c, uint32_t bits)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t staged = c.sbits + bits, nvec = staged >> 7, b0 = c.gw0 * 4u;
+	uint4 *stg4 = reinterpret_cast<uint4 *>(ws.stg_mem + 4);
+
+	__syncwarp();
+	for (uint32_t v = lane; v < nvec; v += 32u) {
+		const uint32_t b = b0 + 16u * v;
+		const uint4 q = stg4[v];
+		if (b >= o.lo && b + 16u <= o.hi) {
+			*reinterpret_cast<uint4 *>(o.base + b) =
+				make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
+		} else {
+			const uint8_t *s8 = reinterpret_cast<const uint8_t *>(stg4 + v);
+#pragma unroll 1
+			for (uint32_t k = 0; k < 16u; k++)
+				if (b + k >= o.lo && b + k < o.hi)
+					o.base[b + k] = s8[k ^ 3u];
+		}
+		stg4[v] = make_uint4(0, 0, 0, 0);
+	}
+	__syncwarp();
+	if (lane == 0 && nvec) {
+		const uint4 carry = stg4[nvec];
+		stg4[nvec] = make_uint4(0, 0, 0, 0);
+		stg4[0] = carry;
+	}
+	__syncwarp();
+	cursor_advance(c, bits);
+}
+
+/* one frame by one warp; returns the stream size or an error */
+__device__ uint32_t small_encode(WarpShared &ws, bool raw)
+{
+	const Pass &P = ws.pass;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t n = P.n, pieces = raw ? 0u : n / 8u;
+	const bool diff = P.pre == CMP_PREPROCESS_DIFF;
+	const uint32_t a = (uint32_t)((uintptr_t)P.dst & 15u);
+	OutWin o;
+	o.base = P.dst - a;
+	o.lo = a + P.hdr_len;
+	o.hi = a + P.cap_eff;
+	Cursor c;
+	c.gw0 = ((8u * (a + P.hdr_len)) >> 7) << 2;
+	c.sbits = (8u * (a + P.hdr_len)) & 127u;
+	c.buf = 0;
+	uint32_t *stg = ws.stg_mem + 4;
+	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
+	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
+
+	if (raw) {
+		/* NONE + UNCOMPRESSED: the samples big endian behind a 16-byte header (dst is 8-byte aligned) */
+		uint32_t *out = reinterpret_cast<uint32_t *>(P.dst + CMP_HDR_SIZE);
+		const uint32_t *in = reinterpret_cast<const uint32_t *>(P.src);
+		for (uint32_t k = lane; k < n / 2u; k += 32u)
+			out[k] = airs_be_pair(__ldg(in + k));
+		if (lane == 0 && (n & 1u)) {
+			const uint32_t x = __ldg(src16 + n - 1u);
+			P.dst[CMP_HDR_SIZE + 2u * (n - 1u)] = (uint8_t)(x >> 8);
+			P.dst[CMP_HDR_SIZE + 2u * (n - 1u) + 1u] = (uint8_t)x;
+		}
+		c.gw0 = 0;
+		c.sbits = 8u * (a + CMP_HDR_SIZE + 2u * n); /* only used for the size below */
+	} else {
+		if (ws.key[0] != P.enc.type || ws.key[1] != P.enc.g || ws.key[2] != P.enc.outlier)
+			build_single_lut(ws, P.enc);
+		const uint32_t R = ws.R;
+		const uint32_t Rb = R * 0x00010001u, B1 = (R + 1u) * 0x00010001u;
+		const uint32_t notmask = ~((2u * R - 1u) * 0x00010001u);
+		const char *lut = reinterpret_cast<const char *>(ws.slut + (kLutR - R));
+		uint32_t front0 = 0; /* lane 0: the word in front of its next segment */
+
+		for (uint32_t p0 = 0; p0 < pieces; p0 += 128u) {
+			bool v[4];
+			uint32_t w[4][4], u[4][4];
+			const uint32_t src_lane = (lane - 1u) & 31u;
+			const bool first = diff && R != 0u && p0 == 0u && lane == 0u;
+			uint32_t chk = 0;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				v[j] = p0 + 32u * j + lane < pieces;
+				const uint4 x = v[j] ? __ldg(src4 + p0 + 32u * j + lane) : make_uint4(0, 0, 0, 0);
+				w[j][0] = x.x; w[j][1] = x.y; w[j][2] = x.z; w[j][3] = x.w;
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				uint32_t pw_word = 0;
+				if (diff) {
+					const uint32_t up = __shfl_sync(kFull, w[j][3], src_lane);
+					pw_word = lane ? up : front0;
+					front0 = up;
+				}
+				seg_residuals(P.pre, w[j], w[j], pw_word, Rb, B1, u[j]);
+				if (j == 0 && first) /* see frame_fast: the frame's first sample goes separately */
+					u[0][0] = (u[0][0] & 0xFFFF0000u) | (Rb & 0xFFFFu);
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					u[j][k] = v[j] ? u[j][k] : Rb;
+					chk |= u[j][k];
+				}
+			}
+			uint32_t n_first = 0, f_hi = 0, f_lo = 0;
+			if (first) {
+				uint32_t fc[3];
+				first_sample_code(P.enc, w[0][0] & 0xFFFFu, fc);
+				f_hi = fc[0];
+				f_lo = fc[1];
+				n_first = fc[2];
+			}
+
+			bool table = R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
+			uint32_t sh_[4], sl_[4], sn_[4];
+			if (table) {
+				uint32_t qchk = 0;
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					uint32_t lo = 0, hi = 0, nb = 0;
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const uint2 e0 = *reinterpret_cast<const uint2 *>(lut + ((u[j][k] & 0xFFFFu) << 3));
+						const uint2 e1 = *reinterpret_cast<const uint2 *>(lut + ((u[j][k] >> 16) << 3));
+						const bool skip = j == 0 && k == 0 && first; /* the stand-in of the first sample */
+						if (!skip) {
+							hi = __funnelshift_l(lo, hi, e0.y);
+							lo = (lo << e0.y) | e0.x;
+							nb += e0.y;
+						}
+						hi = __funnelshift_l(lo, hi, e1.y);
+						lo = (lo << e1.y) | e1.x;
+						nb += e1.y;
+					}
+					qchk |= nb + 63u;
+					sl_[j] = v[j] ? lo : 0u;
+					sh_[j] = v[j] ? hi : 0u;
+					sn_[j] = v[j] ? nb : 0u;
+				}
+				table = __all_sync(kFull, (qchk & 128u) == 0u);
+			}
+			uint32_t d[16];
+			uint32_t b01, b23;
+			if (table) {
+				b01 = (sn_[0] + n_first) | (sn_[1] << 16);
+				b23 = sn_[2] | (sn_[3] << 16);
+			} else {
+				const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						d[4 * j + k] = __vadd2(u[j][k], negRb);
+				if (first)
+					d[0] = (d[0] & 0xFFFF0000u) | (w[0][0] & 0xFFFFu);
+				slow_bits(P.enc, d, 16u, b01, b23);
+				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
+				b23 = (v[2] ? b23 & 0xFFFFu : 0u) | (v[3] ? b23 & 0xFFFF0000u : 0u);
+			}
+			/* warp scan: segment 0 of all lanes, then segment 1, ... */
+			uint32_t i01 = b01, i23 = b23;
+#pragma unroll
+			for (int dd = 1; dd < 32; dd <<= 1) {
+				const uint32_t t0 = __shfl_up_sync(kFull, i01, dd), t1 = __shfl_up_sync(kFull, i23, dd);
+				if (lane >= (uint32_t)dd) {
+					i01 += t0;
+					i23 += t1;
+				}
+			}
+			const uint32_t t01 = __shfl_sync(kFull, i01, 31), t23 = __shfl_sync(kFull, i23, 31);
+			const uint32_t tot0 = t01 & 0xFFFFu, tot01 = tot0 + (t01 >> 16), tot012 = tot01 + (t23 & 0xFFFFu);
+			const uint32_t tile_bits = tot012 + (t23 >> 16);
+			const uint32_t e01 = i01 - b01, e23 = i23 - b23;
+			uint32_t pos[4];
+			pos[0] = c.sbits + (e01 & 0xFFFFu);
+			pos[1] = c.sbits + tot0 + (e01 >> 16);
+			pos[2] = c.sbits + tot01 + (e23 & 0xFFFFu);
+			pos[3] = c.sbits + tot012 + (e23 >> 16);
+
+			if (table) {
+				if (first) {
+					int32_t ne = -(int32_t)pos[0];
+					put_unit(stg, ne, f_hi, f_lo, n_first);
+					pos[0] += n_first;
+				}
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					int32_t ne = -(int32_t)pos[j];
+					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
+				}
+			} else {
+#pragma unroll 1
+				for (uint32_t j = 0; j < 4u; j++)
+					if (p0 + 32u * j + lane < pieces)
+						slow_put(P.enc, d + 4 * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
+			}
+			warp_copy_out(ws, o, c, tile_bits);
+		}
+
+		/* the last n % 8 samples, one after the other on lane 0 */
+		uint32_t tail_bits = 0;
+		if (lane == 0) {
+			int32_t ne = -(int32_t)c.sbits;
+			for (uint32_t i = pieces * 8u; i < n; i++) {
+				const uint32_t x = __ldg(src16 + i);
+				const uint32_t r = (diff && i) ? x - __ldg(src16 + i - 1u) : x;
+				uint32_t cw, cl, rw, rl;
+				encode_mapped_rt(P.enc, airs_zigzag16(r), cw, cl, rw, rl);
+				put_unit(stg, ne, __funnelshift_lc(cw, 0u, rl), __funnelshift_lc(0u, cw, rl) | rw, cl + rl);
+				tail_bits += cl + rl;
+			}
+		}
+		tail_bits = __shfl_sync(kFull, tail_bits, 0);
+		warp_copy_out(ws, o, c, tail_bits);
+	}
+
+	const uint32_t frame_bits = c.gw0 * 32u + c.sbits - 8u * a;
+	const uint32_t payload_end = (frame_bits + 7u) >> 3;
+	const uint32_t size = payload_end + (P.checksum ? 4u : 0u);
+	uint32_t result = size > P.cap_eff ? AIRS_ERR(DST_TOO_SMALL) : size;
+
+	if (!raw && lane == 0) { /* last partial group, zero padded */
+		const uint32_t nb = (c.sbits + 7u) >> 3;
+		for (uint32_t k = 0; k < nb; k++) {
+			const uint32_t b = c.gw0 * 4u + k;
+			if (b >= o.lo && b < o.hi)
+				o.base[b] = (uint8_t)(stg[k >> 2] >> (24 - 8 * (k & 3)));
+		}
+		stg[0] = stg[1] = stg[2] = stg[3] = 0;
+	}
+	if (P.checksum) {
+		const uint32_t h = frame_checksum(P);
+		if (lane < 4) {
+			const uint32_t b = a + payload_end + lane;
+			if (b < o.hi)
+				o.base[b] = (uint8_t)(h >> (24 - 8 * lane));
+		}
+	}
+	if (!airs_failed(result) && lane < P.hdr_len)
+		P.dst[lane] = (uint8_t)header_byte(P, lane, size);
+	__syncwarp();
+	return result;
+}
+
 } /* namespace */
 
 __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
@@ -1388,10 +1687,35 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	if (j >= b.n_jobs)
 		return;
 	JobPlan pl;
-	airs_make_plan(pl, b.jobs[j], b.src, b.work);
+	const airs_job &job = b.jobs[j];
+	airs_make_plan(pl, job, b.src, b.work);
+	/* Short single-frame jobs without model, with a Golomb encoder, none / diff preprocessing,
+	 * an aligned 16-bit source and nothing that could fail before the encoding go to
+	 * airs_small_kernel (one warp per job); everything else to airs_encode_kernel.  The lists
+	 * are filled in no particular order, except in the CONCAT layout and on the host-shim path,
+	 * where every job is "big" and the list is the identity (the look-back scan needs the
+	 * frames to start in result order). */
+	const bool listed = b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io;
+	const bool small = listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
+			   !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 && pl.n <= kSmallMaxSamples &&
+			   (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
+			   pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
+			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
+			   pl.cap_eff >= (CMP_HDR_SIZE + 6u);
+	if (small)
+		pl.flags |= AIRS_PF_SMALL;
 	b.plans[j] = pl;
 	if (b.init_results && !b.ctx_io)
 		b.init_results[j] = pl.init_result;
+	if (!listed) {
+		b.big_list[j] = j;
+		if (j == 0)
+			b.ticket[2] = b.n_jobs;
+	} else if (small) {
+		b.small_list[atomicAdd(&b.ticket[3], 1u)] = j;
+	} else {
+		b.big_list[atomicAdd(&b.ticket[2], 1u)] = j;
+	}
 }
 
 __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_kernel(AirsLaunch b)
@@ -1409,9 +1733,9 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 
 	for (;;) {
 		__syncthreads();
-		const uint32_t job = sh.ticket;
-		if (job >= b.n_jobs)
+		if (sh.ticket >= b.ticket[2]) /* entries of big_list, written by airs_plan_kernel */
 			break;
+		const uint32_t job = b.big_list[sh.ticket];
 		/* plan (32 words) and job descriptor (30 words) into shared memory, coalesced */
 		if (tid < 32)
 			((uint32_t *)&sh.plan)[tid] = ((const uint32_t *)&b.plans[job])[tid];
@@ -1512,6 +1836,76 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 	}
 }
 
+__global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_kernel(AirsLaunch b)
+{
+	__shared__ WarpShared wsh[kWarps];
+	const uint32_t lane = threadIdx.x & 31u;
+	WarpShared &ws = wsh[threadIdx.x >> 5];
+	const uint32_t n_small = b.ticket[3]; /* entries of small_list, written by airs_plan_kernel */
+
+	for (uint32_t w = lane; w < 4u + kWStgWords; w += 32u)
+		ws.stg_mem[w] = 0;
+	if (lane == 0) {
+		ws.key[0] = 0xFFFFFFFFu;
+		ws.R = 0;
+	}
+	__syncwarp();
+
+	for (;;) {
+		uint32_t t = 0;
+		if (lane == 0)
+			t = atomicAdd(&b.ticket[1], 1u);
+		t = __shfl_sync(kFull, t, 0);
+		if (t >= n_small)
+			break;
+		const uint32_t job = b.small_list[t];
+		((uint32_t *)&ws.plan)[lane] = ((const uint32_t *)&b.plans[job])[lane];
+		if (lane < 30)
+			((uint32_t *)&ws.job)[lane] = ((const uint32_t *)&b.jobs[job])[lane];
+		__syncwarp();
+		if (lane == 0) { /* the pass of a fresh context's first frame (ref cmp.c:228-294, 438-465) */
+			const JobPlan &pl = ws.plan;
+			const airs_job &j = ws.job;
+			Pass &P = ws.pass;
+			P.enc = pl.enc[0];
+			P.src = b.src + j.src_offset;
+			P.dst = b.dst + j.dst_offset;
+			P.work = nullptr;
+			/* cmp_initialise draws one identifier, the primary pass the next one */
+			P.identifier = (j.identifier_base + 1u) & kMask48;
+			P.pre = pl.pre[0];
+			P.n = pl.n;
+			P.dtype = j.dtype;
+			P.hdr_len = (CMP_HDR_SIZE + 6u);
+			P.cap_eff = pl.cap_eff;
+			P.trip = pl.trip;
+			P.model_mode = 0;
+			P.rate = pl.rate;
+			P.is_signed = 0;
+			P.checksum = (pl.flags & AIRS_PF_CHECKSUM) ? 1u : 0u;
+			P.seq = 0;
+			P.err = 0;
+		}
+		__syncwarp();
+		uint32_t r = small_encode(ws, false);
+		if ((ws.plan.flags & AIRS_PF_FALLBACK_OK) && r == AIRS_ERR(DST_TOO_SMALL)) {
+			/* stored raw as a fresh primary pass: two more identifiers drawn (ref cmp.c:380-392) */
+			if (lane == 0) {
+				Pass &P = ws.pass;
+				P.identifier = (ws.job.identifier_base + 3u) & kMask48;
+				P.pre = CMP_PREPROCESS_NONE;
+				P.enc.type = CMP_ENCODER_UNCOMPRESSED;
+				P.hdr_len = CMP_HDR_SIZE;
+			}
+			__syncwarp();
+			r = small_encode(ws, true);
+		}
+		if (lane == 0)
+			b.results[ws.job.first_result] = r;
+		__syncwarp();
+	}
+}
+
 extern "C" cudaError_t airs_launch_plan(const AirsLaunch *b, cudaStream_t stream)
 {
 	airs_plan_kernel<<<(b->n_jobs + 127) / 128, 128, 0, stream>>>(*b);
@@ -1532,11 +1926,20 @@ extern "C" cudaError_t airs_encode_ctas_per_sm(int *out)
 	e = cudaFuncSetAttribute(airs_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 	if (e != cudaSuccess)
 		return e;
+	e = cudaFuncSetAttribute(airs_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+	if (e != cudaSuccess)
+		return e;
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, airs_encode_kernel, AIRS_THREADS, 0);
 }
 
 extern "C" cudaError_t airs_launch_encode(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
 {
 	airs_encode_kernel<<<grid, AIRS_THREADS, 0, stream>>>(*b);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t airs_launch_small(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
+{
+	airs_small_kernel<<<grid, AIRS_THREADS, 0, stream>>>(*b);
 	return cudaGetLastError();
 }

@@ -15,6 +15,7 @@
 #define AIRS_PF_CHECKSUM     4u
 #define AIRS_PF_FALLBACK_OK  8u  /* fallback enabled and capacity >= raw size (cmp.c:363) */
 #define AIRS_PF_SIGNED      16u  /* i16 containers: model update sign-extends (cmp.c:132-142) */
+#define AIRS_PF_SMALL       32u  /* one short frame without model: a warp of airs_small_kernel encodes it */
 
 /* 128 bytes, read by the encode kernel with one coalesced 32-lane load */
 struct JobPlan {
