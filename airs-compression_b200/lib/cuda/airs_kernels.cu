@@ -1477,11 +1477,14 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 	const uint32_t a = (uint32_t)((uintptr_t)P.dst & 15u);
 	OutWin o;
 	o.base = P.dst - a;
-	o.lo = a + P.hdr_len;
+	/* the 22 header bytes travel through the staging area like the codewords behind them
+	 * (size field zero, patched at the end): the stream leaves in whole 16-byte groups from its
+	 * first byte on */
+	o.lo = a;
 	o.hi = a + P.cap_eff;
 	Cursor c;
-	c.gw0 = ((8u * (a + P.hdr_len)) >> 7) << 2;
-	c.sbits = (8u * (a + P.hdr_len)) & 127u;
+	c.gw0 = 0;
+	c.sbits = 8u * a;
 	c.buf = 0;
 	uint32_t *stg = ws.stg_mem + 4;
 	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
@@ -1498,7 +1501,6 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 			P.dst[CMP_HDR_SIZE + 2u * (n - 1u)] = (uint8_t)(x >> 8);
 			P.dst[CMP_HDR_SIZE + 2u * (n - 1u) + 1u] = (uint8_t)x;
 		}
-		c.gw0 = 0;
 		c.sbits = 8u * (a + CMP_HDR_SIZE + 2u * n); /* only used for the size below */
 	} else {
 		if (ws.key[0] != P.enc.type || ws.key[1] != P.enc.g || ws.key[2] != P.enc.outlier)
@@ -1508,6 +1510,15 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 		const uint32_t notmask = ~((2u * R - 1u) * 0x00010001u);
 		const char *lut = reinterpret_cast<const char *>(ws.slut + (kLutR - R));
 		uint32_t front0 = 0; /* lane 0: the word in front of its next segment */
+
+		if (lane == 0) { /* header (ref cmp_hdr_serialize, header.c:24-67; fields cmp.c:265-279), size 0 */
+			int32_t ne = -(int32_t)c.sbits;
+			const uint32_t id_hi = (uint32_t)(P.identifier >> 16), id_lo = (uint32_t)P.identifier & 0xFFFFu;
+			put_unit(stg, ne, ((0x8000u | CMP_VERSION_NUMBER) << 16), (2u * n) & 0xFFFFFFu, 64u);
+			put_unit(stg, ne, id_hi, (id_lo << 16) | (P.seq << 8) | (P.pre << 4) | (P.checksum << 3) | P.enc.type, 64u);
+			put_unit(stg, ne, P.enc.g >> 8, ((P.enc.g & 0xFFu) << 24) | (P.enc.outlier & 0xFFFFFFu), 48u);
+		}
+		c.sbits += 8u * (CMP_HDR_SIZE + 6u);
 
 		for (uint32_t p0 = 0; p0 < pieces; p0 += 128u) {
 			bool v[4];
@@ -1672,8 +1683,14 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 				o.base[b] = (uint8_t)(h >> (24 - 8 * lane));
 		}
 	}
-	if (!airs_failed(result) && lane < P.hdr_len)
-		P.dst[lane] = (uint8_t)header_byte(P, lane, size);
+	if (!airs_failed(result)) {
+		if (raw) {
+			if (lane < P.hdr_len)
+				P.dst[lane] = (uint8_t)header_byte(P, lane, size);
+		} else if (lane < 3) { /* the size field of the header that went out with the stream */
+			P.dst[2u + lane] = (uint8_t)(size >> (16 - 8 * lane));
+		}
+	}
 	__syncwarp();
 	return result;
 }
@@ -1851,13 +1868,15 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_ker
 	}
 	__syncwarp();
 
+	uint32_t t_next = 0;
+	if (lane == 0)
+		t_next = atomicAdd(&b.ticket[1], 1u);
 	for (;;) {
-		uint32_t t = 0;
-		if (lane == 0)
-			t = atomicAdd(&b.ticket[1], 1u);
-		t = __shfl_sync(kFull, t, 0);
+		const uint32_t t = __shfl_sync(kFull, t_next, 0);
 		if (t >= n_small)
 			break;
+		if (lane == 0) /* the next ticket is drawn now and looked at after this job: the atomic's round trip is hidden */
+			t_next = atomicAdd(&b.ticket[1], 1u);
 		const uint32_t job = b.small_list[t];
 		((uint32_t *)&ws.plan)[lane] = ((const uint32_t *)&b.plans[job])[lane];
 		if (lane < 30)
