@@ -59,7 +59,7 @@ constexpr uint32_t kLutStride = 2 * kLutR;
 constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair codeword */
 constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
 constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
-constexpr uint32_t kSmallMaxSamples = 8192; /* longest frame a single warp encodes (airs_small_kernel) */
+constexpr uint32_t kSmallMaxSamples = 32768; /* longest frame a single warp encodes (airs_small_kernel); measured crossover */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 

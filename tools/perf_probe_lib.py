@@ -75,15 +75,18 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         pf = {"c3": p_mixed, "c3plain": p_plain, "c3cs": p_cs, "c3multi": p_multi}[case]
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, pf)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
-    if case in ("c4", "c1", "c4b"):
-        n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17)}[case]
+    if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k"):
+        n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
+                       "c32k": (1 << 14, 1 << 15), "c8k": (1 << 16, 1 << 13)}[case]
         data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_plain)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
-    if case in ("c2", "c2one"):
-        R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "0")) or pkg.load_library().airs_cuda_concurrent_jobs()) if case == "c2" else 1, 256, 32768
+    def p_model_cs(p, idx):
+        p_model(p, idx); p["checksum_enabled"] = 1
+    if case in ("c2", "c2one", "c2cs"):
+        R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "0")) or pkg.load_library().airs_cuda_concurrent_jobs()) if case in ("c2", "c2cs") else 1, 256, 32768
         print("c2 contexts:", R)
         data = synth.frames_torch(1, 0, R, F, n, device=dev)
-        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, cap=2 * n + 64, model=True)
+        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model_cs if case == "c2cs" else p_model, cap=2 * n + 64, model=True)
         return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
     raise SystemExit("unknown case " + case)
