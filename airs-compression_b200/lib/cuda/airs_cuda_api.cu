@@ -178,8 +178,8 @@ extern "C" int airs_cuda_concurrent_jobs(void)
 
 extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)
 {
-	/* header | one look-back word per frame (+1) | one 128-byte plan per job | two job lists */
-	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs + 64;
+	/* header | one look-back word per frame (+1) | one 128-byte plan per job | two job lists | job of every frame */
+	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs + 4 * (size_t)n_results + 64;
 }
 
 static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
@@ -217,6 +217,8 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.plans = (struct JobPlan *)((uint8_t *)b->scratch + kScratchHeader + lookback_bytes(b->n_results));
 	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
 	l.small_list = l.big_list + b->n_jobs;
+	l.result_job = l.small_list + b->n_jobs;
+	CU(cudaMemsetAsync(l.result_job, 0xFF, 4 * (size_t)b->n_results, stream));
 	l.ctx_io = ctx_io;
 	l.dst_size = b->dst_size;
 	l.n_jobs = b->n_jobs;
@@ -231,6 +233,8 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 		CU(airs_launch_small(&l, (unsigned int)resident, stream));
 		g_launches = 3;
 	}
+	CU(airs_launch_checksum(&l, stream));
+	g_launches++;
 	return AIRS_OK;
 }
 

@@ -30,6 +30,9 @@
  * Reference being replaced: compress_engine and cmp_compress_generic
  * (lib/compress/cmp.c:213-393), preprocess.c:268-411, encoder.c:274-378,
  * bitstream_writer.h:124-227, header.c:24-67,137-163.  See DESIGN.md.
+ *
+ * airs_small_kernel     one warp per short single-frame job (see there).
+ * airs_checksum_kernel  one thread per frame: the XXH32 trailers, behind the encoders.
  */
 #include <cuda_runtime.h>
 
@@ -109,7 +112,6 @@ struct Shared {
 	CtxState ctx;
 	uint64_t offset;
 	uint32_t ticket;
-	uint32_t checksum;
 };
 
 /* byte window of the destination a pass may write, in the 16-byte aligned
@@ -311,68 +313,71 @@ __device__ __noinline__ void iwt_global(const Pass &P)
 }
 
 /* -------------------------------------------------------------------------
- * XXH32 of the big-endian samples (ref cmp_checksum, header.c:137-163): the
- * four lanes of the hash run on lanes 0-3 of the calling warp.
+ * XXH32 of the big-endian samples of one frame (ref cmp_checksum,
+ * header.c:137-163; xxHash 0.8.3 XXH32), by ONE thread: the hash is a serial
+ * chain per stream, its four accumulators are the thread's instruction level
+ * parallelism, and a batch has thousands of streams (airs_checksum_kernel).
  * ---------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t pair_at(const Pass &P, bool al4, uint32_t i)
+__device__ __forceinline__ uint32_t sample_pair_at(const uint8_t *src, uint32_t dtype, bool al4, uint32_t i)
 {
-	if (P.dtype == AIRS_DTYPE_I16_IN_I32) {
-		const uint32_t *p = (const uint32_t *)P.src;
+	if (dtype == AIRS_DTYPE_I16_IN_I32) {
+		const uint32_t *p = (const uint32_t *)src;
 		return (__ldg(p + i) & 0xFFFFu) | (__ldg(p + i + 1) << 16);
 	}
 	if (al4)
-		return __ldg((const uint32_t *)((const uint16_t *)P.src + i));
-	const uint16_t *p = (const uint16_t *)P.src;
+		return __ldg((const uint32_t *)((const uint16_t *)src + i));
+	const uint16_t *p = (const uint16_t *)src;
 	return (uint32_t)__ldg(p + i) | ((uint32_t)__ldg(p + i + 1) << 16);
 }
 
-__device__ __noinline__ uint32_t frame_checksum(const Pass &P)
+__device__ uint32_t stream_checksum(const uint8_t *src, uint32_t dtype, uint32_t n)
 {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t n = P.n, nbytes = n * 2u;
-	const uint32_t stripes = n / 8u;
-	const bool al4 = ((uintptr_t)P.src & 3u) == 0;
+	const uint32_t nbytes = n * 2u, stripes = n / 8u;
 	const uint32_t seed = AIRS_CHECKSUM_SEED;
-	uint32_t v = lane == 0 ? seed + AIRS_XP1 + AIRS_XP2 : lane == 1 ? seed + AIRS_XP2 : lane == 2 ? seed : seed - AIRS_XP1;
+	uint32_t v0 = seed + AIRS_XP1 + AIRS_XP2, v1 = seed + AIRS_XP2, v2 = seed, v3 = seed - AIRS_XP1;
+	uint32_t s = 0;
 
-	if (lane < 4) {
-		uint32_t s = 0;
-		for (; s + 4 <= stripes; s += 4) {
-			uint32_t w0 = pair_at(P, al4, (s + 0) * 8 + 2 * lane);
-			uint32_t w1 = pair_at(P, al4, (s + 1) * 8 + 2 * lane);
-			uint32_t w2 = pair_at(P, al4, (s + 2) * 8 + 2 * lane);
-			uint32_t w3 = pair_at(P, al4, (s + 3) * 8 + 2 * lane);
-			v = airs_xxh_round(v, airs_be_pair(w0));
-			v = airs_xxh_round(v, airs_be_pair(w1));
-			v = airs_xxh_round(v, airs_be_pair(w2));
-			v = airs_xxh_round(v, airs_be_pair(w3));
+	if (dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)src & 15u) == 0) {
+		/* whole 128-byte lines: 8 x LDG.128 in flight, then 8 stripes of rounds */
+		const uint4 *p = (const uint4 *)src;
+		for (; s + 8 <= stripes; s += 8) {
+			uint4 q[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++)
+				q[k] = __ldg(p + s + k);
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				v0 = airs_xxh_round(v0, airs_be_pair(q[k].x));
+				v1 = airs_xxh_round(v1, airs_be_pair(q[k].y));
+				v2 = airs_xxh_round(v2, airs_be_pair(q[k].z));
+				v3 = airs_xxh_round(v3, airs_be_pair(q[k].w));
+			}
 		}
-		for (; s < stripes; s++)
-			v = airs_xxh_round(v, airs_be_pair(pair_at(P, al4, s * 8 + 2 * lane)));
 	}
-	uint32_t v1 = __shfl_sync(kFull, v, 1);
-	uint32_t v2 = __shfl_sync(kFull, v, 2);
-	uint32_t v3 = __shfl_sync(kFull, v, 3);
-	uint32_t h = 0;
-	if (lane == 0) {
-		h = nbytes >= 16 ? airs_rotl(v, 1) + airs_rotl(v1, 7) + airs_rotl(v2, 12) + airs_rotl(v3, 18)
-				 : seed + AIRS_XP5;
-		h += nbytes;
-		uint32_t i = stripes * 8;
-		for (; i + 2 <= n; i += 2)
-			h = airs_rotl(h + airs_be_pair(pair_at(P, false, i)) * AIRS_XP3, 17) * AIRS_XP4;
-		if (i < n) {
-			uint32_t sv = sample_at(P.src, P.dtype, i);
-			h = airs_rotl(h + (sv >> 8) * AIRS_XP5, 11) * AIRS_XP1;
-			h = airs_rotl(h + (sv & 0xFFu) * AIRS_XP5, 11) * AIRS_XP1;
-		}
-		h ^= h >> 15;
-		h *= AIRS_XP2;
-		h ^= h >> 13;
-		h *= AIRS_XP3;
-		h ^= h >> 16;
+	const bool al4 = ((uintptr_t)src & 3u) == 0;
+	for (; s < stripes; s++) {
+		v0 = airs_xxh_round(v0, airs_be_pair(sample_pair_at(src, dtype, al4, s * 8)));
+		v1 = airs_xxh_round(v1, airs_be_pair(sample_pair_at(src, dtype, al4, s * 8 + 2)));
+		v2 = airs_xxh_round(v2, airs_be_pair(sample_pair_at(src, dtype, al4, s * 8 + 4)));
+		v3 = airs_xxh_round(v3, airs_be_pair(sample_pair_at(src, dtype, al4, s * 8 + 6)));
 	}
-	return __shfl_sync(kFull, h, 0);
+	uint32_t h = nbytes >= 16 ? airs_rotl(v0, 1) + airs_rotl(v1, 7) + airs_rotl(v2, 12) + airs_rotl(v3, 18)
+				  : seed + AIRS_XP5;
+	h += nbytes;
+	uint32_t i = stripes * 8;
+	for (; i + 2 <= n; i += 2)
+		h = airs_rotl(h + airs_be_pair(sample_pair_at(src, dtype, false, i)) * AIRS_XP3, 17) * AIRS_XP4;
+	if (i < n) {
+		const uint32_t sv = sample_at(src, dtype, i);
+		h = airs_rotl(h + (sv >> 8) * AIRS_XP5, 11) * AIRS_XP1;
+		h = airs_rotl(h + (sv & 0xFFu) * AIRS_XP5, 11) * AIRS_XP1;
+	}
+	h ^= h >> 15;
+	h *= AIRS_XP2;
+	h ^= h >> 13;
+	h *= AIRS_XP3;
+	h ^= h >> 16;
+	return h;
 }
 
 /* -------------------------------------------------------------------------
@@ -1313,12 +1318,7 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 	if (size_only)
 		return result;
 
-	/* checksum of the samples while another warp flushes the tail */
-	if (P.checksum && !suppress && tid < 32) {
-		uint32_t h = frame_checksum(P);
-		if (tid == 0)
-			sh.checksum = h;
-	}
+	/* (the 4 checksum bytes behind the stream are filled in by airs_checksum_kernel) */
 	if (tid == 32) { /* last partial group, zero padded (ref bitstream_writer.h:205-227) */
 		const uint32_t nb = (c.sbits + 7u) >> 3;
 		uint32_t *stg = stg_of(sh, c.buf);
@@ -1331,11 +1331,6 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 	}
 	__syncthreads();
 
-	if (P.checksum && !suppress && tid < 4) { /* trailer, big endian (ref cmp.c:314-319) */
-		uint64_t b = (uint64_t)a + payload_end + tid;
-		if (b < o.hi)
-			o.base[b] = (uint8_t)(sh.checksum >> (24 - 8 * tid));
-	}
 	if (!airs_failed(result) && !suppress && tid < P.hdr_len) /* header with the final size (ref cmp.c:329-334) */
 		P.dst[tid] = (uint8_t)header_byte(P, tid, size);
 	return result;
@@ -1404,7 +1399,6 @@ struct WarpShared {
 	JobPlan plan;
 	airs_job job;
 	Pass pass;
-	uint32_t checksum;
 };
 
 /* single-sample table of one warp; residuals qualify while their codeword is at most 16 bits long */
@@ -1675,14 +1669,6 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 		}
 		stg[0] = stg[1] = stg[2] = stg[3] = 0;
 	}
-	if (P.checksum) {
-		const uint32_t h = frame_checksum(P);
-		if (lane < 4) {
-			const uint32_t b = a + payload_end + lane;
-			if (b < o.hi)
-				o.base[b] = (uint8_t)(h >> (24 - 8 * lane));
-		}
-	}
 	if (!airs_failed(result)) {
 		if (raw) {
 			if (lane < P.hdr_len)
@@ -1724,6 +1710,10 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	b.plans[j] = pl;
 	if (b.init_results && !b.ctx_io)
 		b.init_results[j] = pl.init_result;
+	for (uint32_t f = 0; f < job.n_frames && job.first_result + f < b.n_results; f++)
+		b.result_job[job.first_result + f] = j;
+	if (pl.flags & AIRS_PF_CHECKSUM)
+		atomicAdd(&b.ticket[4], 1u);
 	if (!listed) {
 		b.big_list[j] = j;
 		if (j == 0)
@@ -1925,6 +1915,34 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_ker
 	}
 }
 
+/* One thread per frame: the XXH32 trailer of every successfully encoded stream whose job
+ * asked for a checksum (ref cmp.c:314-319: zero padded to a byte, then 4 bytes big endian).
+ * Runs behind the encode kernels; a batch without checksums costs one launch of early exits. */
+__global__ void __launch_bounds__(128) airs_checksum_kernel(AirsLaunch b)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (b.ticket[4] == 0 || k >= b.n_results)
+		return;
+	const uint32_t j = b.result_job[k];
+	if (j >= b.n_jobs)
+		return;
+	const JobPlan &pl = b.plans[j];
+	const uint32_t r = b.results[k];
+	if (!(pl.flags & AIRS_PF_CHECKSUM) || airs_failed(r) || r < 4u)
+		return;
+	const airs_job &job = b.jobs[j];
+	const uint32_t f = k - job.first_result;
+	const uint8_t *src = b.src + job.src_offset + (uint64_t)f * job.src_frame_stride;
+	uint8_t *stream = b.layout == AIRS_LAYOUT_CONCAT ? b.dst + b.out_offsets[k]
+							 : b.dst + job.dst_offset + (uint64_t)f * job.dst_frame_stride;
+	const uint32_t h = stream_checksum(src, job.dtype, pl.n);
+	stream[r - 4u] = (uint8_t)(h >> 24);
+	stream[r - 3u] = (uint8_t)(h >> 16);
+	stream[r - 2u] = (uint8_t)(h >> 8);
+	stream[r - 1u] = (uint8_t)h;
+}
+
 extern "C" cudaError_t airs_launch_plan(const AirsLaunch *b, cudaStream_t stream)
 {
 	airs_plan_kernel<<<(b->n_jobs + 127) / 128, 128, 0, stream>>>(*b);
@@ -1954,6 +1972,12 @@ extern "C" cudaError_t airs_encode_ctas_per_sm(int *out)
 extern "C" cudaError_t airs_launch_encode(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
 {
 	airs_encode_kernel<<<grid, AIRS_THREADS, 0, stream>>>(*b);
+	return cudaGetLastError();
+}
+
+extern "C" cudaError_t airs_launch_checksum(const AirsLaunch *b, cudaStream_t stream)
+{
+	airs_checksum_kernel<<<(b->n_results + 127) / 128, 128, 0, stream>>>(*b);
 	return cudaGetLastError();
 }
 

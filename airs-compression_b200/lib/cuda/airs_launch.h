@@ -26,9 +26,11 @@ struct AirsLaunch {
 	uint32_t *init_results;
 	uint64_t *out_offsets;
 	uint32_t *ticket;      /* zeroed before the launch: [0] next entry of big_list, [1] of small_list,
-				  [2] entries in big_list, [3] entries in small_list */
+				  [2] entries in big_list, [3] entries in small_list,
+				  [4] jobs with checksum */
 	uint32_t *big_list;    /* job indices for airs_encode_kernel, filled by airs_plan_kernel */
 	uint32_t *small_list;  /* job indices for airs_small_kernel (SLOTS layout only) */
+	uint32_t *result_job;  /* n_results entries: the job a frame belongs to (airs_checksum_kernel) */
 	struct JobPlan *plans; /* n_jobs plans written by airs_plan_kernel */
 	uint64_t *lookback;    /* CONCAT: one status word per job, zeroed before the launch */
 	struct airs_ctx_state *ctx_io; /* host-shim path: context state in/out per job, else NULL */
@@ -45,6 +47,7 @@ cudaError_t airs_launch_plan(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_encode_ctas_per_sm(int *out);
 cudaError_t airs_launch_small(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
+cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
 #ifdef __cplusplus
 }
 #endif
