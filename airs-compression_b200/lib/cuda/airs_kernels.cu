@@ -891,9 +891,10 @@ __device__ __forceinline__ void seg_residuals(uint32_t pre, const uint32_t (&w)[
  * frame (n_pieces); a warp then owns 32, 64, 96 or 128 pieces, whatever keeps
  * all warps busy.
  *
- * Three arms per warp and tile: "table" - every residual hits the pair table and
+ * Arms per warp and tile: "table" - every residual hits the pair table and
  * the eight codewords of every segment fit 64 bits: one string per segment, 3
- * shared memory reductions each; "raw" - the uncompressed encoder, two 64-bit strings
+ * shared memory reductions each; "wide table" - all in the table but a segment
+ * longer than 64 bits: one string per pair, looked up again behind the scan; "raw" - the uncompressed encoder, two 64-bit strings
  * per segment; "arithmetic" - everything else, sample by sample from reloaded
  * data (rolled loops).
  *
@@ -1081,9 +1082,10 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	} while (0)
 
 		/* ---- table arm, first half: codewords of pairs, quads, segments */
-		bool table = !unc && R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
+		const bool hit = !unc && R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
+		bool table = hit;
 		uint32_t sh_[SEG], sl_[SEG], sn_[SEG]; /* one string per segment: hi, lo, length */
-		if (table) {
+		if (hit) {
 			uint32_t qchk = 0;
 #pragma unroll
 			for (int j = 0; j < SEG; j++) {
@@ -1130,6 +1132,40 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				_Pragma("unroll") for (int j = 0; j < SEG; j++) {
 					int32_t ne = -(int32_t)pos[j];
 					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
+				}
+			});
+		} else if (hit) {
+			/* ---- wide table arm: every residual is in the table, but a segment is longer than
+			 * 64 bits (more than 8 bits per sample).  The lengths are known; the biased
+			 * residuals wait in local memory and are looked up again pair by pair. */
+			uint32_t d[SEG * 4];
+#pragma unroll
+			for (int j = 0; j < SEG; j++)
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					d[4 * j + k] = u[j][k];
+			const uint32_t n_first = first ? sh.first_code[2] : 0u;
+			tile_bits = tile_scan<SEG>(sh, t & 1u, lane, warp, (sn_[0] + n_first) | (sn_[1] << 16),
+					      SEG > 2 ? sn_[SEG - 2] | (sn_[SEG - 1] << 16) : 0u, c.sbits, pos);
+			AIRS_AFTER_SCAN({
+				_Pragma("unroll 1") for (uint32_t j = 0; j < (uint32_t)SEG; j++) {
+					if (PARTIAL && !(j < nseg && pw + 32u * j + lane < n_pieces))
+						continue;
+					int32_t ne = -(int32_t)(j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
+					if (j == 0u && first)
+						put_unit(stg, ne, sh.first_code[0], sh.first_code[1], n_first);
+					_Pragma("unroll 1") for (uint32_t k = 0; k < 4u; k++) {
+						const uint32_t uu = d[4u * j + k];
+						const uint32_t off = ((uu << 2) & (4u * (kLutStride - 1u))) | (uu >> 8);
+						const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
+						uint32_t pc = ent & ((1u << kLutLenShift) - 1u);
+						uint32_t pl = ent >> kLutLenShift;
+						if (j == 0u && k == 0u && first) { /* drop the stand-in's codeword */
+							pl -= sh.slut[kLutR].y;
+							pc &= (1u << pl) - 1u;
+						}
+						put_unit(stg, ne, 0u, pc, pl);
+					}
 				}
 			});
 		} else if (unc) {

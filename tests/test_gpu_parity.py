@@ -68,6 +68,29 @@ def test_host_batch_pipelined(gpu, oracle, pkg):
     jobgen.compare(want, got, js, "gpu-host-pipelined", check_tail=False)
 
 
+@pytest.mark.parametrize("enc,g,outl", [(1, 2, 0), (2, 3, 40), (1, 16, 0)])
+def test_wide_table_arm(gpu, oracle, pkg, enc, g, outl):
+    """Residuals that all sit in the codeword table but cost more than 8 bits per sample: the fast path's
+    wide arm (one string per pair instead of per segment), next to ordinary and escape-heavy stretches."""
+    abi = pkg.abi
+    rng = np.random.default_rng(77 + g)
+    n = 5 * 4096 + 24
+    amp = 7 if g < 16 else 31
+    steps = np.where(np.arange(n) % 2 == 0, amp, -amp) + rng.integers(-1, 1, size=n)   # |diff| close to the table edge
+    steps[8192:12288] = rng.integers(-2, 3, size=4096)                                  # an easy stretch
+    steps[13000:13040] = rng.integers(-3000, 3000, size=40)                             # and a few escapes
+    x = (20000 + np.cumsum(steps)).astype(np.int64) & 0xFFFF
+    frames = np.stack([x, (x + rng.integers(-amp, amp, size=n)) & 0xFFFF]).astype(np.uint16)
+    for pre2, iters in ((abi.PRE_MODEL, 1), (abi.PRE_DIFF, 0)):
+        p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=enc, primary_encoder_param=g,
+                            primary_encoder_outlier=outl, secondary_iterations=iters, secondary_preprocessing=pre2,
+                            secondary_encoder_type=enc, secondary_encoder_param=g, secondary_encoder_outlier=outl,
+                            model_rate=3)
+        js = _uniform_jobs(pkg, 3, n, 2, p)
+        js["src"] = np.concatenate([frames.reshape(-1)] * 3).view(np.uint8)
+        jobgen.compare(jobgen.run_cpu(oracle, js), gpu.run_jobs_device(js), js, "wide-arm")
+
+
 def _uniform_jobs(pkg, n_jobs, n, n_frames, params, dtype=2, cap=None):
     abi = pkg.abi
     jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
