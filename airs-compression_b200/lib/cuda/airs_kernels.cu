@@ -830,6 +830,15 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p, uint64_t pol)
 	return v;
 }
 
+/* 8 samples held in the low halves of 8 consecutive 32-bit words (ref sample_read_i16,
+ * sample_reader.h:63-72), packed like a 16-bit container's */
+__device__ __forceinline__ uint4 ld_stream32(const uint4 *p, uint64_t pol)
+{
+	const uint4 a = ld_stream(p, pol), b = ld_stream(p + 1, pol);
+	return make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410), __byte_perm(b.x, b.y, 0x5410),
+			  __byte_perm(b.z, b.w, 0x5410));
+}
+
 __device__ __forceinline__ uint4 ld_keep(const uint4 *p, uint64_t pol)
 {
 	uint4 v;
@@ -913,6 +922,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	/* MM 2 / 3: model update with a rate of 1..15, zero- / sign-extended operands */
 	const uint32_t mm = MM >= 0 ? (MM >= 2 ? 2u : (uint32_t)MM) : (size_only ? 0u : P.model_mode);
 	const bool unc = UNC >= 0 ? UNC != 0 : P.enc.type == CMP_ENCODER_UNCOMPRESSED;
+	/* samples in the low halves of 32-bit words (catch-all instantiations only) */
+	const bool c32 = PRE < 0 && P.dtype == AIRS_DTYPE_I16_IN_I32;
 	/* table of this pass: built for this encoder (encode_pass) */
 	const bool have_lut = !unc && sh.plut_key[0] == P.enc.type && sh.plut_key[1] == P.enc.g &&
 			      sh.plut_key[2] == P.enc.outlier;
@@ -945,10 +956,12 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 
 	/* samples / work words of segment j_ of the tile whose warp starts at piece pw_ (none beyond the frame) */
 #define AIRS_SEG_VALID(pw_, j_) (!PARTIAL || ((j_) < nseg && (pw_) + 32u * (j_) + lane < n_pieces))
-#define AIRS_LOAD_X(pw_, j_) ((need_x && AIRS_SEG_VALID(pw_, j_)) ? ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream) : zero4)
+#define AIRS_LOAD_X(pw_, j_) ((need_x && AIRS_SEG_VALID(pw_, j_)) ? (c32 ? ld_stream32(src4 + 2u * ((pw_) + 32u * (j_) + lane), pol_stream) \
+									       : ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream)) : zero4)
 #define AIRS_LOAD_M(pw_, j_) ((need_m && AIRS_SEG_VALID(pw_, j_)) ? ld_keep(work4 + (pw_) + 32u * (j_) + lane, pol_keep) : zero4)
 	/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */
-#define AIRS_LOAD_PS(pw_) ((diff && lane == 0 && (pw_) != 0 && AIRS_SEG_VALID(pw_, 0)) ? (uint32_t)__ldg(src16 + 8u * (pw_) - 1u) : 0u)
+#define AIRS_LOAD_PS(pw_) ((diff && lane == 0 && (pw_) != 0 && AIRS_SEG_VALID(pw_, 0)) ? \
+	(c32 ? __ldg(reinterpret_cast<const uint32_t *>(src16) + 8u * (pw_) - 1u) & 0xFFFFu : (uint32_t)__ldg(src16 + 8u * (pw_) - 1u)) : 0u)
 
 	/* the whole next tile is loaded one tile ahead (the scheduler pulls the first consumers of
 	 * all four segments to the top of the loop body, so a later load would be waited for) */
@@ -1195,7 +1208,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 					for (int k = 0; k < 4; k++)
 						d[4 * j + k] = __vadd2(u[j][k], negRb);
 				if (first) /* the stand-in goes, the sample comes back */
-					d[0] = (d[0] & 0xFFFF0000u) | (uint32_t)__ldg(src16);
+					d[0] = (d[0] & 0xFFFF0000u) | sample_at(P.src, P.dtype, 0);
 			}
 			uint32_t b01, b23;
 			slow_bits(P.enc, d, 4u * SEG, b01, b23);
@@ -1247,6 +1260,13 @@ __device__ __noinline__ uint32_t frame_fast_full_rt(Shared &sh, const OutWin o, 
 	return frame_fast<-1, -1, -1, -1, false, kSeg>(sh, o, a, c, t0, n_tiles, 0u, n_pieces, size_only);
 }
 
+/* ... with half-size tiles: the uncompressed encoder's 16 bits per sample must fit the staging area */
+__device__ __noinline__ uint32_t frame_fast_half_rt(Shared &sh, const OutWin o, uint32_t a, Cursor &c, uint32_t t0,
+						    uint32_t n_tiles, uint32_t n_pieces, bool size_only)
+{
+	return frame_fast<-1, -1, -1, -1, false, kSegModel>(sh, o, a, c, t0, n_tiles, 0u, n_pieces, size_only);
+}
+
 __device__ __noinline__ uint32_t frame_fast_tail_rt(Shared &sh, const OutWin o, uint32_t a, Cursor &c, uint32_t p0,
 						    uint32_t n_pieces, bool size_only)
 {
@@ -1267,10 +1287,11 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 	uint32_t key = P.pre * 4u + P.model_mode;
 	if (P.model_mode == 2u)
 		key = (P.rate >= 1u && P.rate <= 15u) ? key + P.is_signed : 99u;
-	if (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only)
+	if (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only || P.dtype == AIRS_DTYPE_I16_IN_I32)
 		key = 99u;
 	const bool model_pass = key == CMP_PREPROCESS_MODEL * 4u + 2u || key == CMP_PREPROCESS_MODEL * 4u + 3u;
-	const uint32_t tp = model_pass ? kThreads * kSegModel : kTilePieces; /* pieces per tile */
+	const bool half = model_pass || P.enc.type == CMP_ENCODER_UNCOMPRESSED;
+	const uint32_t tp = half ? kThreads * kSegModel : kTilePieces; /* pieces per tile */
 	const uint32_t n_full = n_pieces / tp;
 
 	for (uint32_t t = 0; t < n_full;) {
@@ -1286,7 +1307,8 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 		AIRS_HOT(CMP_PREPROCESS_MODEL, 3, kSegModel)
 #undef AIRS_HOT
 		default:
-			t = frame_fast_full_rt(sh, o, a, c, t, n_full, n_pieces, size_only);
+			t = half ? frame_fast_half_rt(sh, o, a, c, t, n_full, n_pieces, size_only)
+				 : frame_fast_full_rt(sh, o, a, c, t, n_full, n_pieces, size_only);
 			break;
 		}
 		if (t < n_full) {
@@ -1324,7 +1346,7 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 		iwt_global(P);
 
 	const uint32_t n = P.n, pre = P.pre, model_mode = P.model_mode;
-	const bool fast_ok = P.dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)P.src & 15u) == 0 &&
+	const bool fast_ok = ((uintptr_t)P.src & 15u) == 0 &&
 			     (((uintptr_t)P.work & 15u) == 0 || (pre < CMP_PREPROCESS_IWT && !model_mode));
 	const uint32_t n_pieces = fast_ok ? n / 8u : 0u;
 	if (n_pieces) {
@@ -1334,7 +1356,7 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 		    (sh.plut_key[0] != e.type || sh.plut_key[1] != e.g || sh.plut_key[2] != e.outlier))
 			build_pair_lut(sh, e);
 		if (tid == 0 && pre == CMP_PREPROCESS_DIFF)
-			first_sample_code(e, __ldg(reinterpret_cast<const uint16_t *>(P.src)), sh.first_code);
+			first_sample_code(e, sample_at(P.src, P.dtype, 0), sh.first_code);
 		frame_fast_any(sh, o, a, c, n_pieces, size_only);
 	}
 	if (n_pieces * 8u < n)

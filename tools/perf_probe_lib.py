@@ -75,6 +75,17 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         pf = {"c3": p_mixed, "c3plain": p_plain, "c3cs": p_cs, "c3multi": p_multi}[case]
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, pf)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
+    def p_iwt(p, idx):
+        p_plain(p, idx); p["primary_preprocessing"] = abi.PRE_IWT
+    def p_none(p, idx):
+        p_plain(p, idx); p["primary_preprocessing"] = abi.PRE_NONE
+    def p_unc(p, idx):
+        p_plain(p, idx); p["primary_encoder_type"] = 0
+    if case in ("iwt", "none", "unc"):
+        n_chunks, n = 4096, 1 << 16
+        data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
+        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc}[case], model=(case == "iwt"))
+        return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k"):
         n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
                        "c32k": (1 << 14, 1 << 15), "c8k": (1 << 16, 1 << 13)}[case]
