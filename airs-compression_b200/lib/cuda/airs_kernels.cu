@@ -1973,32 +1973,104 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_ker
 	}
 }
 
-/* One thread per frame: the XXH32 trailer of every successfully encoded stream whose job
- * asked for a checksum (ref cmp.c:314-319: zero padded to a byte, then 4 bytes big endian).
- * Runs behind the encode kernels; a batch without checksums costs one launch of early exits. */
+/* XXH32 with one lane per accumulator: four consecutive lanes share a stream (16-byte aligned
+ * 16-bit container), 16 stripes in flight per lane.  All 32 lanes must call it; streams whose
+ * group is idle pass n = 0. */
+__device__ uint32_t stream_checksum_lanes(const uint8_t *src, uint32_t n)
+{
+	const uint32_t k = threadIdx.x & 3u; /* accumulator of this lane */
+	const uint32_t nbytes = n * 2u, stripes = n / 8u;
+	const uint32_t seed = AIRS_CHECKSUM_SEED;
+	uint32_t v = k == 0 ? seed + AIRS_XP1 + AIRS_XP2 : k == 1 ? seed + AIRS_XP2 : k == 2 ? seed : seed - AIRS_XP1;
+	const uint32_t *p = (const uint32_t *)src + k;
+	uint32_t s = 0;
+
+	for (; s + 16 <= stripes; s += 16) {
+		uint32_t q[16];
+#pragma unroll
+		for (int i = 0; i < 16; i++)
+			q[i] = __ldg(p + 4u * (s + i));
+#pragma unroll
+		for (int i = 0; i < 16; i++)
+			v = airs_xxh_round(v, airs_be_pair(q[i]));
+	}
+	for (; s < stripes; s++)
+		v = airs_xxh_round(v, airs_be_pair(__ldg(p + 4u * s)));
+	const uint32_t base = threadIdx.x & 28u;
+	const uint32_t v0 = __shfl_sync(kFull, v, base), v1 = __shfl_sync(kFull, v, base + 1u);
+	const uint32_t v2 = __shfl_sync(kFull, v, base + 2u), v3 = __shfl_sync(kFull, v, base + 3u);
+	uint32_t h = nbytes >= 16 ? airs_rotl(v0, 1) + airs_rotl(v1, 7) + airs_rotl(v2, 12) + airs_rotl(v3, 18)
+				  : seed + AIRS_XP5;
+	h += nbytes;
+	uint32_t i = stripes * 8;
+	for (; i + 2 <= n; i += 2)
+		h = airs_rotl(h + airs_be_pair(sample_pair_at(src, AIRS_DTYPE_U16, true, i)) * AIRS_XP3, 17) * AIRS_XP4;
+	if (i < n) {
+		const uint32_t sv = sample_at(src, AIRS_DTYPE_U16, i);
+		h = airs_rotl(h + (sv >> 8) * AIRS_XP5, 11) * AIRS_XP1;
+		h = airs_rotl(h + (sv & 0xFFu) * AIRS_XP5, 11) * AIRS_XP1;
+	}
+	h ^= h >> 15;
+	h *= AIRS_XP2;
+	h ^= h >> 13;
+	h *= AIRS_XP3;
+	h ^= h >> 16;
+	return h;
+}
+
+/* The XXH32 trailer of every successfully encoded stream whose job asked for a checksum (ref
+ * cmp.c:314-319: zero padded to a byte, then 4 bytes big endian).  Runs behind the encode
+ * kernels; a batch without checksums costs one launch of early exits.  LANES = 1: one thread
+ * per frame (many frames).  LANES = 4: four lanes per frame, one per accumulator (few, long
+ * frames: the chain of a stream cannot be split further). */
+template <int LANES>
 __global__ void __launch_bounds__(128) airs_checksum_kernel(AirsLaunch b)
 {
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
 
-	if (b.ticket[4] == 0 || k >= b.n_results)
+	if (b.ticket[4] == 0)
 		return;
-	const uint32_t j = b.result_job[k];
-	if (j >= b.n_jobs)
-		return;
-	const JobPlan &pl = b.plans[j];
-	const uint32_t r = b.results[k];
-	if (!(pl.flags & AIRS_PF_CHECKSUM) || airs_failed(r) || r < 4u)
-		return;
-	const airs_job &job = b.jobs[j];
-	const uint32_t f = k - job.first_result;
-	const uint8_t *src = b.src + job.src_offset + (uint64_t)f * job.src_frame_stride;
-	uint8_t *stream = b.layout == AIRS_LAYOUT_CONCAT ? b.dst + b.out_offsets[k]
-							 : b.dst + job.dst_offset + (uint64_t)f * job.dst_frame_stride;
-	const uint32_t h = stream_checksum(src, job.dtype, pl.n);
-	stream[r - 4u] = (uint8_t)(h >> 24);
-	stream[r - 3u] = (uint8_t)(h >> 16);
-	stream[r - 2u] = (uint8_t)(h >> 8);
-	stream[r - 1u] = (uint8_t)h;
+	bool todo = false;
+	const uint8_t *src = nullptr;
+	uint8_t *stream = nullptr;
+	uint32_t r = 0, n = 0, dtype = AIRS_DTYPE_U16;
+	if (k < b.n_results) {
+		const uint32_t j = b.result_job[k];
+		if (j < b.n_jobs) {
+			const JobPlan &pl = b.plans[j];
+			r = b.results[k];
+			if ((pl.flags & AIRS_PF_CHECKSUM) && !airs_failed(r) && r >= 4u) {
+				const airs_job &job = b.jobs[j];
+				const uint32_t f = k - job.first_result;
+				src = b.src + job.src_offset + (uint64_t)f * job.src_frame_stride;
+				stream = b.layout == AIRS_LAYOUT_CONCAT ? b.dst + b.out_offsets[k]
+									 : b.dst + job.dst_offset + (uint64_t)f * job.dst_frame_stride;
+				n = pl.n;
+				dtype = job.dtype;
+				todo = true;
+			}
+		}
+	}
+	uint32_t h;
+	if (LANES == 4) {
+		/* the lanes of a group agree on todo; unaligned or 32-bit containers fall to lane 0 of the group */
+		const bool lanes_ok = todo && dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)src & 15u) == 0;
+		h = stream_checksum_lanes(src, lanes_ok ? n : 0u);
+		if (todo && !lanes_ok && (threadIdx.x & 3u) == 0)
+			h = stream_checksum(src, dtype, n);
+		if ((threadIdx.x & 3u) != 0)
+			todo = false;
+	} else {
+		if (!todo)
+			return;
+		h = stream_checksum(src, dtype, n);
+	}
+	if (todo) {
+		stream[r - 4u] = (uint8_t)(h >> 24);
+		stream[r - 3u] = (uint8_t)(h >> 16);
+		stream[r - 2u] = (uint8_t)(h >> 8);
+		stream[r - 1u] = (uint8_t)h;
+	}
 }
 
 extern "C" cudaError_t airs_launch_plan(const AirsLaunch *b, cudaStream_t stream)
@@ -2035,7 +2107,10 @@ extern "C" cudaError_t airs_launch_encode(const AirsLaunch *b, unsigned int grid
 
 extern "C" cudaError_t airs_launch_checksum(const AirsLaunch *b, cudaStream_t stream)
 {
-	airs_checksum_kernel<<<(b->n_results + 127) / 128, 128, 0, stream>>>(*b);
+	if (b->n_results >= 32768u) /* enough frames to fill the device with one thread each */
+		airs_checksum_kernel<1><<<(b->n_results + 127) / 128, 128, 0, stream>>>(*b);
+	else
+		airs_checksum_kernel<4><<<(4 * b->n_results + 127) / 128, 128, 0, stream>>>(*b);
 	return cudaGetLastError();
 }
 

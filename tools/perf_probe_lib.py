@@ -81,6 +81,32 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         p_plain(p, idx); p["primary_preprocessing"] = abi.PRE_NONE
     def p_unc(p, idx):
         p_plain(p, idx); p["primary_encoder_type"] = 0
+    if case == "sweep":
+        # BASELINE config 4 (named subset): preprocessing x encoder x options, 4096 chunks x 128 KiB of u16 each
+        n_chunks, n = 4096, 1 << 16
+        data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
+        frames2 = synth.frames_torch(1, 0, 512, 8, n, device=dev)
+        rows = []
+        for name, pre, enc, g, outl, cs, fb, dt in [
+                ("NONE+UNCOMPRESSED", 0, 0, 0, 0, 0, 0, 2), ("DIFF+UNCOMPRESSED", 1, 0, 0, 0, 0, 0, 2),
+                ("DIFF+ZERO g1", 1, 1, 1, 0, 0, 0, 2), ("DIFF+ZERO g8", 1, 1, 8, 0, 0, 0, 2), ("DIFF+ZERO g16", 1, 1, 16, 0, 0, 0, 2),
+                ("DIFF+ZERO g255", 1, 1, 255, 0, 0, 0, 2), ("DIFF+MULTI g16 o200", 1, 2, 16, 200, 0, 0, 2),
+                ("DIFF+MULTI g3 o16", 1, 2, 3, 16, 0, 0, 2), ("DIFF+ZERO g16 +checksum", 1, 1, 16, 0, 1, 0, 2),
+                ("DIFF+ZERO g16 +fallback", 1, 1, 16, 0, 0, 1, 2), ("DIFF+ZERO g16 i16", 1, 1, 16, 0, 0, 0, 0),
+                ("IWT+ZERO g16", 2, 1, 16, 0, 0, 0, 2), ("NONE+ZERO g16", 0, 1, 16, 0, 0, 0, 2)]:
+            def pf(p, idx, pre=pre, enc=enc, g=g, outl=outl, cs=cs, fb=fb):
+                p["primary_preprocessing"] = pre; p["primary_encoder_type"] = enc; p["primary_encoder_param"] = g
+                p["primary_encoder_outlier"] = outl; p["checksum_enabled"] = cs; p["uncompressed_fallback_enabled"] = fb
+            jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, pf, model=(pre == 2))
+            jobs["dtype"] = dt
+            rows.append((name, time_batch(name, data, jobs, dsz, wsz, n_chunks, steps, warmup)))
+        for name, rate, g2 in [("DIFF g16 -> MODEL g8 rate 8 (8 frames)", 8, 8), ("DIFF g16 -> MODEL g16 rate 11 (8 frames)", 11, 16)]:
+            def pm(p, idx, rate=rate, g2=g2):
+                p_plain(p, idx); p["secondary_iterations"] = 255; p["secondary_preprocessing"] = abi.PRE_MODEL
+                p["secondary_encoder_type"] = 1; p["secondary_encoder_param"] = g2; p["model_rate"] = rate
+            jobs, dsz, wsz = make_uniform_jobs(512, n, 8, pm, model=True)
+            rows.append((name, time_batch(name, frames2, jobs, dsz, wsz, 512 * 8, steps, warmup)))
+        return rows
     if case in ("iwt", "none", "unc"):
         n_chunks, n = 4096, 1 << 16
         data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
