@@ -282,34 +282,75 @@ __device__ __forceinline__ int16_t wrap16(int32_t v)
 	return (int16_t)(uint16_t)(uint32_t)v;
 }
 
-__device__ __noinline__ void iwt_global(const Pass &P)
+/* one level of the transform at stride s over w[0..n), restricted to the positions lo <= i < hi
+ * whose neighbours lie inside [lo, hi) or outside the frame; w is addressed as w[i - lo] */
+__device__ __forceinline__ void iwt_level(int16_t *w, uint32_t s, uint32_t lo, uint32_t hi, uint32_t n)
+{
+	const uint32_t tid = threadIdx.x;
+	const uint32_t first_d = (lo + s - 1u) / (2u * s) * (2u * s) + s; /* first odd multiple of s >= lo ... */
+	for (uint32_t i = (first_d >= lo + 2u * s ? first_d - 2u * s : first_d) + 2u * s * tid; i < hi; i += 2u * s * kThreads) {
+		if (i < lo || i - s < lo)
+			continue;
+		if (i + s < n) {
+			if (i + s < hi)
+				w[i - lo] = wrap16(w[i - lo] - wrap16(((int32_t)w[i - s - lo] + w[i + s - lo]) >> 1));
+		} else {
+			w[i - lo] = wrap16(w[i - lo] - w[i - s - lo]);
+		}
+	}
+	__syncthreads();
+	const uint32_t first_a = (lo + 2u * s - 1u) / (2u * s) * (2u * s);
+	for (uint32_t i = first_a + 2u * s * tid; i < hi; i += 2u * s * kThreads) {
+		const bool has_l = i >= s, has_r = i + s < n;
+		if ((has_l && i - s < lo) || (has_r && i + s >= hi))
+			continue;
+		if (has_l && has_r)
+			w[i - lo] = wrap16(w[i - lo] + wrap16(((int32_t)w[i - s - lo] + w[i + s - lo]) >> 2));
+		else if (has_r)
+			w[i - lo] = wrap16(w[i - lo] + wrap16((int32_t)w[i + s - lo] >> 1));
+		else if (has_l)
+			w[i - lo] = wrap16(w[i - lo] + wrap16((int32_t)w[i - s - lo] >> 1));
+	}
+	__syncthreads();
+}
+
+/* The transform of a whole frame into the work buffer.  The first four levels (strides 1, 2,
+ * 4, 8: 15/16 of the lifting steps) run in shared memory, tile by tile with a halo of 32
+ * samples (a level-4 coefficient depends on samples up to 30 positions away); the coarser
+ * levels run over the work buffer.  `buf` is idle staging memory and is handed back zeroed. */
+constexpr uint32_t kIwtTile = 4096, kIwtHalo = 32, kIwtSmemLevels = 4;
+
+__device__ __noinline__ void iwt_global(const Pass &P, uint32_t *buf32)
 {
 	int16_t *w = (int16_t *)P.work;
-	const uint64_t n = P.n;
+	int16_t *buf = (int16_t *)buf32;
+	const uint32_t n = P.n;
 	const uint32_t tid = threadIdx.x;
+	uint32_t s = 1;
 
-	for (uint64_t i = tid; i < n; i += kThreads)
-		w[i] = (int16_t)sample_at(P.src, P.dtype, (uint32_t)i);
-	__syncthreads();
-	for (uint64_t s = 1; s < n; s <<= 1) {
-		for (uint64_t i = s + 2 * s * tid; i < n; i += 2 * s * kThreads) {
-			if (i + s < n)
-				w[i] = wrap16(w[i] - wrap16(((int32_t)w[i - s] + w[i + s]) >> 1));
-			else
-				w[i] = wrap16(w[i] - w[i - s]);
+	if (n >= 4u * kIwtHalo) {
+		for (uint32_t t0 = 0; t0 < n; t0 += kIwtTile) {
+			const uint32_t lo = t0 >= kIwtHalo ? t0 - kIwtHalo : 0u;
+			const uint32_t hi = min(t0 + kIwtTile + kIwtHalo, n);
+			for (uint32_t i = lo + tid; i < hi; i += kThreads)
+				buf[i - lo] = (int16_t)sample_at(P.src, P.dtype, i);
+			__syncthreads();
+			for (uint32_t l = 0, ss = 1; l < kIwtSmemLevels; l++, ss <<= 1)
+				iwt_level(buf, ss, lo, hi, n);
+			for (uint32_t i = t0 + tid; i < min(t0 + kIwtTile, n); i += kThreads)
+				w[i] = buf[i - lo];
+			__syncthreads();
 		}
-		__syncthreads();
-		for (uint64_t i = 2 * s * tid; i < n; i += 2 * s * kThreads) {
-			bool has_l = i >= s, has_r = i + s < n;
-			if (has_l && has_r)
-				w[i] = wrap16(w[i] + wrap16(((int32_t)w[i - s] + w[i + s]) >> 2));
-			else if (has_r)
-				w[i] = wrap16(w[i] + wrap16((int32_t)w[i + s] >> 1));
-			else if (has_l)
-				w[i] = wrap16(w[i] + wrap16((int32_t)w[i - s] >> 1));
-		}
-		__syncthreads();
+		for (uint32_t i = tid; i < (kIwtTile + 2u * kIwtHalo) / 2u; i += kThreads)
+			buf32[i] = 0;
+		s = 1u << kIwtSmemLevels;
+	} else {
+		for (uint32_t i = tid; i < n; i += kThreads)
+			w[i] = (int16_t)sample_at(P.src, P.dtype, i);
 	}
+	__syncthreads();
+	for (; s < n; s <<= 1)
+		iwt_level(w, s, 0u, n, n);
 }
 
 /* -------------------------------------------------------------------------
@@ -1343,7 +1384,7 @@ __device__ __forceinline__ uint32_t encode_pass(Shared &sh, bool size_only, bool
 	c.buf = 0;
 
 	if (P.pre == CMP_PREPROCESS_IWT)
-		iwt_global(P);
+		iwt_global(P, &sh.stg_mem[0][0]);
 
 	const uint32_t n = P.n, pre = P.pre, model_mode = P.model_mode;
 	const bool fast_ok = ((uintptr_t)P.src & 15u) == 0 &&
