@@ -757,14 +757,17 @@ __device__ __noinline__ void first_sample_code(const EncConst &e, uint32_t x0, u
 	out[2] = cl + rl;
 }
 
-/* bit counts of the segments d[0..3], d[4..7], ..: b01 = segment 0 | segment 1 << 16, b23 likewise */
-__device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t &b01,
-					  uint32_t &b23)
+/* bit counts of the segments d[0..3], d[4..7], .. whose bit is set in `rows`: b01 = segment 0 |
+ * segment 1 << 16, b23 likewise */
+__device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t rows,
+					  uint32_t &b01, uint32_t &b23)
 {
 	b01 = 0;
 	b23 = 0;
 #pragma unroll 1
 	for (uint32_t k = 0; k < n_words; k++) {
+		if (!((rows >> (k >> 2)) & 1u)) /* segment k / 4 is not asked for */
+			continue;
 		const uint32_t z = zigzag2(d[k]);
 		uint32_t cw, cl, rw, rl, n;
 		encode_mapped_rt(e, z & 0xFFFFu, cw, cl, rw, rl);
@@ -1238,31 +1241,83 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				}
 			});
 		} else {
-			/* ---- arithmetic arm: plain residuals from reloaded data into local memory, then
-			 * rolled loops over them */
-			uint32_t d[SEG * 4];
+			/* ---- arithmetic arm, row by row: a "row" is segment j of all 32 lanes (256 samples).
+			 * Rows whose residuals are all in the table (and whose segments fit 64 bits) still
+			 * go through the table, one string per segment; the other rows are encoded sample by
+			 * sample from plain residuals.  A few outliers in a tile thus cost their rows, not
+			 * the whole warp tile.  Everything lives in local memory and rolled loops: this arm
+			 * must not cost the table arm its registers. */
+			uint32_t d[SEG * 4];    /* biased residuals; plain ones in the rows encoded arithmetically */
+			uint32_t rstr[SEG * 3]; /* hi, lo, length of the strings of the rows on the table */
+			uint32_t miss = 0;      /* bit j: row j is encoded arithmetically */
+#pragma unroll
+			for (int j = 0; j < SEG; j++)
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					d[4 * j + k] = u[j][k];
 			{
 				const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
-#pragma unroll
-				for (int j = 0; j < SEG; j++)
+				uint32_t b01 = 0, b23 = 0;
+#pragma unroll 1
+				for (uint32_t j = 0; j < (uint32_t)SEG; j++) {
+					const bool valid = !PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces);
+					uint32_t w4[4];
 #pragma unroll
 					for (int k = 0; k < 4; k++)
-						d[4 * j + k] = __vadd2(u[j][k], negRb);
-				if (first) /* the stand-in goes, the sample comes back */
+						w4[k] = d[4u * j + k];
+					bool row_hit = !unc && R != 0u && !(diff && pw == 0u && j == 0u) &&
+						       __all_sync(kFull, ((w4[0] | w4[1] | w4[2] | w4[3]) & notmask) == 0u);
+					if (row_hit) {
+						uint32_t lo = 0, hi = 0, n = 0;
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							const uint32_t off = ((w4[k] << 2) & (4u * (kLutStride - 1u))) | (w4[k] >> 8);
+							const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
+							const uint32_t pl = ent >> kLutLenShift;
+							hi = __funnelshift_l(lo, hi, pl);
+							lo = (lo << pl) | (ent & ((1u << kLutLenShift) - 1u));
+							n += pl;
+						}
+						row_hit = __all_sync(kFull, n <= 64u);
+						rstr[3u * j] = valid ? hi : 0u;
+						rstr[3u * j + 1u] = valid ? lo : 0u;
+						rstr[3u * j + 2u] = valid ? n : 0u;
+						if (row_hit) {
+							if (j < 2u)
+								b01 += (valid ? n : 0u) << (16u * (j & 1u));
+							else
+								b23 += (valid ? n : 0u) << (16u * (j & 1u));
+						}
+					}
+					if (!row_hit) {
+						miss |= 1u << j;
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							d[4u * j + k] = __vadd2(w4[k], negRb);
+					}
+				}
+				if (first) /* the stand-in goes, the sample comes back (its row is never on the table) */
 					d[0] = (d[0] & 0xFFFF0000u) | sample_at(P.src, P.dtype, 0);
+				uint32_t a01, a23;
+				slow_bits(P.enc, d, 4u * SEG, miss, a01, a23);
+				if (PARTIAL) {
+					a01 = (v[0] ? a01 & 0xFFFFu : 0u) | (v[1] ? a01 & 0xFFFF0000u : 0u);
+					if (SEG > 2)
+						a23 = (v[SEG - 2] ? a23 & 0xFFFFu : 0u) | (v[SEG - 1] ? a23 & 0xFFFF0000u : 0u);
+				}
+				tile_bits = tile_scan<SEG>(sh, t & 1u, lane, warp, a01 + b01, a23 + b23, c.sbits, pos);
 			}
-			uint32_t b01, b23;
-			slow_bits(P.enc, d, 4u * SEG, b01, b23);
-			if (PARTIAL) {
-				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
-				if (SEG > 2)
-					b23 = (v[SEG - 2] ? b23 & 0xFFFFu : 0u) | (v[SEG - 1] ? b23 & 0xFFFF0000u : 0u);
-			}
-			tile_bits = tile_scan<SEG>(sh, t & 1u, lane, warp, b01, b23, c.sbits, pos);
 			AIRS_AFTER_SCAN({
-				_Pragma("unroll 1") for (uint32_t j = 0; j < (uint32_t)SEG; j++)
-					if (!PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces))
-						slow_put(P.enc, d + 4 * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
+				_Pragma("unroll 1") for (uint32_t j = 0; j < (uint32_t)SEG; j++) {
+					const uint32_t pj = j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3];
+					if ((miss >> j) & 1u) {
+						if (!PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces))
+							slow_put(P.enc, d + 4 * j, stg, pj);
+					} else {
+						int32_t ne = -(int32_t)pj;
+						put_unit(stg, ne, rstr[3u * j], rstr[3u * j + 1u], rstr[3u * j + 2u]);
+					}
+				}
 			});
 		}
 #undef AIRS_AFTER_SCAN
@@ -1693,7 +1748,7 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 						d[4 * j + k] = __vadd2(u[j][k], negRb);
 				if (first)
 					d[0] = (d[0] & 0xFFFF0000u) | (w[0][0] & 0xFFFFu);
-				slow_bits(P.enc, d, 16u, b01, b23);
+				slow_bits(P.enc, d, 16u, 0xFu, b01, b23);
 				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
 				b23 = (v[2] ? b23 & 0xFFFFu : 0u) | (v[3] ? b23 & 0xFFFF0000u : 0u);
 			}
