@@ -85,6 +85,35 @@ class AirsHostBatch(C.Structure):
                 ("layout", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+# include/airs_cuda_decode.h
+DEC_ERRORS = {"CHECKSUM": 110, "NO_MODEL": 111, "CORRUPT": 112}
+
+DEC_JOB_DTYPE = np.dtype([
+    ("src_offset", "<u8"), ("src_frame_stride", "<u8"), ("dst_offset", "<u8"),
+    ("dst_frame_stride", "<u8"), ("src_size", "<u4"), ("dst_capacity", "<u4"), ("n_frames", "<u4"),
+    ("dtype", "<u4"), ("first_result", "<u4"), ("reserved", "<u4"),
+])
+assert DEC_JOB_DTYPE.itemsize == 56
+
+FRAME_INFO_DTYPE = np.dtype([
+    ("identifier", "<u8"), ("compressed_size", "<u4"), ("original_size", "<u4"),
+    ("encoder_outlier", "<u4"), ("version", "<u2"), ("encoder_param", "<u2"),
+    ("sequence_number", "u1"), ("preprocessing", "u1"), ("checksum_enabled", "u1"),
+    ("encoder_type", "u1"), ("model_rate", "u1"), ("header_size", "u1"), ("reserved", "u1", (2,)),
+])
+assert FRAME_INFO_DTYPE.itemsize == 32
+
+
+class AirsDecBatch(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("jobs", C.c_void_p),
+                ("results", C.c_void_p), ("info", C.c_void_p), ("scratch", C.c_void_p),
+                ("n_jobs", C.c_uint32), ("n_results", C.c_uint32)]
+
+
+def dec_err(name):
+    return (0x100000000 - DEC_ERRORS[name]) & 0xFFFFFFFF
+
+
 def make_params(primary_preprocessing=PRE_NONE, primary_encoder_type=ENC_UNCOMPRESSED,
                 primary_encoder_param=0, primary_encoder_outlier=0, secondary_iterations=0,
                 secondary_preprocessing=PRE_NONE, secondary_encoder_type=ENC_UNCOMPRESSED,

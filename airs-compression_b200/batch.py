@@ -110,3 +110,81 @@ def run_jobs_host(js, fill=0xA5, work_fill=0x5A):
         raise RuntimeError("airs_cuda_compress_batch_host failed (%d): %s"
                            % (rc, lib.airs_cuda_last_error().decode()))
     return dst, results, init[:n_jobs], offs if js["layout"] == abi.LAYOUT_CONCAT else None, work
+
+
+class DeviceDecodeBatch:
+    """Streams resident in HBM -> samples in HBM (include/airs_cuda_decode.h)."""
+
+    def __init__(self, streams, dec_jobs, dst_size, n_results, device="cuda:0", fill=None):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        self.n_jobs = len(dec_jobs)
+        self.n_results = int(n_results)
+        self.src = streams if isinstance(streams, torch.Tensor) else _dev_u8(streams, self.device)
+        self.jobs = dec_jobs if isinstance(dec_jobs, torch.Tensor) else _dev_u8(dec_jobs, self.device)
+        self.dst = torch.empty(max(int(dst_size), 16), dtype=torch.uint8, device=self.device)
+        if fill is not None:
+            self.dst.fill_(fill)
+        self.results = torch.zeros(max(self.n_results, 1), dtype=torch.int32, device=self.device)
+        self.info = torch.zeros(max(self.n_results, 1) * abi.FRAME_INFO_DTYPE.itemsize, dtype=torch.uint8,
+                                device=self.device)
+        nscratch = self.lib.airs_cuda_decode_scratch_size(self.n_jobs, self.n_results)
+        self.scratch = torch.empty(nscratch, dtype=torch.uint8, device=self.device)
+        b = abi.AirsDecBatch()
+        b.src = self.src.data_ptr()
+        b.dst = self.dst.data_ptr()
+        b.jobs = self.jobs.data_ptr()
+        b.results = self.results.data_ptr()
+        b.info = self.info.data_ptr()
+        b.scratch = self.scratch.data_ptr()
+        b.n_jobs = self.n_jobs
+        b.n_results = self.n_results
+        self.desc = b
+
+    def run(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.airs_cuda_decompress_batch(C.byref(self.desc), C.c_void_p(s.cuda_stream))
+        if rc != 0:
+            raise RuntimeError("airs_cuda_decompress_batch failed (%d): %s"
+                               % (rc, self.lib.airs_cuda_last_error().decode()))
+        return self
+
+    def fetch(self):
+        """(samples as bytes, results, parsed headers) as numpy, after a sync."""
+        torch.cuda.synchronize(self.device)
+        return (self.dst.cpu().numpy(), self.results.cpu().numpy().view(np.uint32)[:self.n_results],
+                self.info.cpu().numpy().view(abi.FRAME_INFO_DTYPE)[:self.n_results])
+
+
+def decode_jobs_for(jobs, results, out_offsets=None):
+    """Decode descriptors for the streams a compression job set produced: one per job, cut off in
+    front of the first frame that failed (the encoder leaves a half-updated model behind a
+    failure, ref cmp.h:300-303).  SLOTS layout unless out_offsets (CONCAT) is given.  The decoded
+    frames of a job lie back to back, 16-byte aligned.  Returns (dec_jobs, dst_size, n_results)."""
+    dj = np.zeros(len(jobs), dtype=abi.DEC_JOB_DTYPE)
+    dst_off = 0
+    for j, job in enumerate(jobs):
+        first, nf = int(job["first_result"]), int(job["n_frames"])
+        good = 0
+        while good < nf and not abi.is_error(int(results[first + good])):
+            good += 1
+        stride = 4 if int(job["dtype"]) == abi.DT_I16_IN_I32 else 2
+        n = int(job["src_size"]) // stride
+        frame = (n * stride + 15) // 16 * 16
+        if out_offsets is None:
+            dj[j]["src_offset"] = job["dst_offset"]
+            dj[j]["src_frame_stride"] = job["dst_frame_stride"]
+            dj[j]["src_size"] = job["dst_capacity"]
+        else:
+            dj[j]["src_offset"] = out_offsets[first]
+            dj[j]["src_frame_stride"] = 0
+            dj[j]["src_size"] = int(out_offsets[first + good]) - int(out_offsets[first])
+        dj[j]["dst_offset"] = dst_off
+        dj[j]["dst_frame_stride"] = frame
+        dj[j]["dst_capacity"] = n * stride
+        dj[j]["n_frames"] = good
+        dj[j]["dtype"] = job["dtype"]
+        dj[j]["first_result"] = first
+        dst_off += frame * nf
+    return dj, dst_off + 64, int(sum(int(j["n_frames"]) for j in jobs))

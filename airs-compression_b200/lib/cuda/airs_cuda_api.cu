@@ -140,6 +140,23 @@ bool on_device(const void *p)
 
 } /* namespace */
 
+/* for the other translation units of the library (airs_decode.cu); not exported */
+extern "C" __attribute__((visibility("hidden"))) int airs_internal_fail(int code, const char *text)
+{
+	return fail(code, "%s", text);
+}
+
+extern "C" __attribute__((visibility("hidden"))) void airs_internal_set_launches(int n)
+{
+	g_launches = n;
+}
+
+extern "C" __attribute__((visibility("hidden"))) int airs_internal_check_device(void)
+{
+	int n = 0;
+	return resident_ctas(&n);
+}
+
 extern "C" const char *airs_cuda_last_error(void)
 {
 	return g_err;

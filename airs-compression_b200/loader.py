@@ -1,4 +1,4 @@
-"""Loads libcmp_b200.so and declares its C-ABI (include/airs_cuda.h, include/cmp.h)."""
+"""Loads libcmp_b200.so and declares its C-ABI (include/airs_cuda.h, include/airs_cuda_decode.h, include/cmp.h)."""
 import ctypes as C
 import os
 
@@ -18,6 +18,8 @@ EXPORTS = [
     "airs_cuda_device_count", "airs_cuda_concurrent_jobs", "airs_cuda_last_error", "airs_cuda_batch_scratch_size",
     "airs_cuda_compress_batch", "airs_cuda_last_launch_count", "airs_cuda_compress_batch_host",
     "airs_cuda_release_cache",
+    # include/airs_cuda_decode.h
+    "airs_cuda_decode_scratch_size", "airs_cuda_decompress_batch",
 ]
 
 
@@ -73,5 +75,9 @@ def load_library():
     lib.airs_cuda_compress_batch_host.argtypes = [C.POINTER(abi.AirsHostBatch)]
     lib.airs_cuda_compress_batch_host.restype = C.c_int
     lib.airs_cuda_release_cache.restype = None
+    lib.airs_cuda_decode_scratch_size.argtypes = [u32, u32]
+    lib.airs_cuda_decode_scratch_size.restype = C.c_size_t
+    lib.airs_cuda_decompress_batch.argtypes = [C.POINTER(abi.AirsDecBatch), vp]
+    lib.airs_cuda_decompress_batch.restype = C.c_int
     _LIB = lib
     return lib

@@ -20,7 +20,7 @@ def lib(pkg):
 
 def test_every_declared_symbol_is_exported(lib, pkg):
     declared = set()
-    for h in ("cmp.h", "cmp_errors.h", "airs_cuda.h"):
+    for h in ("cmp.h", "cmp_errors.h", "airs_cuda.h", "airs_cuda_decode.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         declared |= set(re.findall(r"\b((?:cmp|airs_cuda)_[a-z0-9_]+)\s*\(", text))
@@ -38,6 +38,7 @@ def test_struct_layouts():
     assert (ctx.magic.offset, ctx.params.offset, ctx.work_buf.offset, ctx.work_buf_size.offset,
             ctx.model_size.offset, ctx.identifier.offset, ctx.sequence_number.offset) == (0, 4, 48, 56, 60, 64, 72)
     assert abi.JOB_DTYPE.itemsize == 120 and C.sizeof(abi.AirsBatch) == 88 and C.sizeof(abi.AirsHostBatch) == 96
+    assert abi.DEC_JOB_DTYPE.itemsize == 56 and abi.FRAME_INFO_DTYPE.itemsize == 32 and C.sizeof(abi.AirsDecBatch) == 56
 
 
 def test_error_helpers(lib):
@@ -120,6 +121,15 @@ def test_no_cpu_fallback(lib):
     src = np.arange(8, dtype=np.uint16)
     assert lib.cmp_compress_u16(C.byref(ctx), dst.ctypes.data, 128, src.ctypes.data, 16) == abi.err("GENERIC")
     assert b"CUDA" in lib.airs_cuda_last_error() or b"cuda" in lib.airs_cuda_last_error()
+    # ... and so does the decoder
+    db = abi.AirsDecBatch()
+    jobs = np.zeros(1, dtype=abi.DEC_JOB_DTYPE)
+    res = np.zeros(1, dtype=np.uint32)
+    scratch = np.zeros(lib.airs_cuda_decode_scratch_size(1, 1) // 8 + 2, dtype=np.uint64)
+    db.src, db.dst, db.jobs, db.results = dst.ctypes.data, src.ctypes.data, jobs.ctypes.data, res.ctypes.data
+    db.scratch = (scratch.ctypes.data + 15) & ~15
+    db.n_jobs = db.n_results = 1
+    assert lib.airs_cuda_decompress_batch(C.byref(db), None) == -1  # AIRS_E_NO_DEVICE
 
 
 def test_golomb_division_trick():
