@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-round-trip", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -276,6 +277,33 @@ def main():
     all_in, all_out, all_err = float(t[1]), float(t[2]), int(t[3])
     value = all_in * args.steps / (total_ms * 1e-3) / 1e9
 
+    # ---- size-independent check at the full size: every stream of the last timed step goes
+    # through the device decoder (airs_cuda_decompress_batch) and must give back the input
+    round_trip = None
+    if not args.no_round_trip:
+        dj = np.zeros(units, dtype=abi.DEC_JOB_DTYPE)
+        for a_, b_ in (("src_offset", "dst_offset"), ("src_frame_stride", "dst_frame_stride"), ("src_size", "dst_capacity"),
+                       ("dst_offset", "src_offset"), ("dst_frame_stride", "src_frame_stride"), ("dst_capacity", "src_size"),
+                       ("n_frames", "n_frames"), ("dtype", "dtype"), ("first_result", "first_result")):
+            dj[a_] = w["jobs"][b_]
+        dec = pkg.batch.DeviceDecodeBatch(db.dst, dj, data.numel(), w["n_results"], device=device)
+        dec.run()                                           # untimed first run
+        torch.cuda.synchronize(device)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        dec.run(stream)
+        d1.record(stream)
+        torch.cuda.synchronize(device)
+        dres = dec.results.cpu().numpy().view(np.uint32)[:w["n_results"]]
+        ok = bool(np.all(dres == w["jobs"]["src_size"][0])) and bool(torch.equal(dec.dst[:data.numel()], data))
+        tr = torch.tensor([0.0 if ok else 1.0, d0.elapsed_time(d1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        round_trip = {"identical": float(tr[0]) == 0.0, "samples": w["n_samples_total"] * world,
+                      "decode_ms": float(tr[1]), "decode_output_gbs": in_bytes * world / (float(tr[1]) * 1e-3) / 1e9,
+                      "what": "streams of the last timed step -> airs_cuda_decompress_batch -> compared with the input, all ranks"}
+        del dec
+
     # ---- end to end through the C-ABI with HOST buffers (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -355,6 +383,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if round_trip:
+        line["config"]["round_trip"] = round_trip
     if world == 1 and not args.no_cpu:
         gbs, info, js, (cdst, cres), _ = cpu_reference_run(pkg, args.workload, 1, 0, target_s=args.cpu_seconds)
         line["cpu_baseline"] = info

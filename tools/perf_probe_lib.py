@@ -47,6 +47,21 @@ def time_batch(name, data, jobs, dst_size, work_size, n_results, steps=5, warmup
     B = in_bytes + out_bytes
     print(f"{name}: {med:.3f} ms (min {ms[0]:.3f}) in {in_bytes/2**30:.2f} GiB ratio {in_bytes/max(out_bytes,1):.2f} "
           f"input {in_bytes/med/1e6:.1f} GB/s  algorithmic {B/med/1e6:.1f} GB/s = {B/med/1e6/6531.6*100:.1f}% of 6531.6  errors {bad}", flush=True)
+    if os.environ.get("AIRS_PROBE_DECODE"):  # the same streams back through the decoder
+        dj = np.zeros(len(jobs), dtype=abi.DEC_JOB_DTYPE)
+        for a_, b_ in (("src_offset", "dst_offset"), ("src_frame_stride", "dst_frame_stride"), ("src_size", "dst_capacity"),
+                       ("dst_offset", "src_offset"), ("dst_frame_stride", "src_frame_stride"), ("dst_capacity", "src_size"),
+                       ("n_frames", "n_frames"), ("dtype", "dtype"), ("first_result", "first_result")):
+            dj[a_] = jobs[b_]
+        dec = pkg.batch.DeviceDecodeBatch(db.dst, dj, in_bytes, n_results)
+        dec.run(); torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a, b in evs:
+            a.record(); dec.run(); b.record()
+        torch.cuda.synchronize()
+        dms = sorted(a.elapsed_time(b) for a, b in evs)[1]
+        same = bool(torch.equal(dec.dst[:in_bytes], data.view(torch.uint8).reshape(-1)))
+        print(f"{name}: decode {dms:.3f} ms, output {in_bytes/dms/1e6:.1f} GB/s, round trip identical: {same}", flush=True)
     return med
 
 
