@@ -283,74 +283,108 @@ __device__ __forceinline__ int16_t wrap16(int32_t v)
 }
 
 /* one level of the transform at stride s over w[0..n), restricted to the positions lo <= i < hi
- * whose neighbours lie inside [lo, hi) or outside the frame; w is addressed as w[i - lo] */
+ * whose neighbours lie inside [lo, hi) or outside the frame; w is addressed as w[i - lo].  lo is a
+ * multiple of 2s (tiles and their halos start at multiples of 32, s <= 8).  Stores truncate to
+ * 16 bits, which is all the reference's casts do. */
 __device__ __forceinline__ void iwt_level(int16_t *w, uint32_t s, uint32_t lo, uint32_t hi, uint32_t n)
 {
-	const uint32_t tid = threadIdx.x;
-	const uint32_t first_d = (lo + s - 1u) / (2u * s) * (2u * s) + s; /* first odd multiple of s >= lo ... */
-	for (uint32_t i = (first_d >= lo + 2u * s ? first_d - 2u * s : first_d) + 2u * s * tid; i < hi; i += 2u * s * kThreads) {
-		if (i < lo || i - s < lo)
-			continue;
-		if (i + s < n) {
-			if (i + s < hi)
-				w[i - lo] = wrap16(w[i - lo] - wrap16(((int32_t)w[i - s - lo] + w[i + s - lo]) >> 1));
-		} else {
-			w[i - lo] = wrap16(w[i - lo] - w[i - s - lo]);
-		}
+	const uint32_t tid = threadIdx.x, s2 = 2u * s;
+	int16_t *b = w - lo; /* b[i] is element i */
+
+	for (uint32_t i = lo + s + s2 * tid; i < hi; i += s2 * kThreads) { /* details: odd multiples of s */
+		if (i + s < hi)
+			b[i] = (int16_t)(b[i] - (((int32_t)b[i - s] + b[i + s]) >> 1));
+		else if (i + s >= n) /* the last one has no right neighbour */
+			b[i] = (int16_t)(b[i] - b[i - s]);
 	}
 	__syncthreads();
-	const uint32_t first_a = (lo + 2u * s - 1u) / (2u * s) * (2u * s);
-	for (uint32_t i = first_a + 2u * s * tid; i < hi; i += 2u * s * kThreads) {
+	for (uint32_t i = lo + s2 * tid; i < hi; i += s2 * kThreads) { /* approximations: even multiples */
 		const bool has_l = i >= s, has_r = i + s < n;
 		if ((has_l && i - s < lo) || (has_r && i + s >= hi))
-			continue;
+			continue; /* a neighbour outside the tile: this element belongs to the halo */
+		int32_t t = 0;
 		if (has_l && has_r)
-			w[i - lo] = wrap16(w[i - lo] + wrap16(((int32_t)w[i - s - lo] + w[i + s - lo]) >> 2));
+			t = ((int32_t)b[i - s] + b[i + s]) >> 2;
 		else if (has_r)
-			w[i - lo] = wrap16(w[i - lo] + wrap16((int32_t)w[i + s - lo] >> 1));
+			t = (int32_t)b[i + s] >> 1;
 		else if (has_l)
-			w[i - lo] = wrap16(w[i - lo] + wrap16((int32_t)w[i - s - lo] >> 1));
+			t = (int32_t)b[i - s] >> 1;
+		b[i] = (int16_t)(b[i] + t);
 	}
 	__syncthreads();
 }
 
-/* The transform of a whole frame into the work buffer.  The first four levels (strides 1, 2,
- * 4, 8: 15/16 of the lifting steps) run in shared memory, tile by tile with a halo of 32
- * samples (a level-4 coefficient depends on samples up to 30 positions away); the coarser
- * levels run over the work buffer.  `buf` is idle staging memory and is handed back zeroed. */
-constexpr uint32_t kIwtTile = 4096, kIwtHalo = 32, kIwtSmemLevels = 4;
+/* The transform of a whole frame into the work buffer, four levels at a time.  Stage 0 takes
+ * the samples, stage 1 every 16th coefficient of the work buffer (the approximations stage 0
+ * left), stage 2 every 256th, ..: to the decimated sequence y[k] = w[k * S] of length ceil(n / S)
+ * levels 1-4 are what levels with the strides S, 2S, 4S, 8S are to w, edges included.  Each
+ * stage runs in shared memory, tile by tile with a halo of 32 elements (a level-4 coefficient
+ * depends on elements up to 30 positions away), so no lifting step ever waits for global
+ * memory.  `buf32` is idle staging memory and is handed back zeroed. */
+constexpr uint32_t kIwtTile = 4096, kIwtHalo = 32, kIwtStageLevels = 4;
 
 __device__ __noinline__ void iwt_global(const Pass &P, uint32_t *buf32)
 {
 	int16_t *w = (int16_t *)P.work;
 	int16_t *buf = (int16_t *)buf32;
+	int16_t *keep = buf + kIwtTile + 2u * kIwtHalo; /* the last 32 untransformed elements of the tile before */
 	const uint32_t n = P.n;
 	const uint32_t tid = threadIdx.x;
-	uint32_t s = 1;
+	/* 16-byte accesses for stage 0: tiles and halos start at multiples of 32 samples */
+	const bool vec = P.dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)P.src & 15u) == 0 && ((uintptr_t)w & 15u) == 0;
 
-	if (n >= 4u * kIwtHalo) {
-		for (uint32_t t0 = 0; t0 < n; t0 += kIwtTile) {
+	for (uint32_t S = 1, stage = 0; stage == 0 || S < n; S <<= kIwtStageLevels, stage++) {
+		const uint32_t m = (n + S - 1u) / S; /* elements of this stage */
+		for (uint32_t t0 = 0; t0 < m; t0 += kIwtTile) {
 			const uint32_t lo = t0 >= kIwtHalo ? t0 - kIwtHalo : 0u;
-			const uint32_t hi = min(t0 + kIwtTile + kIwtHalo, n);
-			for (uint32_t i = lo + tid; i < hi; i += kThreads)
-				buf[i - lo] = (int16_t)sample_at(P.src, P.dtype, i);
+			const uint32_t hi = min(t0 + kIwtTile + kIwtHalo, m);
+			const uint32_t t1 = min(t0 + kIwtTile, m);
+			if (stage == 0 && vec) {
+				const uint4 *s4 = reinterpret_cast<const uint4 *>(P.src) + lo / 8u;
+				uint4 *b4 = reinterpret_cast<uint4 *>(buf);
+				const uint32_t nv = (hi - lo) / 8u;
+				for (uint32_t v0 = tid; v0 < nv; v0 += 2u * kThreads) { /* two loads in flight per thread */
+					const uint4 q0 = __ldg(s4 + v0);
+					const uint4 q1 = v0 + kThreads < nv ? __ldg(s4 + v0 + kThreads) : make_uint4(0, 0, 0, 0);
+					b4[v0] = q0;
+					if (v0 + kThreads < nv)
+						b4[v0 + kThreads] = q1;
+				}
+				for (uint32_t i = lo + nv * 8u + tid; i < hi; i += kThreads)
+					buf[i - lo] = (int16_t)sample_at(P.src, P.dtype, i);
+			} else if (stage == 0) {
+				for (uint32_t i = lo + tid; i < hi; i += kThreads)
+					buf[i - lo] = (int16_t)sample_at(P.src, P.dtype, i);
+			} else {
+				/* in place: the elements in front of the tile have been transformed already; their
+				 * old values wait in `keep` */
+				for (uint32_t i = lo + tid; i < hi; i += kThreads)
+					buf[i - lo] = i < t0 ? keep[i - lo] : w[(size_t)i * S];
+				__syncthreads();
+				if (tid < kIwtHalo && t1 == t0 + kIwtTile)
+					keep[tid] = buf[t1 - kIwtHalo - lo + tid];
+			}
 			__syncthreads();
-			for (uint32_t l = 0, ss = 1; l < kIwtSmemLevels; l++, ss <<= 1)
-				iwt_level(buf, ss, lo, hi, n);
-			for (uint32_t i = t0 + tid; i < min(t0 + kIwtTile, n); i += kThreads)
-				w[i] = buf[i - lo];
+			for (uint32_t l = 0, ss = 1; l < kIwtStageLevels && ss < m; l++, ss <<= 1)
+				iwt_level(buf, ss, lo, hi, m);
+			if (stage == 0 && vec) {
+				uint4 *w4 = reinterpret_cast<uint4 *>(w) + t0 / 8u;
+				const uint4 *b4 = reinterpret_cast<const uint4 *>(buf + (t0 - lo));
+				const uint32_t nv = (t1 - t0) / 8u;
+				for (uint32_t v = tid; v < nv; v += kThreads)
+					w4[v] = b4[v];
+				for (uint32_t i = t0 + nv * 8u + tid; i < t1; i += kThreads)
+					w[i] = buf[i - lo];
+			} else {
+				for (uint32_t i = t0 + tid; i < t1; i += kThreads)
+					w[(size_t)i * S] = buf[i - lo];
+			}
 			__syncthreads();
 		}
-		for (uint32_t i = tid; i < (kIwtTile + 2u * kIwtHalo) / 2u; i += kThreads)
-			buf32[i] = 0;
-		s = 1u << kIwtSmemLevels;
-	} else {
-		for (uint32_t i = tid; i < n; i += kThreads)
-			w[i] = (int16_t)sample_at(P.src, P.dtype, i);
 	}
+	for (uint32_t i = tid; i < (kIwtTile + 3u * kIwtHalo) / 2u; i += kThreads)
+		buf32[i] = 0;
 	__syncthreads();
-	for (; s < n; s <<= 1)
-		iwt_level(w, s, 0u, n, n);
 }
 
 /* -------------------------------------------------------------------------

@@ -122,10 +122,12 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
             jobs, dsz, wsz = make_uniform_jobs(512, n, 8, pm, model=True)
             rows.append((name, time_batch(name, frames2, jobs, dsz, wsz, 512 * 8, steps, warmup)))
         return rows
-    if case in ("iwt", "none", "unc"):
+    def p_iwtunc(p, idx):
+        p_plain(p, idx); p["primary_preprocessing"] = abi.PRE_IWT; p["primary_encoder_type"] = 0
+    if case in ("iwt", "none", "unc", "iwtunc"):
         n_chunks, n = 4096, 1 << 16
         data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
-        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc}[case], model=(case == "iwt"))
+        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc, "iwtunc": p_iwtunc}[case], model=(case in ("iwt", "iwtunc")))
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k", "c4b_esc1", "c4b_esc8"):
         n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
