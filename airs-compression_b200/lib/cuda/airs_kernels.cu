@@ -730,6 +730,17 @@ __device__ __forceinline__ uint32_t zigzag2(uint32_t d)
 	return ((d << 1) & 0xFFFEFFFEu) ^ sign;
 }
 
+/* pair table entry of the biased residual pair u (u0 | u1 << 16, both below 64): the entry index
+ * u0 + 64 u1 is one IDP.2A (two 16-bit x 8-bit products), the address one LEA; lut_s is the
+ * table's address in the shared window */
+__device__ __forceinline__ uint32_t lut_pair(uint32_t lut_s, uint32_t u)
+{
+	uint32_t idx, ent;
+	asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(idx) : "r"(u), "r"(1u | (kLutStride << 8)), "r"(0u));
+	asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(lut_s + (idx << 2)));
+	return ent;
+}
+
 /* OR a bit string of len <= 64 bits (hi:lo, right aligned) into the staging
  * words.  ne = -(bit position where the string starts), updated to the start of
  * the next one.  Three funnel shifts and three reductions whatever the length;
@@ -1021,6 +1032,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	uint4 *work4 = reinterpret_cast<uint4 *>(P.work);
 	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
 	const char *lut = reinterpret_cast<const char *>(sh.plut);
+	const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(sh.plut);
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
 	const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
 	/* stream bits at which the reference's writer gives up, in staging coordinates */
@@ -1183,8 +1195,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				uint32_t pc[4], pl[4];
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					const uint32_t off = ((u[j][k] << 2) & (4u * (kLutStride - 1u))) | (u[j][k] >> 8);
-					const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
+					const uint32_t ent = lut_pair(lut_s, u[j][k]);
 					pc[k] = ent & ((1u << kLutLenShift) - 1u);
 					pl[k] = ent >> kLutLenShift;
 				}
