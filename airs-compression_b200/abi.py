@@ -74,7 +74,7 @@ class AirsBatch(C.Structure):
                 ("jobs", C.c_void_p), ("results", C.c_void_p), ("init_results", C.c_void_p),
                 ("out_offsets", C.c_void_p), ("scratch", C.c_void_p), ("dst_size", C.c_uint64),
                 ("n_jobs", C.c_uint32), ("n_results", C.c_uint32), ("layout", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("tmp", C.c_void_p), ("tmp_size", C.c_uint64)]
 
 
 class AirsHostBatch(C.Structure):

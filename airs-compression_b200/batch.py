@@ -20,7 +20,8 @@ class DeviceBatch:
     """A batch resident in HBM: source, destination, work buffers, job table, results."""
 
     def __init__(self, src, jobs, dst_size, work_size, n_results, layout=abi.LAYOUT_SLOTS,
-                 device="cuda:0", fill=None, work_fill=None):
+                 device="cuda:0", fill=None, work_fill=None, concat_tmp=0):
+        """concat_tmp: bytes of temporary memory for the two-phase CONCAT path (0: single phase)."""
         self.lib = load_library()
         self.device = torch.device(device)
         self.layout = layout
@@ -52,6 +53,11 @@ class DeviceBatch:
         b.n_jobs = self.n_jobs
         b.n_results = self.n_results
         b.layout = layout
+        self.tmp = None
+        if layout == abi.LAYOUT_CONCAT and concat_tmp:
+            self.tmp = torch.empty(int(concat_tmp), dtype=torch.uint8, device=self.device)
+            b.tmp = self.tmp.data_ptr()
+            b.tmp_size = int(concat_tmp)
         self.desc = b
 
     def run(self, stream=None):
@@ -76,12 +82,18 @@ class DeviceBatch:
                 self.work.cpu().numpy())
 
 
-def run_jobs_device(js, device="cuda:0", fill=0xA5, work_fill=0x5A):
+def concat_tmp_size(jobs, n_results):
+    """Bytes of temporary memory the two-phase CONCAT path needs for a (host-side) job table."""
+    caps = int((jobs["n_frames"].astype(np.uint64) * jobs["dst_capacity"].astype(np.uint64)).sum())
+    return int(load_library().airs_cuda_concat_tmp_size(caps, int(n_results)))
+
+
+def run_jobs_device(js, device="cuda:0", fill=0xA5, work_fill=0x5A, concat_tmp=0):
     """Run a job set (tests/jobgen.py layout) on the GPU; same return shape as jobgen.run_cpu."""
     if not torch.cuda.is_available():
         raise RuntimeError("no CUDA device: this backend has no CPU path")
     db = DeviceBatch(js["src"], js["jobs"], js["dst_size"], js["work_size"], js["n_results"],
-                     layout=js["layout"], device=device, fill=fill, work_fill=work_fill)
+                     layout=js["layout"], device=device, fill=fill, work_fill=work_fill, concat_tmp=concat_tmp)
     db.run()
     dst, res, init, offs, work = db.fetch()
     return dst, res, init, offs, work[:js["work_size"]]

@@ -37,7 +37,9 @@ int fail(int code, const char *fmt, ...)
 				    "%s: %s", #call, cudaGetErrorString(e_));                 \
 	} while (0)
 
-constexpr size_t kScratchHeader = 256; /* ticket counter and friends */
+constexpr size_t kScratchHeader = 512; /* ticket counters and friends: words 0..63 of the batch (word 5: the gate
+					* of the two-phase CONCAT path), words 64..127 of its single-phase rerun */
+constexpr uint32_t kGateWord = 5;
 
 size_t lookback_bytes(uint32_t n_results)
 {
@@ -101,7 +103,7 @@ struct DevBuf {
 constexpr int kMaxGroups = 64; /* pipeline stages of one host batch */
 
 struct Cache {
-	DevBuf src, dst, work, jobs, results, init, offs, scratch, state;
+	DevBuf src, dst, work, jobs, results, init, offs, scratch, state, tmp;
 	cudaStream_t stream = nullptr;            /* compute (and everything of the unpipelined paths) */
 	cudaStream_t s_in = nullptr, s_out = nullptr; /* host-to-device / device-to-host copies of the pipelined path */
 	cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_start = nullptr;
@@ -195,8 +197,33 @@ extern "C" int airs_cuda_concurrent_jobs(void)
 
 extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results)
 {
-	/* header | one look-back word per frame (+1) | one 128-byte plan per job | two job lists | job of every frame */
-	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs + 4 * (size_t)n_results + 64;
+	/* header | one look-back word per frame (+1) | one 128-byte plan per job | two job lists | job of every frame |
+	 * the job table on temporary slots (two-phase CONCAT) */
+	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs +
+	       4 * (size_t)n_results + 64 + sizeof(struct airs_job) * (size_t)n_jobs + 64 +
+	       airs_concat_scratch_bytes(n_jobs, n_results);
+}
+
+extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results)
+{
+	/* every slot is rounded up to 16 bytes; 32 bytes of slack behind the last one */
+	return (size_t)(sum_of_capacities + 16ull * n_results + 64);
+}
+
+/* plan, encode (CTA per job), encode (warp per job, SLOTS only), checksums */
+static int launch_kernels(const AirsLaunch &l, int resident, cudaStream_t stream)
+{
+	unsigned int grid = l.n_jobs < (uint32_t)resident ? l.n_jobs : (unsigned int)resident;
+	CU(airs_launch_plan(&l, stream));
+	CU(airs_launch_encode(&l, grid, stream));
+	g_launches += 2;
+	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) { /* short single-frame jobs: one warp each */
+		CU(airs_launch_small(&l, (unsigned int)resident, stream));
+		g_launches++;
+	}
+	CU(airs_launch_checksum(&l, stream));
+	g_launches++;
+	return AIRS_OK;
 }
 
 static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
@@ -242,17 +269,52 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.n_results = b->n_results;
 	l.layout = b->layout;
 
-	unsigned int grid = b->n_jobs < (uint32_t)resident ? b->n_jobs : (unsigned int)resident;
-	CU(airs_launch_plan(&l, stream));
-	CU(airs_launch_encode(&l, grid, stream));
-	g_launches = 2;
-	if (b->layout == AIRS_LAYOUT_SLOTS && !ctx_io) { /* short single-frame jobs: one warp each */
-		CU(airs_launch_small(&l, (unsigned int)resident, stream));
-		g_launches = 3;
+	if (b->layout == AIRS_LAYOUT_CONCAT && b->tmp && b->tmp_size && b->dst && !ctx_io && !((uintptr_t)b->tmp & 15u)) {
+		/* two phases (airs_concat.cu): SLOTS-style into temporary slots, scan, copy.  Everything is
+		 * enqueued at once; word kGateWord of the header decides on the device which kernels run:
+		 * 0 = the two-phase path, set = the single-phase path below (temporary slots or
+		 * destination too small). */
+		AirsConcat c;
+		memset(&c, 0, sizeof(c));
+		c.jobs = b->jobs;
+		c.slot_jobs = (struct airs_job *)(((uintptr_t)(l.result_job + b->n_results) + 63u) & ~(uintptr_t)63u);
+		c.sums = (uint64_t *)(((uintptr_t)(c.slot_jobs + b->n_jobs) + 63u) & ~(uintptr_t)63u);
+		c.n_big = (uint32_t *)(c.sums + (b->n_jobs + 1023u) / 1024u + (b->n_results + 1023u) / 1024u + 4);
+		c.big_list = c.n_big + 4;
+		c.results = b->results;
+		c.result_job = l.result_job;
+		c.out_offsets = b->out_offsets;
+		c.tmp = (uint8_t *)b->tmp;
+		c.dst = (uint8_t *)b->dst;
+		c.flag = l.ticket + kGateWord;
+		c.tmp_size = b->tmp_size;
+		c.dst_size = b->dst_size;
+		c.n_jobs = b->n_jobs;
+		c.n_results = b->n_results;
+		CU(airs_launch_concat_slots(&c, stream));
+		g_launches += 3;
+
+		AirsLaunch l1 = l;
+		l1.jobs = c.slot_jobs;
+		l1.dst = c.tmp;
+		l1.dst_size = b->tmp_size;
+		l1.out_offsets = nullptr;
+		l1.layout = AIRS_LAYOUT_SLOTS;
+		l1.gate = c.flag;
+		l1.gate_want = 0;
+		if ((rc = launch_kernels(l1, resident, stream)))
+			return rc;
+		/* one CTA per long stream, one warp per short one: as many CTAs as there are frames, at most
+		 * a few per SM (latency bound copies: many warps in flight) */
+		unsigned int cap = (unsigned int)resident * 2u;
+		CU(airs_launch_concat_gather(&c, b->n_results < cap ? b->n_results : cap, stream));
+		g_launches += 4;
+
+		l.ticket = (uint32_t *)b->scratch + 64; /* fresh counters for the rerun */
+		l.gate = c.flag;
+		l.gate_want = 1;
 	}
-	CU(airs_launch_checksum(&l, stream));
-	g_launches++;
-	return AIRS_OK;
+	return launch_kernels(l, resident, stream);
 }
 
 extern "C" int airs_cuda_compress_batch(const struct airs_batch *b, void *stream)
@@ -402,6 +464,21 @@ extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
 	b.n_jobs = hb->n_jobs;
 	b.n_results = hb->n_results;
 	b.layout = hb->layout;
+	if (hb->layout == AIRS_LAYOUT_CONCAT) {
+		/* temporary slots for the two-phase path, if the device has room for them */
+		uint64_t caps = 0;
+		for (uint32_t j = 0; j < hb->n_jobs; j++)
+			caps += (uint64_t)hb->jobs[j].n_frames * hb->jobs[j].dst_capacity;
+		const size_t need = airs_cuda_concat_tmp_size(caps, hb->n_results);
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (need <= c.tmp.cap || need < free_b / 2) &&
+		    c.tmp.reserve(need) == AIRS_OK) {
+			b.tmp = c.tmp.p;
+			b.tmp_size = need;
+		} else {
+			cudaGetLastError();
+		}
+	}
 	rc = launch_batch(&b, nullptr, s);
 	if (rc)
 		return rc;
@@ -440,6 +517,7 @@ extern "C" void airs_cuda_release_cache(void)
 	c.offs.release();
 	c.scratch.release();
 	c.state.release();
+	c.tmp.release();
 	if (c.stream) {
 		cudaStreamDestroy(c.stream);
 		cudaStreamDestroy(c.s_in);

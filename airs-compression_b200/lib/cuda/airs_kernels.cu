@@ -1882,11 +1882,17 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 
 } /* namespace */
 
+/* two-phase CONCAT: is this launch the phase that runs? (see airs_launch.h) */
+__device__ __forceinline__ bool gate_closed(const AirsLaunch &b)
+{
+	return b.gate && (*b.gate != 0u) != (b.gate_want != 0u);
+}
+
 __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 
-	if (j >= b.n_jobs)
+	if (j >= b.n_jobs || gate_closed(b))
 		return;
 	JobPlan pl;
 	const airs_job &job = b.jobs[j];
@@ -1928,6 +1934,9 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 {
 	__shared__ Shared sh;
 	const uint32_t tid = threadIdx.x;
+
+	if (gate_closed(b))
+		return;
 
 	for (uint32_t w = tid; w < 2u * (4u + kStgWords); w += kThreads)
 		(&sh.stg_mem[0][0])[w] = 0;
@@ -2047,6 +2056,8 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_ker
 	__shared__ WarpShared wsh[kWarps];
 	const uint32_t lane = threadIdx.x & 31u;
 	WarpShared &ws = wsh[threadIdx.x >> 5];
+	if (gate_closed(b))
+		return;
 	const uint32_t n_small = b.ticket[3]; /* entries of small_list, written by airs_plan_kernel */
 
 	for (uint32_t w = lane; w < 4u + kWStgWords; w += 32u)
@@ -2169,7 +2180,7 @@ __global__ void __launch_bounds__(128) airs_checksum_kernel(AirsLaunch b)
 {
 	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
 
-	if (b.ticket[4] == 0)
+	if (b.ticket[4] == 0 || gate_closed(b))
 		return;
 	bool todo = false;
 	const uint8_t *src = nullptr;

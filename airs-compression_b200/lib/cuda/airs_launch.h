@@ -38,6 +38,29 @@ struct AirsLaunch {
 	uint32_t n_jobs;
 	uint32_t n_results;
 	uint32_t layout;
+	/* two-phase CONCAT (airs_cuda_api.cu): the kernels of a phase return at once unless
+	 * (*gate != 0) == gate_want; NULL: no gate */
+	const uint32_t *gate;
+	uint32_t gate_want;
+};
+
+/* what the two-phase CONCAT path adds: temporary slots, the job table rewritten onto them */
+struct AirsConcat {
+	const struct airs_job *jobs;  /* the caller's jobs */
+	struct airs_job *slot_jobs;   /* n_jobs copies whose dst_offset / dst_frame_stride address the temporary slots */
+	const uint32_t *results;
+	const uint32_t *result_job;   /* the job of every frame (airs_plan_kernel) */
+	uint64_t *out_offsets;
+	uint8_t *tmp;
+	uint8_t *dst;
+	uint32_t *flag;               /* set when the path has to be abandoned: tmp or dst too small */
+	uint64_t *sums;               /* airs_concat_scratch_bytes(): tile sums of the scans ... */
+	uint32_t *big_list;           /* ... the frames whose streams a whole CTA copies ... */
+	uint32_t *n_big;              /* ... and their number */
+	uint64_t tmp_size;
+	uint64_t dst_size;
+	uint32_t n_jobs;
+	uint32_t n_results;
 };
 
 #ifdef __cplusplus
@@ -48,6 +71,9 @@ cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cu
 cudaError_t airs_encode_ctas_per_sm(int *out);
 cudaError_t airs_launch_small(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
+size_t airs_concat_scratch_bytes(uint32_t n_jobs, uint32_t n_results);
+cudaError_t airs_launch_concat_slots(const struct AirsConcat *c, cudaStream_t stream);
+cudaError_t airs_launch_concat_gather(const struct AirsConcat *c, unsigned int grid, cudaStream_t stream);
 #ifdef __cplusplus
 }
 #endif

@@ -88,7 +88,19 @@ struct airs_batch {
 	uint32_t n_results;          /* total number of frames */
 	uint32_t layout;             /* AIRS_LAYOUT_* */
 	uint32_t reserved;
+	void *tmp;                   /* CONCAT: temporary device memory, 16-byte aligned, or NULL (see below) */
+	uint64_t tmp_size;           /* bytes behind tmp */
 };
+
+/*
+ * CONCAT with temporary memory: the batch is encoded into temporary slots at the speed of the
+ * SLOTS layout, one scan turns sizes into offsets and a copy lays the streams out back to back.
+ * tmp must hold airs_cuda_concat_tmp_size(S) bytes, S = sum over the jobs of
+ * n_frames * dst_capacity.  Without tmp (or with too little of it, or when the streams do not
+ * all fit dst_size) the single-phase path runs: every frame is sized, then encoded at its final
+ * place - same bytes, no extra memory, about twice the work and contexts one after the other.
+ */
+size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results);
 
 /* 0 on success, else a negative value; airs_cuda_last_error() explains. */
 #define AIRS_OK              0

@@ -37,7 +37,7 @@ def test_struct_layouts():
     ctx = abi.CmpContext
     assert (ctx.magic.offset, ctx.params.offset, ctx.work_buf.offset, ctx.work_buf_size.offset,
             ctx.model_size.offset, ctx.identifier.offset, ctx.sequence_number.offset) == (0, 4, 48, 56, 60, 64, 72)
-    assert abi.JOB_DTYPE.itemsize == 120 and C.sizeof(abi.AirsBatch) == 88 and C.sizeof(abi.AirsHostBatch) == 96
+    assert abi.JOB_DTYPE.itemsize == 120 and C.sizeof(abi.AirsBatch) == 104 and C.sizeof(abi.AirsHostBatch) == 96
     assert abi.DEC_JOB_DTYPE.itemsize == 56 and abi.FRAME_INFO_DTYPE.itemsize == 32 and C.sizeof(abi.AirsDecBatch) == 56
 
 

@@ -39,6 +39,41 @@ def test_concat_layout(gpu, oracle, seed):
     jobgen.compare(want, got, js, "gpu-concat")
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_concat_two_phase(gpu, oracle, seed):
+    """CONCAT with temporary memory: SLOTS-style encoding into temporary slots, scan, copy - the
+    same bytes, offsets and results as the oracle loop (and as the single-phase path)."""
+    rng = np.random.default_rng(320 + seed)
+    js = jobgen.build_jobs(rng, 300, sizes=SMALL + [2048, 2049, 4099, 9000], max_frames=4,
+                           allow_invalid=True, layout=1)
+    want = jobgen.run_cpu(oracle, js)
+    tmp = gpu.concat_tmp_size(js["jobs"], js["n_results"])
+    got = gpu.run_jobs_device(js, concat_tmp=tmp)
+    jobgen.compare(want, got, js, "gpu-concat-two-phase")
+
+
+def test_concat_two_phase_gives_way(gpu, oracle):
+    """Too little temporary memory, or a destination that cannot hold all streams: the gate on the
+    device hands the batch to the single-phase path, which follows the reference loop through the
+    overflow (a frame that does not fit fails and its context goes on from there)."""
+    rng = np.random.default_rng(340)
+    js = jobgen.build_jobs(rng, 120, sizes=[64, 257, 2048, 4099], max_frames=4, layout=1,
+                           capacity_modes=["bound", "raw", "big"])
+    want = jobgen.run_cpu(oracle, js)
+    tmp = gpu.concat_tmp_size(js["jobs"], js["n_results"])
+    got = gpu.run_jobs_device(js, concat_tmp=tmp // 3)          # slots do not fit
+    jobgen.compare(want, got, js, "gpu-concat-small-tmp")
+    # the reference loop knows no bound of the concatenation; the single-phase path defines it
+    total = int(want[3][-1])
+    js2 = dict(js, dst_size=(total * 2 // 3 + 63) // 64 * 64)    # streams do not fit
+    one = gpu.run_jobs_device(js2)
+    assert any(int(r) == jobgen.abi.err("DST_TOO_SMALL") for r in one[1])
+    two = gpu.run_jobs_device(js2, concat_tmp=tmp)
+    assert np.array_equal(one[1], two[1]) and np.array_equal(one[3], two[3])
+    fit = int(js2["dst_size"])
+    assert np.array_equal(one[0][:fit], two[0][:fit])
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 def test_host_batch(gpu, oracle, layout):
     """airs_cuda_compress_batch_host: host buffers in, host buffers out."""

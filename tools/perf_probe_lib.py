@@ -30,7 +30,10 @@ def make_uniform_jobs(n_jobs, n_samples, n_frames, params_fn, cap=None, model=Fa
     return jobs, slot * n_frames * n_jobs, (fb * n_jobs if model else 0)
 
 def time_batch(name, data, jobs, dst_size, work_size, n_results, steps=5, warmup=2):
-    db = pkg.batch.DeviceBatch(data.view(torch.uint8).reshape(-1), jobs, dst_size, work_size, n_results)
+    layout = int(os.environ.get("AIRS_PROBE_LAYOUT", "0"))  # 1: CONCAT
+    tmp = pkg.batch.concat_tmp_size(jobs, n_results) if layout == 1 and os.environ.get("AIRS_PROBE_TMP") else 0
+    db = pkg.batch.DeviceBatch(data.view(torch.uint8).reshape(-1), jobs, dst_size, work_size, n_results, layout=layout,
+                               concat_tmp=tmp)
     for _ in range(warmup):
         db.run()
     torch.cuda.synchronize()
@@ -47,7 +50,7 @@ def time_batch(name, data, jobs, dst_size, work_size, n_results, steps=5, warmup
     B = in_bytes + out_bytes
     print(f"{name}: {med:.3f} ms (min {ms[0]:.3f}) in {in_bytes/2**30:.2f} GiB ratio {in_bytes/max(out_bytes,1):.2f} "
           f"input {in_bytes/med/1e6:.1f} GB/s  algorithmic {B/med/1e6:.1f} GB/s = {B/med/1e6/6531.6*100:.1f}% of 6531.6  errors {bad}", flush=True)
-    if os.environ.get("AIRS_PROBE_DECODE"):  # the same streams back through the decoder
+    if os.environ.get("AIRS_PROBE_DECODE") and layout == 0:  # the same streams back through the decoder
         dj = np.zeros(len(jobs), dtype=abi.DEC_JOB_DTYPE)
         for a_, b_ in (("src_offset", "dst_offset"), ("src_frame_stride", "dst_frame_stride"), ("src_size", "dst_capacity"),
                        ("dst_offset", "src_offset"), ("dst_frame_stride", "src_frame_stride"), ("dst_capacity", "src_size"),
