@@ -844,6 +844,72 @@ __device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, u
 	}
 }
 
+/* The arithmetic encoders with memory: every code word is computed once.  slow_codes() leaves
+ * the code words of the segments whose bit is set in `rows` in cw[] - per sample the low 32
+ * bits, then the high 16 bits | length << 16 (a code word has at most 48 bits) - and returns
+ * the bit counts like slow_bits(); slow_put_codes() stages the 8 samples of one segment from
+ * there, the two code words of a pair as one string where they fit 64 bits. */
+template <int ENC>
+__device__ __forceinline__ void slow_codes_t(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t rows,
+					     uint32_t *cw, uint32_t &b01, uint32_t &b23)
+{
+	b01 = 0;
+	b23 = 0;
+#pragma unroll 4
+	for (uint32_t k = 0; k < n_words; k++) {
+		if (!((rows >> (k >> 2)) & 1u)) /* segment k / 4 is not asked for */
+			continue;
+		const uint32_t z = zigzag2(d[k]);
+		uint32_t n = 0;
+#pragma unroll
+		for (uint32_t h = 0; h < 2u; h++) {
+			uint32_t c, cl, rw, rl;
+			airs_encode_mapped<ENC>(e, h ? z >> 16 : z & 0xFFFFu, c, cl, rw, rl);
+			if (ENC == CMP_ENCODER_GOLOMB_ZERO) { /* one string of at most 32 bits */
+				cw[4u * k + 2u * h] = c;
+				cw[4u * k + 2u * h + 1u] = cl << 16;
+			} else { /* codeword then raw escape bits */
+				cw[4u * k + 2u * h] = __funnelshift_lc(0u, c, rl) | rw;
+				cw[4u * k + 2u * h + 1u] = __funnelshift_lc(c, 0u, rl) | ((cl + rl) << 16);
+			}
+			n += cl + rl;
+		}
+		n = (k & 4u) ? n << 16 : n;
+		if (k < 8u)
+			b01 += n;
+		else
+			b23 += n;
+	}
+}
+
+__device__ __forceinline__ void slow_codes(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t rows,
+					   uint32_t *cw, uint32_t &b01, uint32_t &b23)
+{
+	if (e.type == CMP_ENCODER_GOLOMB_ZERO)
+		slow_codes_t<CMP_ENCODER_GOLOMB_ZERO>(e, d, n_words, rows, cw, b01, b23);
+	else
+		slow_codes_t<CMP_ENCODER_GOLOMB_MULTI>(e, d, n_words, rows, cw, b01, b23);
+}
+
+__device__ __forceinline__ void slow_put_codes(const uint32_t *cw, uint32_t *stg, uint32_t start)
+{
+	int32_t ne = -(int32_t)start;
+#pragma unroll
+	for (uint32_t k = 0; k < 4u; k++) {
+		const uint32_t lo0 = cw[4u * k], hn0 = cw[4u * k + 1u], lo1 = cw[4u * k + 2u], hn1 = cw[4u * k + 3u];
+		const uint32_t n0 = hn0 >> 16, n1 = hn1 >> 16;
+		if (n0 + n1 <= 64u) {
+			const unsigned long long c0 = (unsigned long long)(hn0 & 0xFFFFu) << 32 | lo0;
+			const unsigned long long c1 = (unsigned long long)(hn1 & 0xFFFFu) << 32 | lo1;
+			const unsigned long long m = (c0 << n1) | c1;
+			put_unit(stg, ne, (uint32_t)(m >> 32), (uint32_t)m, n0 + n1);
+		} else {
+			put_unit(stg, ne, hn0 & 0xFFFFu, lo0, n0);
+			put_unit(stg, ne, hn1 & 0xFFFFu, lo1, n1);
+		}
+	}
+}
+
 /* One scan for the four segments of every thread: b01 = bits of segment 0 |
  * segment 1 << 16, b23 likewise.  Stream order inside a warp: segment 0 of all
  * lanes, then segment 1 of all lanes, ...  Returns the bits of the whole tile
@@ -1294,6 +1360,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			 * must not cost the table arm its registers. */
 			uint32_t d[SEG * 4];    /* biased residuals; plain ones in the rows encoded arithmetically */
 			uint32_t rstr[SEG * 3]; /* hi, lo, length of the strings of the rows on the table */
+			uint32_t cwords[SEG * 16]; /* code words of the other rows, computed once (slow_codes) */
 			uint32_t miss = 0;      /* bit j: row j is encoded arithmetically */
 #pragma unroll
 			for (int j = 0; j < SEG; j++)
@@ -1344,7 +1411,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 				if (first) /* the stand-in goes, the sample comes back (its row is never on the table) */
 					d[0] = (d[0] & 0xFFFF0000u) | sample_at(P.src, P.dtype, 0);
 				uint32_t a01, a23;
-				slow_bits(P.enc, d, 4u * SEG, miss, a01, a23);
+				slow_codes(P.enc, d, 4u * SEG, miss, cwords, a01, a23);
 				if (PARTIAL) {
 					a01 = (v[0] ? a01 & 0xFFFFu : 0u) | (v[1] ? a01 & 0xFFFF0000u : 0u);
 					if (SEG > 2)
@@ -1357,7 +1424,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 					const uint32_t pj = j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3];
 					if ((miss >> j) & 1u) {
 						if (!PARTIAL || (j < nseg && pw + 32u * j + lane < n_pieces))
-							slow_put(P.enc, d + 4 * j, stg, pj);
+							slow_put_codes(cwords + 16u * j, stg, pj);
 					} else {
 						int32_t ne = -(int32_t)pj;
 						put_unit(stg, ne, rstr[3u * j], rstr[3u * j + 1u], rstr[3u * j + 2u]);
@@ -1780,6 +1847,7 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 				table = __all_sync(kFull, (qchk & 128u) == 0u);
 			}
 			uint32_t d[16];
+			uint32_t cwords[64]; /* arithmetic path: the code words of the 32 samples, computed once */
 			uint32_t b01, b23;
 			if (table) {
 				b01 = (sn_[0] + n_first) | (sn_[1] << 16);
@@ -1793,7 +1861,7 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 						d[4 * j + k] = __vadd2(u[j][k], negRb);
 				if (first)
 					d[0] = (d[0] & 0xFFFF0000u) | (w[0][0] & 0xFFFFu);
-				slow_bits(P.enc, d, 16u, 0xFu, b01, b23);
+				slow_codes(P.enc, d, 16u, 0xFu, cwords, b01, b23);
 				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
 				b23 = (v[2] ? b23 & 0xFFFFu : 0u) | (v[3] ? b23 & 0xFFFF0000u : 0u);
 			}
@@ -1832,7 +1900,7 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 #pragma unroll 1
 				for (uint32_t j = 0; j < 4u; j++)
 					if (p0 + 32u * j + lane < pieces)
-						slow_put(P.enc, d + 4 * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
+						slow_put_codes(cwords + 16u * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
 			}
 			warp_copy_out(ws, o, c, tile_bits);
 		}
