@@ -33,6 +33,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "airs_device.cuh"
@@ -156,10 +157,14 @@ struct Reader {
 	}
 	__device__ __forceinline__ void open(const uint8_t *stream, uint32_t size, uint32_t start_byte)
 	{
+		open_bits(stream, size, 8u * start_byte);
+	}
+	__device__ __forceinline__ void open_bits(const uint8_t *stream, uint32_t size, uint32_t start_bit)
+	{
 		const uint32_t lead = (uint32_t)((uintptr_t)stream & 3u);
 		wb = reinterpret_cast<const uint32_t *>(stream - lead);
 		limit = lead + size;
-		const uint32_t bit = 8u * (lead + start_byte), i = bit >> 5, sk = bit & 31u;
+		const uint32_t bit = 8u * lead + start_bit, i = bit >> 5, sk = bit & 31u;
 		buf = ((uint64_t)fetch(i) << 32 | fetch(i + 1u)) << sk;
 		cnt = 64u - sk;
 		next = i + 2u;
@@ -320,15 +325,21 @@ __device__ void decode_samples(Reader &rd, const DecConst &dc, uint32_t n, bool 
 	}
 }
 
-__global__ void __launch_bounds__(64) dec_stream_kernel(DecLaunch b)
-{
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= b.n_results)
-		return;
-	DecFrame fr = b.frames[k];
-	airs_frame_info inf;
-	memset(&inf, 0, sizeof(inf));
+/* what both stream kernels need of a frame: header read and checked, code constants */
+struct StreamPlan {
+	const uint8_t *s;
+	uint8_t *out;
+	uint32_t err, hdr_size, csize, n, pre, enc, tail;
+	bool c32, diff;
+	DecConst dc;
+};
 
+/* header: ref cmp_hdr_deserialize, header.c:89-134; then what the encoder can have written (ref
+ * cmp.c:265-279, cmp_initialise cmp.c:152-209) */
+__device__ void plan_stream(const DecLaunch &b, uint32_t k, DecFrame &fr, airs_frame_info &inf, StreamPlan &sp)
+{
+	memset(&inf, 0, sizeof(inf));
+	memset(&sp, 0, sizeof(sp));
 	if (fr.job >= b.n_jobs) { /* a result index no job claims */
 		fr.err = DEC_ERR(CMP_ERR_GENERIC);
 		fr.job = 0;
@@ -336,9 +347,9 @@ __global__ void __launch_bounds__(64) dec_stream_kernel(DecLaunch b)
 	const airs_dec_job job = b.jobs[fr.job];
 	const uint8_t *s = b.src + fr.off;
 	uint32_t err = fr.err;
-
-	/* header: ref cmp_hdr_deserialize, header.c:89-134 */
 	uint32_t hdr_size = 0, csize = 0, n = 0, pre = 0, enc = 0;
+	DecConst &dc = sp.dc;
+
 	if (!err && (!b.src || !b.dst))
 		err = DEC_ERR(!b.src ? CMP_ERR_SRC_NULL : CMP_ERR_DST_NULL);
 	if (!err && job.dtype > AIRS_DTYPE_U16)
@@ -369,12 +380,9 @@ __global__ void __launch_bounds__(64) dec_stream_kernel(DecLaunch b)
 		}
 		inf.header_size = err ? 0 : (uint8_t)hdr_size;
 	}
-	/* what the encoder can have written (ref cmp.c:265-279, cmp_initialise cmp.c:152-209) */
-	DecConst dc;
-	memset(&dc, 0, sizeof(dc));
+	const uint32_t tail = inf.checksum_enabled ? 4u : 0u;
 	if (!err) {
 		n = inf.original_size / 2u;
-		const uint32_t tail = inf.checksum_enabled ? 4u : 0u;
 		if (inf.version != kVersionWord || (inf.original_size & 1u) || n == 0u || pre > CMP_PREPROCESS_MODEL ||
 		    enc > CMP_ENCODER_GOLOMB_MULTI || csize < hdr_size + tail ||
 		    (pre == CMP_PREPROCESS_MODEL && (inf.model_rate > 16u || inf.sequence_number == 0u)))
@@ -401,34 +409,214 @@ __global__ void __launch_bounds__(64) dec_stream_kernel(DecLaunch b)
 			}
 		}
 	}
-	if (!err) {
-		const uint32_t tail = inf.checksum_enabled ? 4u : 0u;
-		uint8_t *out = b.dst + job.dst_offset + (uint64_t)(k - job.first_result) * job.dst_frame_stride;
-		const bool c32 = job.dtype == AIRS_DTYPE_I16_IN_I32, diff = pre == CMP_PREPROCESS_DIFF;
-		bool bad = false;
-		Reader rd;
-		rd.open(s, csize - tail, hdr_size);
-		if (enc == CMP_ENCODER_UNCOMPRESSED)
-			decode_samples<CMP_ENCODER_UNCOMPRESSED>(rd, dc, n, diff, out, c32, bad);
-		else if (enc == CMP_ENCODER_GOLOMB_ZERO)
-			decode_samples<CMP_ENCODER_GOLOMB_ZERO>(rd, dc, n, diff, out, c32, bad);
-		else
-			decode_samples<CMP_ENCODER_GOLOMB_MULTI>(rd, dc, n, diff, out, c32, bad);
-		/* the code words are padded to a byte, then comes the trailer (ref cmp.c:314-332) */
-		if (bad || hdr_size + (rd.used + 7u) / 8u + tail != csize)
-			err = DEC_ERR(AIRS_DEC_ERR_CORRUPT);
-		if (tail)
-			fr.trailer = (uint32_t)be16(s + csize - 4u) << 16 | be16(s + csize - 2u);
-	}
-	fr.err = err;
+	if (!err && tail)
+		fr.trailer = (uint32_t)be16(s + csize - 4u) << 16 | be16(s + csize - 2u);
+	sp.s = s;
+	sp.out = b.dst ? b.dst + job.dst_offset + (uint64_t)(k - job.first_result) * job.dst_frame_stride : nullptr;
+	sp.err = err;
+	sp.hdr_size = hdr_size;
+	sp.csize = csize;
+	sp.n = n;
+	sp.pre = pre;
+	sp.enc = enc;
+	sp.tail = tail;
+	sp.c32 = job.dtype == AIRS_DTYPE_I16_IN_I32;
+	sp.diff = pre == CMP_PREPROCESS_DIFF;
 	fr.n = n;
 	fr.pre = (uint8_t)pre;
 	fr.seq = inf.sequence_number;
 	fr.rate = inf.model_rate;
 	fr.cks = inf.checksum_enabled;
+}
+
+/* one thread per frame: the kernel for batches of many frames */
+__global__ void __launch_bounds__(64) dec_stream_kernel(DecLaunch b)
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= b.n_results)
+		return;
+	DecFrame fr = b.frames[k];
+	airs_frame_info inf;
+	StreamPlan sp;
+	plan_stream(b, k, fr, inf, sp);
+	uint32_t err = sp.err;
+	if (!err) {
+		bool bad = false;
+		Reader rd;
+		rd.open(sp.s, sp.csize - sp.tail, sp.hdr_size);
+		if (sp.enc == CMP_ENCODER_UNCOMPRESSED)
+			decode_samples<CMP_ENCODER_UNCOMPRESSED>(rd, sp.dc, sp.n, sp.diff, sp.out, sp.c32, bad);
+		else if (sp.enc == CMP_ENCODER_GOLOMB_ZERO)
+			decode_samples<CMP_ENCODER_GOLOMB_ZERO>(rd, sp.dc, sp.n, sp.diff, sp.out, sp.c32, bad);
+		else
+			decode_samples<CMP_ENCODER_GOLOMB_MULTI>(rd, sp.dc, sp.n, sp.diff, sp.out, sp.c32, bad);
+		/* the code words are padded to a byte, then comes the trailer (ref cmp.c:314-332) */
+		if (bad || sp.hdr_size + (rd.used + 7u) / 8u + sp.tail != sp.csize)
+			err = DEC_ERR(AIRS_DEC_ERR_CORRUPT);
+	}
+	fr.err = err;
 	b.frames[k] = fr;
 	if (b.info)
 		b.info[k] = inf;
+}
+
+/*
+ * One WARP per frame: the kernel for batches of few frames, where a thread per frame leaves the
+ * device empty.  Code words are self-delimiting, and a decoder that starts inside a code word
+ * falls into step with the true sequence of code word boundaries after a few symbols.  The
+ * stream is taken in windows of 32 x 128 bits: lane l decodes from bit 128 l of the window on
+ * (lane 0 from the exact start) until it passes the end of its 128 bits, and remembers where
+ * it ended.  Then every lane whose predecessor ended somewhere else than where it started
+ * decodes again from there, until nothing changes any more - lane l is final after l + 1
+ * rounds at the latest, in practice after two.  The symbols wait in shared memory, one row
+ * per lane; the warp writes them out side by side (running sum for DIFF frames by a warp scan).
+ */
+constexpr uint32_t kSubBits = 128;             /* bits per lane and window: at most 128 symbols */
+constexpr uint32_t kSymStride = kSubBits + 2u; /* halfwords per row: rows start in different banks */
+constexpr uint32_t kWarpsPerCta = 4;
+
+template <int ENC>
+__device__ __forceinline__ uint32_t decode_run(const StreamPlan &sp, uint32_t start, uint32_t stop, uint32_t data_end,
+					       uint32_t max_sym, uint16_t *row, uint32_t &cnt, bool &bad)
+{
+	cnt = 0;
+	bad = false;
+	if (start >= stop || start >= data_end)
+		return start;
+	Reader rd;
+	rd.open_bits(sp.s, sp.csize - sp.tail, 8u * sp.hdr_size + start);
+	uint32_t pos = start;
+	while (pos < stop && pos < data_end && cnt < max_sym) {
+		const uint32_t r = decode_one<ENC>(rd, sp.dc, bad);
+		if (row)
+			row[cnt] = (uint16_t)r;
+		cnt++;
+		pos = start + rd.used;
+	}
+	return pos;
+}
+
+template <int ENC>
+__device__ uint32_t decode_stream_warp(const StreamPlan &sp, uint16_t (*sym)[kSymStride])
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t data_end = 8u * (sp.csize - sp.tail - sp.hdr_size); /* code word bits, padding included */
+	const uint32_t n = sp.n;
+	uint32_t wstart = 0; /* bits from the first code word to the start of the window: exact */
+	uint32_t done = 0;   /* symbols written */
+	uint32_t prev = 0;   /* DIFF: the sample in front */
+	uint32_t end_bits = 0;
+	bool bad = false;
+
+	while (done < n) {
+		if (wstart >= data_end) { /* the stream ends before the samples do */
+			bad = true;
+			break;
+		}
+		const uint32_t stop = wstart + (lane + 1u) * kSubBits;
+		uint32_t start = wstart + lane * kSubBits, endp = 0, cnt = 0;
+		bool lbad = false, dirty = true;
+		for (uint32_t round = 0; round < 33u; round++) {
+			if (dirty)
+				endp = decode_run<ENC>(sp, start, stop, data_end, kSubBits, sym[lane], cnt, lbad);
+			const uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, endp, 1);
+			const uint32_t want = lane == 0u ? wstart : pe;
+			dirty = want != start;
+			start = want;
+			if (!__any_sync(0xFFFFFFFFu, dirty))
+				break;
+		}
+		/* symbols of the window: exclusive prefix of the counts */
+		uint32_t inc = cnt;
+		for (uint32_t d = 1; d < 32u; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+			if (lane >= d)
+				inc += t;
+		}
+		const uint32_t excl = inc - cnt, total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+		const uint32_t take = min(total, n - done);
+		if (lbad && excl < take)
+			bad = true;
+		__syncwarp();
+		for (uint32_t i0 = 0; i0 < take; i0 += 32u) {
+			const uint32_t i = i0 + lane;
+			/* the row of symbol i: the last one that starts at or in front of it */
+			uint32_t row = 0;
+			for (uint32_t step = 16u; step; step >>= 1) {
+				const uint32_t cand = row + step;
+				const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, cand & 31u);
+				if (cand < 32u && ex <= i)
+					row = cand;
+			}
+			const uint32_t ex_row = __shfl_sync(0xFFFFFFFFu, excl, row);
+			uint32_t v = i < take ? sym[row][i - ex_row] : 0u;
+			if (sp.diff) { /* ref diff_process, preprocess.c:284-290, undone by a running sum */
+				for (uint32_t d = 1; d < 32u; d <<= 1) {
+					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+					if (lane >= d)
+						v += t;
+				}
+				v = (v + prev) & 0xFFFFu;
+				prev = __shfl_sync(0xFFFFFFFFu, v, 31);
+			}
+			if (i < take) {
+				if (sp.c32)
+					reinterpret_cast<uint32_t *>(sp.out)[done + i] = sext16(v);
+				else
+					reinterpret_cast<uint16_t *>(sp.out)[done + i] = (uint16_t)v;
+			}
+		}
+		__syncwarp();
+		done += take;
+		if (done == n) { /* where the last symbol ends: the lane that holds it knows, or counts again */
+			uint32_t row = 0;
+			for (uint32_t step = 16u; step; step >>= 1) {
+				const uint32_t cand = row + step;
+				const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, cand & 31u);
+				if (cand < 32u && ex <= take - 1u)
+					row = cand;
+			}
+			uint32_t e = endp;
+			if (lane == row && take - excl != cnt) {
+				uint32_t c2;
+				bool b2;
+				e = decode_run<ENC>(sp, start, stop, data_end, take - excl, nullptr, c2, b2);
+			}
+			end_bits = __shfl_sync(0xFFFFFFFFu, e, row);
+		}
+		wstart = __shfl_sync(0xFFFFFFFFu, endp, 31);
+	}
+	if (__any_sync(0xFFFFFFFFu, bad) || sp.hdr_size + (end_bits + 7u) / 8u + sp.tail != sp.csize)
+		return DEC_ERR(AIRS_DEC_ERR_CORRUPT);
+	return 0;
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) dec_stream_warp_kernel(DecLaunch b)
+{
+	__shared__ uint16_t sym[kWarpsPerCta][32][kSymStride];
+	const uint32_t k = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (k >= b.n_results)
+		return;
+	DecFrame fr = b.frames[k];
+	airs_frame_info inf;
+	StreamPlan sp;
+	plan_stream(b, k, fr, inf, sp); /* every lane: the loads are broadcasts */
+	uint32_t err = sp.err;
+	if (!err) {
+		uint16_t (*rows)[kSymStride] = sym[threadIdx.x >> 5];
+		if (sp.enc == CMP_ENCODER_UNCOMPRESSED)
+			err = decode_stream_warp<CMP_ENCODER_UNCOMPRESSED>(sp, rows);
+		else if (sp.enc == CMP_ENCODER_GOLOMB_ZERO)
+			err = decode_stream_warp<CMP_ENCODER_GOLOMB_ZERO>(sp, rows);
+		else
+			err = decode_stream_warp<CMP_ENCODER_GOLOMB_MULTI>(sp, rows);
+	}
+	if ((threadIdx.x & 31u) == 0) {
+		fr.err = err;
+		b.frames[k] = fr;
+		if (b.info)
+			b.info[k] = inf;
+	}
 }
 
 /* ------------------------------------------------------------------------- */
@@ -661,7 +849,12 @@ extern "C" int airs_cuda_decompress_batch(const struct airs_dec_batch *bt, void 
 	e = cudaMemsetAsync(l.frames, 0xFF, sizeof(DecFrame) * (size_t)bt->n_results, stream);
 	if (e == cudaSuccess) {
 		dec_index_kernel<<<(bt->n_jobs + 127u) / 128u, 128, 0, stream>>>(l);
-		dec_stream_kernel<<<(bt->n_results + 63u) / 64u, 64, 0, stream>>>(l);
+		/* a warp per frame until a thread per frame fills the device */
+		const char *ov = getenv("AIRS_DEC_WARP_MAX"); /* development switch */
+		if (bt->n_results < (ov ? (uint32_t)atoi(ov) : 64u * 1024u))
+			dec_stream_warp_kernel<<<(bt->n_results + kWarpsPerCta - 1u) / kWarpsPerCta, 32 * kWarpsPerCta, 0, stream>>>(l);
+		else
+			dec_stream_kernel<<<(bt->n_results + 63u) / 64u, 64, 0, stream>>>(l);
 		dec_iwt_kernel<<<bt->n_results, 256, 0, stream>>>(l);
 		dec_model_kernel<<<bt->n_jobs * l.split, 256, 0, stream>>>(l);
 		dec_verify_kernel<<<(bt->n_results + 63u) / 64u, 64, 0, stream>>>(l);

@@ -201,3 +201,16 @@ def test_round_trip_config4_size(gpu, pkg):
                             primary_encoder_outlier=outl, checksum_enabled=1)
         same, ratio = _device_round_trip(pkg, gpu, x, 512, 1 << 20, 1, p)
         assert same, (pre, enc, g)
+
+
+def test_round_trip_many_short_frames(gpu, pkg):
+    """From 65536 frames on the decoder takes one thread per frame instead of one warp: 70000 chunks of
+    1 KiB, DIFF + both Golomb encoders, checksum on, through both containers."""
+    import torch
+    abi, synth = pkg.abi, pkg.synth
+    x = synth.chunks_torch(3, 0, 70000, 512, esc=4).view(-1).view(dtype=torch.uint8)
+    for enc, g, outl, dtype in [(1, 7, 0, 2), (2, 16, 60, 0)]:
+        p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=enc, primary_encoder_param=g,
+                            primary_encoder_outlier=outl, checksum_enabled=1)
+        same, ratio = _device_round_trip(pkg, gpu, x, 70000, 512, 1, p, dtype=dtype)
+        assert same, (enc, g, dtype)
