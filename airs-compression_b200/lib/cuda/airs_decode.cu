@@ -33,7 +33,6 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "airs_device.cuh"
@@ -850,8 +849,7 @@ extern "C" int airs_cuda_decompress_batch(const struct airs_dec_batch *bt, void 
 	if (e == cudaSuccess) {
 		dec_index_kernel<<<(bt->n_jobs + 127u) / 128u, 128, 0, stream>>>(l);
 		/* a warp per frame until a thread per frame fills the device */
-		const char *ov = getenv("AIRS_DEC_WARP_MAX"); /* development switch */
-		if (bt->n_results < (ov ? (uint32_t)atoi(ov) : 64u * 1024u))
+		if (bt->n_results < 64u * 1024u)
 			dec_stream_warp_kernel<<<(bt->n_results + kWarpsPerCta - 1u) / kWarpsPerCta, 32 * kWarpsPerCta, 0, stream>>>(l);
 		else
 			dec_stream_kernel<<<(bt->n_results + 63u) / 64u, 64, 0, stream>>>(l);
