@@ -269,10 +269,10 @@ __device__ __forceinline__ uint32_t sext16(uint32_t v)
  * preprocess.c:284-290: the first residual is the sample itself) */
 template <int ENC>
 __device__ void decode_samples(Reader &rd, const DecConst &dc, uint32_t n, bool diff, uint8_t *out, bool c32,
-			       bool &bad)
+			       bool &bad, uint32_t prev = 0)
 {
 	const bool vec = ((uintptr_t)out & 15u) == 0;
-	uint32_t prev = 0, i = 0;
+	uint32_t i = 0;
 
 	for (; i + 8u <= n; i += 8u) {
 		uint32_t pk[4];
@@ -505,6 +505,7 @@ __device__ uint32_t decode_stream_warp(const StreamPlan &sp, uint16_t (*sym)[kSy
 	uint32_t done = 0;   /* symbols written */
 	uint32_t prev = 0;   /* DIFF: the sample in front */
 	uint32_t end_bits = 0;
+	uint32_t slow_windows = 0; /* windows in a row that took many rounds */
 	bool bad = false;
 
 	while (done < n) {
@@ -515,7 +516,8 @@ __device__ uint32_t decode_stream_warp(const StreamPlan &sp, uint16_t (*sym)[kSy
 		const uint32_t stop = wstart + (lane + 1u) * kSubBits;
 		uint32_t start = wstart + lane * kSubBits, endp = 0, cnt = 0;
 		bool lbad = false, dirty = true;
-		for (uint32_t round = 0; round < 33u; round++) {
+		uint32_t round = 0;
+		for (; round < 33u; round++) {
 			if (dirty)
 				endp = decode_run<ENC>(sp, start, stop, data_end, kSubBits, sym[lane], cnt, lbad);
 			const uint32_t pe = __shfl_up_sync(0xFFFFFFFFu, endp, 1);
@@ -584,6 +586,21 @@ __device__ uint32_t decode_stream_warp(const StreamPlan &sp, uint16_t (*sym)[kSy
 			end_bits = __shfl_sync(0xFFFFFFFFu, e, row);
 		}
 		wstart = __shfl_sync(0xFFFFFFFFu, endp, 31);
+		slow_windows = round > 6u ? slow_windows + 1u : 0u;
+		if (slow_windows >= 3u && done < n) {
+			/* three windows in a row: the lanes keep correcting each other - code words of (nearly) fixed length, or raw
+			 * escape bits everywhere, never fall into step.  The rest of the stream is one
+			 * lane's work, straight to the destination. */
+			if (lane == 0u) {
+				Reader rd;
+				rd.open_bits(sp.s, sp.csize - sp.tail, 8u * sp.hdr_size + wstart);
+				decode_samples<ENC>(rd, sp.dc, n - done, sp.diff, sp.out + (size_t)done * (sp.c32 ? 4u : 2u), sp.c32,
+						    bad, prev);
+				end_bits = wstart + rd.used;
+			}
+			end_bits = __shfl_sync(0xFFFFFFFFu, end_bits, 0);
+			break;
+		}
 	}
 	if (__any_sync(0xFFFFFFFFu, bad) || sp.hdr_size + (end_bits + 7u) / 8u + sp.tail != sp.csize)
 		return DEC_ERR(AIRS_DEC_ERR_CORRUPT);
