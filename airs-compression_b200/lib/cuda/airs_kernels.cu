@@ -1960,7 +1960,26 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 {
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
 
-	if (j >= b.n_jobs || gate_closed(b))
+	if (gate_closed(b))
+		return;
+	/* the job of every frame (airs_checksum_kernel, the CONCAT copy): short jobs by their own
+	 * thread, long ones by the whole warp */
+	{
+		const uint32_t first = j < b.n_jobs ? b.jobs[j].first_result : 0u;
+		const uint32_t nf = j < b.n_jobs ? b.jobs[j].n_frames : 0u;
+		const bool wide = nf > 16u;
+		if (!wide)
+			for (uint32_t f = 0; f < nf && (uint64_t)first + f < b.n_results; f++)
+				b.result_job[first + f] = j;
+		for (uint32_t todo = __ballot_sync(kFull, wide); todo; todo &= todo - 1u) {
+			const int l = __ffs((int)todo) - 1;
+			const uint32_t fl = __shfl_sync(kFull, first, l), nl = __shfl_sync(kFull, nf, l);
+			const uint32_t jl = __shfl_sync(kFull, j, l);
+			for (uint32_t f = threadIdx.x & 31u; f < nl && (uint64_t)fl + f < b.n_results; f += 32u)
+				b.result_job[fl + f] = jl;
+		}
+	}
+	if (j >= b.n_jobs)
 		return;
 	JobPlan pl;
 	const airs_job &job = b.jobs[j];
@@ -1983,8 +2002,6 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	b.plans[j] = pl;
 	if (b.init_results && !b.ctx_io)
 		b.init_results[j] = pl.init_result;
-	for (uint32_t f = 0; f < job.n_frames && job.first_result + f < b.n_results; f++)
-		b.result_job[job.first_result + f] = j;
 	if (pl.flags & AIRS_PF_CHECKSUM)
 		atomicAdd(&b.ticket[4], 1u);
 	if (!listed) {
