@@ -206,3 +206,33 @@ def test_synth_torch_matches_numpy(gpu, pkg):
     a = np.stack([pkg.synth.frames(2, c, 5, 513) for c in range(3, 5)])
     b = pkg.synth.frames_torch(2, 3, 2, 5, 513, device="cuda").cpu().numpy().view(np.uint16)
     assert np.array_equal(a, b)
+
+
+def test_concat_two_phase_config2_size(gpu, pkg):
+    """Config 2 batched (32 contexts x 256 frames x 64 KiB, model update, checksum): the concatenation
+    of the two-phase CONCAT path holds exactly the streams the SLOTS layout produces, in result order."""
+    import torch
+    abi, synth = pkg.abi, pkg.synth
+    p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16,
+                        secondary_iterations=255, secondary_preprocessing=abi.PRE_MODEL,
+                        secondary_encoder_type=1, secondary_encoder_param=8, model_rate=8, checksum_enabled=1)
+    n_ctx, nf, n = 32, 256, 32768
+    x = synth.frames_torch(1, 0, n_ctx, nf, n).view(-1).view(dtype=torch.uint8)
+    js = _uniform_jobs(pkg, n_ctx, n, nf, p, cap=2 * n + 64)
+    slots = gpu.DeviceBatch(x, js["jobs"], js["dst_size"], js["work_size"], js["n_results"]).run()
+    tmp = gpu.concat_tmp_size(js["jobs"], js["n_results"])
+    cat = gpu.DeviceBatch(x, js["jobs"], js["dst_size"], js["work_size"], js["n_results"], layout=1,
+                          concat_tmp=tmp).run()
+    torch.cuda.synchronize()
+    res_s = slots.results.cpu().numpy().view(np.uint32)
+    res_c = cat.results.cpu().numpy().view(np.uint32)
+    assert np.array_equal(res_s, res_c) and not np.any(res_s > 0xFFFFFF80)
+    offs = cat.out_offsets.cpu().numpy()
+    assert np.array_equal(np.diff(offs), res_s.astype(np.int64))
+    # gather the slot streams on the device and compare with the concatenation
+    stride = int(js["jobs"][0]["dst_frame_stride"])
+    sizes = torch.from_numpy(res_s.astype(np.int64)).cuda()
+    starts = torch.arange(js["n_results"], device="cuda", dtype=torch.int64) * stride
+    total = int(offs[-1])
+    idx = torch.repeat_interleave(starts - torch.from_numpy(offs[:-1]).cuda(), sizes) + torch.arange(total, device="cuda")
+    assert torch.equal(slots.dst[idx], cat.dst[:total])
