@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-round-trip", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -304,6 +305,39 @@ def main():
                       "what": "streams of the last timed step -> airs_cuda_decompress_batch -> compared with the input, all ranks"}
         del dec
 
+    # ---- N > 1: the epilogue of SURVEY.md 8e, reported apart from the metric - every rank lays a part
+    # of its shard out as ONE concatenated stream (CONCAT layout, device-wide scan), then sizes and
+    # streams are gathered over NCCL so that every rank holds the whole output in rank order
+    gather = None
+    if world > 1 and not args.no_gather:
+        try:
+            g_units = min(units, 128) if args.workload == "c2" else min(units, 1 << 17)
+            wg = build_workload(pkg, args.workload, g_units, first_unit, device=device)
+            gdata = wg["data"].view(torch.uint8).reshape(-1)
+            tmp = pkg.batch.concat_tmp_size(wg["jobs"], wg["n_results"])
+            cb = pkg.batch.DeviceBatch(gdata, wg["jobs"], gdata.numel(), wg["work_size"], wg["n_results"],
+                                       layout=abi.LAYOUT_CONCAT, device=device, concat_tmp=tmp)
+            cb.run()
+            torch.cuda.synchronize(device)
+            total = int(cb.out_offsets[-1].item())
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            sizes_all, counts = pkg.parallel.allgather_sizes(cb.results)
+            streams_all, offs = pkg.parallel.allgather_streams(cb.dst[:total])
+            g1.record(stream)
+            barrier()
+            tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            ok = int(streams_all.numel()) == int(sizes_all.to(torch.int64).clamp(min=0).sum().item())
+            gather = {"contexts_or_chunks_per_rank": g_units, "frames": int(sizes_all.numel()),
+                      "gathered_bytes": int(streams_all.numel()), "ms": float(tg[0]),
+                      "gbs": streams_all.numel() / (float(tg[0]) * 1e-3) / 1e9, "sizes_match_streams": ok,
+                      "what": "CONCAT layout per rank, then all_gather of sizes and streams (NCCL), max over ranks"}
+            del cb, streams_all
+        except Exception as exc:  # the metric line must survive a failing epilogue
+            gather = {"error": repr(exc)[:200]}
+
     # ---- end to end through the C-ABI with HOST buffers (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -385,6 +419,8 @@ def main():
         line["e2e"] = e2e
     if round_trip:
         line["config"]["round_trip"] = round_trip
+    if gather:
+        line["config"]["gather"] = gather
     if world == 1 and not args.no_cpu:
         gbs, info, js, (cdst, cres), _ = cpu_reference_run(pkg, args.workload, 1, 0, target_s=args.cpu_seconds)
         line["cpu_baseline"] = info
