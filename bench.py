@@ -341,47 +341,50 @@ def main():
     # ---- end to end through the C-ABI with HOST buffers (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
-        # a quarter of the device-resident workload (c2: 222 contexts = 3.7 GB of samples per step)
-        e_units = max(1, min(units, max(8, units // 4) if args.workload == "c2" else 1 << 17))
-        we = build_workload(pkg, args.workload, e_units, first_unit, device=device)
-        src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
-        src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
-        cap_total = we["dst_size"]
-        dst_h = torch.empty(cap_total, dtype=torch.uint8).pin_memory()
-        jobs_h = np.ascontiguousarray(we["jobs"])
-        results_h = np.zeros(we["n_results"], dtype=np.uint32)
-        init_h = np.zeros(e_units, dtype=np.uint32)
-        offs_h = np.zeros(we["n_results"] + 1, dtype=np.uint64)
-        import ctypes as C
-        hb = abi.AirsHostBatch()
-        hb.src, hb.src_size = src_h.data_ptr(), src_h.numel()
-        hb.dst, hb.dst_size = dst_h.data_ptr(), dst_h.numel()
-        hb.work, hb.work_size = None, we["work_size"]
-        hb.jobs, hb.results, hb.init_results = jobs_h.ctypes.data, results_h.ctypes.data, init_h.ctypes.data
-        hb.out_offsets = offs_h.ctypes.data
-        # independent chunks: CONCAT (only the streams travel back); multi-frame contexts: SLOTS
-        e_layout = abi.LAYOUT_CONCAT if args.workload == "c3" else abi.LAYOUT_SLOTS
-        hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], e_layout
-        e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
-        torch.cuda.synchronize(device)
-        dt = time.perf_counter() - t0
-        td = torch.tensor([dt], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        e_in = we["n_samples_total"] * 2
-        e2e = {"value": e_in * world * e_steps / float(td[0]) / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(src_h.numel() + jobs_h.nbytes),
-               "d2h_bytes_per_step": (int(offs_h[-1]) + offs_h.nbytes if e_layout == abi.LAYOUT_CONCAT
-                                      else dst_h.numel()) + results_h.nbytes + init_h.nbytes,
-               "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, %s layout)" % ("CONCAT" if e_layout else "SLOTS"),
-               "timing": "host wall clock, max over ranks, %d steps" % e_steps}
-        lib.airs_cuda_release_cache()
+        try:
+            # a quarter of the device-resident workload (c2: 222 contexts = 3.7 GB of samples per step)
+            e_units = max(1, min(units, max(8, units // 4) if args.workload == "c2" else 1 << 17))
+            we = build_workload(pkg, args.workload, e_units, first_unit, device=device)
+            src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
+            src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
+            cap_total = we["dst_size"]
+            dst_h = torch.empty(cap_total, dtype=torch.uint8).pin_memory()
+            jobs_h = np.ascontiguousarray(we["jobs"])
+            results_h = np.zeros(we["n_results"], dtype=np.uint32)
+            init_h = np.zeros(e_units, dtype=np.uint32)
+            offs_h = np.zeros(we["n_results"] + 1, dtype=np.uint64)
+            import ctypes as C
+            hb = abi.AirsHostBatch()
+            hb.src, hb.src_size = src_h.data_ptr(), src_h.numel()
+            hb.dst, hb.dst_size = dst_h.data_ptr(), dst_h.numel()
+            hb.work, hb.work_size = None, we["work_size"]
+            hb.jobs, hb.results, hb.init_results = jobs_h.ctypes.data, results_h.ctypes.data, init_h.ctypes.data
+            hb.out_offsets = offs_h.ctypes.data
+            # independent chunks: CONCAT (only the streams travel back); multi-frame contexts: SLOTS
+            e_layout = abi.LAYOUT_CONCAT if args.workload == "c3" else abi.LAYOUT_SLOTS
+            hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], e_layout
+            e_steps = max(3, min(args.steps, 10))
+            for _ in range(2):
+                assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
+            torch.cuda.synchronize(device)
+            dt = time.perf_counter() - t0
+            td = torch.tensor([dt], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            e_in = we["n_samples_total"] * 2
+            e2e = {"value": e_in * world * e_steps / float(td[0]) / 1e9, "unit": "GB/s",
+                   "h2d_bytes_per_step": int(src_h.numel() + jobs_h.nbytes),
+                   "d2h_bytes_per_step": (int(offs_h[-1]) + offs_h.nbytes if e_layout == abi.LAYOUT_CONCAT
+                                          else dst_h.numel()) + results_h.nbytes + init_h.nbytes,
+                   "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, %s layout)" % ("CONCAT" if e_layout else "SLOTS"),
+                   "timing": "host wall clock, max over ranks, %d steps" % e_steps}
+            lib.airs_cuda_release_cache()
+        except Exception as exc:  # the metric line must survive (host memory, pinning)
+            e2e = {"error": repr(exc)[:200]}
 
     if rank != 0:
         if world > 1:
