@@ -110,6 +110,11 @@ class AirsDecBatch(C.Structure):
                 ("n_jobs", C.c_uint32), ("n_results", C.c_uint32)]
 
 
+STATS_DTYPE = np.dtype([("sum_mapped", "<u8"), ("n_samples", "<u4"), ("max_mapped", "<u4"),
+                        ("log2_hist", "<u4", (17,)), ("reserved", "<u4")])
+assert STATS_DTYPE.itemsize == 88
+
+
 def dec_err(name):
     return (0x100000000 - DEC_ERRORS[name]) & 0xFFFFFFFF
 

@@ -200,3 +200,23 @@ def decode_jobs_for(jobs, results, out_offsets=None):
         dj[j]["first_result"] = first
         dst_off += frame * nf
     return dj, dst_off + 64, int(sum(int(j["n_frames"]) for j in jobs))
+
+
+def residual_stats(src, jobs, device="cuda:0"):
+    """Per job: sum / count / maximum / log2 histogram of the zig-zag mapped residuals of its first
+    frame (airs_cuda_residual_stats).  src, jobs: device tensors or host arrays.  Returns a numpy
+    record array of abi.STATS_DTYPE."""
+    lib = load_library()
+    dev = torch.device(device)
+    s = src if isinstance(src, torch.Tensor) else _dev_u8(src, dev)
+    n_jobs = len(jobs)
+    j = jobs if isinstance(jobs, torch.Tensor) else _dev_u8(jobs, dev)
+    out = torch.zeros(max(n_jobs, 1) * abi.STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.airs_cuda_residual_stats(C.c_void_p(s.data_ptr()), C.c_void_p(j.data_ptr()), n_jobs,
+                                          C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError("airs_cuda_residual_stats failed (%d): %s" % (rc, lib.airs_cuda_last_error().decode()))
+    torch.cuda.synchronize(dev)
+    return out.cpu().numpy().view(abi.STATS_DTYPE)[:n_jobs]

@@ -16,7 +16,7 @@ EXPORTS = [
     "cmp_get_error_code", "cmp_get_error_message", "cmp_get_error_string",
     # include/airs_cuda.h
     "airs_cuda_device_count", "airs_cuda_concurrent_jobs", "airs_cuda_last_error", "airs_cuda_batch_scratch_size",
-    "airs_cuda_concat_tmp_size",
+    "airs_cuda_concat_tmp_size", "airs_cuda_residual_stats", "airs_cuda_golomb_param_for_mean",
     "airs_cuda_compress_batch", "airs_cuda_last_launch_count", "airs_cuda_compress_batch_host",
     "airs_cuda_release_cache",
     # include/airs_cuda_decode.h
@@ -72,6 +72,10 @@ def load_library():
     lib.airs_cuda_batch_scratch_size.restype = C.c_size_t
     lib.airs_cuda_concat_tmp_size.argtypes = [C.c_uint64, u32]
     lib.airs_cuda_concat_tmp_size.restype = C.c_size_t
+    lib.airs_cuda_residual_stats.argtypes = [vp, vp, u32, vp, vp]
+    lib.airs_cuda_residual_stats.restype = C.c_int
+    lib.airs_cuda_golomb_param_for_mean.argtypes = [C.c_uint64, u32]
+    lib.airs_cuda_golomb_param_for_mean.restype = u32
     lib.airs_cuda_compress_batch.argtypes = [C.POINTER(abi.AirsBatch), vp]
     lib.airs_cuda_compress_batch.restype = C.c_int
     lib.airs_cuda_last_launch_count.restype = C.c_int

@@ -166,6 +166,28 @@ struct airs_host_batch {
 };
 int airs_cuda_compress_batch_host(const struct airs_host_batch *batch);
 
+/*
+ * Residual statistics per job, for choosing encoder parameters (the reference leaves them to
+ * the user, lib/cmp.h:64-112).  For the first frame of every job, under the job's primary
+ * preprocessing (NONE: the samples; anything else: first differences, ref
+ * lib/compress/preprocess.c:268-290): sum, maximum and a log2 histogram of the zig-zag mapped
+ * residuals (ref map_to_unsigned, lib/compress/encoder.c:274-286).  Bin 0 counts the value 0, bin b
+ * the values 2^(b-1) .. 2^b - 1.  src, jobs and stats are device pointers; asynchronous on `stream`.
+ */
+struct airs_stats {
+	uint64_t sum_mapped;
+	uint32_t n_samples;
+	uint32_t max_mapped;
+	uint32_t log2_hist[17];
+	uint32_t reserved;
+};
+int airs_cuda_residual_stats(const void *src, const struct airs_job *jobs, uint32_t n_jobs,
+			     struct airs_stats *stats, void *stream);
+
+/* Golomb parameter g for a mean mapped residual sum / n: the code is shortest near g = mean * ln 2.
+ * Plain integer arithmetic (ln 2 = 45426 / 65536), 1 <= g <= 65535.  Host function. */
+uint32_t airs_cuda_golomb_param_for_mean(uint64_t sum_mapped, uint32_t n_samples);
+
 /* Release cached device staging buffers of this thread (optional). */
 void airs_cuda_release_cache(void);
 

@@ -38,7 +38,20 @@ def test_struct_layouts():
     assert (ctx.magic.offset, ctx.params.offset, ctx.work_buf.offset, ctx.work_buf_size.offset,
             ctx.model_size.offset, ctx.identifier.offset, ctx.sequence_number.offset) == (0, 4, 48, 56, 60, 64, 72)
     assert abi.JOB_DTYPE.itemsize == 120 and C.sizeof(abi.AirsBatch) == 104 and C.sizeof(abi.AirsHostBatch) == 96
+    assert abi.STATS_DTYPE.itemsize == 88
     assert abi.DEC_JOB_DTYPE.itemsize == 56 and abi.FRAME_INFO_DTYPE.itemsize == 32 and C.sizeof(abi.AirsDecBatch) == 56
+
+
+def test_golomb_param_for_mean(lib):
+    """g = mean * ln 2 in integers: 1 <= g <= 65535, monotone in the mean."""
+    assert lib.airs_cuda_golomb_param_for_mean(0, 0) == 1 and lib.airs_cuda_golomb_param_for_mean(0, 100) == 1
+    assert lib.airs_cuda_golomb_param_for_mean(100 * 23, 100) == int(23 * 0.693147)
+    assert lib.airs_cuda_golomb_param_for_mean(65535 * (1 << 20), 1 << 20) == int(65535 * 45426 / 65536)
+    last = 0
+    for mean in (1, 2, 3, 10, 100, 1000, 30000, 65535):
+        g = lib.airs_cuda_golomb_param_for_mean(mean * 977, 977)
+        assert 1 <= g <= 65535 and g >= last
+        last = g
 
 
 def test_error_helpers(lib):
