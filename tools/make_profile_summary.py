@@ -1,0 +1,69 @@
+"""Rebuilds profiles/r01_final_ncu_summary.md (bench section) and profiles/roofline_traffic.json from
+gpurun_out/r01_bench_final.ncu-rep and profiles/r01_bench_line.json.  Development tool, runs without a GPU."""
+import csv, json, subprocess, sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.chdir(ROOT)
+rep = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/r01_bench_final.ncu-rep'
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines())); h, u, v = rows[0], rows[1], rows[2]
+d = {h[i]: (v[i], u[i]) for i in range(len(h))}
+keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_ld.sum",
+        "l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.max", "sm__cycles_active.avg"]
+tab = "| metric | value | unit |\n|---|---|---|\n" + "".join(f"| {k} | {d[k][0]} | {d[k][1]} |\n" for k in keys if k in d)
+st = [(k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), float(d[k][0]))
+      for k in d if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and "not_issued" not in k]
+stalls = ", ".join("%s %.2f" % kv for kv in sorted(st, key=lambda x: -x[1])[:10])
+lines = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "26"], capture_output=True, text=True).stdout
+def G(x):
+    val, unit = d[x]
+    return float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[unit]
+traffic = G("dram__bytes_read.sum") + G("dram__bytes_write.sum")
+json.dump({"c2": {"units": 888, "dram_bytes_per_launch": traffic,
+                  "source": "profiles/r01_final_ncu_summary.md (ncu --set full, bench.py default workload)"}},
+          open("profiles/roofline_traffic.json", "w"))
+bl = json.load(open("profiles/r01_bench_line.json"))
+old = open("profiles/r01_final_ncu_summary.md").read()
+c4b = old[old.index("## c4b:"):]
+kt = float(d["gpu__time_duration.sum"][0])
+md = f"""# Round 1, final kernel - ncu --set full summaries
+
+Captured on a B200 with `ncu --set full --clock-control none --import-source on -k regex:airs_encode -c 1`
+after the same command had exited 0 without ncu.  Numbers taken under ncu are never bench values; the bench
+line of the same commit is `profiles/r01_bench_line.json` (value {bl['value']:.1f} GB/s input, roofline frac
+{bl['roofline']['frac']:.3f}, e2e {bl['e2e']['value']:.1f} GB/s, CPU reference {bl['cpu_baseline']['value']:.2f} GB/s on {bl['cpu_baseline']['cores']} cores, round trip of all
+{bl['config']['round_trip']['samples']} samples through the decoder identical: {bl['config']['round_trip']['identical']}).
+Launch list of the bench command (`--metrics gpu__time_duration.sum -k regex:airs -c 20`): `profiles/r01_launches_bench.csv` -
+per step one `airs_plan_kernel` (18 us under ncu, cold and serialised), one `airs_encode_kernel` (8.15 ms), and the
+`airs_small_kernel` / `airs_checksum_kernel` launches that find nothing to do in this workload (5 us, 3 us): the encode
+kernel is 99.7 % of a step, as in the device-timed run ({bl['ms_per_step']:.3f} ms per step).
+
+## bench.py default workload (config 2 batched: 888 contexts x 256 frames x 64 KiB, DIFF g16 -> MODEL g8)
+
+`python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-round-trip`, launch 5 of airs_encode_kernel ({kt:.3f} ms under ncu).
+
+{tab}
+Warp stall reasons (warps stalled per issue-active cycle): {stalls}
+
+DRAM traffic {traffic/1e9:.2f} GB per launch against {bl['roofline']['algorithmic_bytes_per_launch']/1e9:.2f} GB of algorithmic bytes (ratio {traffic/bl['roofline']['algorithmic_bytes_per_launch']:.2f}):
+the excess is model traffic - 888 models of 64 KiB (58 MB) are read and rewritten once per frame and do not all stay in
+the L2 next to the streaming samples, although their loads and stores carry an evict_last policy.  The kernel is bound
+by instruction issue (56 % of the issue slots; an experiment without block barriers raised that to 69 % and was
+slower, DESIGN.md section 4: what counts is the number of instructions) and by the LSU data pipe (table lookups with
+bank conflicts and the shared-memory reductions of the bit packing), not by DRAM.
+
+Top source lines (warp instructions / stall samples):
+
+```
+{lines}```
+
+"""
+open("profiles/r01_final_ncu_summary.md", "w").write(md + c4b)
+print(md[:900])
