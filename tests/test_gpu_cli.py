@@ -60,3 +60,20 @@ def test_reference_cli_writes_air_files(files, tmp_path):
     assert subprocess.run([REF, "-c", "--params", p, "-o", str(out_ref)] + files[:1], timeout=120).returncode == 0
     assert subprocess.run([B200, "-c", "--params", p, "-o", str(out_b200)] + files[:1], timeout=300).returncode == 0
     assert out_b200.read_bytes() == out_ref.read_bytes()
+
+
+def test_reference_example_program():
+    """examples/simple_compression.c of the reference, compiled against include/cmp.h (our headers) and
+    linked with libcmp_b200.so: prints the two streams the reference build prints."""
+    ex_ref = os.path.join(ROOT, "oracle", "_ref", "example_ref")
+    ex_b200 = os.path.join(ROOT, "oracle", "_ref", "example_b200")
+    if not (os.path.exists(ex_ref) and os.path.exists(ex_b200)):
+        pytest.skip("oracle/_ref/example_{ref,b200} not built")
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    ref = subprocess.run([ex_ref], capture_output=True, timeout=60)
+    b200 = subprocess.run([ex_b200], capture_output=True, timeout=300)
+    assert ref.returncode == 0 and b200.returncode == 0, (ref.stderr[:300], b200.stderr[:300])
+    assert b"82 58 00 00 1A 00 00 06 00 00 00 00 00 04 00 08 00 00 00 01 00 02 55 15 04 C6" in ref.stdout
+    assert b200.stdout == ref.stdout
