@@ -778,9 +778,7 @@ __device__ __forceinline__ uint32_t model_update2(uint32_t x, uint32_t m, uint32
 	return __byte_perm(tl, th, 0x6521);
 }
 
-/* arithmetic encoders for a warp that missed the table.  Rolled loops over the
- * packed residuals d[0..7] (local memory): small code, no calls, so that the
- * table path around them keeps its registers. */
+/* one zig-zag mapped residual through the encoder the pass names at run time */
 __device__ __forceinline__ void encode_mapped_rt(const EncConst &e, uint32_t m, uint32_t &cw, uint32_t &cl,
 						 uint32_t &rw, uint32_t &rl)
 {
@@ -802,53 +800,13 @@ __device__ __noinline__ void first_sample_code(const EncConst &e, uint32_t x0, u
 	out[2] = cl + rl;
 }
 
-/* bit counts of the segments d[0..3], d[4..7], .. whose bit is set in `rows`: b01 = segment 0 |
- * segment 1 << 16, b23 likewise */
-__device__ __forceinline__ void slow_bits(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t rows,
-					  uint32_t &b01, uint32_t &b23)
-{
-	b01 = 0;
-	b23 = 0;
-#pragma unroll 1
-	for (uint32_t k = 0; k < n_words; k++) {
-		if (!((rows >> (k >> 2)) & 1u)) /* segment k / 4 is not asked for */
-			continue;
-		const uint32_t z = zigzag2(d[k]);
-		uint32_t cw, cl, rw, rl, n;
-		encode_mapped_rt(e, z & 0xFFFFu, cw, cl, rw, rl);
-		n = cl + rl;
-		encode_mapped_rt(e, z >> 16, cw, cl, rw, rl);
-		n += cl + rl;
-		n = (k & 4u) ? n << 16 : n;
-		if (k < 8u)
-			b01 += n;
-		else
-			b23 += n;
-	}
-}
-
-/* the 8 samples of d[0..3] into the staging words from bit `start` on */
-__device__ __forceinline__ void slow_put(const EncConst &e, const uint32_t *d, uint32_t *stg, uint32_t start)
-{
-	int32_t ne = -(int32_t)start;
-#pragma unroll 1
-	for (uint32_t k = 0; k < 4u; k++) {
-		const uint32_t z = zigzag2(d[k]);
-#pragma unroll 1
-		for (uint32_t h = 0; h < 2u; h++) {
-			uint32_t cw, cl, rw, rl;
-			encode_mapped_rt(e, h ? z >> 16 : z & 0xFFFFu, cw, cl, rw, rl);
-			/* codeword then raw escape bits: at most 48 */
-			put_unit(stg, ne, __funnelshift_lc(cw, 0u, rl), __funnelshift_lc(0u, cw, rl) | rw, cl + rl);
-		}
-	}
-}
-
-/* The arithmetic encoders with memory: every code word is computed once.  slow_codes() leaves
- * the code words of the segments whose bit is set in `rows` in cw[] - per sample the low 32
- * bits, then the high 16 bits | length << 16 (a code word has at most 48 bits) - and returns
- * the bit counts like slow_bits(); slow_put_codes() stages the 8 samples of one segment from
- * there, the two code words of a pair as one string where they fit 64 bits. */
+/* The arithmetic encoders: every code word is computed once.  slow_codes() takes the packed
+ * residuals of the segments d[0..3], d[4..7], .. whose bit is set in `rows`, leaves their code
+ * words in cw[] - per sample the low 32 bits, then the high 16 bits | length << 16 (a code word
+ * has at most 48 bits) - and returns the bit counts of the segments (b01 = segment 0 | segment 1
+ * << 16, b23 likewise); slow_put_codes() stages the 8 samples of one segment from there, the two
+ * code words of a pair as one string where they fit 64 bits.  Rolled loops over local memory:
+ * small code, no calls, so that the table path around them keeps its registers. */
 template <int ENC>
 __device__ __forceinline__ void slow_codes_t(const EncConst &e, const uint32_t *d, uint32_t n_words, uint32_t rows,
 					     uint32_t *cw, uint32_t &b01, uint32_t &b23)
