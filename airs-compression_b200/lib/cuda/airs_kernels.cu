@@ -679,7 +679,8 @@ __device__ __noinline__ Cursor generic_span(Shared &sh, const OutWin o, uint32_t
  * until that holds, 0 = no table for this encoder.
  * All threads call it; two barriers.
  * ---------------------------------------------------------------------- */
-__device__ __noinline__ void build_pair_lut(Shared &sh, const EncConst &e)
+template <class S>
+__device__ __noinline__ void build_pair_lut(S &sh, const EncConst &e)
 {
 	const uint32_t tid = threadIdx.x;
 	uint32_t bad = 0; /* bit i: a residual with |r| <= 8 << i does not qualify */
@@ -1625,6 +1626,23 @@ struct WarpShared {
 	Pass pass;
 };
 
+/* the pair table of a CTA of airs_small_kernel<true>: built once per launch for the encoder of job 0,
+ * read by every warp whose job uses that encoder (a batch of chunks with one parameter set) */
+struct PairShared {
+	uint32_t plut[kLutStride * kLutStride];
+	uint2 slut[kLutStride];
+	uint32_t plut_key[3];
+	uint32_t plut_R;
+};
+
+template <bool P>
+struct PairHolder {
+	PairShared t;
+};
+template <>
+struct PairHolder<false> {
+};
+
 /* single-sample table of one warp; residuals qualify while their codeword is at most 16 bits long */
 __device__ __noinline__ void build_single_lut(WarpShared &ws, const EncConst &e)
 {
@@ -1686,7 +1704,7 @@ __device__ __forceinline__ void warp_copy_out(WarpShared &ws, const OutWin &o, C
 }
 
 /* one frame by one warp; returns the stream size or an error */
-__device__ uint32_t small_encode(WarpShared &ws, bool raw)
+__device__ uint32_t small_encode(WarpShared &ws, bool raw, const PairShared *ps)
 {
 	const Pass &P = ws.pass;
 	const uint32_t lane = threadIdx.x & 31u;
@@ -1721,9 +1739,14 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 		}
 		c.sbits = 8u * (a + CMP_HDR_SIZE + 2u * n); /* only used for the size below */
 	} else {
-		if (ws.key[0] != P.enc.type || ws.key[1] != P.enc.g || ws.key[2] != P.enc.outlier)
+		/* the CTA's pair table when it was built for this encoder, else the warp's own single-sample table */
+		const bool pair = ps && ps->plut_R != 0u && ps->plut_key[0] == P.enc.type && ps->plut_key[1] == P.enc.g &&
+				  ps->plut_key[2] == P.enc.outlier;
+		if (!pair && (ws.key[0] != P.enc.type || ws.key[1] != P.enc.g || ws.key[2] != P.enc.outlier))
 			build_single_lut(ws, P.enc);
-		const uint32_t R = ws.R;
+		const uint32_t R = pair ? ps->plut_R : ws.R;
+		const uint32_t lut_s = pair ? (uint32_t)__cvta_generic_to_shared(ps->plut) : 0u;
+		const uint32_t standin_len = pair ? ps->slut[kLutR].y : 0u; /* bits of the code word of residual 0 */
 		const uint32_t Rb = R * 0x00010001u, B1 = (R + 1u) * 0x00010001u;
 		const uint32_t notmask = ~((2u * R - 1u) * 0x00010001u);
 		const char *lut = reinterpret_cast<const char *>(ws.slut + (kLutR - R));
@@ -1778,7 +1801,35 @@ __device__ uint32_t small_encode(WarpShared &ws, bool raw)
 
 			bool table = R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
 			uint32_t sh_[4], sl_[4], sn_[4];
-			if (table) {
+			if (table && pair) { /* as the table arm of frame_fast: one lookup per pair */
+				uint32_t qchk = 0;
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					uint32_t pc[4], pl[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const uint32_t ent = lut_pair(lut_s, u[j][k]);
+						pc[k] = ent & ((1u << kLutLenShift) - 1u);
+						pl[k] = ent >> kLutLenShift;
+					}
+					if (j == 0 && first) { /* drop the stand-in's codeword from the head of pair 0 */
+						pl[0] -= standin_len;
+						pc[0] &= (1u << pl[0]) - 1u;
+					}
+					uint32_t lo = pc[0], hi = 0u, nb = pl[0];
+#pragma unroll
+					for (int k = 1; k < 4; k++) {
+						hi = __funnelshift_l(lo, hi, pl[k]);
+						lo = (lo << pl[k]) | pc[k];
+						nb += pl[k];
+					}
+					qchk |= nb + 63u;
+					sl_[j] = v[j] ? lo : 0u;
+					sh_[j] = v[j] ? hi : 0u;
+					sn_[j] = v[j] ? nb : 0u;
+				}
+				table = __all_sync(kFull, (qchk & 128u) == 0u);
+			} else if (table) {
 				uint32_t qchk = 0;
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
@@ -1955,8 +2006,15 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			   pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
 			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
 			   pl.cap_eff >= (CMP_HDR_SIZE + 6u);
-	if (small)
+	if (small) {
 		pl.flags |= AIRS_PF_SMALL;
+		/* airs_small_kernel<true> holds a pair table for the primary encoder of job 0 */
+		const cmp_params &p0 = b.jobs[0].params, &pj = job.params;
+		if (pj.primary_encoder_type == p0.primary_encoder_type && pj.primary_encoder_param == p0.primary_encoder_param &&
+		    (pj.primary_encoder_type != CMP_ENCODER_GOLOMB_MULTI || pl.enc[0].outlier ==
+		     airs_derive_outlier(p0.primary_encoder_type, p0.primary_encoder_param, p0.primary_encoder_outlier)))
+			atomicAdd(&b.ticket[8], 1u);
+	}
 	b.plans[j] = pl;
 	if (b.init_results && !b.ctx_io)
 		b.init_results[j] = pl.init_result;
@@ -2094,14 +2152,30 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 	}
 }
 
-__global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_kernel(AirsLaunch b)
+/* PAIR: the CTA holds a pair table for the primary encoder of job 0 (5 CTAs per SM instead of 6); the
+ * launch that runs is the one that fits the batch - PAIR when at least three of four short jobs use
+ * that encoder (counted by airs_plan_kernel in ticket[8]) */
+template <bool PAIR>
+__global__ void __launch_bounds__(AIRS_THREADS, PAIR ? AIRS_CTAS_PER_SM - 1 : AIRS_CTAS_PER_SM) airs_small_kernel(AirsLaunch b)
 {
 	__shared__ WarpShared wsh[kWarps];
+	__shared__ PairHolder<PAIR> psh;
 	const uint32_t lane = threadIdx.x & 31u;
 	WarpShared &ws = wsh[threadIdx.x >> 5];
 	if (gate_closed(b))
 		return;
 	const uint32_t n_small = b.ticket[3]; /* entries of small_list, written by airs_plan_kernel */
+	const bool mostly_one_encoder = 4u * b.ticket[8] >= 3u * n_small;
+	if (n_small == 0u || mostly_one_encoder != PAIR)
+		return;
+	const PairShared *ps = nullptr;
+	if constexpr (PAIR) {
+		EncConst e0;
+		const cmp_params &p0 = b.jobs[0].params;
+		airs_enc_const(&e0, p0.primary_encoder_type, p0.primary_encoder_param, p0.primary_encoder_outlier);
+		build_pair_lut(psh.t, e0); /* all threads: two block barriers */
+		ps = &psh.t;
+	}
 
 	for (uint32_t w = lane; w < 4u + kWStgWords; w += 32u)
 		ws.stg_mem[w] = 0;
@@ -2149,7 +2223,7 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_ker
 			P.err = 0;
 		}
 		__syncwarp();
-		uint32_t r = small_encode(ws, false);
+		uint32_t r = small_encode(ws, false, ps);
 		if ((ws.plan.flags & AIRS_PF_FALLBACK_OK) && r == AIRS_ERR(DST_TOO_SMALL)) {
 			/* stored raw as a fresh primary pass: two more identifiers drawn (ref cmp.c:380-392) */
 			if (lane == 0) {
@@ -2160,7 +2234,7 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_small_ker
 				P.hdr_len = CMP_HDR_SIZE;
 			}
 			__syncwarp();
-			r = small_encode(ws, true);
+			r = small_encode(ws, true, ps);
 		}
 		if (lane == 0)
 			b.results[ws.job.first_result] = r;
@@ -2288,7 +2362,10 @@ extern "C" cudaError_t airs_encode_ctas_per_sm(int *out)
 	e = cudaFuncSetAttribute(airs_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 	if (e != cudaSuccess)
 		return e;
-	e = cudaFuncSetAttribute(airs_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+	e = cudaFuncSetAttribute(airs_small_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+	if (e != cudaSuccess)
+		return e;
+	e = cudaFuncSetAttribute(airs_small_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 	if (e != cudaSuccess)
 		return e;
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, airs_encode_kernel, AIRS_THREADS, 0);
@@ -2311,6 +2388,8 @@ extern "C" cudaError_t airs_launch_checksum(const AirsLaunch *b, cudaStream_t st
 
 extern "C" cudaError_t airs_launch_small(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
 {
-	airs_small_kernel<<<grid, AIRS_THREADS, 0, stream>>>(*b);
+	/* both are launched; ticket[8] (airs_plan_kernel) decides on the device which one works */
+	airs_small_kernel<true><<<grid, AIRS_THREADS, 0, stream>>>(*b);
+	airs_small_kernel<false><<<grid, AIRS_THREADS, 0, stream>>>(*b);
 	return cudaGetLastError();
 }

@@ -27,7 +27,8 @@ struct AirsLaunch {
 	uint64_t *out_offsets;
 	uint32_t *ticket;      /* zeroed before the launch: [0] next entry of big_list, [1] of small_list,
 				  [2] entries in big_list, [3] entries in small_list,
-				  [4] jobs with checksum */
+				  [4] jobs with checksum, [5] gate of the two-phase CONCAT path,
+				  [8] short jobs that use the primary encoder of job 0 */
 	uint32_t *big_list;    /* job indices for airs_encode_kernel, filled by airs_plan_kernel */
 	uint32_t *small_list;  /* job indices for airs_small_kernel (SLOTS layout only) */
 	uint32_t *result_job;  /* n_results entries: the job a frame belongs to (airs_checksum_kernel) */
