@@ -236,3 +236,19 @@ def test_concat_two_phase_config2_size(gpu, pkg):
     total = int(offs[-1])
     idx = torch.repeat_interleave(starts - torch.from_numpy(offs[:-1]).cuda(), sizes) + torch.arange(total, device="cuda")
     assert torch.equal(slots.dst[idx], cat.dst[:total])
+
+
+@pytest.mark.parametrize("enc,g,outl,n", [(1, 16, 0, 2048), (2, 8, 40, 777), (1, 255, 0, 4099), (1, 3, 0, 20000)])
+def test_short_jobs_with_one_encoder(gpu, oracle, pkg, enc, g, outl, n):
+    """A batch of short chunks with one parameter set takes the warp-per-job kernel with the pair table per
+    CTA (airs_small_kernel<true>); one job in eight uses another encoder and falls back to its warp's own
+    table inside the same kernel."""
+    abi, synth = pkg.abi, pkg.synth
+    n_chunks = 1500
+    x = synth.chunks(5, 0, n_chunks, n, esc=1)
+    p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=enc, primary_encoder_param=g,
+                        primary_encoder_outlier=outl, checksum_enabled=1)
+    js = _uniform_jobs(pkg, n_chunks, n, 1, p)
+    js["jobs"]["params"]["primary_encoder_param"][7::8] = g + 1
+    js["src"] = x.view(np.uint8).reshape(-1)
+    jobgen.compare(jobgen.run_cpu(oracle, js, threads=8), gpu.run_jobs_device(js), js, "short-one-encoder")
