@@ -219,7 +219,7 @@ static int launch_kernels(const AirsLaunch &l, int resident, cudaStream_t stream
 	g_launches += 2;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) { /* short single-frame jobs: one warp each */
 		CU(airs_launch_small(&l, (unsigned int)resident, stream));
-		g_launches++;
+		g_launches += 2; /* both instantiations; one of them finds its gate closed */
 	}
 	CU(airs_launch_checksum(&l, stream));
 	g_launches++;

@@ -42,7 +42,7 @@ line of the same commit is `profiles/r01_bench_line.json` (value {bl['value']:.1
 {bl['config']['round_trip']['samples']} samples through the decoder identical: {bl['config']['round_trip']['identical']}).
 Launch list of the bench command (`--metrics gpu__time_duration.sum -k regex:airs -c 20`): `profiles/r01_launches_bench.csv` -
 per step one `airs_plan_kernel` (18 us under ncu, cold and serialised), one `airs_encode_kernel` (8.15 ms), and the
-`airs_small_kernel` / `airs_checksum_kernel` launches that find nothing to do in this workload (5 us, 3 us): the encode
+two `airs_small_kernel` instantiations and the `airs_checksum_kernel` that find nothing to do in this workload (3-5 us each): the encode
 kernel is 99.7 % of a step, as in the device-timed run ({bl['ms_per_step']:.3f} ms per step).
 
 ## bench.py default workload (config 2 batched: 888 contexts x 256 frames x 64 KiB, DIFF g16 -> MODEL g8)
