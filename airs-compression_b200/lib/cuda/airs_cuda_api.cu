@@ -201,7 +201,7 @@ extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_resul
 	 * the job table on temporary slots (two-phase CONCAT) */
 	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs +
 	       4 * (size_t)n_results + 64 + sizeof(struct airs_job) * (size_t)n_jobs + 64 +
-	       airs_concat_scratch_bytes(n_jobs, n_results);
+	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 64 * (size_t)n_jobs;
 }
 
 extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results)
@@ -218,8 +218,16 @@ static int launch_kernels(const AirsLaunch &l, int resident, cudaStream_t stream
 	CU(airs_launch_encode(&l, grid, stream));
 	g_launches += 2;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) { /* short single-frame jobs: one warp each */
-		CU(airs_launch_small(&l, (unsigned int)resident, stream));
-		g_launches += 2; /* both instantiations; one of them finds its gate closed */
+		static thread_local int fast_dev = -1, fast_ctas = 0;
+		int dev;
+		CU(cudaGetDevice(&dev));
+		if (dev != fast_dev) {
+			CU(airs_fast_resident_ctas(&fast_ctas));
+			fast_dev = dev;
+		}
+		const unsigned int want = (l.n_jobs + AIRS_FAST_THREADS / 32 - 1) / (AIRS_FAST_THREADS / 32);
+		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
+		g_launches++;
 	}
 	CU(airs_launch_checksum(&l, stream));
 	g_launches++;
@@ -262,6 +270,8 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
 	l.small_list = l.big_list + b->n_jobs;
 	l.result_job = l.small_list + b->n_jobs;
+	l.fast_jobs = (uint8_t *)b->scratch +
+		      ((airs_cuda_batch_scratch_size(b->n_jobs, b->n_results) - 64 * (size_t)b->n_jobs) & ~(size_t)63);
 	CU(cudaMemsetAsync(l.result_job, 0xFF, 4 * (size_t)b->n_results, stream));
 	l.ctx_io = ctx_io;
 	l.dst_size = b->dst_size;

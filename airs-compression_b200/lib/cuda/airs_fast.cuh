@@ -1,0 +1,71 @@
+/*
+ * airs_fast.cuh - what airs_plan_kernel hands to airs_fast_kernel (airs_fast.cu): one
+ * 64-byte record per short single-frame job, in ticket order, holding everything the
+ * warp that encodes the job needs (no second look at the 120-byte job descriptor or
+ * the 128-byte plan).
+ */
+#ifndef AIRS_FAST_CUH
+#define AIRS_FAST_CUH
+
+#include "airs_plan.cuh"
+
+/* flags of a FastJob */
+#define AIRS_FJ_PRE_DIFF    1u  /* DIFF preprocessing (else NONE) */
+#define AIRS_FJ_MULTI       2u  /* GOLOMB_MULTI (else GOLOMB_ZERO) */
+#define AIRS_FJ_CHECKSUM    4u
+#define AIRS_FJ_FALLBACK_OK 8u
+
+/* largest Golomb parameter of the multiply-high division used by the fast kernels (below) */
+#define AIRS_FAST_MAX_G 32767u
+
+struct FastJob {
+	uint64_t src;          /* device address of the frame's samples (16-byte aligned, 16-bit container) */
+	uint64_t dst;          /* device address of its slot (8-byte aligned) */
+	uint64_t identifier;   /* of the primary pass: identifier_base + 1 (ref cmp.c:208,229) */
+	uint32_t n;            /* samples */
+	uint32_t cap_eff;      /* bytes the pass may write */
+	uint32_t flags;
+	uint32_t first_result;
+	uint32_t g;
+	uint32_t outlier;      /* derived outlier (header field, encoder.c:185-224) */
+	uint32_t magic;        /* airs_fast_magic(g) */
+	uint32_t L;            /* floor(log2 g) */
+	uint32_t pad[2];
+};
+static_assert(sizeof(FastJob) == 64, "FastJob is read as 16 words");
+
+/*
+ * floor(x / g) for 0 <= x <= 65536 + g and 1 <= g <= AIRS_FAST_MAX_G as one multiply-high:
+ *   g >= 2: M = ceil(2^32 / g), q = umulhi(x, M).  With e = M g - 2^32 (0 <= e < g) the result is
+ *           exact while x e < 2^32, and (65536 + g) g < 2^32 for g < 2^15.
+ *   g == 1: M = 2^32 - 1 and the caller adds 1 to x: umulhi(x + 1, 2^32 - 1) = x.
+ * tests/test_abi.py checks every g against every dividend at and next to the multiples of g.
+ */
+__host__ __device__ inline uint32_t airs_fast_magic(uint32_t g)
+{
+	return g <= 1u ? 0xFFFFFFFFu : (uint32_t)((0x100000000ull + g - 1u) / g);
+}
+
+#ifdef __CUDACC__
+__device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const JobPlan &pl, const uint8_t *src_base,
+					  uint8_t *dst_base)
+{
+	f.src = (uint64_t)(uintptr_t)(src_base + job.src_offset);
+	f.dst = (uint64_t)(uintptr_t)(dst_base + job.dst_offset);
+	f.identifier = (job.identifier_base + 1u) & 0xFFFFFFFFFFFFull;
+	f.n = pl.n;
+	f.cap_eff = pl.cap_eff;
+	f.flags = (pl.pre[0] == CMP_PREPROCESS_DIFF ? AIRS_FJ_PRE_DIFF : 0u) |
+		  (pl.enc[0].type == CMP_ENCODER_GOLOMB_MULTI ? AIRS_FJ_MULTI : 0u) |
+		  ((pl.flags & AIRS_PF_CHECKSUM) ? AIRS_FJ_CHECKSUM : 0u) |
+		  ((pl.flags & AIRS_PF_FALLBACK_OK) ? AIRS_FJ_FALLBACK_OK : 0u);
+	f.first_result = job.first_result;
+	f.g = pl.enc[0].g;
+	f.outlier = pl.enc[0].outlier;
+	f.magic = airs_fast_magic(pl.enc[0].g);
+	f.L = pl.enc[0].L;
+	f.pad[0] = f.pad[1] = 0;
+}
+#endif
+
+#endif /* AIRS_FAST_CUH */

@@ -37,6 +37,7 @@
 #include <cuda_runtime.h>
 
 #include "airs_device.cuh"
+#include "airs_fast.cuh"
 #include "airs_launch.h"
 #include "airs_plan.cuh"
 #include "airs_private.h"
@@ -59,6 +60,14 @@ constexpr uint32_t kStgWords = kStgBits / 32 + 4;
 static_assert(kGenTile * 48 + 128 <= kStgBits, "a generic tile must fit the staging area");
 constexpr uint32_t kLutR = 32;              /* pair table covers residuals in [-32, 32) */
 constexpr uint32_t kLutStride = 2 * kLutR;
+#ifndef AIRS_LUT_PITCH
+#define AIRS_LUT_PITCH 65
+#endif
+/* entries between consecutive rows of the pair table: odd, so that the shared-memory bank of entry
+ * [u_hi][u_lo] depends on both residuals (with a pitch of 64 it would be u_lo mod 32 alone, and lanes
+ * with equal u_lo but different u_hi would queue up at one bank) */
+constexpr uint32_t kLutPitch = AIRS_LUT_PITCH;
+static_assert(kLutPitch >= kLutStride && kLutPitch < 256, "the pitch is a byte weight of the index IDP.2A");
 constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair codeword */
 constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
 constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
@@ -96,7 +105,7 @@ struct CtxState {
 };
 
 struct Shared {
-	uint32_t plut[kLutStride * kLutStride]; /* pair table: length << 26 | merged codeword at [u_hi * 64 + u_lo] */
+	uint32_t plut[kLutStride * kLutPitch]; /* pair table: length << 26 | merged codeword at [u_hi * kLutPitch + u_lo] */
 	/* two staging areas (the fast path fills one while the other one drains): MSB-first
 	 * 32-bit words of the stream being assembled, all zero when idle; the 4 pad words in
 	 * front absorb the zeros that strings ending in word 0 or 1 OR below the area */
@@ -706,7 +715,7 @@ __device__ __noinline__ void build_pair_lut(S &sh, const EncConst &e)
 			const uint32_t u0 = idx % kLutStride, u1 = idx / kLutStride;
 			if (u0 < 2u * R && u1 < 2u * R) {
 				const uint2 e0 = sh.slut[u0 + kLutR - R], e1 = sh.slut[u1 + kLutR - R];
-				sh.plut[idx] = ((e0.y + e1.y) << kLutLenShift) | (e0.x << e1.y) | e1.x;
+				sh.plut[u1 * kLutPitch + u0] = ((e0.y + e1.y) << kLutLenShift) | (e0.x << e1.y) | e1.x;
 			}
 		}
 	}
@@ -737,7 +746,7 @@ __device__ __forceinline__ uint32_t zigzag2(uint32_t d)
 __device__ __forceinline__ uint32_t lut_pair(uint32_t lut_s, uint32_t u)
 {
 	uint32_t idx, ent;
-	asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(idx) : "r"(u), "r"(1u | (kLutStride << 8)), "r"(0u));
+	asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(idx) : "r"(u), "r"(1u | (kLutPitch << 8)), "r"(0u));
 	asm("ld.shared.u32 %0, [%1];" : "=r"(ent) : "r"(lut_s + (idx << 2)));
 	return ent;
 }
@@ -1283,7 +1292,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 						put_unit(stg, ne, sh.first_code[0], sh.first_code[1], n_first);
 					_Pragma("unroll 1") for (uint32_t k = 0; k < 4u; k++) {
 						const uint32_t uu = d[4u * j + k];
-						const uint32_t off = ((uu << 2) & (4u * (kLutStride - 1u))) | (uu >> 8);
+						const uint32_t off = 4u * ((uu & 0xFFFFu) + kLutPitch * (uu >> 16));
 						const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
 						uint32_t pc = ent & ((1u << kLutLenShift) - 1u);
 						uint32_t pl = ent >> kLutLenShift;
@@ -1342,7 +1351,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 						uint32_t lo = 0, hi = 0, n = 0;
 #pragma unroll
 						for (int k = 0; k < 4; k++) {
-							const uint32_t off = ((w4[k] << 2) & (4u * (kLutStride - 1u))) | (w4[k] >> 8);
+							const uint32_t off = 4u * ((w4[k] & 0xFFFFu) + kLutPitch * (w4[k] >> 16));
 							const uint32_t ent = *reinterpret_cast<const uint32_t *>(lut + off);
 							const uint32_t pl = ent >> kLutLenShift;
 							hi = __funnelshift_l(lo, hi, pl);
@@ -1629,7 +1638,7 @@ struct WarpShared {
 /* the pair table of a CTA of airs_small_kernel<true>: built once per launch for the encoder of job 0,
  * read by every warp whose job uses that encoder (a batch of chunks with one parameter set) */
 struct PairShared {
-	uint32_t plut[kLutStride * kLutStride];
+	uint32_t plut[kLutStride * kLutPitch];
 	uint2 slut[kLutStride];
 	uint32_t plut_key[3];
 	uint32_t plut_R;
@@ -2005,7 +2014,7 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			   (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
 			   pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
 			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
-			   pl.cap_eff >= (CMP_HDR_SIZE + 6u);
+			   pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
 	if (small) {
 		pl.flags |= AIRS_PF_SMALL;
 		/* airs_small_kernel<true> holds a pair table for the primary encoder of job 0 */
@@ -2025,7 +2034,9 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 		if (j == 0)
 			b.ticket[2] = b.n_jobs;
 	} else if (small) {
-		b.small_list[atomicAdd(&b.ticket[3], 1u)] = j;
+		const uint32_t slot = atomicAdd(&b.ticket[3], 1u);
+		b.small_list[slot] = j;
+		airs_fill_fast_job(reinterpret_cast<FastJob *>(b.fast_jobs)[slot], job, pl, b.src, b.dst);
 	} else {
 		b.big_list[atomicAdd(&b.ticket[2], 1u)] = j;
 	}

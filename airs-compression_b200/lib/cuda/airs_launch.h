@@ -17,6 +17,13 @@ struct JobPlan;
 #define AIRS_CTAS_PER_SM 6 /* resident CTAs per SM the encode kernel is compiled for */
 #endif
 
+#ifndef AIRS_FAST_THREADS
+#define AIRS_FAST_THREADS 128
+#endif
+#ifndef AIRS_FAST_CTAS_PER_SM
+#define AIRS_FAST_CTAS_PER_SM 6 /* resident CTAs per SM airs_fast_kernel is compiled for */
+#endif
+
 struct AirsLaunch {
 	const uint8_t *src;
 	uint8_t *dst;
@@ -31,6 +38,7 @@ struct AirsLaunch {
 				  [8] short jobs that use the primary encoder of job 0 */
 	uint32_t *big_list;    /* job indices for airs_encode_kernel, filled by airs_plan_kernel */
 	uint32_t *small_list;  /* job indices for airs_small_kernel (SLOTS layout only) */
+	void *fast_jobs;       /* one 64-byte FastJob (airs_fast.cuh) per short job, in the order of small_list */
 	uint32_t *result_job;  /* n_results entries: the job a frame belongs to (airs_checksum_kernel) */
 	struct JobPlan *plans; /* n_jobs plans written by airs_plan_kernel */
 	uint64_t *lookback;    /* CONCAT: one status word per job, zeroed before the launch */
@@ -71,6 +79,8 @@ cudaError_t airs_launch_plan(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_encode_ctas_per_sm(int *out);
 cudaError_t airs_launch_small(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
+cudaError_t airs_launch_fast(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
+cudaError_t airs_fast_resident_ctas(int *out);
 cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
 size_t airs_concat_scratch_bytes(uint32_t n_jobs, uint32_t n_results);
 cudaError_t airs_launch_concat_slots(const struct AirsConcat *c, cudaStream_t stream);

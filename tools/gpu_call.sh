@@ -1,0 +1,19 @@
+#!/bin/bash
+# One gpurun call of round 2 (development tool): usage tools/gpu_call.sh <step>...
+mkdir -p gpurun_out
+for step in "$@"; do
+case $step in
+probe:*)
+  IFS=: read -r _ lib cases <<< "$step"
+  echo "=== $lib $cases" >> gpurun_out/probe.log
+  AIRS_PROBE_LIB=$lib timeout 600 python tools/perf_probe.py ${cases//,/ } >> gpurun_out/probe.log 2>&1 ;;
+tests)
+  timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/tests.log ;;
+smoke)
+  timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log ;;
+*) echo "unknown step $step" ;;
+esac
+done
+tail -n 40 gpurun_out/probe.log 2>/dev/null
+tail -n 30 gpurun_out/tests.log 2>/dev/null
+tail -n 5 gpurun_out/smoke.log 2>/dev/null
