@@ -40,7 +40,21 @@ constexpr uint32_t kFWarps = AIRS_FAST_THREADS / 32;
 constexpr uint32_t kRows = 2;                        /* pieces per lane and unit */
 constexpr uint32_t kUnitPieces = 32 * kRows;
 constexpr uint32_t kUnit = 8 * kUnitPieces;          /* 512 samples */
-constexpr uint32_t kStgWords = kUnit * 48 / 32 + 4;  /* one unit at 48 bits per sample + the carried 16-byte group */
+/* one unit at 48 bits per sample behind what is staged already: less than 128 carried bits, or the 22 header
+ * bytes behind up to 8 bytes of alignment */
+constexpr uint32_t kStgWords = kUnit * 48 / 32 + 8;
+
+/* AIRS_BOUNDS_CHECK builds: the shared-memory window of the warp's staging words, and a counter of the
+ * strings that would have left it (airs_fast_bounds_violations() reads and clears it) */
+#ifdef AIRS_BOUNDS_CHECK
+__device__ unsigned int airs_bounds_violations;
+struct Dbg {
+	uint32_t lo, hi;
+};
+#else
+struct Dbg {
+};
+#endif
 
 /* the staging words of one warp: MSB-first 32-bit words of the stream under construction, all
  * zero when idle; the pad in front absorbs the zeros that strings ending in word 0 or 1 OR
@@ -89,14 +103,20 @@ __device__ __forceinline__ void encode_k(const FK &k, uint32_t m, uint32_t &hi, 
 		n = esc ? k.esc_len : l;
 		hi = 0;
 	} else {
+		/* escape: Golomb code word of outlier + level, then d = m - outlier in 2 level + 2 bits, level =
+		 * d < 4 ? 0 : floor(log2 d) / 2 (encoder.c:356-372).  level <= d, so min(m, outlier + level) is
+		 * the value to encode whether the sample escapes or not (d wraps to a huge number if not) */
 		const bool esc = m >= k.outlier;
 		const uint32_t d = m - k.outlier;
-		const uint32_t level = (31u - (uint32_t)__clz((int)(d | 1u))) >> 1; /* d < 4 ? 0 : floor(log2 d) / 2 */
+		uint32_t msb;
+		asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(d | 1u));
+		const uint32_t level = msb >> 1;
 		uint32_t c, l;
-		golomb_k(k, esc ? k.outlier + level : m, c, l);
-		const uint32_t rl = esc ? 2u * level + 2u : 0u;
-		hi = __funnelshift_l(c, 0u, rl); /* (c << rl) | d as 64 bits; rl <= 16 */
-		lo = (c << rl) | (esc ? d : 0u);
+		golomb_k(k, min(m, k.outlier + level), c, l);
+		const uint32_t rl = esc ? 2u * level + 2u : 0u; /* raw bits */
+		const uint32_t pw = 1u << rl;
+		lo = c * pw + (esc ? d : 0u);
+		hi = __umulhi(c, pw);
 		n = l + rl;
 	}
 }
@@ -104,11 +124,19 @@ __device__ __forceinline__ void encode_k(const FK &k, uint32_t m, uint32_t &hi, 
 /* OR a bit string of len <= 64 bits (hi:lo, right aligned) into the staging words.  ne = -(absolute
  * bit address where the string starts: 8 * shared-memory byte address + bit), updated to the start of
  * the next string.  Three funnel shifts and three reductions whatever the length. */
-__device__ __forceinline__ void put(int32_t &ne, uint32_t hi, uint32_t lo, uint32_t len)
+__device__ __forceinline__ void put(const Dbg &dbg, int32_t &ne, uint32_t hi, uint32_t lo, uint32_t len)
 {
 	ne -= (int32_t)len;
 	const uint32_t s = (uint32_t)ne;               /* wrap-mode shifts use s & 31 = the bits free behind the string */
 	const uint32_t a = ~(uint32_t)(ne >> 3) & ~3u; /* shared-memory address of the word holding its last bit */
+#ifdef AIRS_BOUNDS_CHECK
+	/* development builds (compute-sanitizer is not available on the GPU pool): every word a string touches
+	 * must lie inside the staging words of the warp, pad included */
+	if (a - 8u < dbg.lo || a >= dbg.hi) {
+		atomicAdd(&airs_bounds_violations, 1u);
+		return;
+	}
+#endif
 	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(__funnelshift_l(0u, lo, s)) : "memory");
 	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a - 4u), "r"(__funnelshift_l(lo, hi, s)) : "memory");
 	asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a - 8u), "r"(__funnelshift_l(hi, 0u, s)) : "memory");
@@ -193,13 +221,13 @@ __device__ __noinline__ uint4 load_partial_piece(const uint16_t *s16, uint32_t f
  * Returns the bits of the unit.
  */
 template <bool MULTI, bool DIFF, bool RAGGED>
-__device__ __forceinline__ uint32_t encode_unit(const FK &k, const uint4 (&x)[kRows], uint32_t &front, const uint32_t (&nv)[kRows],
+__device__ __forceinline__ uint32_t encode_unit(const Dbg &dbg, const FK &k, const uint4 (&x)[kRows], uint32_t &front, const uint32_t (&nv)[kRows],
 						uint32_t lane, uint32_t abs_bit)
 {
-	uint32_t s_hi[kRows][4], s_lo[kRows][4], s_n[kRows][4], row_bits[kRows];
-	bool pairable = true;
-	/* GOLOMB_MULTI: per-sample strings kept for units whose pairs do not all fit 64 bits */
-	uint32_t e_hi[MULTI ? kRows : 1][8], e_lo[MULTI ? kRows : 1][8], e_n[MULTI ? kRows : 1][8];
+	/* GOLOMB_ZERO: one string per pair of samples (two code words of at most 31 bits): hi, lo, bits.
+	 * GOLOMB_MULTI: one string of at most 48 bits per sample: lo, and hi | bits << 16 */
+	constexpr int kStr = MULTI ? 8 : 4;
+	uint32_t s_a[kRows][kStr], s_lo[kRows][kStr], s_n[kRows][MULTI ? 1 : 4], row_bits[kRows];
 
 #pragma unroll
 	for (uint32_t j = 0; j < kRows; j++) {
@@ -239,50 +267,49 @@ __device__ __forceinline__ uint32_t encode_unit(const FK &k, const uint4 (&x)[kR
 				if (2u * i + 1u >= nv[j])
 					h1 = l1 = n1 = 0;
 			}
-			if (!MULTI) { /* both code words have at most 31 bits */
-				s_hi[j][i] = __funnelshift_l(l0, 0u, n1);
+			if (!MULTI) {
+				s_a[j][i] = __funnelshift_l(l0, 0u, n1);
 				s_lo[j][i] = (l0 << n1) | l1;
+				s_n[j][i] = n0 + n1;
 			} else {
-				e_hi[j][2 * i] = h0; e_lo[j][2 * i] = l0; e_n[j][2 * i] = n0;
-				e_hi[j][2 * i + 1] = h1; e_lo[j][2 * i + 1] = l1; e_n[j][2 * i + 1] = n1;
-				pairable = pairable && n1 <= 32u && n0 + n1 <= 64u;
-				s_hi[j][i] = __funnelshift_lc(l0, h0, n1) | h1; /* garbage unless pairable */
-				s_lo[j][i] = __funnelshift_lc(0u, l0, n1) | l1;
+				s_a[j][2 * i] = h0 | (n0 << 16);
+				s_lo[j][2 * i] = l0;
+				s_a[j][2 * i + 1] = h1 | (n1 << 16);
+				s_lo[j][2 * i + 1] = l1;
 			}
-			s_n[j][i] = n0 + n1;
 			bits += n0 + n1;
 		}
 		row_bits[j] = bits;
 	}
 
-	/* one scan for both rows: stream order is row 0 of all lanes, then row 1 of all lanes */
+	/* one scan for both rows: stream order is row 0 of all lanes, then row 1 of all lanes.  The
+	 * shuffle's "source lane exists" predicate feeds the adds directly. */
 	const uint32_t b = row_bits[0] | (row_bits[1] << 16);
 	uint32_t incl = b;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const uint32_t t = __shfl_up_sync(kFull, incl, d);
-		if (lane >= (uint32_t)d)
-			incl += t;
-	}
+#define AIRS_SCAN_STEP(d_)                                                                    \
+	asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t0;\n\t"                                  \
+		     "shfl.sync.up.b32 t0|p, %0, " #d_ ", 0, 0xffffffff;\n\t"                     \
+		     "@p add.u32 %0, %0, t0;\n\t}"                                               \
+		     : "+r"(incl))
+	AIRS_SCAN_STEP(1);
+	AIRS_SCAN_STEP(2);
+	AIRS_SCAN_STEP(4);
+	AIRS_SCAN_STEP(8);
+	AIRS_SCAN_STEP(16);
+#undef AIRS_SCAN_STEP
 	const uint32_t tot = __shfl_sync(kFull, incl, 31), excl = incl - b;
 	const uint32_t tot0 = tot & 0xFFFFu;
 	const uint32_t pos[kRows] = {abs_bit + (excl & 0xFFFFu), abs_bit + tot0 + (excl >> 16)};
 
-	if (!MULTI || __all_sync(kFull, pairable)) {
 #pragma unroll
-		for (uint32_t j = 0; j < kRows; j++) {
-			int32_t ne = -(int32_t)pos[j];
+	for (uint32_t j = 0; j < kRows; j++) {
+		int32_t ne = -(int32_t)pos[j];
 #pragma unroll
-			for (int i = 0; i < 4; i++)
-				put(ne, s_hi[j][i], s_lo[j][i], s_n[j][i]);
-		}
-	} else {
-#pragma unroll
-		for (uint32_t j = 0; j < kRows; j++) {
-			int32_t ne = -(int32_t)pos[j];
-#pragma unroll
-			for (int i = 0; i < 8; i++)
-				put(ne, e_hi[MULTI ? j : 0][i], e_lo[MULTI ? j : 0][i], e_n[MULTI ? j : 0][i]);
+		for (int i = 0; i < kStr; i++) {
+			if (!MULTI)
+				put(dbg, ne, s_a[j][i], s_lo[j][i], s_n[j][i]);
+			else
+				put(dbg, ne, s_a[j][i] & 0xFFFFu, s_lo[j][i], s_a[j][i] >> 16);
 		}
 	}
 	return tot0 + (tot >> 16);
@@ -290,7 +317,7 @@ __device__ __forceinline__ uint32_t encode_unit(const FK &k, const uint4 (&x)[kR
 
 /* the pass of one job through its units */
 template <bool MULTI, bool DIFF>
-__device__ __forceinline__ void encode_units(const FK &k, FastWarp &ws, Out &o, const uint8_t *src, uint32_t n, uint32_t lane)
+__device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWarp &ws, Out &o, const uint8_t *src, uint32_t n, uint32_t lane)
 {
 	const uint32_t n_whole = n / 8u;         /* complete pieces */
 	const uint32_t n_full_units = n / kUnit; /* units whose 64 pieces are all complete */
@@ -314,7 +341,7 @@ __device__ __forceinline__ void encode_units(const FK &k, FastWarp &ws, Out &o, 
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++)
 			nx[j] = p1 + 32u * j < n_whole ? __ldg(src4 + p1 + 32u * j) : zero4;
-		const uint32_t bits = encode_unit<MULTI, DIFF, false>(k, x, front, full_nv, lane, stg_bit + o.sbits);
+		const uint32_t bits = encode_unit<MULTI, DIFF, false>(dbg, k, x, front, full_nv, lane, stg_bit + o.sbits);
 		drain(ws, o, bits, lane);
 	}
 	if (u * kUnit < n) { /* the ragged last unit */
@@ -326,7 +353,7 @@ __device__ __forceinline__ void encode_units(const FK &k, FastWarp &ws, Out &o, 
 			if (nv[j] != 0u && nv[j] != 8u)
 				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j]);
 		}
-		const uint32_t bits = encode_unit<MULTI, DIFF, true>(k, nx, front, nv, lane, stg_bit + o.sbits);
+		const uint32_t bits = encode_unit<MULTI, DIFF, true>(dbg, k, nx, front, nv, lane, stg_bit + o.sbits);
 		drain(ws, o, bits, lane);
 	}
 }
@@ -347,6 +374,11 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 	for (uint32_t w = lane; w < 4u + kStgWords; w += 32u)
 		ws.pad[w] = 0;
 	__syncwarp();
+	Dbg dbg;
+#ifdef AIRS_BOUNDS_CHECK
+	dbg.lo = (uint32_t)__cvta_generic_to_shared(&ws);
+	dbg.hi = dbg.lo + (uint32_t)sizeof(FastWarp);
+#endif
 
 	/* tickets are drawn two jobs ahead and the record of the next job one job ahead, so that neither
 	 * the atomic's round trip nor the record's load is waited for */
@@ -400,22 +432,22 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 			int32_t ne = -(int32_t)(8u * (uint32_t)__cvta_generic_to_shared(ws.stg) + o.sbits);
 			const uint32_t pre = (flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE;
 			const uint32_t enc = multi ? CMP_ENCODER_GOLOMB_MULTI : CMP_ENCODER_GOLOMB_ZERO;
-			put(ne, (0x8000u | CMP_VERSION_NUMBER) << 16, (2u * n) & 0xFFFFFFu, 64u);
-			put(ne, (id_hi << 16) | (id_lo >> 16), (id_lo << 16) | (pre << 4) | (checksum << 3) | enc, 64u);
-			put(ne, g >> 8, ((g & 0xFFu) << 24) | (outlier & 0xFFFFFFu), 48u);
+			put(dbg, ne, (0x8000u | CMP_VERSION_NUMBER) << 16, (2u * n) & 0xFFFFFFu, 64u);
+			put(dbg, ne, (id_hi << 16) | (id_lo >> 16), (id_lo << 16) | (pre << 4) | (checksum << 3) | enc, 64u);
+			put(dbg, ne, g >> 8, ((g & 0xFFu) << 24) | (outlier & 0xFFFFFFu), 48u);
 		}
 		o.sbits += 8u * (CMP_HDR_SIZE + 6u);
 
 		if (multi) {
 			if (flags & AIRS_FJ_PRE_DIFF)
-				encode_units<true, true>(k, ws, o, src, n, lane);
+				encode_units<true, true>(dbg, k, ws, o, src, n, lane);
 			else
-				encode_units<true, false>(k, ws, o, src, n, lane);
+				encode_units<true, false>(dbg, k, ws, o, src, n, lane);
 		} else {
 			if (flags & AIRS_FJ_PRE_DIFF)
-				encode_units<false, true>(k, ws, o, src, n, lane);
+				encode_units<false, true>(dbg, k, ws, o, src, n, lane);
 			else
-				encode_units<false, false>(k, ws, o, src, n, lane);
+				encode_units<false, false>(dbg, k, ws, o, src, n, lane);
 		}
 
 		const uint32_t frame_bits = o.gw0 * 32u + o.sbits - 8u * a;
@@ -481,6 +513,20 @@ extern "C" cudaError_t airs_launch_fast(const AirsLaunch *b, unsigned int grid, 
 {
 	airs_fast_kernel<<<grid, AIRS_FAST_THREADS, 0, stream>>>(*b);
 	return cudaGetLastError();
+}
+
+/* AIRS_BOUNDS_CHECK builds: strings that would have been staged outside their warp's words since the last call
+ * (-1: not such a build) */
+extern "C" int airs_fast_bounds_violations(void)
+{
+#ifdef AIRS_BOUNDS_CHECK
+	unsigned int v = 0, zero = 0;
+	cudaMemcpyFromSymbol(&v, airs_bounds_violations, sizeof(v));
+	cudaMemcpyToSymbol(airs_bounds_violations, &zero, sizeof(zero));
+	return (int)v;
+#else
+	return -1;
+#endif
 }
 
 /* resident CTAs of airs_fast_kernel on the current device */

@@ -252,3 +252,27 @@ def test_short_jobs_with_one_encoder(gpu, oracle, pkg, enc, g, outl, n):
     js["jobs"]["params"]["primary_encoder_param"][7::8] = g + 1
     js["src"] = x.view(np.uint8).reshape(-1)
     jobgen.compare(jobgen.run_cpu(oracle, js, threads=8), gpu.run_jobs_device(js), js, "short-one-encoder")
+
+
+@pytest.mark.parametrize("enc,g,outl,pre,n", [(2, 3, 107, 0, 2048), (2, 1, 200, 0, 1000), (1, 3000, 0, 0, 4104), (2, 3, 107, 1, 1531)])
+def test_short_jobs_longest_code_words(gpu, oracle, pkg, enc, g, outl, pre, n):
+    """Warp-per-job kernel at its staging limit: every sample escapes with the longest code word the encoder has
+    (48 bits for GOLOMB_MULTI with a small g, 28 for GOLOMB_ZERO with g = 3000), in every warp of every CTA."""
+    abi = pkg.abi
+    n_chunks = 64
+    rng = np.random.default_rng(n)
+    if pre == 0:
+        x = np.full((n_chunks, n), 40000, dtype=np.uint16)           # zig-zag 51071: level 7 escapes
+        x[1::2] += rng.integers(0, 3000, size=(n_chunks // 2, n)).astype(np.uint16)
+    else:
+        x = np.where(np.arange(n) % 2 == 0, 100, 30000)[None, :].repeat(n_chunks, 0).astype(np.uint16)   # |diff| 29900
+    p = abi.make_params(primary_preprocessing=pre, primary_encoder_type=enc, primary_encoder_param=g,
+                        primary_encoder_outlier=outl)
+    js = _uniform_jobs(pkg, n_chunks, n, 1, p)
+    js["jobs"]["dst_offset"] += 8 * (np.arange(n_chunks) % 2).astype(np.uint64)   # half of the slots 8 mod 16
+    js["dst_size"] += 16
+    js["src"] = x.view(np.uint8).reshape(-1)
+    want = jobgen.run_cpu(oracle, js)
+    res = want[1]
+    assert int(res.max()) >= n * (48 if enc == 2 else 28) // 8          # the streams really are that long
+    jobgen.compare(want, gpu.run_jobs_device(js), js, "longest-code-words")

@@ -11,6 +11,11 @@ tests)
   timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/tests.log ;;
 smoke)
   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log ;;
+ncu:*)
+  IFS=: read -r _ case kern name <<< "$step"
+  timeout 300 python tools/ncu_case.py $case > gpurun_out/ncu_plain_$name.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kern -s 1 -c 1 -f -o gpurun_out/$name python tools/ncu_case.py $case > gpurun_out/ncu_$name.log 2>&1
+  tail -n 3 gpurun_out/ncu_$name.log ;;
 *) echo "unknown step $step" ;;
 esac
 done
