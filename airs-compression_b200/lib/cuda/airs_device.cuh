@@ -104,7 +104,12 @@ __host__ __device__ inline void airs_enc_const(EncConst *e, uint32_t type, uint3
 	e->outlier = airs_derive_outlier(type, g, user);
 	e->two_l1 = 2u << e->L;
 	e->bias = g - (e->two_l1 - g) + 1u;
-	e->magic = (uint32_t)((((uint64_t)1 << (32 + e->L)) - 1) / g);
+	{ /* floor((2^(32+L) - 1) / g) by two 32-bit divisions: the dividend is (2^L - 1) 2^32 + (2^32 - 1) and
+	   * 2^L - 1 < g < 2^16, so both partial dividends stay below g 2^16 */
+		const uint32_t t1 = (((1u << e->L) - 1u) << 16) | 0xFFFFu;
+		const uint32_t q1 = t1 / g, r1 = t1 - q1 * g;
+		e->magic = (q1 << 16) + (((r1 << 16) | 0xFFFFu) / g);
+	}
 }
 
 #ifdef __CUDACC__

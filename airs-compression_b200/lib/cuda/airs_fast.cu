@@ -40,9 +40,11 @@ constexpr uint32_t kFWarps = AIRS_FAST_THREADS / 32;
 constexpr uint32_t kRows = 2;                        /* pieces per lane and unit */
 constexpr uint32_t kUnitPieces = 32 * kRows;
 constexpr uint32_t kUnit = 8 * kUnitPieces;          /* 512 samples */
-/* one unit at 48 bits per sample behind what is staged already: less than 128 carried bits, or the 22 header
- * bytes behind up to 8 bytes of alignment */
-constexpr uint32_t kStgWords = kUnit * 48 / 32 + 8;
+/* The staging words are drained when more than one unit at 48 bits per sample is staged (for most data: every
+ * few units, so that the fixed cost of a drain is shared); the next unit then still fits, and so do the 22
+ * header bytes behind up to 8 bytes of alignment in front of the first one */
+constexpr uint32_t kUnitMaxBits = kUnit * 48;
+constexpr uint32_t kStgWords = 2 * kUnitMaxBits / 32 + 8;
 
 /* AIRS_BOUNDS_CHECK builds: the shared-memory window of the warp's staging words, and a counter of the
  * strings that would have left it (airs_fast_bounds_violations() reads and clears it) */
@@ -143,8 +145,8 @@ __device__ __forceinline__ void put(const Dbg &dbg, int32_t &ne, uint32_t hi, ui
 }
 
 /* where the stream of the job stands: word 0 of the staging area is 32-bit word gw0 (a multiple of 4)
- * of the 16-byte aligned space that starts at base = dst - (dst & 15) and already holds sbits (< 128)
- * bits; [lo, hi) is the byte window of that space the job may write */
+ * of the 16-byte aligned space that starts at base = dst - (dst & 15) and holds sbits bits (< 128 behind a
+ * drain); [lo, hi) is the byte window of that space the job may write */
 struct Out {
 	uint8_t *base;
 	uint32_t lo, hi;
@@ -152,9 +154,9 @@ struct Out {
 };
 
 /* complete 16-byte groups of the staging area leave as coalesced stores; the partial group moves to the front */
-__device__ __forceinline__ void drain(FastWarp &ws, Out &o, uint32_t bits, uint32_t lane)
+__device__ __forceinline__ void drain(FastWarp &ws, Out &o, uint32_t lane)
 {
-	const uint32_t staged = o.sbits + bits, nvec = staged >> 7, b0 = o.gw0 * 4u;
+	const uint32_t staged = o.sbits, nvec = staged >> 7, b0 = o.gw0 * 4u;
 	uint4 *stg4 = reinterpret_cast<uint4 *>(ws.stg);
 
 	__syncwarp();
@@ -341,8 +343,9 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++)
 			nx[j] = p1 + 32u * j < n_whole ? __ldg(src4 + p1 + 32u * j) : zero4;
-		const uint32_t bits = encode_unit<MULTI, DIFF, false>(dbg, k, x, front, full_nv, lane, stg_bit + o.sbits);
-		drain(ws, o, bits, lane);
+		o.sbits += encode_unit<MULTI, DIFF, false>(dbg, k, x, front, full_nv, lane, stg_bit + o.sbits);
+		if (o.sbits > kUnitMaxBits)
+			drain(ws, o, lane);
 	}
 	if (u * kUnit < n) { /* the ragged last unit */
 		uint32_t nv[kRows];
@@ -353,9 +356,9 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 			if (nv[j] != 0u && nv[j] != 8u)
 				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j]);
 		}
-		const uint32_t bits = encode_unit<MULTI, DIFF, true>(dbg, k, nx, front, nv, lane, stg_bit + o.sbits);
-		drain(ws, o, bits, lane);
+		o.sbits += encode_unit<MULTI, DIFF, true>(dbg, k, nx, front, nv, lane, stg_bit + o.sbits);
 	}
+	drain(ws, o, lane);
 }
 
 } /* namespace */
@@ -426,16 +429,21 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 		o.gw0 = 0;
 		o.sbits = 8u * a;
 
-		/* the 22 header bytes travel through the staging words in front of the code words (size
-		 * field zero, patched at the end): ref cmp_hdr_serialize, header.c:24-67; fields cmp.c:265-279 */
+		/* the 22 header bytes travel through the staging words in front of the code words (size field zero,
+		 * patched at the end), as five and a half big-endian words: ref cmp_hdr_serialize, header.c:24-67;
+		 * fields cmp.c:265-279.  The area is all zero here, a is 0 or 8: plain stores */
 		if (lane == 0) {
-			int32_t ne = -(int32_t)(8u * (uint32_t)__cvta_generic_to_shared(ws.stg) + o.sbits);
+			uint32_t *h = ws.stg + a / 4u;
 			const uint32_t pre = (flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE;
 			const uint32_t enc = multi ? CMP_ENCODER_GOLOMB_MULTI : CMP_ENCODER_GOLOMB_ZERO;
-			put(dbg, ne, (0x8000u | CMP_VERSION_NUMBER) << 16, (2u * n) & 0xFFFFFFu, 64u);
-			put(dbg, ne, (id_hi << 16) | (id_lo >> 16), (id_lo << 16) | (pre << 4) | (checksum << 3) | enc, 64u);
-			put(dbg, ne, g >> 8, ((g & 0xFFu) << 24) | (outlier & 0xFFFFFFu), 48u);
+			h[0] = (0x8000u | CMP_VERSION_NUMBER) << 16;
+			h[1] = (2u * n) & 0xFFFFFFu;
+			h[2] = (id_hi << 16) | (id_lo >> 16);
+			h[3] = (id_lo << 16) | (pre << 4) | (checksum << 3) | enc;
+			h[4] = (g << 8) | ((outlier >> 16) & 0xFFu);
+			h[5] = outlier << 16;
 		}
+		__syncwarp();
 		o.sbits += 8u * (CMP_HDR_SIZE + 6u);
 
 		if (multi) {
@@ -536,8 +544,13 @@ extern "C" cudaError_t airs_fast_resident_ctas(int *out)
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e == cudaSuccess)
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	if (e == cudaSuccess)
-		e = cudaFuncSetAttribute(airs_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+	if (e == cudaSuccess) {
+		/* shared memory for the CTAs the kernel is compiled for (1 KiB per CTA is reserved by the system); the
+		 * rest of the 228 KiB stays L1 */
+		const size_t need = (size_t)AIRS_FAST_CTAS_PER_SM * (sizeof(FastWarp) * kFWarps + 1024);
+		const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+		e = cudaFuncSetAttribute(airs_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+	}
 	if (e == cudaSuccess)
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_fast_kernel, AIRS_FAST_THREADS, 0);
 	*out = sms * per_sm;

@@ -18,7 +18,7 @@
 /* largest Golomb parameter of the multiply-high division used by the fast kernels (below) */
 #define AIRS_FAST_MAX_G 32767u
 
-struct FastJob {
+struct alignas(16) FastJob {
 	uint64_t src;          /* device address of the frame's samples (16-byte aligned, 16-bit container) */
 	uint64_t dst;          /* device address of its slot (8-byte aligned) */
 	uint64_t identifier;   /* of the primary pass: identifier_base + 1 (ref cmp.c:208,229) */
@@ -43,7 +43,7 @@ static_assert(sizeof(FastJob) == 64, "FastJob is read as 16 words");
  */
 __host__ __device__ inline uint32_t airs_fast_magic(uint32_t g)
 {
-	return g <= 1u ? 0xFFFFFFFFu : (uint32_t)((0x100000000ull + g - 1u) / g);
+	return g <= 1u ? 0xFFFFFFFFu : 0xFFFFFFFFu / g + 1u; /* ceil(2^32 / g) */
 }
 
 #ifdef __CUDACC__

@@ -1974,17 +1974,43 @@ __device__ __forceinline__ bool gate_closed(const AirsLaunch &b)
 	return b.gate && (*b.gate != 0u) != (b.gate_want != 0u);
 }
 
+/* Job descriptors come in through shared memory: the 32 jobs of a warp are 3840 consecutive bytes, fetched with
+ * coalesced 16-byte loads; a thread that reads its own 120-byte descriptor field by field from global memory
+ * waits for one dependent load after the other.  Plans and fast-job records stay in registers and leave with
+ * 16-byte stores. */
+struct PlanWarp {
+	alignas(16) uint32_t job[32 * sizeof(airs_job) / 4];
+};
+
 __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 {
+	__shared__ PlanWarp psh[4];
+	PlanWarp &pw = psh[threadIdx.x >> 5];
 	const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u, j0 = j - lane;
 
 	if (gate_closed(b))
 		return;
+	const uint32_t in_warp = j0 < b.n_jobs ? min(32u, b.n_jobs - j0) : 0u; /* jobs of this warp */
+	{
+		constexpr uint32_t kVec = sizeof(airs_job) / 4u; /* a descriptor is 30 words; 32 of them are 240 x 16 bytes */
+		const uint32_t *src = reinterpret_cast<const uint32_t *>(b.jobs + j0);
+		if (((uintptr_t)b.jobs & 15u) == 0 && in_warp == 32u) {
+			for (uint32_t v = lane; v < 32u * kVec / 4u; v += 32u)
+				reinterpret_cast<uint4 *>(pw.job)[v] = __ldg(reinterpret_cast<const uint4 *>(src) + v);
+		} else {
+			for (uint32_t w = lane; w < in_warp * kVec; w += 32u)
+				pw.job[w] = __ldg(src + w);
+		}
+		__syncwarp();
+	}
+	const bool have = j < b.n_jobs;
+	const airs_job &job = *reinterpret_cast<const airs_job *>(pw.job + (have ? lane : 0u) * (sizeof(airs_job) / 4u));
 	/* the job of every frame (airs_checksum_kernel, the CONCAT copy): short jobs by their own
 	 * thread, long ones by the whole warp */
 	{
-		const uint32_t first = j < b.n_jobs ? b.jobs[j].first_result : 0u;
-		const uint32_t nf = j < b.n_jobs ? b.jobs[j].n_frames : 0u;
+		const uint32_t first = have ? job.first_result : 0u;
+		const uint32_t nf = have ? job.n_frames : 0u;
 		const bool wide = nf > 16u;
 		if (!wide)
 			for (uint32_t f = 0; f < nf && (uint64_t)first + f < b.n_results; f++)
@@ -1993,52 +2019,62 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			const int l = __ffs((int)todo) - 1;
 			const uint32_t fl = __shfl_sync(kFull, first, l), nl = __shfl_sync(kFull, nf, l);
 			const uint32_t jl = __shfl_sync(kFull, j, l);
-			for (uint32_t f = threadIdx.x & 31u; f < nl && (uint64_t)fl + f < b.n_results; f += 32u)
+			for (uint32_t f = lane; f < nl && (uint64_t)fl + f < b.n_results; f += 32u)
 				b.result_job[fl + f] = jl;
 		}
 	}
-	if (j >= b.n_jobs)
+	if (in_warp == 0u)
 		return;
 	JobPlan pl;
-	const airs_job &job = b.jobs[j];
 	airs_make_plan(pl, job, b.src, b.work);
 	/* Short single-frame jobs without model, with a Golomb encoder, none / diff preprocessing,
 	 * an aligned 16-bit source and nothing that could fail before the encoding go to
-	 * airs_small_kernel (one warp per job); everything else to airs_encode_kernel.  The lists
-	 * are filled in no particular order, except in the CONCAT layout and on the host-shim path,
-	 * where every job is "big" and the list is the identity (the look-back scan needs the
-	 * frames to start in result order). */
+	 * airs_fast_kernel (one warp per job); everything else to airs_encode_kernel.  Jobs keep their
+	 * order inside a warp of this kernel, warps take their places in the lists as they come, except
+	 * in the CONCAT layout and on the host-shim path, where every job is "big" and the list is the
+	 * identity (the look-back scan needs the frames to start in result order). */
 	const bool listed = b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io;
-	const bool small = listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
+	const bool small = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
 			   !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 && pl.n <= kSmallMaxSamples &&
 			   (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
 			   pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
 			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
 			   pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
-	if (small) {
+	if (small)
 		pl.flags |= AIRS_PF_SMALL;
-		/* airs_small_kernel<true> holds a pair table for the primary encoder of job 0 */
-		const cmp_params &p0 = b.jobs[0].params, &pj = job.params;
-		if (pj.primary_encoder_type == p0.primary_encoder_type && pj.primary_encoder_param == p0.primary_encoder_param &&
-		    (pj.primary_encoder_type != CMP_ENCODER_GOLOMB_MULTI || pl.enc[0].outlier ==
-		     airs_derive_outlier(p0.primary_encoder_type, p0.primary_encoder_param, p0.primary_encoder_outlier)))
-			atomicAdd(&b.ticket[8], 1u);
-	}
-	b.plans[j] = pl;
-	if (b.init_results && !b.ctx_io)
+	if (have && b.init_results && !b.ctx_io)
 		b.init_results[j] = pl.init_result;
-	if (pl.flags & AIRS_PF_CHECKSUM)
-		atomicAdd(&b.ticket[4], 1u);
-	if (!listed) {
-		b.big_list[j] = j;
-		if (j == 0)
-			b.ticket[2] = b.n_jobs;
-	} else if (small) {
-		const uint32_t slot = atomicAdd(&b.ticket[3], 1u);
-		b.small_list[slot] = j;
-		airs_fill_fast_job(reinterpret_cast<FastJob *>(b.fast_jobs)[slot], job, pl, b.src, b.dst);
-	} else {
-		b.big_list[atomicAdd(&b.ticket[2], 1u)] = j;
+	/* one atomic per warp and counter: the lanes' places follow from the ballots */
+	const uint32_t below = (1u << lane) - 1u;
+	const uint32_t m_cs = __ballot_sync(kFull, have && (pl.flags & AIRS_PF_CHECKSUM));
+	const uint32_t m_small = __ballot_sync(kFull, small);
+	const uint32_t m_big = __ballot_sync(kFull, have && listed && !small);
+	uint32_t base_small = 0, base_big = 0;
+	if (lane == 0) {
+		if (m_cs)
+			atomicAdd(&b.ticket[4], (uint32_t)__popc(m_cs));
+		if (m_small)
+			base_small = atomicAdd(&b.ticket[3], (uint32_t)__popc(m_small));
+		if (m_big)
+			base_big = atomicAdd(&b.ticket[2], (uint32_t)__popc(m_big));
+	}
+	base_small = __shfl_sync(kFull, base_small, 0);
+	base_big = __shfl_sync(kFull, base_big, 0);
+	if (have) {
+		if (!listed) {
+			b.big_list[j] = j;
+			if (j == 0)
+				b.ticket[2] = b.n_jobs;
+		} else if (small) {
+			const uint32_t slot = base_small + (uint32_t)__popc(m_small & below);
+			b.small_list[slot] = j;
+			FastJob fj;
+			airs_fill_fast_job(fj, job, pl, b.src, b.dst);
+			reinterpret_cast<FastJob *>(b.fast_jobs)[slot] = fj;
+		} else {
+			b.big_list[base_big + (uint32_t)__popc(m_big & below)] = j;
+		}
+		b.plans[j] = pl;
 	}
 }
 
@@ -2047,7 +2083,7 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 	__shared__ Shared sh;
 	const uint32_t tid = threadIdx.x;
 
-	if (gate_closed(b))
+	if (gate_closed(b) || b.ticket[2] == 0u) /* not this phase's launch, or no job for this kernel */
 		return;
 
 	for (uint32_t w = tid; w < 2u * (4u + kStgWords); w += kThreads)

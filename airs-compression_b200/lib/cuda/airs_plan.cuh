@@ -18,7 +18,7 @@
 #define AIRS_PF_SMALL       32u  /* one short frame without model: a warp of airs_small_kernel encodes it */
 
 /* 128 bytes, read by the encode kernel with one coalesced 32-lane load */
-struct JobPlan {
+struct alignas(16) JobPlan {
 	EncConst enc[2];      /* [0] primary, [1] secondary encoder constants            (56 B) */
 	uint32_t pre[2];      /* preprocessing of primary / secondary passes                    */
 	uint32_t pre_err[2];  /* work-buffer error of that preprocessing or 0 (pre.c:321-393)   */

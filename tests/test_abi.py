@@ -162,3 +162,18 @@ def test_golomb_division_trick():
         u = u[(u >= 0) & (u < top)].astype(np.uint64)
         q = (((u + np.uint64(1)) * np.uint64(magic)) >> np.uint64(32)) >> np.uint64(L)
         assert np.array_equal(q, u // g), int(g)
+
+
+def test_fast_kernel_division():
+    """airs_fast_kernel's quotient (airs_fast.cuh): q = umulhi(x, ceil(2^32 / g)) for 2 <= g <= 32767, and
+    umulhi(x + 1, 2^32 - 1) for g = 1, is floor(x / g) for every dividend the encoders can form
+    (0 <= x <= 65536 + g).  Every g; every dividend at and next to a multiple of g, plus random ones."""
+    rng = np.random.default_rng(5)
+    for g in range(1, 32768):
+        m = 0xFFFFFFFF if g == 1 else 0xFFFFFFFF // g + 1
+        top = 65536 + g
+        k = np.arange(0, top // g + 2, dtype=np.uint64) * np.uint64(g)
+        x = np.concatenate([k, k + np.uint64(1), k[1:] - np.uint64(1), rng.integers(0, top + 1, 64).astype(np.uint64)])
+        x = x[x <= top]
+        q = ((x + np.uint64(1 if g == 1 else 0)) * np.uint64(m)) >> np.uint64(32)
+        assert np.array_equal(q, x // np.uint64(g)), g

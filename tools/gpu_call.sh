@@ -16,6 +16,11 @@ ncu:*)
   timeout 300 python tools/ncu_case.py $case > gpurun_out/ncu_plain_$name.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kern -s 1 -c 1 -f -o gpurun_out/$name python tools/ncu_case.py $case > gpurun_out/ncu_$name.log 2>&1
   tail -n 3 gpurun_out/ncu_$name.log ;;
+launches:*)
+  IFS=: read -r _ case name <<< "$step"
+  timeout 300 python tools/ncu_case.py $case > gpurun_out/ncu_plain_$name.log 2>&1 &&
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:airs\|concat\|Memset -c 40 --csv --log-file gpurun_out/$name.csv python tools/ncu_case.py $case > gpurun_out/ncu_$name.log 2>&1
+  tail -n 3 gpurun_out/ncu_$name.log ;;
 *) echo "unknown step $step" ;;
 esac
 done
