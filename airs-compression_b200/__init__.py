@@ -8,7 +8,7 @@ from .loader import load_library, library_path  # noqa: F401
 
 
 def __getattr__(name):
-    if name in ("batch", "parallel"):  # need torch; imported on demand
+    if name in ("batch", "parallel", "workloads"):  # need torch; imported on demand
         import importlib
         return importlib.import_module(__name__ + "." + name)
     raise AttributeError(name)

@@ -73,6 +73,16 @@ class DeviceBatch:
     def launches(self):
         return int(self.lib.airs_cuda_last_launch_count())
 
+    def hash_streams(self, stream=None):
+        """64-bit hash of every stream of the last run (include/airs_stream_hash.h), a device int64 tensor."""
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        out = torch.zeros(max(self.n_results, 1), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.airs_cuda_hash_streams(C.byref(self.desc), C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream))
+        if rc != 0:
+            raise RuntimeError("airs_cuda_hash_streams failed (%d): %s" % (rc, self.lib.airs_cuda_last_error().decode()))
+        return out[:self.n_results]
+
     def fetch(self):
         """(dst, results, init_results, out_offsets-or-None, work) as numpy, after a sync."""
         torch.cuda.synchronize(self.device)
@@ -80,6 +90,21 @@ class DeviceBatch:
         return (self.dst.cpu().numpy(), self.results.cpu().numpy().view(np.uint32),
                 self.init_results.cpu().numpy().view(np.uint32)[:self.n_jobs], offs,
                 self.work.cpu().numpy())
+
+
+def hash_ranges(base, offsets, sizes):
+    """64-bit hashes (include/airs_stream_hash.h) of the byte ranges base[offsets[k] : offsets[k] + sizes[k]];
+    base uint8, offsets int64, sizes int32 device tensors."""
+    lib = load_library()
+    n = int(sizes.numel())
+    out = torch.zeros(max(n, 1), dtype=torch.int64, device=base.device)
+    s = torch.cuda.current_stream(base.device)
+    with torch.cuda.device(base.device):
+        rc = lib.airs_cuda_hash_ranges(C.c_void_p(base.data_ptr()), C.c_void_p(offsets.data_ptr()), C.c_void_p(sizes.data_ptr()),
+                                       n, C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream))
+    if rc != 0:
+        raise RuntimeError("airs_cuda_hash_ranges failed (%d): %s" % (rc, lib.airs_cuda_last_error().decode()))
+    return out[:n]
 
 
 def concat_tmp_size(jobs, n_results):

@@ -234,6 +234,32 @@ static int launch_kernels(const AirsLaunch &l, int resident, cudaStream_t stream
 	return AIRS_OK;
 }
 
+/* the batch as the kernels see it: where everything lies in the scratch memory */
+static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_ctx_state *ctx_io)
+{
+	memset(&l, 0, sizeof(l));
+	l.src = (const uint8_t *)b->src;
+	l.dst = (uint8_t *)b->dst;
+	l.work = (uint8_t *)b->work;
+	l.jobs = b->jobs;
+	l.results = b->results;
+	l.init_results = b->init_results;
+	l.out_offsets = b->out_offsets;
+	l.ticket = (uint32_t *)b->scratch;
+	l.lookback = (uint64_t *)((uint8_t *)b->scratch + kScratchHeader);
+	l.plans = (struct JobPlan *)((uint8_t *)b->scratch + kScratchHeader + lookback_bytes(b->n_results));
+	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
+	l.small_list = l.big_list + b->n_jobs;
+	l.result_job = l.small_list + b->n_jobs;
+	l.fast_jobs = (uint8_t *)b->scratch +
+		      ((airs_cuda_batch_scratch_size(b->n_jobs, b->n_results) - 64 * (size_t)b->n_jobs) & ~(size_t)63);
+	l.ctx_io = ctx_io;
+	l.dst_size = b->dst_size;
+	l.n_jobs = b->n_jobs;
+	l.n_results = b->n_results;
+	l.layout = b->layout;
+}
+
 static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
 {
 	g_launches = 0;
@@ -256,28 +282,8 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	CU(cudaMemsetAsync(b->scratch, 0, kScratchHeader + lookback_bytes(b->n_results), stream));
 
 	AirsLaunch l;
-	memset(&l, 0, sizeof(l));
-	l.src = (const uint8_t *)b->src;
-	l.dst = (uint8_t *)b->dst;
-	l.work = (uint8_t *)b->work;
-	l.jobs = b->jobs;
-	l.results = b->results;
-	l.init_results = b->init_results;
-	l.out_offsets = b->out_offsets;
-	l.ticket = (uint32_t *)b->scratch;
-	l.lookback = (uint64_t *)((uint8_t *)b->scratch + kScratchHeader);
-	l.plans = (struct JobPlan *)((uint8_t *)b->scratch + kScratchHeader + lookback_bytes(b->n_results));
-	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
-	l.small_list = l.big_list + b->n_jobs;
-	l.result_job = l.small_list + b->n_jobs;
-	l.fast_jobs = (uint8_t *)b->scratch +
-		      ((airs_cuda_batch_scratch_size(b->n_jobs, b->n_results) - 64 * (size_t)b->n_jobs) & ~(size_t)63);
+	fill_launch(l, b, ctx_io);
 	CU(cudaMemsetAsync(l.result_job, 0xFF, 4 * (size_t)b->n_results, stream));
-	l.ctx_io = ctx_io;
-	l.dst_size = b->dst_size;
-	l.n_jobs = b->n_jobs;
-	l.n_results = b->n_results;
-	l.layout = b->layout;
 
 	if (b->layout == AIRS_LAYOUT_CONCAT && b->tmp && b->tmp_size && b->dst && !ctx_io && !((uintptr_t)b->tmp & 15u)) {
 		/* two phases (airs_concat.cu): SLOTS-style into temporary slots, scan, copy.  Everything is
@@ -330,6 +336,27 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 extern "C" int airs_cuda_compress_batch(const struct airs_batch *b, void *stream)
 {
 	return launch_batch(b, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int airs_cuda_hash_streams(const struct airs_batch *b, uint64_t *hashes, void *stream)
+{
+	if (!b || !b->jobs || !b->results || !b->scratch || !hashes)
+		return fail(AIRS_E_ARGUMENT, "hash: batch, jobs, results, scratch and hashes must be non-NULL");
+	if (b->layout == AIRS_LAYOUT_CONCAT && !b->out_offsets)
+		return fail(AIRS_E_ARGUMENT, "the CONCAT layout needs out_offsets");
+	AirsLaunch l;
+	fill_launch(l, b, nullptr);
+	CU(airs_launch_hash(&l, hashes, (cudaStream_t)stream));
+	return AIRS_OK;
+}
+
+extern "C" int airs_cuda_hash_ranges(const void *base, const uint64_t *offsets, const uint32_t *sizes, uint32_t n,
+				     uint64_t *hashes, void *stream)
+{
+	if (n && (!base || !offsets || !sizes || !hashes))
+		return fail(AIRS_E_ARGUMENT, "hash: base, offsets, sizes and hashes must be non-NULL");
+	CU(airs_launch_hash_ranges((const uint8_t *)base, offsets, sizes, n, hashes, (cudaStream_t)stream));
+	return AIRS_OK;
 }
 
 /*

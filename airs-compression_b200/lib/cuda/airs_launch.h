@@ -82,6 +82,9 @@ cudaError_t airs_launch_small(const struct AirsLaunch *b, unsigned int grid, cud
 cudaError_t airs_launch_fast(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_fast_resident_ctas(int *out);
 cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
+cudaError_t airs_launch_hash(const struct AirsLaunch *b, uint64_t *hashes, cudaStream_t stream);
+cudaError_t airs_launch_hash_ranges(const uint8_t *base, const uint64_t *offsets, const uint32_t *sizes, uint32_t n,
+				    uint64_t *hashes, cudaStream_t stream);
 size_t airs_concat_scratch_bytes(uint32_t n_jobs, uint32_t n_results);
 cudaError_t airs_launch_concat_slots(const struct AirsConcat *c, cudaStream_t stream);
 cudaError_t airs_launch_concat_gather(const struct AirsConcat *c, unsigned int grid, cudaStream_t stream);

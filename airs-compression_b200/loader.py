@@ -18,7 +18,7 @@ EXPORTS = [
     "airs_cuda_device_count", "airs_cuda_concurrent_jobs", "airs_cuda_last_error", "airs_cuda_batch_scratch_size",
     "airs_cuda_concat_tmp_size", "airs_cuda_residual_stats", "airs_cuda_golomb_param_for_mean",
     "airs_cuda_compress_batch", "airs_cuda_last_launch_count", "airs_cuda_compress_batch_host",
-    "airs_cuda_release_cache",
+    "airs_cuda_release_cache", "airs_cuda_hash_streams", "airs_cuda_hash_ranges",
     # include/airs_cuda_decode.h
     "airs_cuda_decode_scratch_size", "airs_cuda_decompress_batch",
 ]
@@ -79,6 +79,10 @@ def load_library():
     lib.airs_cuda_compress_batch.argtypes = [C.POINTER(abi.AirsBatch), vp]
     lib.airs_cuda_compress_batch.restype = C.c_int
     lib.airs_cuda_last_launch_count.restype = C.c_int
+    lib.airs_cuda_hash_streams.argtypes = [C.POINTER(abi.AirsBatch), vp, vp]
+    lib.airs_cuda_hash_streams.restype = C.c_int
+    lib.airs_cuda_hash_ranges.argtypes = [vp, vp, vp, u32, vp, vp]
+    lib.airs_cuda_hash_ranges.restype = C.c_int
     lib.airs_cuda_compress_batch_host.argtypes = [C.POINTER(abi.AirsHostBatch)]
     lib.airs_cuda_compress_batch_host.restype = C.c_int
     lib.airs_cuda_release_cache.restype = None

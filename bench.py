@@ -3,12 +3,15 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
     python bench.py --impl reference ...                     (the reference's CPU library, rank 0 only)
+    python bench.py --workload c2|c3|c4|c5 ...               (default c3)
 
 Metric (BASELINE.json): input GB/s compressed, device-timed; one JSON line on rank 0.
-A "step" is one pass of the batched driver (airs_cuda_compress_batch) over the whole
-workload of this rank, inputs resident in HBM.  Default workload = BASELINE config 2,
-batched: R independent contexts x 256 consecutive 64 KiB frames, DIFF+Golomb primary
-pass, MODEL+Golomb secondary passes with model update (inputs far larger than L2).
+A "step" is one pass of the batched driver (airs_cuda_compress_batch) over the whole workload of this
+rank, inputs resident in HBM.  Default workload = BASELINE config 3 (the largest single-GPU configuration
+BASELINE.json names): 1 Mi independent 4 KiB chunks per GPU, DIFF, mixed Golomb zero / multi parameters,
+escape-heavy data.  Every stream of the last timed step is then compared with the CPU reference
+(oracle/parity.py: sizes and 64-bit hashes of ALL frames, bytes of every 100th job) - `config.parity`.
+At N = 1 the default run also times config 2 batched and the named subset of config 4 (`config.all`).
 """
 import argparse
 import json
@@ -25,75 +28,29 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 METRIC = "input GB/s compressed (device-timed)"
-FRAMES, FRAME_SAMPLES = 256, 32768
-CHUNK_SAMPLES = 2048
 
 
-# --------------------------------------------------------------------------- workloads
-
-def c2_params(abi):
-    return abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=abi.ENC_GOLOMB_ZERO,
-                           primary_encoder_param=16, secondary_iterations=255,
-                           secondary_preprocessing=abi.PRE_MODEL, secondary_encoder_type=abi.ENC_GOLOMB_ZERO,
-                           secondary_encoder_param=8, model_rate=8)
-
-
-def uniform_jobs(abi, n_jobs, n, n_frames, cap, first_job=0, model=True):
-    jobs = np.zeros(n_jobs, dtype=abi.JOB_DTYPE)
-    fb = 2 * n
-    slot = (cap + 15) // 16 * 16
-    idx = np.arange(n_jobs, dtype=np.uint64)
-    jobs["src_offset"] = idx * np.uint64(fb * n_frames)
-    jobs["src_frame_stride"] = fb
-    jobs["dst_offset"] = idx * np.uint64(slot * n_frames)
-    jobs["dst_frame_stride"] = slot
-    jobs["work_offset"] = idx * np.uint64(fb)
-    jobs["identifier_base"] = (idx + np.uint64(first_job)) * np.uint64(1 << 16)
-    jobs["src_size"] = fb
-    jobs["dst_capacity"] = cap
-    jobs["work_size"] = fb if model else 0
-    jobs["n_frames"] = n_frames
-    jobs["dtype"] = abi.DT_U16
-    jobs["first_result"] = (idx * np.uint64(n_frames)).astype(np.uint32)
-    return jobs, int(slot) * n_frames * n_jobs, (fb * n_jobs if model else 16)
-
-
-def build_workload(pkg, name, units, first_unit, device=None):
-    """Returns dict(data=int16 tensor or numpy, jobs, dst_size, work_size, n_results, desc)."""
-    abi, synth = pkg.abi, pkg.synth
+def build_workload(pkg, name, units, first_unit, device=None, row=None):
+    wl = pkg.workloads
     if name == "c2":
-        n, nf = FRAME_SAMPLES, FRAMES
-        cap = 2 * n + 64
-        jobs, dsz, wsz = uniform_jobs(abi, units, n, nf, cap, first_unit)
-        jobs["params"] = c2_params(abi)
-        if device is None:
-            data = np.stack([synth.frames(1, first_unit + c, nf, n) for c in range(units)])
-        else:
-            data = synth.frames_torch(1, first_unit, units, nf, n, device=device)
-        desc = "config2 batched: %d contexts x %d frames x 64 KiB u16, DIFF+GOLOMB_ZERO g16 -> MODEL+GOLOMB_ZERO g8, " \
-               "255 secondary iterations, model_rate 8" % (units, nf)
-    elif name == "c3":
-        n, nf = CHUNK_SAMPLES, 1
-        cap = abi.compress_bound(2 * n)
-        jobs, dsz, wsz = uniform_jobs(abi, units, n, nf, cap, first_unit, model=False)
-        idx = np.arange(first_unit, first_unit + units, dtype=np.uint64)
-        h = synth.mix(np.uint64(1) ^ idx)
-        gtab = np.array([1, 2, 4, 7, 16, 60, 255, 1055], dtype=np.uint32)
-        otab = np.array([5, 42, 107, 200], dtype=np.uint32)
-        P = jobs["params"]
-        P["primary_preprocessing"] = abi.PRE_DIFF
-        P["primary_encoder_type"] = 1 + (idx & np.uint64(1)).astype(np.uint32)
-        P["primary_encoder_param"] = gtab[(h & np.uint64(7)).astype(np.int64)]
-        P["primary_encoder_outlier"] = otab[((h >> np.uint64(3)) & np.uint64(3)).astype(np.int64)]
-        if device is None:
-            data = synth.chunks(1, first_unit, units, n, esc=32)
-        else:
-            data = synth.chunks_torch(1, first_unit, units, n, esc=32, device=device)
-        desc = "config3: %d independent 4 KiB chunks, DIFF, mixed Golomb zero/multi parameters, escape heavy" % units
-    else:
-        raise SystemExit("unknown workload " + name)
-    return dict(data=data, jobs=jobs, dst_size=dsz, work_size=wsz, n_results=units * nf, desc=desc,
-                n_samples_total=units * nf * n, model_bytes=(2 * 2 * n * units if name == "c2" else 0))
+        return wl.config2(units, first_unit, device)
+    if name == "c3":
+        return wl.config3(units, first_unit, device)
+    if name == "c5":
+        return wl.config5(units, first_unit, device)
+    if name == "c4":
+        return wl.config4_row(row, device=device, first_unit=first_unit)
+    raise SystemExit("unknown workload " + name)
+
+
+def default_units(pkg, lib, name, world):
+    if name == "c2":
+        return lib.airs_cuda_concurrent_jobs()      # one context per resident CTA: all contexts side by side
+    if name == "c3":
+        return 1 << 20                              # config 3 as stated, per GPU (weak scaling)
+    if name == "c5":
+        return (1 << 15) // max(world, 2)           # the 64 GiB stream cut over the ranks (N = 1: half of it)
+    return 0
 
 
 # --------------------------------------------------------------------------- clocks
@@ -143,47 +100,90 @@ class ClockSampler:
 # --------------------------------------------------------------------------- CPU arm
 
 def cpu_reference_run(pkg, workload, steps, warmup, target_s):
-    """Times the reference's own CPU library (oracle/_ref, else the oracle port) on a bounded
-    sample of the workload with every host core.  Returns (GB/s, info dict, sample job set, outputs)."""
-    from oracle import oracle_py  # the one place bench.py executes oracle/: the CPU baseline
-    if oracle_py.have_ref():
-        lib, kind = oracle_py.load_ref(), "reference"
-    else:
-        lib, kind = oracle_py.load_oracle(), "port"
+    """Times the reference's own CPU library (oracle/_ref, else the oracle port) on a bounded sample of the
+    workload with every host core.  Returns (GB/s, info dict, ms per step)."""
+    from oracle import parity  # the CPU legs are the one place bench.py executes oracle/
+    lib, kind = parity.cpu_library()
     cores = os.cpu_count() or 1
-    abi = pkg.abi
-    # pilot: one unit per core to size the sample
-    unit_bytes = (FRAMES * FRAME_SAMPLES * 2) if workload == "c2" else CHUNK_SAMPLES * 2
-    per_core = 1 if workload == "c2" else 256
-    units = cores * per_core
-    w = build_workload(pkg, workload, units, 0)
+    wl = pkg.workloads
+    if workload == "c2":
+        w = wl.config2(cores, 0)
+    elif workload == "c5":
+        w = wl.config5(cores, 0)
+    elif workload == "c4":
+        w = wl.config4_row(wl.CONFIG4_ROWS[5], total_samples=cores << 20)
+    else:
+        w = wl.config3(cores * 256, 0)
     src = np.ascontiguousarray(w["data"]).view(np.uint8).reshape(-1)
-    js = dict(src=src, jobs=w["jobs"], dst_size=w["dst_size"], work_size=w["work_size"], n_results=w["n_results"], layout=0)
-    dst = np.zeros(js["dst_size"], dtype=np.uint8)
-    work = np.zeros(js["work_size"], dtype=np.uint8)
+    dst = np.zeros(w["dst_size"], dtype=np.uint8)
+    work = np.zeros(w["work_size"], dtype=np.uint8)
 
     def once():
         t0 = time.perf_counter()
-        res, init, _ = lib.run_jobs(src, dst, work, js["jobs"], 0, threads=cores)
-        return time.perf_counter() - t0, res
-    t_pilot, res = once()
+        lib.run_jobs(src, dst, work, w["jobs"], 0, threads=cores)
+        return time.perf_counter() - t0
+    t_pilot = once()
     reps = max(1, int(target_s / max(t_pilot, 1e-3)))   # repeat the sample so a step lasts ~target_s
     times = []
     for s in range(warmup + steps):
-        t = 0.0
-        for _ in range(reps):
-            dt, res = once()
-            t += dt
+        t = sum(once() for _ in range(reps))
         if s >= warmup:
             times.append(t)
-    in_bytes = units * unit_bytes * reps
+    in_bytes = src.nbytes * reps
     gbs = in_bytes * len(times) / sum(times) / 1e9
     info = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind,
-            "sample": "%d x (%s) per step, %.1f s per step, %d threads" % (reps, w["desc"], sum(times) / len(times), cores)}
-    return gbs, info, js, (dst, res), sum(times) / len(times) * 1e3
+            "sample": "%d x (%s) per step, %.1f s per step, %d threads" % (reps, w["desc"], sum(times) / len(times), cores),
+            "note": "same workload generator, parameters and per-chunk shape as the GPU arm, fewer chunks: a per-byte rate"}
+    return gbs, info, sum(times) / len(times) * 1e3
 
 
-# --------------------------------------------------------------------------- main
+# --------------------------------------------------------------------------- GPU arm
+
+def timed_steps(db, steps, warmup, device, barrier, sampler=None):
+    """W untimed steps, then K steps between CUDA events on the launching stream.  Returns (total ms, ms per
+    step, kernels launched)."""
+    import torch
+    for _ in range(warmup):
+        db.run()
+    barrier()
+    if sampler:
+        sampler.mark()
+    stream = torch.cuda.current_stream(device)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    barrier()
+    evs[0].record(stream)
+    launches = 0
+    for s in range(steps):
+        db.run(stream)
+        launches += db.launches()
+        evs[s + 1].record(stream)
+    barrier()
+    return evs[0].elapsed_time(evs[-1]), [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)], launches
+
+
+def run_workload(pkg, w, device, steps, warmup, barrier, peak, sampler=None, parity_opts=None):
+    """One workload on this rank: timing, sizes, roofline numbers and (parity_opts) the comparison with the CPU
+    reference.  Returns (summary dict, DeviceBatch, device data tensor)."""
+    import torch
+    abi = pkg.abi
+    data = w["data"].view(torch.uint8).reshape(-1)
+    db = pkg.batch.DeviceBatch(data, w["jobs"], w["dst_size"], w["work_size"], w["n_results"],
+                               layout=abi.LAYOUT_SLOTS, device=device)
+    total_ms, step_ms, launches = timed_steps(db, steps, warmup, device, barrier, sampler)
+    res = db.results.cpu().numpy().view(np.uint32)
+    n_err = int((res > 0xFFFFFF80).sum())
+    out_bytes = int(res[res <= 0xFFFFFF80].astype(np.int64).sum())
+    in_bytes = w["n_samples_total"] * 2
+    alg = in_bytes + out_bytes + w["model_bytes"]
+    launch_ms = float(np.mean(step_ms))
+    out = {"desc": w["desc"], "in_bytes": in_bytes, "out_bytes": out_bytes, "errors": n_err, "total_ms": total_ms,
+           "launch_ms": launch_ms, "launches": launches, "alg_bytes": alg,
+           "input_gbs": in_bytes / (launch_ms * 1e-3) / 1e9, "frac": alg / (launch_ms * 1e-3) / 1e9 / peak}
+    if parity_opts is not None:
+        from oracle import parity  # CPU leg: the checker
+        out["parity"] = parity.check_device_batch(db, w["jobs"], data, **parity_opts)
+    return out, db, data
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -191,13 +191,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
-    ap.add_argument("--units", type=int, default=0, help="contexts (c2) or chunks (c3) per GPU")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--units", type=int, default=0, help="contexts (c2) or chunks (c3, c5) per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--parity-jobs", type=int, default=0, help="compare only the first N jobs with the CPU reference (0: all)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-round-trip", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -210,7 +212,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        gbs, info, _, _, ms = cpu_reference_run(pkg, args.workload, args.steps, args.warmup, target_s=3.0)
+        gbs, info, ms = cpu_reference_run(pkg, args.workload, args.steps, args.warmup, target_s=3.0)
         print(json.dumps({
             "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -230,97 +232,90 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = pkg.load_library()
-    sms = torch.cuda.get_device_properties(device).multi_processor_count
-
-    # one context per resident CTA of the encode kernel: all contexts of a rank run side by side
-    units = args.units or (lib.airs_cuda_concurrent_jobs() if args.workload == "c2" else 1 << 20)
-    first_unit = rank * units                                   # weak scaling: fixed work per GPU
-    w = build_workload(pkg, args.workload, units, first_unit, device=device)
-    data = w["data"].view(torch.uint8).reshape(-1)
-    db = pkg.batch.DeviceBatch(data, w["jobs"], w["dst_size"], w["work_size"], w["n_results"],
-                               layout=abi.LAYOUT_SLOTS, device=device)
-    in_bytes = w["n_samples_total"] * 2
+    wl = pkg.workloads
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
+    parity_opts = None if args.no_parity else {"threads": cores, "sample_every": 100,
+                                               "max_jobs": args.parity_jobs or None}
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        db.run()
-    barrier()
-    sampler.mark()
-    stream = torch.cuda.current_stream(device)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    evs[0].record(stream)
-    launches = 0
-    for s in range(args.steps):
-        db.run(stream)
-        launches += db.launches()
-        evs[s + 1].record(stream)
-    barrier()
+    rows = None
+    if args.workload == "c4":
+        # the named subset of config 4, 1 GiB per row, default cut of 512 x 2 MiB; value = all rows together
+        rows, tot_in, tot_out, tot_alg, tot_ms, tot_err, launches = [], 0, 0, 0, 0.0, 0, 0
+        par_ok, par_frames = True, 0
+        for row in wl.CONFIG4_ROWS:
+            w = wl.config4_row(row, device=device, first_unit=rank * 512)
+            r, db, data = run_workload(pkg, w, device, args.steps, args.warmup, barrier, peak, sampler, parity_opts)
+            rows.append({"row": row[0], "input_gbs": r["input_gbs"], "frac": r["frac"], "ms": r["launch_ms"],
+                         "ratio": r["in_bytes"] / max(r["out_bytes"], 1), "errors": r["errors"],
+                         "parity": ({k: r["parity"][k] for k in ("frames", "identical", "byte_compared_frames")}
+                                    if "parity" in r else None)})
+            tot_in += r["in_bytes"]; tot_out += r["out_bytes"]; tot_alg += r["alg_bytes"]
+            tot_ms += r["total_ms"]; tot_err += r["errors"]; launches += r["launches"]
+            if "parity" in r:
+                par_ok &= r["parity"]["identical"]; par_frames += r["parity"]["frames"]
+            del db, data, w
+            torch.cuda.empty_cache()
+        main_r = {"desc": "config4: named subset of %d (preprocessing, encoder, option) rows, 1 GiB each as 512 x 2 MiB chunks "
+                          "(model rows: 64 contexts x 8 frames)" % len(rows),
+                  "in_bytes": tot_in, "out_bytes": tot_out, "errors": tot_err, "total_ms": tot_ms,
+                  "launch_ms": tot_ms / args.steps, "launches": launches, "alg_bytes": tot_alg}
+        if parity_opts is not None:
+            main_r["parity"] = {"identical": par_ok, "frames": par_frames, "jobs": None}
+        db = data = w = None
+        units = 0
+    else:
+        units = args.units or default_units(pkg, lib, args.workload, world)
+        first_unit = rank * units                                   # contiguous shards, identifiers by global index
+        w = build_workload(pkg, args.workload, units, first_unit, device=device)
+        main_r, db, data = run_workload(pkg, w, device, args.steps, args.warmup, barrier, peak, sampler, parity_opts)
     clocks = sampler.stop()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    res = db.results.cpu().numpy().view(np.uint32)
-    n_err = int((res > 0xFFFFFF80).sum())
-    out_bytes = int(res[res <= 0xFFFFFF80].astype(np.int64).sum())
 
-    t = torch.tensor([total_ms, float(in_bytes), float(out_bytes), float(n_err)], dtype=torch.float64, device=device)
+    in_bytes, out_bytes = main_r["in_bytes"], main_r["out_bytes"]
+    par = main_r.get("parity")
+    t = torch.tensor([main_r["total_ms"], float(in_bytes), float(out_bytes), float(main_r["errors"]),
+                      0.0 if (par is None or par["identical"]) else 1.0, float(par["frames"]) if par else 0.0],
+                     dtype=torch.float64, device=device)
+    total_ms = main_r["total_ms"]
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         total_ms = float(tmax[0])
-    all_in, all_out, all_err = float(t[1]), float(t[2]), int(t[3])
+    all_in, all_out, all_err, par_bad, par_frames = float(t[1]), float(t[2]), int(t[3]), float(t[4]), int(t[5])
     value = all_in * args.steps / (total_ms * 1e-3) / 1e9
 
-    # ---- size-independent check at the full size: every stream of the last timed step goes
-    # through the device decoder (airs_cuda_decompress_batch) and must give back the input
-    round_trip = None
-    if not args.no_round_trip:
-        dj = np.zeros(units, dtype=abi.DEC_JOB_DTYPE)
-        for a_, b_ in (("src_offset", "dst_offset"), ("src_frame_stride", "dst_frame_stride"), ("src_size", "dst_capacity"),
-                       ("dst_offset", "src_offset"), ("dst_frame_stride", "src_frame_stride"), ("dst_capacity", "src_size"),
-                       ("n_frames", "n_frames"), ("dtype", "dtype"), ("first_result", "first_result")):
-            dj[a_] = w["jobs"][b_]
-        dec = pkg.batch.DeviceDecodeBatch(db.dst, dj, data.numel(), w["n_results"], device=device)
-        dec.run()                                           # untimed first run
-        torch.cuda.synchronize(device)
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(stream)
-        dec.run(stream)
-        d1.record(stream)
-        torch.cuda.synchronize(device)
-        dres = dec.results.cpu().numpy().view(np.uint32)[:w["n_results"]]
-        ok = bool(np.all(dres == w["jobs"]["src_size"][0])) and bool(torch.equal(dec.dst[:data.numel()], data))
-        tr = torch.tensor([0.0 if ok else 1.0, d0.elapsed_time(d1)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-        round_trip = {"identical": float(tr[0]) == 0.0, "samples": w["n_samples_total"] * world,
-                      "decode_ms": float(tr[1]), "decode_output_gbs": in_bytes * world / (float(tr[1]) * 1e-3) / 1e9,
-                      "what": "streams of the last timed step -> airs_cuda_decompress_batch -> compared with the input, all ranks"}
-        del dec
-
-    # ---- N > 1: the epilogue of SURVEY.md 8e, reported apart from the metric - every rank lays a part
-    # of its shard out as ONE concatenated stream (CONCAT layout, device-wide scan), then sizes and
-    # streams are gathered over NCCL so that every rank holds the whole output in rank order
+    # ---- N > 1: the epilogue of SURVEY.md 8e, reported apart from the metric - every rank lays (a part of) its
+    # shard out as ONE concatenated stream (CONCAT layout, device-wide scan), then sizes and streams are gathered
+    # over NCCL so that every rank holds the whole output in rank order; the gathered bytes are hashed stream by
+    # stream and compared with the hashes every rank took of its own part
     gather = None
-    if world > 1 and not args.no_gather:
+    if world > 1 and not args.no_gather and args.workload != "c4":
         try:
-            g_units = min(units, 128) if args.workload == "c2" else min(units, 1 << 17)
-            wg = build_workload(pkg, args.workload, g_units, first_unit, device=device)
+            g_units = {"c2": min(units, 128), "c3": min(units, 1 << 18), "c5": min(units, 4096)}[args.workload]
+            wg = build_workload(pkg, args.workload, g_units, rank * units, device=device)
             gdata = wg["data"].view(torch.uint8).reshape(-1)
             tmp = pkg.batch.concat_tmp_size(wg["jobs"], wg["n_results"])
             cb = pkg.batch.DeviceBatch(gdata, wg["jobs"], gdata.numel(), wg["work_size"], wg["n_results"],
                                        layout=abi.LAYOUT_CONCAT, device=device, concat_tmp=tmp)
             cb.run()
+            own_hashes = cb.hash_streams()
             torch.cuda.synchronize(device)
             total = int(cb.out_offsets[-1].item())
             barrier()
+            stream = torch.cuda.current_stream(device)
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(stream)
             sizes_all, counts = pkg.parallel.allgather_sizes(cb.results)
@@ -329,26 +324,35 @@ def main():
             barrier()
             tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
             dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            ok = int(streams_all.numel()) == int(sizes_all.to(torch.int64).clamp(min=0).sum().item())
+            hashes_all, _ = pkg.parallel.allgather_sizes(own_hashes)
+            # hash the gathered bytes: one CONCAT "batch" over all ranks' frames
+            sz = sizes_all.to(torch.int64)
+            sz = torch.where(sz < 0, torch.zeros_like(sz), sz)
+            gathered_ok = int(streams_all.numel()) == int(sz.sum().item())
+            if gathered_ok:
+                starts = torch.cumsum(sz, 0) - sz
+                got = pkg.batch.hash_ranges(streams_all, starts.contiguous(), sizes_all.view(torch.int32).contiguous())
+                gathered_ok = bool(torch.equal(got, hashes_all))
             gather = {"contexts_or_chunks_per_rank": g_units, "frames": int(sizes_all.numel()),
                       "gathered_bytes": int(streams_all.numel()), "ms": float(tg[0]),
-                      "gbs": streams_all.numel() / (float(tg[0]) * 1e-3) / 1e9, "sizes_match_streams": ok,
-                      "what": "CONCAT layout per rank, then all_gather of sizes and streams (NCCL), max over ranks"}
+                      "gbs": streams_all.numel() / (float(tg[0]) * 1e-3) / 1e9, "gathered_bytes_match_rank_hashes": gathered_ok,
+                      "what": "CONCAT layout per rank, then sizes and streams broadcast into one buffer in rank order (NCCL), "
+                              "max over ranks; every gathered stream re-hashed and compared with its rank's hash"}
             del cb, streams_all
         except Exception as exc:  # the metric line must survive a failing epilogue
-            gather = {"error": repr(exc)[:200]}
+            gather = {"error": repr(exc)[:300]}
 
     # ---- end to end through the C-ABI with HOST buffers (copies inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.workload != "c4":
         try:
-            # a quarter of the device-resident workload (c2: 222 contexts = 3.7 GB of samples per step)
-            e_units = max(1, min(units, max(8, units // 4) if args.workload == "c2" else 1 << 17))
-            we = build_workload(pkg, args.workload, e_units, first_unit, device=device)
+            e_units = {"c2": max(8, units // 4), "c3": 1 << 18, "c5": 512}[args.workload]
+            e_units = max(1, min(units, e_units))
+            we = build_workload(pkg, args.workload, e_units, rank * units, device=device)
             src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
             src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
-            cap_total = we["dst_size"]
-            dst_h = torch.empty(cap_total, dtype=torch.uint8).pin_memory()
+            # every workload goes through the CONCAT layout: only the compressed bytes travel back
+            dst_h = torch.empty(int(we["n_samples_total"] * 2 * 1.1) + (1 << 20), dtype=torch.uint8).pin_memory()
             jobs_h = np.ascontiguousarray(we["jobs"])
             results_h = np.zeros(we["n_results"], dtype=np.uint32)
             init_h = np.zeros(e_units, dtype=np.uint32)
@@ -360,9 +364,7 @@ def main():
             hb.work, hb.work_size = None, we["work_size"]
             hb.jobs, hb.results, hb.init_results = jobs_h.ctypes.data, results_h.ctypes.data, init_h.ctypes.data
             hb.out_offsets = offs_h.ctypes.data
-            # independent chunks: CONCAT (only the streams travel back); multi-frame contexts: SLOTS
-            e_layout = abi.LAYOUT_CONCAT if args.workload == "c3" else abi.LAYOUT_SLOTS
-            hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], e_layout
+            hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], abi.LAYOUT_CONCAT
             e_steps = max(3, min(args.steps, 10))
             for _ in range(2):
                 assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
@@ -378,69 +380,87 @@ def main():
             e_in = we["n_samples_total"] * 2
             e2e = {"value": e_in * world * e_steps / float(td[0]) / 1e9, "unit": "GB/s",
                    "h2d_bytes_per_step": int(src_h.numel() + jobs_h.nbytes),
-                   "d2h_bytes_per_step": (int(offs_h[-1]) + offs_h.nbytes if e_layout == abi.LAYOUT_CONCAT
-                                          else dst_h.numel()) + results_h.nbytes + init_h.nbytes,
-                   "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, %s layout)" % ("CONCAT" if e_layout else "SLOTS"),
+                   "d2h_bytes_per_step": int(offs_h[-1]) + offs_h.nbytes + results_h.nbytes + init_h.nbytes,
+                   "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, CONCAT layout)",
                    "timing": "host wall clock, max over ranks, %d steps" % e_steps}
             lib.airs_cuda_release_cache()
+            del we, src_h, dst_h
         except Exception as exc:  # the metric line must survive (host memory, pinning)
-            e2e = {"error": repr(exc)[:200]}
+            e2e = {"error": repr(exc)[:300]}
+
+    # ---- N = 1, default workload: the other single-GPU configurations beside the headline
+    extras = None
+    if world == 1 and args.workload == "c3" and not args.no_extras:
+        try:
+            del db, data, w
+            torch.cuda.empty_cache()
+            extras = {}
+            po = None if args.no_parity else {"threads": cores, "sample_every": 100, "max_jobs": 64}
+            w2 = wl.config2(lib.airs_cuda_concurrent_jobs(), 0, device)
+            r2, db2, d2 = run_workload(pkg, w2, device, 3, 3, barrier, peak, None, po)
+            extras["c2b"] = {"workload": r2["desc"], "input_gbs": r2["input_gbs"], "frac": r2["frac"], "ms": r2["launch_ms"],
+                             "parity_first_64_contexts": r2.get("parity", {}).get("identical"),
+                             "parity_frames": r2.get("parity", {}).get("frames")}
+            del w2, db2, d2
+            torch.cuda.empty_cache()
+            extras["c4"] = []
+            po = None if args.no_parity else {"threads": cores, "sample_every": 100, "max_jobs": None}
+            for row in wl.CONFIG4_ROWS:
+                w4 = wl.config4_row(row, device=device)
+                r4, db4, d4 = run_workload(pkg, w4, device, 3, 3, barrier, peak, None, po)
+                extras["c4"].append({"row": row[0], "input_gbs": round(r4["input_gbs"], 1), "frac": round(r4["frac"], 4),
+                                     "parity": r4.get("parity", {}).get("identical"), "frames": r4.get("parity", {}).get("frames")})
+                del w4, db4, d4
+                torch.cuda.empty_cache()
+            extras["what"] = "device-timed like the headline (3 steps after 3 warm-up steps each); c4 = named subset of config 4, " \
+                             "1 GiB per row as 512 x 2 MiB chunks, every frame compared with the CPU reference"
+        except Exception as exc:
+            extras = {"error": repr(exc)[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = in_bytes + out_bytes + w["model_bytes"]         # per launch, this rank
-    launch_ms = float(np.mean(step_ms))
+    alg_bytes = main_r["alg_bytes"]                                # per launch, this rank
+    launch_ms = main_r["launch_ms"]
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         tr = json.load(open(tpath)).get(args.workload)
         if tr and tr.get("units") == units:
-            traffic = tr["dram_bytes_per_launch"]
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr.get("source")
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": w["desc"], "per_gpu_input_bytes": in_bytes, "layout": "SLOTS",
+        "scaling": "strong" if args.workload == "c5" and world > 1 else "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": main_r["desc"], "per_gpu_input_bytes": in_bytes, "layout": "SLOTS",
                    "l2": "inputs (%.1f GiB per GPU) larger than the 126 MB L2; no flush needed" % (in_bytes / 2**30),
                    "compression_ratio": all_in / max(all_out, 1), "frames_with_errors": all_err},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "airs_encode_kernel",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "airs_fast_kernel" if args.workload == "c3" else "airs_encode_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
-                     "bytes_per_sample": alg_bytes / w["n_samples_total"]},
-        "clocks": clocks, "gpu_launches": launches,
+                     "bytes_per_sample": alg_bytes / (in_bytes / 2)},
+        "clocks": clocks, "gpu_launches": main_r["launches"],
     }
+    if par is not None:
+        line["config"]["parity"] = dict(par, frames_all_ranks=par_frames,
+                                        what="every stream of the last timed step against the CPU %s: sizes and 64-bit hashes of all "
+                                             "frames, bytes of every 100th job" % par.get("cpu", "reference"))
+        line["parity_full"] = bool(par_bad == 0.0 and not args.parity_jobs and all_err == 0)
+    if rows is not None:
+        line["config"]["rows"] = rows
     if e2e:
         line["e2e"] = e2e
-    if round_trip:
-        line["config"]["round_trip"] = round_trip
     if gather:
         line["config"]["gather"] = gather
+    if extras:
+        line["config"]["all"] = extras
     if world == 1 and not args.no_cpu:
-        gbs, info, js, (cdst, cres), _ = cpu_reference_run(pkg, args.workload, 1, 0, target_s=args.cpu_seconds)
+        gbs, info, _ = cpu_reference_run(pkg, args.workload, 1, 0, target_s=args.cpu_seconds)
         line["cpu_baseline"] = info
-        # parity spot check: the CPU sample is a prefix of this rank's workload
-        k = len(cres)
-        gres = res[:k]
-        same = bool(np.array_equal(gres, cres))
-        if same:
-            jobs = js["jobs"]
-            gdst = db.dst
-            for j in (0, len(jobs) // 2, len(jobs) - 1):
-                for f in (0, int(jobs[j]["n_frames"]) - 1):
-                    r = int(cres[int(jobs[j]["first_result"]) + f])
-                    o = int(jobs[j]["dst_offset"]) + f * int(jobs[j]["dst_frame_stride"])
-                    og = int(w["jobs"][j]["dst_offset"]) + f * int(w["jobs"][j]["dst_frame_stride"])
-                    same &= bool(np.array_equal(cdst[o:o + r], gdst[og:og + r].cpu().numpy()))
-        line["config"]["parity_vs_cpu_reference_sample"] = same
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

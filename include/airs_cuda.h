@@ -136,6 +136,21 @@ size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_results);
  */
 int airs_cuda_compress_batch(const struct airs_batch *batch, void *stream);
 
+/*
+ * Verification aid: the 64-bit hash of include/airs_stream_hash.h over every stream a batch
+ * produced (0 for a frame that failed), hashes[n_results] in device memory.  Call after
+ * airs_cuda_compress_batch() with the same descriptor (the scratch memory still holds the
+ * frame-to-job map), on the same stream.  The CPU side of the comparison hashes the reference's
+ * output the same way (oracle/hash_jobs.h), so whole workloads are compared through 12 bytes per
+ * stream.  No reference counterpart.
+ */
+int airs_cuda_hash_streams(const struct airs_batch *batch, uint64_t *hashes, void *stream);
+
+/* ... and the same hash over n byte ranges base + offsets[k], sizes[k] bytes (a size that is an error code
+ * hashes to 0): streams that were moved, e.g. gathered from other GPUs.  All pointers are device pointers. */
+int airs_cuda_hash_ranges(const void *base, const uint64_t *offsets, const uint32_t *sizes, uint32_t n,
+			  uint64_t *hashes, void *stream);
+
 /* Number of kernels the last airs_cuda_compress_batch() on this thread launched. */
 int airs_cuda_last_launch_count(void);
 

@@ -693,3 +693,7 @@ int oracle_run_jobs(const void *src, void *dst, void *work, const struct airs_jo
 	free(bounce);
 	return 0;
 }
+
+/* the same loop, streams hashed in scratch memory of the calling thread instead of kept (hash_jobs.h) */
+#include "hash_jobs.h"
+AIRS_DEFINE_HASH_JOBS(oracle_hash_jobs, oracle_run_jobs)

@@ -35,7 +35,29 @@ class _Lib:
         self.run = getattr(self.lib, prefix + "_run_jobs")
         self.run.argtypes = _RUN_ARGS
         self.run.restype = C.c_int
+        self.hash = getattr(self.lib, prefix + "_hash_jobs")
+        self.hash.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        self.hash.restype = C.c_int
         self.kind = prefix
+
+    def hash_jobs(self, src, jobs, threads=1, job_begin=0, job_end=None):
+        """The batch loop with every stream hashed where it was produced (oracle/hash_jobs.h) instead of kept:
+        returns (results, hashes) for the frames of jobs[job_begin:job_end]; other entries stay 0.
+        src: contiguous numpy array, or an integer host address (pinned torch memory)."""
+        n_jobs = len(jobs)
+        job_end = n_jobs if job_end is None else job_end
+        n_results = int(jobs["first_result"][-1] + jobs["n_frames"][-1]) if n_jobs else 0
+        results = np.zeros(n_results, dtype=np.uint32)
+        hashes = np.zeros(n_results, dtype=np.uint64)
+        addr = src if isinstance(src, int) else src.ctypes.data
+        count = max(job_end - job_begin, 0)
+        threads = max(1, min(threads, count))
+        edges = (job_begin + np.linspace(0, count, threads + 1)).astype(np.int64)
+        with ThreadPoolExecutor(threads) as ex:
+            futs = [ex.submit(self.hash, addr, jobs.ctypes.data, int(edges[t]), int(edges[t + 1]),
+                              results.ctypes.data, hashes.ctypes.data) for t in range(threads)]
+            assert all(f.result() == 0 for f in futs)
+        return results, hashes
 
     def run_jobs(self, src, dst, work, jobs, layout=0, threads=1):
         """Run the batch loop.  src/dst/work: contiguous numpy uint8-viewable arrays (work may

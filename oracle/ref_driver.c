@@ -13,6 +13,7 @@
 #include "cmp.h"        /* the reference's lib/cmp.h (found first via -I) */
 #include "cmp_errors.h"
 #include "../include/airs_cuda.h" /* struct airs_job; its cmp.h include is guarded out */
+#include "hash_jobs.h"
 
 /* one counter per thread so that jobs can be spread over threads */
 static __thread uint64_t tls_counter;
@@ -110,3 +111,6 @@ int ref_run_jobs(const void *src, void *dst, void *work, const struct airs_job *
 	free(bounce);
 	return 0;
 }
+
+/* the same loop, streams hashed in scratch memory of the calling thread instead of kept (hash_jobs.h) */
+AIRS_DEFINE_HASH_JOBS(ref_hash_jobs, ref_run_jobs)

@@ -9,6 +9,14 @@ probe:*)
   AIRS_PROBE_LIB=$lib timeout 600 python tools/perf_probe.py ${cases//,/ } >> gpurun_out/probe.log 2>&1 ;;
 tests)
   timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/tests.log ;;
+pytest:*)
+  IFS=: read -r _ what <<< "$step"
+  timeout 2400 python -m pytest ${what//,/ } -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+  tail -n 25 gpurun_out/pytest.log ;;
+bench:*)
+  IFS=: read -r _ name bargs <<< "$step"
+  timeout 1500 python bench.py ${bargs//,/ } > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "bench rc=$?"
+  tail -n 5 gpurun_out/$name.err; head -c 6000 gpurun_out/$name.json ;;
 smoke)
   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log ;;
 ncu:*)
