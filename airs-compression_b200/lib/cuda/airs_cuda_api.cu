@@ -201,7 +201,7 @@ extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_resul
 	 * the job table on temporary slots (two-phase CONCAT) */
 	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs +
 	       4 * (size_t)n_results + 64 + sizeof(struct airs_job) * (size_t)n_jobs + 64 +
-	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 64 * (size_t)n_jobs;
+	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 64 * (size_t)n_jobs + 64 + 16 * (size_t)AIRS_TILE_RING;
 }
 
 extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results)
@@ -210,27 +210,30 @@ extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t
 	return (size_t)(sum_of_capacities + 16ull * n_results + 64);
 }
 
-/* plan, encode (CTA per job), encode (warp per job, SLOTS only), checksums */
+/* plan; short jobs (one warp each) and the tiles of long frames (SLOTS only); everything else, and what the
+ * two fast kernels handed back, one CTA per job; checksums */
 static int launch_kernels(const AirsLaunch &l, int resident, cudaStream_t stream)
 {
 	unsigned int grid = l.n_jobs < (uint32_t)resident ? l.n_jobs : (unsigned int)resident;
 	CU(airs_launch_plan(&l, stream));
-	CU(airs_launch_encode(&l, grid, stream));
-	g_launches += 2;
-	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) { /* short single-frame jobs: one warp each */
-		static thread_local int fast_dev = -1, fast_ctas = 0;
+	g_launches++;
+	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) {
+		static thread_local int fast_dev = -1, fast_ctas = 0, tile_ctas = 0;
 		int dev;
 		CU(cudaGetDevice(&dev));
 		if (dev != fast_dev) {
 			CU(airs_fast_resident_ctas(&fast_ctas));
+			CU(airs_tile_resident_ctas(&tile_ctas));
 			fast_dev = dev;
 		}
 		const unsigned int want = (l.n_jobs + AIRS_FAST_THREADS / 32 - 1) / (AIRS_FAST_THREADS / 32);
 		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
-		g_launches++;
+		CU(airs_launch_tile(&l, (unsigned int)tile_ctas, stream));
+		g_launches += 2;
 	}
+	CU(airs_launch_encode(&l, grid, stream));
 	CU(airs_launch_checksum(&l, stream));
-	g_launches++;
+	g_launches += 2;
 	return AIRS_OK;
 }
 
@@ -251,8 +254,12 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
 	l.small_list = l.big_list + b->n_jobs;
 	l.result_job = l.small_list + b->n_jobs;
-	l.fast_jobs = (uint8_t *)b->scratch +
-		      ((airs_cuda_batch_scratch_size(b->n_jobs, b->n_results) - 64 * (size_t)b->n_jobs) & ~(size_t)63);
+	{ /* from the end of the scratch memory: tile rings, then the fast-job records in front of them */
+		const size_t end = airs_cuda_batch_scratch_size(b->n_jobs, b->n_results);
+		const size_t ring = (end - 16 * (size_t)AIRS_TILE_RING) & ~(size_t)63;
+		l.tile_ring = (uint64_t *)((uint8_t *)b->scratch + ring);
+		l.fast_jobs = (uint8_t *)b->scratch + ((ring - 64 * (size_t)b->n_jobs) & ~(size_t)63);
+	}
 	l.ctx_io = ctx_io;
 	l.dst_size = b->dst_size;
 	l.n_jobs = b->n_jobs;
@@ -284,6 +291,8 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	AirsLaunch l;
 	fill_launch(l, b, ctx_io);
 	CU(cudaMemsetAsync(l.result_job, 0xFF, 4 * (size_t)b->n_results, stream));
+	if (b->layout == AIRS_LAYOUT_SLOTS || b->tmp)
+		CU(cudaMemsetAsync(l.tile_ring, 0, 16 * (size_t)AIRS_TILE_RING, stream));
 
 	if (b->layout == AIRS_LAYOUT_CONCAT && b->tmp && b->tmp_size && b->dst && !ctx_io && !((uintptr_t)b->tmp & 15u)) {
 		/* two phases (airs_concat.cu): SLOTS-style into temporary slots, scan, copy.  Everything is

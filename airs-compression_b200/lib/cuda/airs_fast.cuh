@@ -15,6 +15,9 @@
 #define AIRS_FJ_CHECKSUM    4u
 #define AIRS_FJ_FALLBACK_OK 8u
 
+/* samples of a tile of airs_tile_kernel */
+#define AIRS_TILE_SAMPLES 2048u
+
 /* largest Golomb parameter of the multiply-high division used by the fast kernels (below) */
 #define AIRS_FAST_MAX_G 32767u
 
@@ -24,13 +27,14 @@ struct alignas(16) FastJob {
 	uint64_t identifier;   /* of the primary pass: identifier_base + 1 (ref cmp.c:208,229) */
 	uint32_t n;            /* samples */
 	uint32_t cap_eff;      /* bytes the pass may write */
-	uint32_t flags;
+	uint32_t flags;        /* AIRS_FJ_* | floor(log2 g) << 8 */
 	uint32_t first_result;
 	uint32_t g;
 	uint32_t outlier;      /* derived outlier (header field, encoder.c:185-224) */
 	uint32_t magic;        /* airs_fast_magic(g) */
-	uint32_t L;            /* floor(log2 g) */
-	uint32_t pad[2];
+	uint32_t job;          /* index of the job in the batch */
+	uint32_t tile_base;    /* airs_tile_kernel: global id of the job's first tile ... */
+	uint32_t n_tiles;      /* ... and the number of its tiles */
 };
 static_assert(sizeof(FastJob) == 64, "FastJob is read as 16 words");
 
@@ -48,7 +52,7 @@ __host__ __device__ inline uint32_t airs_fast_magic(uint32_t g)
 
 #ifdef __CUDACC__
 __device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const JobPlan &pl, const uint8_t *src_base,
-					  uint8_t *dst_base)
+					  uint8_t *dst_base, uint32_t job_index, uint32_t tile_base, uint32_t n_tiles)
 {
 	f.src = (uint64_t)(uintptr_t)(src_base + job.src_offset);
 	f.dst = (uint64_t)(uintptr_t)(dst_base + job.dst_offset);
@@ -58,13 +62,14 @@ __device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const
 	f.flags = (pl.pre[0] == CMP_PREPROCESS_DIFF ? AIRS_FJ_PRE_DIFF : 0u) |
 		  (pl.enc[0].type == CMP_ENCODER_GOLOMB_MULTI ? AIRS_FJ_MULTI : 0u) |
 		  ((pl.flags & AIRS_PF_CHECKSUM) ? AIRS_FJ_CHECKSUM : 0u) |
-		  ((pl.flags & AIRS_PF_FALLBACK_OK) ? AIRS_FJ_FALLBACK_OK : 0u);
+		  ((pl.flags & AIRS_PF_FALLBACK_OK) ? AIRS_FJ_FALLBACK_OK : 0u) | (pl.enc[0].L << 8);
 	f.first_result = job.first_result;
 	f.g = pl.enc[0].g;
 	f.outlier = pl.enc[0].outlier;
 	f.magic = airs_fast_magic(pl.enc[0].g);
-	f.L = pl.enc[0].L;
-	f.pad[0] = f.pad[1] = 0;
+	f.job = job_index;
+	f.tile_base = tile_base;
+	f.n_tiles = n_tiles;
 }
 #endif
 

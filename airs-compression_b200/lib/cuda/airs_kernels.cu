@@ -1609,363 +1609,6 @@ __device__ uint64_t lookback_offset(volatile uint64_t *st, uint32_t k, uint32_t 
 	return excl;
 }
 
-/* -------------------------------------------------------------------------
- * airs_small_kernel: one warp per short single-frame job (AIRS_PF_SMALL).
- *
- * The same stages as the fast path of airs_encode_kernel, but warp-synchronous:
- * a warp owns its job, its staging area and its (single-sample) codeword table,
- * so nothing waits at a block barrier and nothing runs on one thread while 127
- * others idle.  Per warp tile of 1024 samples: 4 x LDG.128 per lane, packed
- * residuals, table arm (8 lookups and one 64-bit string per segment) or
- * arithmetic arm, shuffle scan, 3 reductions per string into the warp's staging
- * words, 128-bit stores.  Fewer than 8 samples at the end of a frame are encoded
- * by lane 0.  ref compress_engine / cmp_compress_generic, cmp.c:213-393.
- * ---------------------------------------------------------------------- */
-
-constexpr uint32_t kWStgBits = 1024u * 48u + 128u; /* one warp tile at 48 bits per sample + the carried group */
-constexpr uint32_t kWStgWords = kWStgBits / 32u + 4u;
-
-struct WarpShared {
-	alignas(16) uint32_t stg_mem[4 + kWStgWords];
-	uint2 slut[kLutStride]; /* {codeword, length} of residual r at [r + 32] */
-	uint32_t key[3];        /* encoder the table was built for */
-	uint32_t R;             /* its usable half range: 32, 16, 8 or 0 */
-	JobPlan plan;
-	airs_job job;
-	Pass pass;
-};
-
-/* the pair table of a CTA of airs_small_kernel<true>: built once per launch for the encoder of job 0,
- * read by every warp whose job uses that encoder (a batch of chunks with one parameter set) */
-struct PairShared {
-	uint32_t plut[kLutStride * kLutPitch];
-	uint2 slut[kLutStride];
-	uint32_t plut_key[3];
-	uint32_t plut_R;
-};
-
-template <bool P>
-struct PairHolder {
-	PairShared t;
-};
-template <>
-struct PairHolder<false> {
-};
-
-/* single-sample table of one warp; residuals qualify while their codeword is at most 16 bits long */
-__device__ __noinline__ void build_single_lut(WarpShared &ws, const EncConst &e)
-{
-	const uint32_t lane = threadIdx.x & 31u;
-	uint32_t bad = 0;
-
-	for (uint32_t idx = lane; idx < kLutStride; idx += 32u) {
-		const uint32_t r = (idx - kLutR) & 0xFFFFu;
-		uint32_t cw, cl, rw, rl;
-		encode_mapped_rt(e, airs_zigzag16(r), cw, cl, rw, rl);
-		const uint32_t len = cl + rl;
-		ws.slut[idx] = make_uint2((cw << rl) | rw, len);
-		if (len > 16u) {
-			const uint32_t dist = idx >= kLutR ? idx - kLutR + 1u : kLutR - idx;
-			bad |= dist <= 8u ? 7u : dist <= 16u ? 6u : 4u;
-		}
-	}
-	bad = __reduce_or_sync(kFull, bad);
-	if (lane == 0) {
-		ws.key[0] = e.type;
-		ws.key[1] = e.g;
-		ws.key[2] = e.outlier;
-		ws.R = (bad & 1u) ? 0u : kLutR >> __popc(bad);
-	}
-	__syncwarp();
-}
-
-/* drain the warp's staging area (see copy_out); the partial group stays in front */
-__device__ __forceinline__ void warp_copy_out(WarpShared &ws, const OutWin &o, Cursor &c, uint32_t bits)
-{
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t staged = c.sbits + bits, nvec = staged >> 7, b0 = c.gw0 * 4u;
-	uint4 *stg4 = reinterpret_cast<uint4 *>(ws.stg_mem + 4);
-
-	__syncwarp();
-	for (uint32_t v = lane; v < nvec; v += 32u) {
-		const uint32_t b = b0 + 16u * v;
-		const uint4 q = stg4[v];
-		if (b >= o.lo && b + 16u <= o.hi) {
-			*reinterpret_cast<uint4 *>(o.base + b) =
-				make_uint4(airs_bswap32(q.x), airs_bswap32(q.y), airs_bswap32(q.z), airs_bswap32(q.w));
-		} else {
-			const uint8_t *s8 = reinterpret_cast<const uint8_t *>(stg4 + v);
-#pragma unroll 1
-			for (uint32_t k = 0; k < 16u; k++)
-				if (b + k >= o.lo && b + k < o.hi)
-					o.base[b + k] = s8[k ^ 3u];
-		}
-		stg4[v] = make_uint4(0, 0, 0, 0);
-	}
-	__syncwarp();
-	if (lane == 0 && nvec) {
-		const uint4 carry = stg4[nvec];
-		stg4[nvec] = make_uint4(0, 0, 0, 0);
-		stg4[0] = carry;
-	}
-	__syncwarp();
-	cursor_advance(c, bits);
-}
-
-/* one frame by one warp; returns the stream size or an error */
-__device__ uint32_t small_encode(WarpShared &ws, bool raw, const PairShared *ps)
-{
-	const Pass &P = ws.pass;
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t n = P.n, pieces = raw ? 0u : n / 8u;
-	const bool diff = P.pre == CMP_PREPROCESS_DIFF;
-	const uint32_t a = (uint32_t)((uintptr_t)P.dst & 15u);
-	OutWin o;
-	o.base = P.dst - a;
-	/* the 22 header bytes travel through the staging area like the codewords behind them
-	 * (size field zero, patched at the end): the stream leaves in whole 16-byte groups from its
-	 * first byte on */
-	o.lo = a;
-	o.hi = a + P.cap_eff;
-	Cursor c;
-	c.gw0 = 0;
-	c.sbits = 8u * a;
-	c.buf = 0;
-	uint32_t *stg = ws.stg_mem + 4;
-	const uint4 *src4 = reinterpret_cast<const uint4 *>(P.src);
-	const uint16_t *src16 = reinterpret_cast<const uint16_t *>(P.src);
-
-	if (raw) {
-		/* NONE + UNCOMPRESSED: the samples big endian behind a 16-byte header (dst is 8-byte aligned) */
-		uint32_t *out = reinterpret_cast<uint32_t *>(P.dst + CMP_HDR_SIZE);
-		const uint32_t *in = reinterpret_cast<const uint32_t *>(P.src);
-		for (uint32_t k = lane; k < n / 2u; k += 32u)
-			out[k] = airs_be_pair(__ldg(in + k));
-		if (lane == 0 && (n & 1u)) {
-			const uint32_t x = __ldg(src16 + n - 1u);
-			P.dst[CMP_HDR_SIZE + 2u * (n - 1u)] = (uint8_t)(x >> 8);
-			P.dst[CMP_HDR_SIZE + 2u * (n - 1u) + 1u] = (uint8_t)x;
-		}
-		c.sbits = 8u * (a + CMP_HDR_SIZE + 2u * n); /* only used for the size below */
-	} else {
-		/* the CTA's pair table when it was built for this encoder, else the warp's own single-sample table */
-		const bool pair = ps && ps->plut_R != 0u && ps->plut_key[0] == P.enc.type && ps->plut_key[1] == P.enc.g &&
-				  ps->plut_key[2] == P.enc.outlier;
-		if (!pair && (ws.key[0] != P.enc.type || ws.key[1] != P.enc.g || ws.key[2] != P.enc.outlier))
-			build_single_lut(ws, P.enc);
-		const uint32_t R = pair ? ps->plut_R : ws.R;
-		const uint32_t lut_s = pair ? (uint32_t)__cvta_generic_to_shared(ps->plut) : 0u;
-		const uint32_t standin_len = pair ? ps->slut[kLutR].y : 0u; /* bits of the code word of residual 0 */
-		const uint32_t Rb = R * 0x00010001u, B1 = (R + 1u) * 0x00010001u;
-		const uint32_t notmask = ~((2u * R - 1u) * 0x00010001u);
-		const char *lut = reinterpret_cast<const char *>(ws.slut + (kLutR - R));
-		uint32_t front0 = 0; /* lane 0: the word in front of its next segment */
-
-		if (lane == 0) { /* header (ref cmp_hdr_serialize, header.c:24-67; fields cmp.c:265-279), size 0 */
-			int32_t ne = -(int32_t)c.sbits;
-			const uint32_t id_hi = (uint32_t)(P.identifier >> 16), id_lo = (uint32_t)P.identifier & 0xFFFFu;
-			put_unit(stg, ne, ((0x8000u | CMP_VERSION_NUMBER) << 16), (2u * n) & 0xFFFFFFu, 64u);
-			put_unit(stg, ne, id_hi, (id_lo << 16) | (P.seq << 8) | (P.pre << 4) | (P.checksum << 3) | P.enc.type, 64u);
-			put_unit(stg, ne, P.enc.g >> 8, ((P.enc.g & 0xFFu) << 24) | (P.enc.outlier & 0xFFFFFFu), 48u);
-		}
-		c.sbits += 8u * (CMP_HDR_SIZE + 6u);
-
-		for (uint32_t p0 = 0; p0 < pieces; p0 += 128u) {
-			bool v[4];
-			uint32_t w[4][4], u[4][4];
-			const uint32_t src_lane = (lane - 1u) & 31u;
-			const bool first = diff && R != 0u && p0 == 0u && lane == 0u;
-			uint32_t chk = 0;
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				v[j] = p0 + 32u * j + lane < pieces;
-				const uint4 x = v[j] ? __ldg(src4 + p0 + 32u * j + lane) : make_uint4(0, 0, 0, 0);
-				w[j][0] = x.x; w[j][1] = x.y; w[j][2] = x.z; w[j][3] = x.w;
-			}
-#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				uint32_t pw_word = 0;
-				if (diff) {
-					const uint32_t up = __shfl_sync(kFull, w[j][3], src_lane);
-					pw_word = lane ? up : front0;
-					front0 = up;
-				}
-				seg_residuals(P.pre, w[j], w[j], pw_word, Rb, B1, u[j]);
-				if (j == 0 && first) /* see frame_fast: the frame's first sample goes separately */
-					u[0][0] = (u[0][0] & 0xFFFF0000u) | (Rb & 0xFFFFu);
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					u[j][k] = v[j] ? u[j][k] : Rb;
-					chk |= u[j][k];
-				}
-			}
-			uint32_t n_first = 0, f_hi = 0, f_lo = 0;
-			if (first) {
-				uint32_t fc[3];
-				first_sample_code(P.enc, w[0][0] & 0xFFFFu, fc);
-				f_hi = fc[0];
-				f_lo = fc[1];
-				n_first = fc[2];
-			}
-
-			bool table = R != 0u && __all_sync(kFull, (chk & notmask) == 0u);
-			uint32_t sh_[4], sl_[4], sn_[4];
-			if (table && pair) { /* as the table arm of frame_fast: one lookup per pair */
-				uint32_t qchk = 0;
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					uint32_t pc[4], pl[4];
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const uint32_t ent = lut_pair(lut_s, u[j][k]);
-						pc[k] = ent & ((1u << kLutLenShift) - 1u);
-						pl[k] = ent >> kLutLenShift;
-					}
-					if (j == 0 && first) { /* drop the stand-in's codeword from the head of pair 0 */
-						pl[0] -= standin_len;
-						pc[0] &= (1u << pl[0]) - 1u;
-					}
-					uint32_t lo = pc[0], hi = 0u, nb = pl[0];
-#pragma unroll
-					for (int k = 1; k < 4; k++) {
-						hi = __funnelshift_l(lo, hi, pl[k]);
-						lo = (lo << pl[k]) | pc[k];
-						nb += pl[k];
-					}
-					qchk |= nb + 63u;
-					sl_[j] = v[j] ? lo : 0u;
-					sh_[j] = v[j] ? hi : 0u;
-					sn_[j] = v[j] ? nb : 0u;
-				}
-				table = __all_sync(kFull, (qchk & 128u) == 0u);
-			} else if (table) {
-				uint32_t qchk = 0;
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					uint32_t lo = 0, hi = 0, nb = 0;
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const uint2 e0 = *reinterpret_cast<const uint2 *>(lut + ((u[j][k] & 0xFFFFu) << 3));
-						const uint2 e1 = *reinterpret_cast<const uint2 *>(lut + ((u[j][k] >> 16) << 3));
-						const bool skip = j == 0 && k == 0 && first; /* the stand-in of the first sample */
-						if (!skip) {
-							hi = __funnelshift_l(lo, hi, e0.y);
-							lo = (lo << e0.y) | e0.x;
-							nb += e0.y;
-						}
-						hi = __funnelshift_l(lo, hi, e1.y);
-						lo = (lo << e1.y) | e1.x;
-						nb += e1.y;
-					}
-					qchk |= nb + 63u;
-					sl_[j] = v[j] ? lo : 0u;
-					sh_[j] = v[j] ? hi : 0u;
-					sn_[j] = v[j] ? nb : 0u;
-				}
-				table = __all_sync(kFull, (qchk & 128u) == 0u);
-			}
-			uint32_t d[16];
-			uint32_t cwords[64]; /* arithmetic path: the code words of the 32 samples, computed once */
-			uint32_t b01, b23;
-			if (table) {
-				b01 = (sn_[0] + n_first) | (sn_[1] << 16);
-				b23 = sn_[2] | (sn_[3] << 16);
-			} else {
-				const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
-#pragma unroll
-				for (int j = 0; j < 4; j++)
-#pragma unroll
-					for (int k = 0; k < 4; k++)
-						d[4 * j + k] = __vadd2(u[j][k], negRb);
-				if (first)
-					d[0] = (d[0] & 0xFFFF0000u) | (w[0][0] & 0xFFFFu);
-				slow_codes(P.enc, d, 16u, 0xFu, cwords, b01, b23);
-				b01 = (v[0] ? b01 & 0xFFFFu : 0u) | (v[1] ? b01 & 0xFFFF0000u : 0u);
-				b23 = (v[2] ? b23 & 0xFFFFu : 0u) | (v[3] ? b23 & 0xFFFF0000u : 0u);
-			}
-			/* warp scan: segment 0 of all lanes, then segment 1, ... */
-			uint32_t i01 = b01, i23 = b23;
-#pragma unroll
-			for (int dd = 1; dd < 32; dd <<= 1) {
-				const uint32_t t0 = __shfl_up_sync(kFull, i01, dd), t1 = __shfl_up_sync(kFull, i23, dd);
-				if (lane >= (uint32_t)dd) {
-					i01 += t0;
-					i23 += t1;
-				}
-			}
-			const uint32_t t01 = __shfl_sync(kFull, i01, 31), t23 = __shfl_sync(kFull, i23, 31);
-			const uint32_t tot0 = t01 & 0xFFFFu, tot01 = tot0 + (t01 >> 16), tot012 = tot01 + (t23 & 0xFFFFu);
-			const uint32_t tile_bits = tot012 + (t23 >> 16);
-			const uint32_t e01 = i01 - b01, e23 = i23 - b23;
-			uint32_t pos[4];
-			pos[0] = c.sbits + (e01 & 0xFFFFu);
-			pos[1] = c.sbits + tot0 + (e01 >> 16);
-			pos[2] = c.sbits + tot01 + (e23 & 0xFFFFu);
-			pos[3] = c.sbits + tot012 + (e23 >> 16);
-
-			if (table) {
-				if (first) {
-					int32_t ne = -(int32_t)pos[0];
-					put_unit(stg, ne, f_hi, f_lo, n_first);
-					pos[0] += n_first;
-				}
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					int32_t ne = -(int32_t)pos[j];
-					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
-				}
-			} else {
-#pragma unroll 1
-				for (uint32_t j = 0; j < 4u; j++)
-					if (p0 + 32u * j + lane < pieces)
-						slow_put_codes(cwords + 16u * j, stg, j == 0u ? pos[0] : j == 1u ? pos[1] : j == 2u ? pos[2] : pos[3]);
-			}
-			warp_copy_out(ws, o, c, tile_bits);
-		}
-
-		/* the last n % 8 samples, one after the other on lane 0 */
-		uint32_t tail_bits = 0;
-		if (lane == 0) {
-			int32_t ne = -(int32_t)c.sbits;
-			for (uint32_t i = pieces * 8u; i < n; i++) {
-				const uint32_t x = __ldg(src16 + i);
-				const uint32_t r = (diff && i) ? x - __ldg(src16 + i - 1u) : x;
-				uint32_t cw, cl, rw, rl;
-				encode_mapped_rt(P.enc, airs_zigzag16(r), cw, cl, rw, rl);
-				put_unit(stg, ne, __funnelshift_lc(cw, 0u, rl), __funnelshift_lc(0u, cw, rl) | rw, cl + rl);
-				tail_bits += cl + rl;
-			}
-		}
-		tail_bits = __shfl_sync(kFull, tail_bits, 0);
-		warp_copy_out(ws, o, c, tail_bits);
-	}
-
-	const uint32_t frame_bits = c.gw0 * 32u + c.sbits - 8u * a;
-	const uint32_t payload_end = (frame_bits + 7u) >> 3;
-	const uint32_t size = payload_end + (P.checksum ? 4u : 0u);
-	uint32_t result = size > P.cap_eff ? AIRS_ERR(DST_TOO_SMALL) : size;
-
-	if (!raw && lane == 0) { /* last partial group, zero padded */
-		const uint32_t nb = (c.sbits + 7u) >> 3;
-		for (uint32_t k = 0; k < nb; k++) {
-			const uint32_t b = c.gw0 * 4u + k;
-			if (b >= o.lo && b < o.hi)
-				o.base[b] = (uint8_t)(stg[k >> 2] >> (24 - 8 * (k & 3)));
-		}
-		stg[0] = stg[1] = stg[2] = stg[3] = 0;
-	}
-	if (!airs_failed(result)) {
-		if (raw) {
-			if (lane < P.hdr_len)
-				P.dst[lane] = (uint8_t)header_byte(P, lane, size);
-		} else if (lane < 3) { /* the size field of the header that went out with the stream */
-			P.dst[2u + lane] = (uint8_t)(size >> (16 - 8 * lane));
-		}
-	}
-	__syncwarp();
-	return result;
-}
-
 } /* namespace */
 
 /* two-phase CONCAT: is this launch the phase that runs? (see airs_launch.h) */
@@ -2034,12 +1677,16 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	 * in the CONCAT layout and on the host-shim path, where every job is "big" and the list is the
 	 * identity (the look-back scan needs the frames to start in result order). */
 	const bool listed = b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io;
-	const bool small = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
-			   !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 && pl.n <= kSmallMaxSamples &&
+	/* what both fast kernels ask of a job */
+	const bool quick = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
+			   !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 &&
 			   (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
 			   pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
 			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
 			   pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
+	const bool small = quick && pl.n <= kSmallMaxSamples; /* one warp per job: airs_fast_kernel */
+	const bool tiled = quick && !small;                   /* tiles over all CTAs: airs_tile_kernel */
+	const uint32_t my_tiles = tiled ? (pl.n + AIRS_TILE_SAMPLES - 1u) / AIRS_TILE_SAMPLES : 0u;
 	if (small)
 		pl.flags |= AIRS_PF_SMALL;
 	if (have && b.init_results && !b.ctx_io)
@@ -2048,8 +1695,17 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	const uint32_t below = (1u << lane) - 1u;
 	const uint32_t m_cs = __ballot_sync(kFull, have && (pl.flags & AIRS_PF_CHECKSUM));
 	const uint32_t m_small = __ballot_sync(kFull, small);
-	const uint32_t m_big = __ballot_sync(kFull, have && listed && !small);
-	uint32_t base_small = 0, base_big = 0;
+	const uint32_t m_tiled = __ballot_sync(kFull, tiled);
+	const uint32_t m_big = __ballot_sync(kFull, have && listed && !quick);
+	uint32_t tiles_incl = my_tiles; /* tiles of the lanes up to this one */
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(kFull, tiles_incl, d);
+		if (lane >= (uint32_t)d)
+			tiles_incl += t;
+	}
+	const uint32_t warp_tiles = __shfl_sync(kFull, tiles_incl, 31);
+	uint32_t base_small = 0, base_big = 0, base_tslot = 0, base_tile = 0;
 	if (lane == 0) {
 		if (m_cs)
 			atomicAdd(&b.ticket[4], (uint32_t)__popc(m_cs));
@@ -2057,10 +1713,19 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			base_small = atomicAdd(&b.ticket[3], (uint32_t)__popc(m_small));
 		if (m_big)
 			base_big = atomicAdd(&b.ticket[2], (uint32_t)__popc(m_big));
+		if (m_tiled) { /* slots and tiles from ONE counter: the order of the slots is the order of their tiles */
+			const unsigned long long got = atomicAdd(reinterpret_cast<unsigned long long *>(b.ticket + 10),
+								 ((unsigned long long)__popc(m_tiled) << 40) | warp_tiles);
+			base_tslot = (uint32_t)(got >> 40);
+			base_tile = (uint32_t)(got & ((1ull << 40) - 1u));
+		}
 	}
 	base_small = __shfl_sync(kFull, base_small, 0);
 	base_big = __shfl_sync(kFull, base_big, 0);
+	base_tslot = __shfl_sync(kFull, base_tslot, 0);
+	base_tile = __shfl_sync(kFull, base_tile, 0);
 	if (have) {
+		FastJob *recs = reinterpret_cast<FastJob *>(b.fast_jobs);
 		if (!listed) {
 			b.big_list[j] = j;
 			if (j == 0)
@@ -2069,8 +1734,13 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			const uint32_t slot = base_small + (uint32_t)__popc(m_small & below);
 			b.small_list[slot] = j;
 			FastJob fj;
-			airs_fill_fast_job(fj, job, pl, b.src, b.dst);
-			reinterpret_cast<FastJob *>(b.fast_jobs)[slot] = fj;
+			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, 0u, 0u);
+			recs[slot] = fj;
+		} else if (tiled) { /* the records of the long jobs fill the array from its end */
+			const uint32_t slot = base_tslot + (uint32_t)__popc(m_tiled & below);
+			FastJob fj;
+			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, base_tile + tiles_incl - my_tiles, my_tiles);
+			recs[b.n_jobs - 1u - slot] = fj;
 		} else {
 			b.big_list[base_big + (uint32_t)__popc(m_big & below)] = j;
 		}
@@ -2199,96 +1869,6 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 	}
 }
 
-/* PAIR: the CTA holds a pair table for the primary encoder of job 0 (5 CTAs per SM instead of 6); the
- * launch that runs is the one that fits the batch - PAIR when at least three of four short jobs use
- * that encoder (counted by airs_plan_kernel in ticket[8]) */
-template <bool PAIR>
-__global__ void __launch_bounds__(AIRS_THREADS, PAIR ? AIRS_CTAS_PER_SM - 1 : AIRS_CTAS_PER_SM) airs_small_kernel(AirsLaunch b)
-{
-	__shared__ WarpShared wsh[kWarps];
-	__shared__ PairHolder<PAIR> psh;
-	const uint32_t lane = threadIdx.x & 31u;
-	WarpShared &ws = wsh[threadIdx.x >> 5];
-	if (gate_closed(b))
-		return;
-	const uint32_t n_small = b.ticket[3]; /* entries of small_list, written by airs_plan_kernel */
-	const bool mostly_one_encoder = 4u * b.ticket[8] >= 3u * n_small;
-	if (n_small == 0u || mostly_one_encoder != PAIR)
-		return;
-	const PairShared *ps = nullptr;
-	if constexpr (PAIR) {
-		EncConst e0;
-		const cmp_params &p0 = b.jobs[0].params;
-		airs_enc_const(&e0, p0.primary_encoder_type, p0.primary_encoder_param, p0.primary_encoder_outlier);
-		build_pair_lut(psh.t, e0); /* all threads: two block barriers */
-		ps = &psh.t;
-	}
-
-	for (uint32_t w = lane; w < 4u + kWStgWords; w += 32u)
-		ws.stg_mem[w] = 0;
-	if (lane == 0) {
-		ws.key[0] = 0xFFFFFFFFu;
-		ws.R = 0;
-	}
-	__syncwarp();
-
-	uint32_t t_next = 0;
-	if (lane == 0)
-		t_next = atomicAdd(&b.ticket[1], 1u);
-	for (;;) {
-		const uint32_t t = __shfl_sync(kFull, t_next, 0);
-		if (t >= n_small)
-			break;
-		if (lane == 0) /* the next ticket is drawn now and looked at after this job: the atomic's round trip is hidden */
-			t_next = atomicAdd(&b.ticket[1], 1u);
-		const uint32_t job = b.small_list[t];
-		((uint32_t *)&ws.plan)[lane] = ((const uint32_t *)&b.plans[job])[lane];
-		if (lane < 30)
-			((uint32_t *)&ws.job)[lane] = ((const uint32_t *)&b.jobs[job])[lane];
-		__syncwarp();
-		if (lane == 0) { /* the pass of a fresh context's first frame (ref cmp.c:228-294, 438-465) */
-			const JobPlan &pl = ws.plan;
-			const airs_job &j = ws.job;
-			Pass &P = ws.pass;
-			P.enc = pl.enc[0];
-			P.src = b.src + j.src_offset;
-			P.dst = b.dst + j.dst_offset;
-			P.work = nullptr;
-			/* cmp_initialise draws one identifier, the primary pass the next one */
-			P.identifier = (j.identifier_base + 1u) & kMask48;
-			P.pre = pl.pre[0];
-			P.n = pl.n;
-			P.dtype = j.dtype;
-			P.hdr_len = (CMP_HDR_SIZE + 6u);
-			P.cap_eff = pl.cap_eff;
-			P.trip = pl.trip;
-			P.model_mode = 0;
-			P.rate = pl.rate;
-			P.is_signed = 0;
-			P.checksum = (pl.flags & AIRS_PF_CHECKSUM) ? 1u : 0u;
-			P.seq = 0;
-			P.err = 0;
-		}
-		__syncwarp();
-		uint32_t r = small_encode(ws, false, ps);
-		if ((ws.plan.flags & AIRS_PF_FALLBACK_OK) && r == AIRS_ERR(DST_TOO_SMALL)) {
-			/* stored raw as a fresh primary pass: two more identifiers drawn (ref cmp.c:380-392) */
-			if (lane == 0) {
-				Pass &P = ws.pass;
-				P.identifier = (ws.job.identifier_base + 3u) & kMask48;
-				P.pre = CMP_PREPROCESS_NONE;
-				P.enc.type = CMP_ENCODER_UNCOMPRESSED;
-				P.hdr_len = CMP_HDR_SIZE;
-			}
-			__syncwarp();
-			r = small_encode(ws, true, ps);
-		}
-		if (lane == 0)
-			b.results[ws.job.first_result] = r;
-		__syncwarp();
-	}
-}
-
 /* XXH32 with one lane per accumulator: four consecutive lanes share a stream (16-byte aligned
  * 16-bit container), 16 stripes in flight per lane.  All 32 lanes must call it; streams whose
  * group is idle pass n = 0. */
@@ -2409,12 +1989,6 @@ extern "C" cudaError_t airs_encode_ctas_per_sm(int *out)
 	e = cudaFuncSetAttribute(airs_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 	if (e != cudaSuccess)
 		return e;
-	e = cudaFuncSetAttribute(airs_small_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-	if (e != cudaSuccess)
-		return e;
-	e = cudaFuncSetAttribute(airs_small_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-	if (e != cudaSuccess)
-		return e;
 	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, airs_encode_kernel, AIRS_THREADS, 0);
 }
 
@@ -2430,13 +2004,5 @@ extern "C" cudaError_t airs_launch_checksum(const AirsLaunch *b, cudaStream_t st
 		airs_checksum_kernel<1><<<(b->n_results + 127) / 128, 128, 0, stream>>>(*b);
 	else
 		airs_checksum_kernel<4><<<(4 * b->n_results + 127) / 128, 128, 0, stream>>>(*b);
-	return cudaGetLastError();
-}
-
-extern "C" cudaError_t airs_launch_small(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
-{
-	/* both are launched; ticket[8] (airs_plan_kernel) decides on the device which one works */
-	airs_small_kernel<true><<<grid, AIRS_THREADS, 0, stream>>>(*b);
-	airs_small_kernel<false><<<grid, AIRS_THREADS, 0, stream>>>(*b);
 	return cudaGetLastError();
 }

@@ -24,6 +24,14 @@ struct JobPlan;
 #define AIRS_FAST_CTAS_PER_SM 6 /* resident CTAs per SM airs_fast_kernel is compiled for */
 #endif
 
+#ifndef AIRS_TILE_THREADS
+#define AIRS_TILE_THREADS 128
+#endif
+#ifndef AIRS_TILE_CTAS_PER_SM
+#define AIRS_TILE_CTAS_PER_SM 6
+#endif
+#define AIRS_TILE_RING 65536u /* tile descriptors kept (a power of two, far more than tiles are in flight) */
+
 struct AirsLaunch {
 	const uint8_t *src;
 	uint8_t *dst;
@@ -35,10 +43,12 @@ struct AirsLaunch {
 	uint32_t *ticket;      /* zeroed before the launch: [0] next entry of big_list, [1] of small_list,
 				  [2] entries in big_list, [3] entries in small_list,
 				  [4] jobs with checksum, [5] gate of the two-phase CONCAT path,
-				  [8] short jobs that use the primary encoder of job 0 */
+				  [10..11] 64-bit: jobs of airs_tile_kernel << 40 | their tiles, [12] next tile */
 	uint32_t *big_list;    /* job indices for airs_encode_kernel, filled by airs_plan_kernel */
-	uint32_t *small_list;  /* job indices for airs_small_kernel (SLOTS layout only) */
-	void *fast_jobs;       /* one 64-byte FastJob (airs_fast.cuh) per short job, in the order of small_list */
+	uint32_t *small_list;  /* job indices of airs_fast_kernel's records, in their order (SLOTS layout only) */
+	void *fast_jobs;       /* n_jobs 64-byte records (FastJob, airs_fast.cuh): the short jobs of airs_fast_kernel from
+				  the front in the order of small_list, the long jobs of airs_tile_kernel from the back */
+	uint64_t *tile_ring;   /* 2 * AIRS_TILE_RING words, zeroed before the launch: tile descriptors, tile tails */
 	uint32_t *result_job;  /* n_results entries: the job a frame belongs to (airs_checksum_kernel) */
 	struct JobPlan *plans; /* n_jobs plans written by airs_plan_kernel */
 	uint64_t *lookback;    /* CONCAT: one status word per job, zeroed before the launch */
@@ -78,9 +88,10 @@ extern "C" {
 cudaError_t airs_launch_plan(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_encode_ctas_per_sm(int *out);
-cudaError_t airs_launch_small(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_launch_fast(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_fast_resident_ctas(int *out);
+cudaError_t airs_launch_tile(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
+cudaError_t airs_tile_resident_ctas(int *out);
 cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_hash(const struct AirsLaunch *b, uint64_t *hashes, cudaStream_t stream);
 cudaError_t airs_launch_hash_ranges(const uint8_t *base, const uint64_t *offsets, const uint32_t *sizes, uint32_t n,

@@ -276,3 +276,16 @@ def test_short_jobs_longest_code_words(gpu, oracle, pkg, enc, g, outl, pre, n):
     res = want[1]
     assert int(res.max()) >= n * (48 if enc == 2 else 28) // 8          # the streams really are that long
     jobgen.compare(want, gpu.run_jobs_device(js), js, "longest-code-words")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_jobs_long_frames(gpu, oracle, seed):
+    """Frames of more than 32768 samples: single-frame jobs among them are cut into tiles that all CTAs share
+    (airs_tile_kernel, bit-granular seams between tiles), the others take the CTA-per-job kernel; every capacity
+    mode (fallback to raw storage and DST_TOO_SMALL included) and both slot alignments."""
+    rng = np.random.default_rng(500 + seed)
+    js = jobgen.build_jobs(rng, 48, sizes=[32769, 33000, 40960, 65536, 70001, 131077, 300000], max_frames=2,
+                           allow_invalid=False)
+    want = jobgen.run_cpu(oracle, js, threads=4)
+    got = gpu.run_jobs_device(js)
+    jobgen.compare(want, got, js, "gpu-vs-oracle-long")

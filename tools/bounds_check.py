@@ -10,9 +10,15 @@ from oracle import oracle_py
 pkg = jobgen.pkg
 pkg.loader.library_path = lambda: os.path.join(ROOT, "airs-compression_b200", "libcheck.so")
 lib = pkg.load_library()
-viol = ctypes.CDLL(os.path.join(ROOT, "airs-compression_b200", "libcheck.so")).airs_fast_bounds_violations
-assert viol() >= 0, "not a bounds-check build"
-SMALL = [1, 2, 3, 5, 7, 8, 63, 64, 65, 255, 256, 257, 1000, 2048, 2049, 4099, 9000]
+_chk = ctypes.CDLL(os.path.join(ROOT, "airs-compression_b200", "libcheck.so"))
+assert _chk.airs_fast_bounds_violations() >= 0 and _chk.airs_tile_bounds_violations() >= 0, "not a bounds-check build"
+
+
+def viol():
+    return _chk.airs_fast_bounds_violations() + _chk.airs_tile_bounds_violations()
+
+
+SMALL = [1, 2, 3, 5, 7, 8, 63, 64, 65, 255, 256, 257, 1000, 2048, 2049, 4099, 9000, 40000, 70001]
 total = 0
 for seed in range(12):
     rng = np.random.default_rng(900 + seed)

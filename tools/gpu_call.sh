@@ -17,6 +17,12 @@ bench:*)
   IFS=: read -r _ name bargs <<< "$step"
   timeout 1500 python bench.py ${bargs//,/ } > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "bench rc=$?"
   tail -n 5 gpurun_out/$name.err; head -c 6000 gpurun_out/$name.json ;;
+bounds)
+  timeout 600 python tools/bounds_check.py > gpurun_out/bounds.log 2>&1; echo "bounds rc=$?" >> gpurun_out/bounds.log; tail -n 8 gpurun_out/bounds.log ;;
+one:*)
+  IFS=: read -r _ what <<< "$step"
+  timeout 300 python -m pytest "${what}" -x -q -m gpu > gpurun_out/one.log 2>&1; echo "one rc=$?" >> gpurun_out/one.log
+  tail -n 25 gpurun_out/one.log ;;
 smoke)
   timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log ;;
 ncu:*)
