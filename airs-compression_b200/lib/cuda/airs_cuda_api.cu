@@ -212,9 +212,11 @@ extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t
 
 /* plan; short jobs (one warp each) and the tiles of long frames (SLOTS only); everything else, and what the
  * two fast kernels handed back, one CTA per job; checksums */
-static int launch_kernels(const AirsLaunch &l, int resident, cudaStream_t stream)
+static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t stream)
 {
+	AirsLaunch l = l_in;
 	unsigned int grid = l.n_jobs < (uint32_t)resident ? l.n_jobs : (unsigned int)resident;
+	l.tile_below_jobs = (uint32_t)resident / 2u;
 	CU(airs_launch_plan(&l, stream));
 	g_launches++;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) {

@@ -1685,7 +1685,10 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
 			   pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
 	const bool small = quick && pl.n <= kSmallMaxSamples; /* one warp per job: airs_fast_kernel */
-	const bool tiled = quick && !small;                   /* tiles over all CTAs: airs_tile_kernel */
+	/* Tiles over all CTAs (airs_tile_kernel, arithmetic code words) for long frames when the batch has too few jobs to
+	 * give every resident CTA of airs_encode_kernel one, or when that kernel's code word table cannot cover the
+	 * residuals anyway (no preprocessing: the samples themselves are coded; tiny g: long code words) */
+	const bool tiled = quick && !small && (b.n_jobs < b.tile_below_jobs || pl.pre[0] == CMP_PREPROCESS_NONE || pl.enc[0].g < 4u);
 	const uint32_t my_tiles = tiled ? (pl.n + AIRS_TILE_SAMPLES - 1u) / AIRS_TILE_SAMPLES : 0u;
 	if (small)
 		pl.flags |= AIRS_PF_SMALL;
@@ -1696,7 +1699,7 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	const uint32_t m_cs = __ballot_sync(kFull, have && (pl.flags & AIRS_PF_CHECKSUM));
 	const uint32_t m_small = __ballot_sync(kFull, small);
 	const uint32_t m_tiled = __ballot_sync(kFull, tiled);
-	const uint32_t m_big = __ballot_sync(kFull, have && listed && !quick);
+	const uint32_t m_big = __ballot_sync(kFull, have && listed && !small && !tiled);
 	uint32_t tiles_incl = my_tiles; /* tiles of the lanes up to this one */
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {

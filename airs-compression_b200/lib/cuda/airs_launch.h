@@ -61,6 +61,7 @@ struct AirsLaunch {
 	 * (*gate != 0) == gate_want; NULL: no gate */
 	const uint32_t *gate;
 	uint32_t gate_want;
+	uint32_t tile_below_jobs; /* batches with fewer jobs send every long single-frame job to airs_tile_kernel */
 };
 
 /* what the two-phase CONCAT path adds: temporary slots, the job table rewritten onto them */

@@ -73,30 +73,25 @@ __device__ __forceinline__ uint64_t make_desc(uint64_t flag, uint32_t T, uint32_
 	return flag | ((uint64_t)(T + 1u) << kValBits) | value;
 }
 
-/* the job (slot) tile T belongs to: tile jobs sit at fast_jobs[n_jobs - 1 - slot] with ascending tile_base;
- * a CTA's tickets only grow, so the search goes forward from the slot of its last tile, 32 slots per step */
-__device__ __forceinline__ void find_slot(TileShared &sh, const FastJob *recs_end, uint32_t n_tjobs, uint32_t T, uint32_t lane)
+/* warp 0, one iteration early: the descriptors of the 32 tiles in front of `ti` and the tail of the one right in
+ * front of it are requested (no waiting here); look_back() looks at the answers behind the tile's code words */
+__device__ __forceinline__ void look_back_early(const TileInfo &ti, const uint64_t *ring, const uint64_t *tails, uint32_t hdr_bits,
+						uint32_t lane, uint64_t &v0, uint64_t &tail0)
 {
-	uint32_t slot = sh.slot, base = sh.slot_base, tiles = sh.slot_tiles;
-	if (T >= base + tiles) {
-		for (;;) {
-			const uint32_t s = slot + 1u + lane;
-			const uint32_t b = s < n_tjobs ? __ldg(&(recs_end - s)->tile_base) : 0xFFFFFFFFu;
-			const uint32_t c = (uint32_t)__popc(__ballot_sync(kFull, b <= T));
-			slot += c;
-			if (c < 32u)
-				break;
-		}
-	}
-	__syncwarp();
-	if (lane == 0)
-		sh.slot = slot;
+	const uint32_t T = ti.T, tidx = ti.tidx;
+	const int64_t j = (int64_t)T - 1 - lane;
+	v0 = (tidx != 0u && j >= (int64_t)T - tidx) ? ld_desc(ring + ((uint32_t)j & (kRing - 1u))) : (kFlagP | hdr_bits);
+	tail0 = tidx != 0u ? ld_desc(tails + ((T - 1u) & (kRing - 1u))) : 0ull;
 }
 
-/* warp 0: where tile `ti` starts in its stream (decoupled look-back), and the bits it shares its first byte with */
+/* warp 0: where tile `ti` starts in its stream (decoupled look-back), and the bits it shares its first byte with.
+ * v0 / tail0: the answers to look_back_early(); only what they leave open is polled */
 __device__ __forceinline__ void look_back(TileInfo &ti, uint64_t *ring, uint64_t *tails, uint32_t hdr_bits, uint32_t lane,
-					  uint32_t *carry_word)
+					  uint32_t *carry_word, uint64_t v0, uint64_t tail0, uint32_t *stats)
 {
+#ifdef AIRS_TILE_STATS
+	uint32_t st_polls = 0, st_tail = 0, st_windows = 0;
+#endif
 	const uint32_t T = ti.T, tidx = ti.tidx;
 	uint32_t excl = hdr_bits;
 
@@ -104,6 +99,7 @@ __device__ __forceinline__ void look_back(TileInfo &ti, uint64_t *ring, uint64_t
 		const int64_t lowest = (int64_t)T - tidx; /* first tile of the job; in front of it: the header */
 		int64_t idx = (int64_t)T - 1;
 		uint32_t sum = 0;
+		bool early = true;
 		for (;;) {
 			const int64_t j = idx - lane;
 			const bool real = j >= lowest;
@@ -113,7 +109,11 @@ __device__ __forceinline__ void look_back(TileInfo &ti, uint64_t *ring, uint64_t
 			do { /* until every descriptor in front of the nearest prefix has been published */
 				if (++spins > (1u << 24))
 					__trap(); /* a predecessor that never answers: fail the launch instead of hanging the device */
-				v = real ? ld_desc(ring + ((uint32_t)j & (kRing - 1u))) : (kFlagP | hdr_bits);
+#ifdef AIRS_TILE_STATS
+				st_polls += early ? 0u : 1u;
+#endif
+				v = early ? v0 : (real ? ld_desc(ring + ((uint32_t)j & (kRing - 1u))) : (kFlagP | hdr_bits));
+				early = false;
 				ready = !real || (((uint32_t)(v >> kValBits) == (uint32_t)j + 1u) && (v >> 62) != 0);
 				nr = __ballot_sync(kFull, !ready);
 				const uint32_t pm = __ballot_sync(kFull, ready && (v >> 62) == 2u);
@@ -130,6 +130,9 @@ __device__ __forceinline__ void look_back(TileInfo &ti, uint64_t *ring, uint64_t
 				break;
 			sum += __reduce_add_sync(kFull, (uint32_t)v & ((1u << kValBits) - 1u)); /* 32 aggregates, no prefix yet */
 			idx -= 32;
+#ifdef AIRS_TILE_STATS
+			st_windows++;
+#endif
 		}
 		excl = sum;
 	}
@@ -137,15 +140,26 @@ __device__ __forceinline__ void look_back(TileInfo &ti, uint64_t *ring, uint64_t
 	uint32_t carry = 0;
 	const uint32_t m = excl & 7u;
 	if (m && tidx != 0u) {
-		uint64_t v;
+		uint64_t v = tail0;
 		uint32_t spins = 0;
-		do {
+		while ((uint32_t)(v >> 8) != T) { /* tag of tile T - 1 is T */
 			v = ld_desc(tails + ((T - 1u) & (kRing - 1u)));
 			if (++spins > (1u << 24))
 				__trap();
-		} while ((uint32_t)(v >> 8) != T); /* tag of tile T - 1 is T */
+#ifdef AIRS_TILE_STATS
+			st_tail++;
+#endif
+		}
 		carry = (uint32_t)v & ((1u << m) - 1u);
 	}
+#ifdef AIRS_TILE_STATS
+	if (lane == 0) {
+		atomicAdd(stats + 0, 1u);
+		atomicAdd(stats + 1, st_polls);
+		atomicAdd(stats + 2, st_tail);
+		atomicAdd(stats + 3, st_windows);
+	}
+#endif
 	if (lane == 0) {
 		ti.excl = excl;
 		*carry_word = carry; /* word -1 of the tile's staging area: the bits in front of its first bit */
@@ -227,22 +241,40 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	}
 	__syncthreads();
 
-	/* fetches tile T (a ticket) into sh.tile[q]: warp-parallel; all lanes of the calling warp */
-	auto fetch = [&](uint32_t q, uint32_t T) {
+	/* Warp 1 finds the job of every tile, in steps spread over three iterations so that no step waits for
+	 * global memory: tickets are drawn three tiles ahead; the tile_base fields of the 32 jobs behind the job of
+	 * the tile before (tile jobs sit at recs_end - slot with ascending tile_base, and a CTA's tickets only grow)
+	 * are requested two tiles ahead; the slot follows from a ballot one tile ahead, when the job's record is
+	 * requested; the record reaches shared memory behind the code words of the tile in front. */
+	uint32_t t1 = 0, t2 = 0, t3 = 0;   /* tickets of tiles k + 1, k + 2, k + 3 (warp 1, lane 0 draws) */
+	uint32_t slot1 = 0xFFFFFFFFu;      /* slot of tile k + 1 once resolved; before: of the tile in front of it */
+	uint32_t fb = 0xFFFFFFFFu;         /* tile_base of slot (slot of tile k) + 1 + lane, requested for tile k + 1 */
+	uint32_t recw = 0;                 /* word `lane` of the record of tile k + 1 */
+	auto probe = [&](uint32_t slot, uint32_t T) -> uint32_t { /* tile_base of the 32 slots behind `slot` */
+		const uint32_t s = slot + 1u + lane;
+		return (T < n_tiles && s < n_tjobs) ? __ldg(&(recs_end - s)->tile_base) : 0xFFFFFFFFu;
+	};
+	auto resolve = [&](uint32_t &slot, uint32_t T, uint32_t first) { /* the slot of tile T, first probe given */
+		if (T >= n_tiles)
+			return;
+		uint32_t v = first;
+		for (;;) {
+			const uint32_t c = (uint32_t)__popc(__ballot_sync(kFull, v <= T));
+			slot += c;
+			if (c < 32u)
+				break;
+			v = probe(slot, T); /* a jump over more than 32 jobs: keep probing */
+		}
+	};
+	auto publish_tile = [&](uint32_t q, uint32_t T, uint32_t word) { /* record word `lane` -> sh.tile[q] */
 		TileInfo &ti = sh.tile[q];
 		if (T < n_tiles) {
-			find_slot(sh, recs_end, n_tjobs, T, lane);
-			__syncwarp();
-			const uint32_t slot = sh.slot;
-			const uint32_t *r = reinterpret_cast<const uint32_t *>(recs_end - slot);
 			if (lane < 16u)
-				ti.rec[lane] = __ldg(r + lane);
-			__syncwarp();
+				ti.rec[lane] = word;
+			const uint32_t base = __shfl_sync(kFull, word, 14);
 			if (lane == 0) {
-				sh.slot_base = ti.rec[14];
-				sh.slot_tiles = ti.rec[15];
 				ti.T = T;
-				ti.tidx = T - ti.rec[14];
+				ti.tidx = T - base;
 				ti.valid = 1;
 			}
 		} else if (lane == 0) {
@@ -250,17 +282,16 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		}
 		__syncwarp();
 	};
-
-	/* prologue: the first tile of this CTA.  Warp 1 draws the tickets, always one iteration before it needs them */
-	uint32_t t_next = 0;
-	if (warp == 1) {
-		if (lane == 0)
-			t_next = atomicAdd(&b.ticket[12], 1u);
-		t_next = __shfl_sync(kFull, t_next, 0);
-		fetch(0, t_next);
-		if (lane == 0)
-			t_next = atomicAdd(&b.ticket[12], 1u);
-		t_next = __shfl_sync(kFull, t_next, 0);
+	if (warp == 1) { /* prologue: tile 0 in full, tile 1 probed, tile 2 drawn */
+		/* the first three tiles of every CTA are dealt out round robin: a CTA must never hold consecutive tiles (the
+		 * second one would be counted an iteration after the first, and every tile behind it would wait for that) */
+		const uint32_t t0 = blockIdx.x;
+		t1 = blockIdx.x + gridDim.x;
+		t2 = blockIdx.x + 2u * gridDim.x;
+		resolve(slot1, t0, probe(slot1, t0));
+		const uint32_t w0 = (t0 < n_tiles && lane < 16u) ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot1) + lane) : 0u;
+		publish_tile(0, t0, w0);
+		fb = probe(slot1, t1);
 	}
 	__syncthreads();
 
@@ -300,6 +331,19 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		if (!have_cur && !have_pend)
 			break;
 
+		/* ---- requests whose answers are looked at behind this tile's code words */
+		uint64_t lb_v0 = 0, lb_tail0 = 0;
+		if (warp == 0 && have_pend)
+			look_back_early(pend, ring, tails, 8u * (CMP_HDR_SIZE + 6u), lane, lb_v0, lb_tail0);
+		if (warp == 1) {
+			resolve(slot1, t1, fb);                                /* job of tile k + 1 */
+			recw = (t1 < n_tiles && lane < 16u) ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot1) + lane) : 0u;
+			t2 = __shfl_sync(kFull, t2, 0);                        /* (drawn one iteration ago) */
+			fb = probe(slot1, t2);                                 /* candidates for tile k + 2 */
+			if (lane == 0)
+				t3 = 3u * gridDim.x + atomicAdd(&b.ticket[12], 1u); /* ticket of tile k + 3 */
+		}
+
 		/* ---- tile k: code words, aggregate, staging (tile_encode holds barrier B1) */
 		if (have_cur) {
 			const uint32_t flags = cur.rec[8];
@@ -324,12 +368,11 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			__syncthreads(); /* B1 of a CTA that only has a tile left to send off */
 		}
 		if (warp == 0 && have_pend) /* (thread 0 wrote pend.bits two barriers ago) */
-			look_back(pend, ring, tails, 8u * (CMP_HDR_SIZE + 6u), lane, &sh.stg[par ^ 1u][kPad - 1u]);
-		if (warp == 1) { /* the tile after this one: ticket drawn one iteration ago */
-			fetch(qn, t_next);
-			if (lane == 0)
-				t_next = atomicAdd(&b.ticket[12], 1u);
-			t_next = __shfl_sync(kFull, t_next, 0);
+			look_back(pend, ring, tails, 8u * (CMP_HDR_SIZE + 6u), lane, &sh.stg[par ^ 1u][kPad - 1u], lb_v0, lb_tail0, b.ticket + 16);
+		if (warp == 1) { /* the record of tile k + 1 has arrived */
+			publish_tile(qn, t1, recw);
+			t1 = t2;
+			t2 = t3; /* lane 0; broadcast when it is needed */
 		}
 		__syncthreads(); /* B2: tile k staged, tile k - 1 placed, tile k + 1 known */
 
@@ -357,32 +400,39 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			uint32_t B1 = last ? (g1 + 7u) >> 3 : g1 >> 3;
 			B1 = min(B1, a + cap_eff);
 			const uint32_t s = g0 & 31u, W0 = g0 >> 5;
-			for (uint32_t G = (B0 >> 4) + tid; 16u * G < B1; G += AIRS_TILE_THREADS) {
+			/* whole 16-byte groups: five staging words, four funnel shifts, one byte-swapped 128-bit store */
+			const uint32_t Gfull0 = (B0 + 15u) >> 4, Gfull1 = B1 >> 4;
+			for (uint32_t G = Gfull0 + tid; G < Gfull1; G += AIRS_TILE_THREADS) {
 				const int32_t i0 = (int32_t)(4u * G) - (int32_t)W0; /* local word of the group's first word */
 				uint32_t wv[5];
 #pragma unroll
 				for (int i = 0; i < 5; i++)
-					wv[i] = stg[i0 - 1 + i]; /* i0 >= -3: inside the pad */
-				uint32_t o[4];
-#pragma unroll
-				for (int i = 0; i < 4; i++)
-					o[i] = __funnelshift_r(wv[i + 1], wv[i], s);
-				const uint32_t byte0 = 16u * G;
-				if (byte0 >= B0 && byte0 + 16u <= B1) {
-					*reinterpret_cast<uint4 *>(base + byte0) =
-						make_uint4(airs_bswap32(o[0]), airs_bswap32(o[1]), airs_bswap32(o[2]), airs_bswap32(o[3]));
-				} else {
-#pragma unroll 1
-					for (uint32_t kb = 0; kb < 16u; kb++)
-						if (byte0 + kb >= B0 && byte0 + kb < B1)
-							base[byte0 + kb] = (uint8_t)(o[kb >> 2] >> (24u - 8u * (kb & 3u)));
+					wv[i] = stg[i0 - 1 + i];
+				*reinterpret_cast<uint4 *>(base + 16u * G) =
+					make_uint4(airs_bswap32(__funnelshift_r(wv[1], wv[0], s)), airs_bswap32(__funnelshift_r(wv[2], wv[1], s)),
+						   airs_bswap32(__funnelshift_r(wv[3], wv[2], s)), airs_bswap32(__funnelshift_r(wv[4], wv[3], s)));
+			}
+			/* the bytes in front of the first and behind the last whole group (fewer than 16 each; all bytes of a
+			 * tile without a whole group): one byte per lane of the last warp */
+			if (warp == kTWarps - 1u) {
+				const uint32_t head_end = min(16u * Gfull0, B1);
+				uint32_t byte = lane < 16u ? B0 + lane : max(16u * Gfull1, head_end) + (lane - 16u);
+				const bool mine = lane < 16u ? byte < head_end : (Gfull1 >= Gfull0 && byte < B1);
+				if (mine) {
+					const int32_t L = (int32_t)(8u * byte) - (int32_t)g0; /* tile-local bit of the byte's first bit: >= -7 */
+					const int32_t wi = L >> 5;
+					const uint32_t v = __funnelshift_l(stg[wi + 1], stg[wi], (uint32_t)L & 31u);
+					base[byte] = (uint8_t)(v >> 24);
 				}
 			}
 			__syncthreads(); /* B3: everybody has read what it needs */
-			{
-				const uint32_t nw = (pend.bits + 31u) / 32u + 1u;
-				for (uint32_t w = tid; w < nw + 1u; w += AIRS_TILE_THREADS)
-					stg[(int32_t)w - 1] = 0;
+			{ /* the area goes back to all zero: word -1 (the carried bits), then whole 16-byte groups */
+				const uint32_t nv4 = ((pend.bits + 31u) / 32u + 1u + 3u) / 4u;
+				uint4 *stg4 = reinterpret_cast<uint4 *>(stg);
+				for (uint32_t v = tid; v < nv4; v += AIRS_TILE_THREADS)
+					stg4[v] = make_uint4(0, 0, 0, 0);
+				if (tid == 0)
+					stg[-1] = 0;
 			}
 			if (last) { /* the frame is complete: header, result (ref cmp.c:321-337) */
 				const uint32_t checksum = (flags & AIRS_FJ_CHECKSUM) ? 1u : 0u;
@@ -429,7 +479,8 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 				}
 			}
 		}
-		__syncthreads(); /* B4: tile structs of iteration k are free */
+		/* (no barrier: what iteration k + 1 writes before its barrier B1 - registers, requests - touches nothing that
+		 * is read here; the tile structs and staging areas change hands behind B1) */
 	}
 }
 

@@ -12,6 +12,7 @@ def num(v):
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 40
 show_sass = "-s" in sys.argv
+by_samples = "--stalls" in sys.argv
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -35,7 +36,7 @@ for r in rows:
 tot_i = sum(a[1] for a in agg.values()) or 1
 tot_s = sum(a[2] for a in agg.values()) or 1
 print("total warp instructions %d, stall samples %d" % (tot_i, tot_s))
-for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][2 if by_samples else 1])[:top]:
     print("%5.1f%% inst %5.1f%% smpl  n=%3d  %s:%d  %s" % (100.0 * a[1] / tot_i, 100.0 * a[2] / tot_s, a[3], key[0], key[1], a[0][:90]))
     if show_sass:
         for ins, ni, ns in sass[key]:
