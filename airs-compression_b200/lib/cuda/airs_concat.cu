@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kScanThreads) concat_top_kernel(AirsConcat c, 
 		/* temporary slots: 32 bytes of slack, the copy reads whole 16-byte groups around the last
 		 * bytes of a stream.  Streams: a destination that cannot hold them all is the business of
 		 * the single-phase path, which follows the reference loop through the overflow. */
-		if (WHAT == 0 ? (carry + 32u > c.tmp_size || !c.tmp || !c.dst) : carry > c.dst_size)
+		if (WHAT == 0 ? (carry + 32u > c.tmp_size || !c.tmp || !c.dst) : carry + (c.base ? *c.base : 0u) > c.dst_size)
 			atomicExch(c.flag, 1u);
 		if (WHAT == 1)
 			*c.n_big = 0;
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kScanThreads) concat_slots_kernel(AirsConcat c
 		airs_job job = c.jobs[j];
 		job.dst_offset = off;
 		job.dst_frame_stride = align16(job.dst_capacity);
+		job.first_result -= c.result_base; /* a slice of a larger batch: results / out_offsets start at its first frame */
 		c.slot_jobs[j] = job;
 	}
 }
@@ -141,14 +142,15 @@ __global__ void __launch_bounds__(kScanThreads) concat_offsets_kernel(AirsConcat
 	const uint32_t k = blockIdx.x * kScanThreads + threadIdx.x;
 	const uint64_t v = k < c.n_results ? frame_bytes(c, k) : 0u;
 	uint64_t total;
-	const uint64_t off = sums[blockIdx.x] + cta_exclusive_scan(v, warp_sums, total);
+	const uint64_t base = c.base ? *c.base : 0u; /* a slice of a larger batch starts where the slice before ended */
+	const uint64_t off = base + sums[blockIdx.x] + cta_exclusive_scan(v, warp_sums, total);
 	if (k < c.n_results) {
 		c.out_offsets[k] = off;
 		if (v >= kBigStream)
 			c.big_list[atomicAdd(c.n_big, 1u)] = k;
 	}
 	if (k == 0)
-		c.out_offsets[c.n_results] = sums[n_tiles];
+		c.out_offsets[c.n_results] = base + sums[n_tiles];
 }
 
 /* 16 bytes from byte position p (any alignment) of a 16-byte aligned source */

@@ -102,11 +102,14 @@ struct DevBuf {
 
 constexpr int kMaxGroups = 64; /* pipeline stages of one host batch */
 
+/* Everything a thread keeps between calls lives on ONE device (stream_dev): when the thread's current device
+ * has changed, cache_stream() gives all of it back under the old device before anything is created on the new one. */
 struct Cache {
 	DevBuf src, dst, work, jobs, results, init, offs, scratch, state, tmp;
 	cudaStream_t stream = nullptr;            /* compute (and everything of the unpipelined paths) */
 	cudaStream_t s_in = nullptr, s_out = nullptr; /* host-to-device / device-to-host copies of the pipelined path */
 	cudaEvent_t ev_in[kMaxGroups] = {}, ev_done[kMaxGroups] = {}, ev_start = nullptr;
+	uint64_t *pin = nullptr;                  /* pinned host memory: 2 words per group (pipelined CONCAT) */
 	int stream_dev = -1;
 };
 thread_local Cache g_cache;
@@ -115,7 +118,13 @@ int cache_stream(cudaStream_t *s)
 {
 	int dev;
 	CU(cudaGetDevice(&dev));
-	if (!g_cache.stream || g_cache.stream_dev != dev) {
+	if (g_cache.stream_dev >= 0 && g_cache.stream_dev != dev) {
+		CU(cudaSetDevice(g_cache.stream_dev));
+		airs_cuda_release_cache();
+		CU(cudaSetDevice(dev));
+	}
+	if (!g_cache.stream) {
+		CU(cudaHostAlloc((void **)&g_cache.pin, 2 * kMaxGroups * sizeof(uint64_t), cudaHostAllocDefault));
 		CU(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
 		CU(cudaStreamCreateWithFlags(&g_cache.s_in, cudaStreamNonBlocking));
 		CU(cudaStreamCreateWithFlags(&g_cache.s_out, cudaStreamNonBlocking));
@@ -269,7 +278,16 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.layout = b->layout;
 }
 
-static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream)
+/* slice: the batch is a run of consecutive jobs of a larger CONCAT batch whose first frame is number
+ * slice->result_base of the whole (results / out_offsets point at that frame) and whose streams start at
+ * *slice->base.  Two-phase path only; if the gate closes nothing is written and the caller starts over. */
+struct ConcatSlice {
+	uint32_t result_base;
+	const uint64_t *base;
+};
+
+static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_io, cudaStream_t stream,
+			const ConcatSlice *slice = nullptr)
 {
 	g_launches = 0;
 	if (!b || !b->jobs || !b->results || !b->scratch)
@@ -318,6 +336,10 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 		c.dst_size = b->dst_size;
 		c.n_jobs = b->n_jobs;
 		c.n_results = b->n_results;
+		if (slice) {
+			c.result_base = slice->result_base;
+			c.base = slice->base;
+		}
 		CU(airs_launch_concat_slots(&c, stream));
 		g_launches += 3;
 
@@ -336,10 +358,14 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 		unsigned int cap = (unsigned int)resident * 2u;
 		CU(airs_launch_concat_gather(&c, b->n_results < cap ? b->n_results : cap, stream));
 		g_launches += 4;
+		if (slice)
+			return AIRS_OK; /* (the caller looks at the gate word) */
 
 		l.ticket = (uint32_t *)b->scratch + 64; /* fresh counters for the rerun */
 		l.gate = c.flag;
 		l.gate_want = 1;
+	} else if (slice) {
+		return fail(AIRS_E_ARGUMENT, "a slice needs the two-phase CONCAT path");
 	}
 	return launch_kernels(l, resident, stream);
 }
@@ -472,6 +498,162 @@ static int host_batch_pipelined(const struct airs_host_batch *hb, cudaStream_t s
 	return AIRS_OK;
 }
 
+/*
+ * CONCAT layout, large batch: groups of consecutive jobs as above, but every group is a slice of the whole
+ * (two-phase path: temporary slots sized for the largest group, the scan of a group starts at the total the
+ * group before left on the device) and only the bytes a group produced travel back - the host learns the
+ * group's end from two words in pinned memory and issues the copy as soon as the group is done.
+ * *redo is set when the batch has to take the unpipelined path after all (frames not numbered in job
+ * order, no room for the temporary slots, a destination that overflows: only the single-phase path follows
+ * the reference loop through that).
+ */
+static int host_batch_concat_pipelined(const struct airs_host_batch *hb, cudaStream_t s_comp, bool *redo)
+{
+	Cache &c = g_cache;
+	const struct airs_job *jobs = hb->jobs;
+	struct Group {
+		uint32_t j0, j1, r0, r1;
+		uint64_t s_lo, s_hi, caps;
+	} grp[kMaxGroups];
+
+	*redo = true;
+	uint64_t bytes_total = 0, frames = 0;
+	for (uint32_t j = 0; j < hb->n_jobs; j++) {
+		if (jobs[j].n_frames && jobs[j].first_result != frames)
+			return AIRS_OK;
+		frames += jobs[j].n_frames;
+		bytes_total += (uint64_t)jobs[j].src_size * jobs[j].n_frames;
+	}
+	if (frames != hb->n_results)
+		return AIRS_OK;
+	int n_groups = (int)(bytes_total / (32u << 20)) + 1; /* ~32 MiB a group: the first copy in and the last copy out are not overlapped */
+	if (n_groups < 4)
+		n_groups = 4;
+	if (n_groups > kMaxGroups)
+		n_groups = kMaxGroups;
+	if ((uint32_t)n_groups > hb->n_jobs)
+		n_groups = (int)hb->n_jobs;
+	const uint64_t per_group = bytes_total / (uint64_t)n_groups + 1;
+
+	int ng = 0;
+	size_t tmp_need = 0;
+	uint32_t j0 = 0, r0 = 0;
+	for (int g = 0; g < n_groups && j0 < hb->n_jobs; g++) {
+		Group &G = grp[ng];
+		uint64_t acc = 0;
+		uint32_t j1 = j0, r1 = r0;
+		G.s_lo = ~0ull;
+		G.s_hi = 0;
+		G.caps = 0;
+		while (j1 < hb->n_jobs && (acc < per_group || g == n_groups - 1)) {
+			const struct airs_job &jb = jobs[j1];
+			const uint64_t nf = jb.n_frames;
+			acc += (uint64_t)jb.src_size * nf;
+			G.caps += nf * jb.dst_capacity;
+			if (nf) {
+				const uint64_t se = jb.src_offset + (nf - 1) * jb.src_frame_stride + jb.src_size;
+				if (jb.src_offset < G.s_lo)
+					G.s_lo = jb.src_offset;
+				if (se > G.s_hi)
+					G.s_hi = se;
+			}
+			r1 += jb.n_frames;
+			j1++;
+		}
+		if (G.s_hi > hb->src_size)
+			G.s_hi = hb->src_size;
+		G.j0 = j0;
+		G.j1 = j1;
+		G.r0 = r0;
+		G.r1 = r1;
+		const size_t need = airs_cuda_concat_tmp_size(G.caps, r1 - r0);
+		if (need > tmp_need)
+			tmp_need = need;
+		j0 = j1;
+		r0 = r1;
+		ng++;
+	}
+	{
+		size_t free_b = 0, total_b = 0;
+		if (!(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (tmp_need <= c.tmp.cap || tmp_need < free_b / 2) &&
+		      c.tmp.reserve(tmp_need) == AIRS_OK)) {
+			cudaGetLastError();
+			return AIRS_OK;
+		}
+	}
+
+	CU(cudaMemcpyAsync(c.jobs.p, hb->jobs, (size_t)hb->n_jobs * sizeof(struct airs_job), cudaMemcpyHostToDevice, c.s_in));
+	if (hb->work && hb->work_size)
+		CU(cudaMemcpyAsync(c.work.p, hb->work, hb->work_size, cudaMemcpyHostToDevice, c.s_in));
+	CU(cudaEventRecord(c.ev_start, c.s_in));
+	CU(cudaStreamWaitEvent(s_comp, c.ev_start, 0));
+
+	int launches = 0;
+	for (int g = 0; g < ng; g++) {
+		const Group &G = grp[g];
+		if (G.s_lo < G.s_hi)
+			CU(cudaMemcpyAsync((uint8_t *)c.src.p + G.s_lo, (const uint8_t *)hb->src + G.s_lo, G.s_hi - G.s_lo,
+					   cudaMemcpyHostToDevice, c.s_in));
+		CU(cudaEventRecord(c.ev_in[g], c.s_in));
+		CU(cudaStreamWaitEvent(s_comp, c.ev_in[g], 0));
+
+		struct airs_batch b;
+		memset(&b, 0, sizeof(b));
+		b.src = c.src.p;
+		b.dst = c.dst.p;
+		b.work = hb->work_size ? c.work.p : nullptr;
+		b.jobs = (const struct airs_job *)c.jobs.p + G.j0;
+		b.results = (uint32_t *)c.results.p + G.r0;
+		b.init_results = (uint32_t *)c.init.p + G.j0;
+		b.out_offsets = (uint64_t *)c.offs.p + G.r0;
+		b.scratch = c.scratch.p;
+		b.dst_size = hb->dst_size;
+		b.n_jobs = G.j1 - G.j0;
+		b.n_results = G.r1 - G.r0;
+		b.layout = AIRS_LAYOUT_CONCAT;
+		b.tmp = c.tmp.p;
+		b.tmp_size = tmp_need;
+		ConcatSlice sl = {G.r0, g ? (const uint64_t *)c.offs.p + G.r0 : nullptr};
+		int rc = launch_batch(&b, nullptr, s_comp, &sl);
+		if (rc)
+			return rc;
+		launches += g_launches;
+		c.pin[2 * g + 1] = 1; /* (overwritten by the gate word) */
+		CU(cudaMemcpyAsync(&c.pin[2 * g], (uint64_t *)c.offs.p + G.r1, 8, cudaMemcpyDeviceToHost, s_comp));
+		CU(cudaMemcpyAsync(&c.pin[2 * g + 1], (uint32_t *)c.scratch.p + kGateWord, 4, cudaMemcpyDeviceToHost, s_comp));
+		CU(cudaEventRecord(c.ev_done[g], s_comp));
+	}
+	g_launches = launches;
+
+	bool ok = true;
+	uint64_t lo = 0;
+	for (int g = 0; g < ng; g++) {
+		CU(cudaEventSynchronize(c.ev_done[g]));
+		const uint64_t hi = c.pin[2 * g];
+		if ((uint32_t)c.pin[2 * g + 1] != 0u || hi < lo || hi > hb->dst_size) {
+			ok = false; /* the gate closed: the groups behind this one saw a base that means nothing */
+			break;
+		}
+		if (hi > lo)
+			CU(cudaMemcpyAsync((uint8_t *)hb->dst + lo, (const uint8_t *)c.dst.p + lo, hi - lo, cudaMemcpyDeviceToHost, c.s_out));
+		lo = hi;
+	}
+	CU(cudaStreamSynchronize(s_comp));
+	if (!ok) {
+		CU(cudaStreamSynchronize(c.s_out));
+		return AIRS_OK; /* *redo stays set */
+	}
+	CU(cudaMemcpyAsync(hb->results, c.results.p, (size_t)hb->n_results * 4, cudaMemcpyDeviceToHost, c.s_out));
+	if (hb->init_results)
+		CU(cudaMemcpyAsync(hb->init_results, c.init.p, (size_t)hb->n_jobs * 4, cudaMemcpyDeviceToHost, c.s_out));
+	CU(cudaMemcpyAsync(hb->out_offsets, c.offs.p, ((size_t)hb->n_results + 1) * 8, cudaMemcpyDeviceToHost, c.s_out));
+	if (hb->work && hb->work_size)
+		CU(cudaMemcpyAsync(hb->work, c.work.p, hb->work_size, cudaMemcpyDeviceToHost, c.s_out));
+	CU(cudaStreamSynchronize(c.s_out));
+	*redo = false;
+	return AIRS_OK;
+}
+
 extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
 {
 	if (!hb || !hb->jobs || !hb->results || !hb->src || !hb->dst)
@@ -490,8 +672,15 @@ extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
 	    (rc = c.offs.reserve(((size_t)hb->n_results + 1) * 8 + 64)) || (rc = c.scratch.reserve(scratch)))
 		return rc;
 
+	if (hb->layout == AIRS_LAYOUT_CONCAT && !hb->out_offsets)
+		return fail(AIRS_E_ARGUMENT, "host batch: the CONCAT layout needs out_offsets");
 	if (hb->layout == AIRS_LAYOUT_SLOTS && hb->n_jobs >= 8 && hb->src_size >= (64u << 20))
 		return host_batch_pipelined(hb, s);
+	if (hb->layout == AIRS_LAYOUT_CONCAT && hb->n_jobs >= 8 && hb->src_size >= (64u << 20)) {
+		bool redo = false;
+		if ((rc = host_batch_concat_pipelined(hb, s, &redo)) || !redo)
+			return rc;
+	}
 
 	CU(cudaMemcpyAsync(c.src.p, hb->src, hb->src_size, cudaMemcpyHostToDevice, s));
 	CU(cudaMemcpyAsync(c.jobs.p, hb->jobs, jobs_bytes, cudaMemcpyHostToDevice, s));
@@ -576,6 +765,9 @@ extern "C" void airs_cuda_release_cache(void)
 			cudaEventDestroy(c.ev_done[i]);
 		}
 	}
+	if (c.pin)
+		cudaFreeHost(c.pin);
+	c.pin = nullptr;
 	c.stream = c.s_in = c.s_out = nullptr;
 	c.stream_dev = -1;
 }

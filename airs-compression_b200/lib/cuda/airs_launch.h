@@ -81,6 +81,11 @@ struct AirsConcat {
 	uint64_t dst_size;
 	uint32_t n_jobs;
 	uint32_t n_results;
+	/* a slice of a larger batch (pipelined host batches): the jobs' first_result counts from result_base (results,
+	 * result_job and out_offsets start at the slice's first frame) and the slice's streams start at *base, the
+	 * total the slice before left in its out_offsets[n_results]; 0 / NULL: a whole batch */
+	uint32_t result_base;
+	const uint64_t *base;
 };
 
 #ifdef __cplusplus

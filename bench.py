@@ -353,10 +353,13 @@ def main():
             src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
             # every workload goes through the CONCAT layout: only the compressed bytes travel back
             dst_h = torch.empty(int(we["n_samples_total"] * 2 * 1.1) + (1 << 20), dtype=torch.uint8).pin_memory()
-            jobs_h = np.ascontiguousarray(we["jobs"])
-            results_h = np.zeros(we["n_results"], dtype=np.uint32)
-            init_h = np.zeros(e_units, dtype=np.uint32)
-            offs_h = np.zeros(we["n_results"] + 1, dtype=np.uint64)
+            def pinned(nbytes, dtype):                   # job table and result arrays in pinned memory as well
+                return torch.zeros(nbytes, dtype=torch.uint8).pin_memory().numpy().view(dtype)
+            jobs_h = pinned(we["jobs"].nbytes, we["jobs"].dtype)
+            jobs_h[:] = we["jobs"]
+            results_h = pinned(4 * we["n_results"], np.uint32)
+            init_h = pinned(4 * e_units, np.uint32)
+            offs_h = pinned(8 * (we["n_results"] + 1), np.uint64)
             import ctypes as C
             hb = abi.AirsHostBatch()
             hb.src, hb.src_size = src_h.data_ptr(), src_h.numel()

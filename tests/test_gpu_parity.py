@@ -103,6 +103,40 @@ def test_host_batch_pipelined(gpu, oracle, pkg):
     jobgen.compare(want, got, js, "gpu-host-pipelined", check_tail=False)
 
 
+def test_host_batch_concat_pipelined(gpu, oracle, pkg):
+    """CONCAT host batches of >= 64 MiB take the pipelined path: every group of jobs is a slice of the whole
+    batch (its scan starts at the total the group before left on the device) and only compressed bytes travel
+    back.  Multi-frame contexts with models and checksums, then 4 KiB chunks with mixed parameters; a destination
+    that cannot hold the streams makes the call start over on the unpipelined path, whose answer is AIRS_E_ARGUMENT."""
+    abi, synth = pkg.abi, pkg.synth
+    n_jobs, n, nf = 48, 1 << 18, 3
+    p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16,
+                        secondary_iterations=2, secondary_preprocessing=abi.PRE_MODEL,
+                        secondary_encoder_type=2, secondary_encoder_param=8, secondary_encoder_outlier=60,
+                        model_rate=11, checksum_enabled=1)
+    js = _uniform_jobs(pkg, n_jobs, n, nf, p, cap=2 * n + 64)
+    js["layout"] = 1
+    x = np.stack([synth.frames(3, c, nf, n) for c in range(n_jobs)])
+    js["src"] = x.view(np.uint8).reshape(-1)
+    assert js["src"].nbytes >= 64 << 20
+    want = jobgen.run_cpu(oracle, js, threads=8)
+    got = gpu.run_jobs_host(js)
+    jobgen.compare(want, got, js, "gpu-host-concat-pipelined", check_tail=False)
+    assert pkg.load_library().airs_cuda_last_launch_count() > 30      # several groups, ~11 launches each
+
+    total = int(want[3][-1])
+    js2 = dict(js, dst_size=(total * 2 // 3 + 63) // 64 * 64)          # streams do not fit: the call starts over on the
+    with pytest.raises(RuntimeError, match="concatenated size"):       # unpipelined path, which reports it
+        gpu.run_jobs_host(js2)
+
+    w = pkg.workloads.config3(1 << 15, 5)                               # 32768 chunks of 4 KiB = 128 MiB
+    js3 = {"src": np.ascontiguousarray(w["data"]).view(np.uint8).reshape(-1), "jobs": w["jobs"], "layout": 1,
+           "dst_size": w["dst_size"], "work_size": 0, "n_results": w["n_results"]}
+    want = jobgen.run_cpu(oracle, js3, threads=8)
+    got = gpu.run_jobs_host(js3)
+    jobgen.compare(want, got, js3, "gpu-host-concat-pipelined-c3", check_tail=False)
+
+
 @pytest.mark.parametrize("enc,g,outl", [(1, 2, 0), (2, 3, 40), (1, 16, 0)])
 def test_wide_table_arm(gpu, oracle, pkg, enc, g, outl):
     """Residuals that all sit in the codeword table but cost more than 8 bits per sample: the fast path's
