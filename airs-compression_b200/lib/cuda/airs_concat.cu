@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) concat_gather_kernel(AirsConcat c)
 
 static inline uint32_t tiles_of(uint32_t n)
 {
-	return (n + kScanThreads - 1u) / kScanThreads;
+	return n ? (n + kScanThreads - 1u) / kScanThreads : 1u; /* (a grid of 0 CTAs is not a launch; the kernels check their index) */
 }
 
 extern "C" size_t airs_concat_scratch_bytes(uint32_t n_jobs, uint32_t n_results)

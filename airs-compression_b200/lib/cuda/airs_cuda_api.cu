@@ -356,7 +356,7 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 		/* one CTA per long stream, one warp per short one: as many CTAs as there are frames, at most
 		 * a few per SM (latency bound copies: many warps in flight) */
 		unsigned int cap = (unsigned int)resident * 2u;
-		CU(airs_launch_concat_gather(&c, b->n_results < cap ? b->n_results : cap, stream));
+		CU(airs_launch_concat_gather(&c, b->n_results < cap ? (b->n_results ? b->n_results : 1u) : cap, stream));
 		g_launches += 4;
 		if (slice)
 			return AIRS_OK; /* (the caller looks at the gate word) */

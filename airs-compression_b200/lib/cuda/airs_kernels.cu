@@ -1872,60 +1872,13 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 	}
 }
 
-/* XXH32 with one lane per accumulator: four consecutive lanes share a stream (16-byte aligned
- * 16-bit container), 16 stripes in flight per lane.  All 32 lanes must call it; streams whose
- * group is idle pass n = 0. */
-__device__ uint32_t stream_checksum_lanes(const uint8_t *src, uint32_t n)
-{
-	const uint32_t k = threadIdx.x & 3u; /* accumulator of this lane */
-	const uint32_t nbytes = n * 2u, stripes = n / 8u;
-	const uint32_t seed = AIRS_CHECKSUM_SEED;
-	uint32_t v = k == 0 ? seed + AIRS_XP1 + AIRS_XP2 : k == 1 ? seed + AIRS_XP2 : k == 2 ? seed : seed - AIRS_XP1;
-	const uint32_t *p = (const uint32_t *)src + k;
-	uint32_t s = 0;
-
-	for (; s + 16 <= stripes; s += 16) {
-		uint32_t q[16];
-#pragma unroll
-		for (int i = 0; i < 16; i++)
-			q[i] = __ldg(p + 4u * (s + i));
-#pragma unroll
-		for (int i = 0; i < 16; i++)
-			v = airs_xxh_round(v, airs_be_pair(q[i]));
-	}
-	for (; s < stripes; s++)
-		v = airs_xxh_round(v, airs_be_pair(__ldg(p + 4u * s)));
-	const uint32_t base = threadIdx.x & 28u;
-	const uint32_t v0 = __shfl_sync(kFull, v, base), v1 = __shfl_sync(kFull, v, base + 1u);
-	const uint32_t v2 = __shfl_sync(kFull, v, base + 2u), v3 = __shfl_sync(kFull, v, base + 3u);
-	uint32_t h = nbytes >= 16 ? airs_rotl(v0, 1) + airs_rotl(v1, 7) + airs_rotl(v2, 12) + airs_rotl(v3, 18)
-				  : seed + AIRS_XP5;
-	h += nbytes;
-	uint32_t i = stripes * 8;
-	for (; i + 2 <= n; i += 2)
-		h = airs_rotl(h + airs_be_pair(sample_pair_at(src, AIRS_DTYPE_U16, true, i)) * AIRS_XP3, 17) * AIRS_XP4;
-	if (i < n) {
-		const uint32_t sv = sample_at(src, AIRS_DTYPE_U16, i);
-		h = airs_rotl(h + (sv >> 8) * AIRS_XP5, 11) * AIRS_XP1;
-		h = airs_rotl(h + (sv & 0xFFu) * AIRS_XP5, 11) * AIRS_XP1;
-	}
-	h ^= h >> 15;
-	h *= AIRS_XP2;
-	h ^= h >> 13;
-	h *= AIRS_XP3;
-	h ^= h >> 16;
-	return h;
-}
-
 /* The XXH32 trailer of every successfully encoded stream whose job asked for a checksum (ref
  * cmp.c:314-319: zero padded to a byte, then 4 bytes big endian).  Runs behind the encode
- * kernels; a batch without checksums costs one launch of early exits.  LANES = 1: one thread
- * per frame (many frames).  LANES = 4: four lanes per frame, one per accumulator (few, long
- * frames: the chain of a stream cannot be split further). */
-template <int LANES>
+ * kernels; a batch without checksums costs one launch of early exits.  One thread per frame: for
+ * batches of many frames (few, long frames: airs_checksum_warp_kernel below). */
 __global__ void __launch_bounds__(128) airs_checksum_kernel(AirsLaunch b)
 {
-	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 
 	if (b.ticket[4] == 0 || gate_closed(b))
 		return;
@@ -1950,21 +1903,142 @@ __global__ void __launch_bounds__(128) airs_checksum_kernel(AirsLaunch b)
 			}
 		}
 	}
-	uint32_t h;
-	if (LANES == 4) {
-		/* the lanes of a group agree on todo; unaligned or 32-bit containers fall to lane 0 of the group */
-		const bool lanes_ok = todo && dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)src & 15u) == 0;
-		h = stream_checksum_lanes(src, lanes_ok ? n : 0u);
-		if (todo && !lanes_ok && (threadIdx.x & 3u) == 0)
-			h = stream_checksum(src, dtype, n);
-		if ((threadIdx.x & 3u) != 0)
-			todo = false;
-	} else {
-		if (!todo)
-			return;
-		h = stream_checksum(src, dtype, n);
+	if (!todo)
+		return;
+	const uint32_t h = stream_checksum(src, dtype, n);
+	{
+		stream[r - 4u] = (uint8_t)(h >> 24);
+		stream[r - 3u] = (uint8_t)(h >> 16);
+		stream[r - 2u] = (uint8_t)(h >> 8);
+		stream[r - 1u] = (uint8_t)h;
 	}
-	if (todo) {
+}
+
+/* -------------------------------------------------------------------------
+ * Few, long frames: FOUR LANES PER FRAME, eight frames per warp.  The XXH32 of a stream is one serial chain per
+ * accumulator (a round is IMAD, SHF, IMAD: ~13 cycles a 16-byte stripe, 0.9 ms for a 2 MiB frame), so what a
+ * frame needs is its bytes waiting in shared memory when the chain asks for them: the four lanes of a group keep
+ * kCsRing - 1 blocks of kCsBlock bytes in flight with 16-byte asynchronous copies (cp.async, one commit group per
+ * block) and run one accumulator each over the block that has landed (conflict-free inside a group: its lanes
+ * read the four words of a stripe).  Nothing in the loop waits for global memory once the ring is full.  A CTA is
+ * one warp; frames are dealt to CTAs first and to the groups of a CTA second, so that a batch of few frames
+ * spreads over all SMs.  (Bulk copies - cp.async.bulk, one per block and mbarrier - were measured first: 1 KiB
+ * copies ran at 1.4 TB/s over the device, a fixed cost of ~200 cycles per copy and SM.)
+ * ---------------------------------------------------------------------- */
+constexpr uint32_t kCsBlock = 2048; /* bytes per ring slot: 128 stripes = 0.9 us of chain */
+constexpr uint32_t kCsRing = 4;
+constexpr uint32_t kCsGroups = 8;   /* frames a warp works on at the same time */
+constexpr uint32_t kCsSmem = kCsGroups * kCsRing * kCsBlock;
+
+/* this lane's quarter of a block: 16-byte pieces acc, acc + 4, ... (a group's copy instruction covers 64 contiguous bytes) */
+__device__ __forceinline__ void cs_request(uint32_t smem_slot, const uint8_t *src, uint32_t bytes, uint32_t acc)
+{
+	for (uint32_t o = 16u * acc; o < bytes; o += 64u)
+		asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_slot + o), "l"(src + o) : "memory");
+}
+
+__global__ void __launch_bounds__(32) airs_checksum_warp_kernel(AirsLaunch b)
+{
+	extern __shared__ __align__(128) uint8_t cs_ring[]; /* [group][slot][kCsBlock] */
+	const uint32_t lane = threadIdx.x, grp = lane >> 2, acc = lane & 3u;
+
+	if (b.ticket[4] == 0 || gate_closed(b))
+		return;
+	const uint8_t *ring = cs_ring + grp * kCsRing * kCsBlock;
+	const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring);
+	const uint32_t seed = AIRS_CHECKSUM_SEED;
+
+	/* the loops are the same for all groups of the warp (a group without a frame, or with a shorter one, idles):
+	 * every barrier in them is a plain warp barrier */
+	for (uint32_t base = blockIdx.x; base < b.n_results; base += kCsGroups * gridDim.x) {
+		const uint32_t k = base + grp * gridDim.x;
+		bool todo = false;
+		const uint8_t *src = nullptr;
+		uint8_t *stream = nullptr;
+		uint32_t r = 0, n = 0, dtype = AIRS_DTYPE_U16;
+		if (k < b.n_results) {
+			const uint32_t j = b.result_job[k];
+			if (j < b.n_jobs) {
+				const JobPlan &pl = b.plans[j];
+				r = b.results[k];
+				if ((pl.flags & AIRS_PF_CHECKSUM) && !airs_failed(r) && r >= 4u) {
+					const airs_job &job = b.jobs[j];
+					const uint32_t f = k - job.first_result;
+					src = b.src + job.src_offset + (uint64_t)f * job.src_frame_stride;
+					stream = b.layout == AIRS_LAYOUT_CONCAT ? b.dst + b.out_offsets[k]
+										 : b.dst + job.dst_offset + (uint64_t)f * job.dst_frame_stride;
+					n = pl.n;
+					dtype = job.dtype;
+					todo = true;
+				}
+			}
+		}
+		const bool staged = todo && dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)src & 15u) == 0;
+		const uint32_t nbytes = 2u * n, full = staged ? nbytes & ~15u : 0u; /* whole stripes */
+		const uint32_t n_blocks = (full + kCsBlock - 1u) / kCsBlock;
+		const uint32_t max_blocks = __reduce_max_sync(kFull, n_blocks);
+		uint32_t v = acc == 0 ? seed + AIRS_XP1 + AIRS_XP2 : acc == 1 ? seed + AIRS_XP2 : acc == 2 ? seed : seed - AIRS_XP1;
+
+		/* one commit group per block, empty ones where a group has nothing to fetch: block blk has landed when at
+		 * most kCsRing - 1 groups were committed behind it */
+		for (uint32_t q = 0; q + 1u < kCsRing; q++) {
+			if (q < n_blocks)
+				cs_request(ring0 + q * kCsBlock, src + (size_t)q * kCsBlock, min(kCsBlock, full - q * kCsBlock), acc);
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		}
+		for (uint32_t blk = 0; blk < max_blocks; blk++) {
+			{ /* the slot read one iteration ago takes the block kCsRing - 1 ahead */
+				const uint32_t nb = blk + kCsRing - 1u;
+				if (nb < n_blocks)
+					cs_request(ring0 + (nb % kCsRing) * kCsBlock, src + (size_t)nb * kCsBlock, min(kCsBlock, full - nb * kCsBlock), acc);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+			}
+			asm volatile("cp.async.wait_group %0;" ::"n"(kCsRing - 1u) : "memory");
+			__syncwarp(); /* the quarters of the other lanes of the group are there as well */
+			if (blk < n_blocks) {
+				const uint32_t nst = min(kCsBlock, full - blk * kCsBlock) / 16u;
+				const uint32_t *w = reinterpret_cast<const uint32_t *>(ring + (blk % kCsRing) * kCsBlock) + acc;
+				uint32_t st = 0;
+				for (; st + 16u <= nst; st += 16u) { /* sixteen words at once: their latency is paid once per sixteen rounds */
+					uint32_t q[16];
+#pragma unroll
+					for (int i = 0; i < 16; i++)
+						q[i] = w[4u * (st + i)];
+#pragma unroll
+					for (int i = 0; i < 16; i++)
+						v = airs_xxh_round(v, airs_be_pair(q[i]));
+				}
+				for (; st < nst; st++)
+					v = airs_xxh_round(v, airs_be_pair(w[4u * st]));
+			}
+			__syncwarp(); /* the slot has been read: it may be filled again */
+		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		const uint32_t l0 = 4u * grp;
+		const uint32_t v0 = __shfl_sync(kFull, v, l0), v1 = __shfl_sync(kFull, v, l0 + 1u);
+		const uint32_t v2 = __shfl_sync(kFull, v, l0 + 2u), v3 = __shfl_sync(kFull, v, l0 + 3u);
+		if (!todo || acc != 0)
+			continue;
+		uint32_t h;
+		if (!staged) { /* no 16-byte copies from this source: plain loads */
+			h = stream_checksum(src, dtype, n);
+		} else {
+			h = nbytes >= 16u ? airs_rotl(v0, 1) + airs_rotl(v1, 7) + airs_rotl(v2, 12) + airs_rotl(v3, 18) : seed + AIRS_XP5;
+			h += nbytes;
+			uint32_t i = full / 2u; /* what is left of the frame behind its last whole stripe */
+			for (; i + 2 <= n; i += 2)
+				h = airs_rotl(h + airs_be_pair(sample_pair_at(src, AIRS_DTYPE_U16, true, i)) * AIRS_XP3, 17) * AIRS_XP4;
+			if (i < n) {
+				const uint32_t sv = sample_at(src, AIRS_DTYPE_U16, i);
+				h = airs_rotl(h + (sv >> 8) * AIRS_XP5, 11) * AIRS_XP1;
+				h = airs_rotl(h + (sv & 0xFFu) * AIRS_XP5, 11) * AIRS_XP1;
+			}
+			h ^= h >> 15;
+			h *= AIRS_XP2;
+			h ^= h >> 13;
+			h *= AIRS_XP3;
+			h ^= h >> 16;
+		}
 		stream[r - 4u] = (uint8_t)(h >> 24);
 		stream[r - 3u] = (uint8_t)(h >> 16);
 		stream[r - 2u] = (uint8_t)(h >> 8);
@@ -2003,9 +2077,26 @@ extern "C" cudaError_t airs_launch_encode(const AirsLaunch *b, unsigned int grid
 
 extern "C" cudaError_t airs_launch_checksum(const AirsLaunch *b, cudaStream_t stream)
 {
-	if (b->n_results >= 32768u) /* enough frames to fill the device with one thread each */
-		airs_checksum_kernel<1><<<(b->n_results + 127) / 128, 128, 0, stream>>>(*b);
-	else
-		airs_checksum_kernel<4><<<(4 * b->n_results + 127) / 128, 128, 0, stream>>>(*b);
+	if (b->n_results == 0)
+		return cudaSuccess;
+	if (b->n_results >= 32768u) { /* enough frames to fill the device with one thread each */
+		airs_checksum_kernel<<<(b->n_results + 127) / 128, 128, 0, stream>>>(*b);
+	} else { /* four lanes per frame, at most the warps the device holds at once (3 one-warp CTAs of 64 KiB per SM) */
+		static thread_local int dev_cached = -1, max_grid = 0;
+		int dev;
+		cudaError_t e = cudaGetDevice(&dev);
+		if (e != cudaSuccess)
+			return e;
+		if (dev != dev_cached) {
+			int sms = 0;
+			if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess)
+				return e;
+			if ((e = cudaFuncSetAttribute(airs_checksum_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCsSmem)) != cudaSuccess)
+				return e;
+			max_grid = 3 * sms;
+			dev_cached = dev;
+		}
+		airs_checksum_warp_kernel<<<b->n_results < (unsigned int)max_grid ? b->n_results : (unsigned int)max_grid, 32, kCsSmem, stream>>>(*b);
+	}
 	return cudaGetLastError();
 }

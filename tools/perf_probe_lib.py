@@ -132,12 +132,13 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc, "iwtunc": p_iwtunc}[case], model=(case in ("iwt", "iwtunc")))
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
-    if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k", "c4b_esc1", "c4b_esc8", "c256"):
+    if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k", "c4b_esc1", "c4b_esc8", "c256", "c4cs", "c4bcs", "c32kcs"):
         n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
                        "c32k": (1 << 14, 1 << 15), "c8k": (1 << 16, 1 << 13), "c4b_esc1": (4096, 1 << 17),
-                       "c4b_esc8": (4096, 1 << 17), "c256": (256, 1 << 21)}[case]
+                       "c4b_esc8": (4096, 1 << 17), "c256": (256, 1 << 21), "c4cs": (512, 1 << 20), "c4bcs": (4096, 1 << 17),
+                       "c32kcs": (1 << 14, 1 << 15)}[case]
         data = synth.chunks_torch(1, 0, n_chunks, n, esc={"c4b_esc1": 1, "c4b_esc8": 8}.get(case, 0), device=dev)
-        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_plain)
+        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, p_cs if case.endswith("cs") else p_plain)
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     def p_model_cs(p, idx):
         p_model(p, idx); p["checksum_enabled"] = 1
