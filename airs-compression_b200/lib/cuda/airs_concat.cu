@@ -76,7 +76,7 @@ template <int WHAT>
 __global__ void __launch_bounds__(kScanThreads) concat_tile_sums_kernel(AirsConcat c, uint32_t n, uint64_t *sums)
 {
 	__shared__ uint64_t warp_sums[33];
-	if (WHAT == 1 && *c.flag)
+	if (WHAT == 1 && (*c.flag || c.flag[1]))
 		return;
 	const uint32_t i = blockIdx.x * kScanThreads + threadIdx.x;
 	const uint64_t v = i < n ? (WHAT == 0 ? job_bytes(c, i) : frame_bytes(c, i)) : 0u;
@@ -90,7 +90,7 @@ template <int WHAT>
 __global__ void __launch_bounds__(kScanThreads) concat_top_kernel(AirsConcat c, uint32_t n_tiles, uint64_t *sums)
 {
 	__shared__ uint64_t warp_sums[33];
-	if (WHAT == 1 && *c.flag)
+	if (WHAT == 1 && (*c.flag || c.flag[1]))
 		return;
 	uint64_t carry = 0;
 	for (uint32_t t0 = 0; t0 < n_tiles; t0 += kScanThreads) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kScanThreads) concat_slots_kernel(AirsConcat c
 __global__ void __launch_bounds__(kScanThreads) concat_offsets_kernel(AirsConcat c, const uint64_t *sums, uint32_t n_tiles)
 {
 	__shared__ uint64_t warp_sums[33];
-	if (*c.flag)
+	if (*c.flag || c.flag[1])
 		return;
 	const uint32_t k = blockIdx.x * kScanThreads + threadIdx.x;
 	const uint64_t v = k < c.n_results ? frame_bytes(c, k) : 0u;
@@ -229,7 +229,7 @@ __device__ __forceinline__ bool stream_of(const AirsConcat &c, uint32_t k, const
  * dealt out to its warps */
 __global__ void __launch_bounds__(256) concat_gather_kernel(AirsConcat c)
 {
-	if (*c.flag)
+	if (*c.flag || c.flag[1])
 		return;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x / 32u;
 	const uint32_t n_warps = gridDim.x * wpc;

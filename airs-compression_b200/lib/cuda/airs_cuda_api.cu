@@ -276,6 +276,7 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.n_jobs = b->n_jobs;
 	l.n_results = b->n_results;
 	l.layout = b->layout;
+	l.ordered = b->layout == AIRS_LAYOUT_CONCAT;
 }
 
 /* slice: the batch is a run of consecutive jobs of a larger CONCAT batch whose first frame is number

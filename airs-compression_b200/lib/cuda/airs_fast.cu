@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 	const uint32_t lane = threadIdx.x & 31u;
 	FastWarp &ws = wsh[threadIdx.x >> 5];
 
-	if (b.gate && (*b.gate != 0u) != (b.gate_want != 0u)) /* two-phase CONCAT: not the phase that runs */
+	if (b.ticket[AIRS_TICKET_INVALID] || (b.gate && (*b.gate != 0u) != (b.gate_want != 0u))) /* a bad job table; two-phase CONCAT: not the phase that runs */
 		return;
 	const uint32_t n_fast = b.ticket[3]; /* entries of fast_jobs, written by airs_plan_kernel */
 	if (n_fast == 0u)

@@ -1614,7 +1614,7 @@ __device__ uint64_t lookback_offset(volatile uint64_t *st, uint32_t k, uint32_t 
 /* two-phase CONCAT: is this launch the phase that runs? (see airs_launch.h) */
 __device__ __forceinline__ bool gate_closed(const AirsLaunch &b)
 {
-	return b.gate && (*b.gate != 0u) != (b.gate_want != 0u);
+	return b.ticket[AIRS_TICKET_INVALID] != 0u || (b.gate && (*b.gate != 0u) != (b.gate_want != 0u));
 }
 
 /* Job descriptors come in through shared memory: the 32 jobs of a warp are 3840 consecutive bytes, fetched with
@@ -1649,6 +1649,23 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	}
 	const bool have = j < b.n_jobs;
 	const airs_job &job = *reinterpret_cast<const airs_job *>(pw.job + (have ? lane : 0u) * (sizeof(airs_job) / 4u));
+	/* The contract of include/airs_cuda.h: every frame has a result index below n_results; in the CONCAT layout the
+	 * jobs list the frames 0 .. n_results - 1 in order (the look-back scan waits for every index in front of a frame:
+	 * an index nobody covers would make it wait forever).  A batch that breaks it is not run: the kernels behind this
+	 * one return at once and the checksum kernel turns every result into CMP_ERR_GENERIC. */
+	if (have) {
+		bool bad = (uint64_t)job.first_result + job.n_frames > b.n_results;
+		if (b.ordered) {
+			uint32_t want = 0;
+			if (j != 0u) {
+				const airs_job &prev = lane ? *reinterpret_cast<const airs_job *>(pw.job + (lane - 1u) * (sizeof(airs_job) / 4u)) : b.jobs[j - 1u];
+				want = prev.first_result + prev.n_frames;
+			}
+			bad = bad || job.first_result != want || (j + 1u == b.n_jobs && job.first_result + job.n_frames != b.n_results);
+		}
+		if (bad)
+			atomicExch(&b.ticket[AIRS_TICKET_INVALID], 1u);
+	}
 	/* the job of every frame (airs_checksum_kernel, the CONCAT copy): short jobs by their own
 	 * thread, long ones by the whole warp */
 	{
@@ -1880,6 +1897,11 @@ __global__ void __launch_bounds__(128) airs_checksum_kernel(AirsLaunch b)
 {
 	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 
+	if (b.ticket[AIRS_TICKET_INVALID]) { /* a job table that breaks the contract: nothing has run */
+		if (k < b.n_results)
+			b.results[k] = AIRS_ERR(GENERIC);
+		return;
+	}
 	if (b.ticket[4] == 0 || gate_closed(b))
 		return;
 	bool todo = false;
@@ -1942,6 +1964,11 @@ __global__ void __launch_bounds__(32) airs_checksum_warp_kernel(AirsLaunch b)
 	extern __shared__ __align__(128) uint8_t cs_ring[]; /* [group][slot][kCsBlock] */
 	const uint32_t lane = threadIdx.x, grp = lane >> 2, acc = lane & 3u;
 
+	if (b.ticket[AIRS_TICKET_INVALID]) { /* a job table that breaks the contract: nothing has run */
+		for (uint32_t k = blockIdx.x * 32u + lane; k < b.n_results; k += gridDim.x * 32u)
+			b.results[k] = AIRS_ERR(GENERIC);
+		return;
+	}
 	if (b.ticket[4] == 0 || gate_closed(b))
 		return;
 	const uint8_t *ring = cs_ring + grp * kCsRing * kCsBlock;

@@ -30,6 +30,7 @@ struct JobPlan;
 #ifndef AIRS_TILE_CTAS_PER_SM
 #define AIRS_TILE_CTAS_PER_SM 6
 #endif
+#define AIRS_TICKET_INVALID 6u
 #define AIRS_TILE_RING 65536u /* tile descriptors kept (a power of two, far more than tiles are in flight) */
 
 struct AirsLaunch {
@@ -43,6 +44,7 @@ struct AirsLaunch {
 	uint32_t *ticket;      /* zeroed before the launch: [0] next entry of big_list, [1] of small_list,
 				  [2] entries in big_list, [3] entries in small_list,
 				  [4] jobs with checksum, [5] gate of the two-phase CONCAT path,
+				  [6] set by airs_plan_kernel when the job table breaks the contract (AIRS_TICKET_INVALID),
 				  [10..11] 64-bit: jobs of airs_tile_kernel << 40 | their tiles, [12] next tile */
 	uint32_t *big_list;    /* job indices for airs_encode_kernel, filled by airs_plan_kernel */
 	uint32_t *small_list;  /* job indices of airs_fast_kernel's records, in their order (SLOTS layout only) */
@@ -62,6 +64,7 @@ struct AirsLaunch {
 	const uint32_t *gate;
 	uint32_t gate_want;
 	uint32_t tile_below_jobs; /* batches with fewer jobs send every long single-frame job to airs_tile_kernel */
+	uint32_t ordered;         /* the caller's layout is CONCAT: the jobs must list the frames 0 .. n_results - 1 in order */
 };
 
 /* what the two-phase CONCAT path adds: temporary slots, the job table rewritten onto them */
@@ -73,7 +76,8 @@ struct AirsConcat {
 	uint64_t *out_offsets;
 	uint8_t *tmp;
 	uint8_t *dst;
-	uint32_t *flag;               /* set when the path has to be abandoned: tmp or dst too small */
+	uint32_t *flag;               /* set when the path has to be abandoned: tmp or dst too small; flag[1] is the
+					 batch's AIRS_TICKET_INVALID word */
 	uint64_t *sums;               /* airs_concat_scratch_bytes(): tile sums of the scans ... */
 	uint32_t *big_list;           /* ... the frames whose streams a whole CTA copies ... */
 	uint32_t *n_big;              /* ... and their number */

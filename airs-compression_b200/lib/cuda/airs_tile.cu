@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	__shared__ TileShared sh;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-	if (b.gate && (*b.gate != 0u) != (b.gate_want != 0u)) /* two-phase CONCAT: not the phase that runs */
+	if (b.ticket[AIRS_TICKET_INVALID] || (b.gate && (*b.gate != 0u) != (b.gate_want != 0u))) /* a bad job table; two-phase CONCAT: not the phase that runs */
 		return;
 	const uint64_t counts = *reinterpret_cast<const uint64_t *>(b.ticket + 10); /* airs_plan_kernel: tile jobs << 40 | tiles */
 	const uint32_t n_tiles = (uint32_t)(counts & ((1ull << 40) - 1u)), n_tjobs = (uint32_t)(counts >> 40);

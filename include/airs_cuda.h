@@ -27,6 +27,14 @@
  * produces, programs/airspacecli.c:131-202): out_offsets[k] is where stream k
  * starts, out_offsets[n_results] the total; a frame that failed contributes 0
  * bytes; dst_capacity still bounds each stream.
+ *
+ * Contract of the job table: the frames of job j have the result indices
+ * first_result .. first_result + n_frames - 1, all below n_results.  In the
+ * CONCAT layout the jobs list the frames 0 .. n_results - 1 in order (job 0
+ * starts at 0, every job where the one before ended, the last one ends at
+ * n_results) - the order of the concatenation is the order of the table.  A
+ * table that breaks this is refused on the device: nothing is encoded and
+ * every results[k] is (uint32_t)-CMP_ERR_GENERIC.
  */
 #ifndef AIRS_CUDA_H
 #define AIRS_CUDA_H

@@ -30,6 +30,18 @@ def test_every_declared_symbol_is_exported(lib, pkg):
         assert hasattr(lib, name), name
 
 
+def test_nothing_else_is_exported(pkg):
+    """... and the other direction: the dynamic symbol table of libcmp_b200.so holds the declared functions and
+    nothing else (no launch helpers, no kernel stubs) - lib/exports.map is the list the linker applies."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg.loader.library_path()], capture_output=True, text=True, check=True)
+    exported = {line.split()[-1] for line in out.stdout.splitlines() if line.strip()}
+    assert exported == set(pkg.loader.EXPORTS), sorted(exported ^ set(pkg.loader.EXPORTS))
+    listed = set(re.findall(r"^\s+((?:cmp|airs_cuda)_[a-z0-9_]+);", open(os.path.join(
+        ROOT, "airs-compression_b200", "lib", "exports.map")).read(), flags=re.M))
+    assert listed == set(pkg.loader.EXPORTS)
+
+
 def test_struct_layouts():
     """params 44 bytes, context 80 bytes with the probed offsets."""
     assert C.sizeof(abi.CmpParams) == 44 and C.sizeof(abi.CmpContext) == 80

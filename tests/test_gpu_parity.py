@@ -74,6 +74,31 @@ def test_concat_two_phase_gives_way(gpu, oracle):
     assert np.array_equal(one[0][:fit], two[0][:fit])
 
 
+def test_bad_job_table_is_refused(gpu, pkg):
+    """include/airs_cuda.h, contract of the job table: result indices beyond n_results (any layout) or frames that
+    are not listed in order (CONCAT) - the batch is refused on the device, every result is CMP_ERR_GENERIC and
+    nothing hangs (the look-back scan of the single-phase CONCAT path would wait for an index nobody covers)."""
+    abi = pkg.abi
+    generic = abi.err("GENERIC")
+    rng = np.random.default_rng(9)
+    for layout, breakage in ((0, "range"), (1, "range"), (1, "gap"), (1, "order")):
+        js = jobgen.build_jobs(rng, 40, sizes=[64, 257, 2048], max_frames=3, layout=layout)
+        jobs = js["jobs"].copy()
+        if breakage == "range":
+            jobs["first_result"][17] = js["n_results"] - 1
+            jobs["n_frames"][17] = 2
+        elif breakage == "gap":
+            jobs["first_result"][20:] += 1
+            js["n_results"] += 1
+        else:
+            a, b = jobs[5].copy(), jobs[6].copy()
+            jobs[5], jobs[6] = b, a
+        js["jobs"] = jobs
+        for tmp in ((0,) if layout == 0 else (0, gpu.concat_tmp_size(jobs, js["n_results"]))):
+            got = gpu.run_jobs_device(js, concat_tmp=tmp)
+            assert all(int(r) == generic for r in got[1]), (layout, breakage, tmp)
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 def test_host_batch(gpu, oracle, layout):
     """airs_cuda_compress_batch_host: host buffers in, host buffers out."""
