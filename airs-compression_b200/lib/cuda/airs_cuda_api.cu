@@ -210,7 +210,7 @@ extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_resul
 	 * the job table on temporary slots (two-phase CONCAT) */
 	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs +
 	       4 * (size_t)n_results + 64 + sizeof(struct airs_job) * (size_t)n_jobs + 64 +
-	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 64 * (size_t)n_jobs + 64 + 16 * (size_t)AIRS_TILE_RING;
+	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 64 * (size_t)n_jobs + 64 + (size_t)AIRS_TILE_RING_BYTES;
 }
 
 extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results)
@@ -267,7 +267,7 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.result_job = l.small_list + b->n_jobs;
 	{ /* from the end of the scratch memory: tile rings, then the fast-job records in front of them */
 		const size_t end = airs_cuda_batch_scratch_size(b->n_jobs, b->n_results);
-		const size_t ring = (end - 16 * (size_t)AIRS_TILE_RING) & ~(size_t)63;
+		const size_t ring = (end - (size_t)AIRS_TILE_RING_BYTES) & ~(size_t)63;
 		l.tile_ring = (uint64_t *)((uint8_t *)b->scratch + ring);
 		l.fast_jobs = (uint8_t *)b->scratch + ((ring - 64 * (size_t)b->n_jobs) & ~(size_t)63);
 	}
@@ -313,7 +313,7 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 	fill_launch(l, b, ctx_io);
 	CU(cudaMemsetAsync(l.result_job, 0xFF, 4 * (size_t)b->n_results, stream));
 	if (b->layout == AIRS_LAYOUT_SLOTS || b->tmp)
-		CU(cudaMemsetAsync(l.tile_ring, 0, 16 * (size_t)AIRS_TILE_RING, stream));
+		CU(cudaMemsetAsync(l.tile_ring, 0, (size_t)AIRS_TILE_RING_BYTES, stream));
 
 	if (b->layout == AIRS_LAYOUT_CONCAT && b->tmp && b->tmp_size && b->dst && !ctx_io && !((uintptr_t)b->tmp & 15u)) {
 		/* two phases (airs_concat.cu): SLOTS-style into temporary slots, scan, copy.  Everything is

@@ -8,9 +8,8 @@
  * staging words and its position in the stream; there is no block barrier and no code that
  * runs on one thread while the others wait.
  *
- * Per unit of 512 samples ("rows" 0 and 1: lane l holds pieces l and 32 + l of 8 samples, so
- * both 128-bit loads of the warp are coalesced; the next unit's loads are in flight while one
- * is encoded):
+ * Per unit of 512 samples ("rows" 0 and 1: lane l holds the pieces 2 l and 2 l + 1 of 8 samples,
+ * see airs_fastcore.cuh; the next unit's loads are in flight while one is encoded):
  *   packed 16x2 residuals (none / diff, VIADD.16x2 + PRMT) -> packed zig-zag -> per sample
  *   the Golomb code word ARITHMETICALLY: quotient by one multiply-high (airs_fast.cuh), code
  *   word by one shift, one multiply-add and one three-input add, escape by two selects (ref
@@ -117,16 +116,16 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 	/* the complete pieces of the next unit are requested while one unit is encoded */
 #pragma unroll
 	for (uint32_t j = 0; j < kRows; j++)
-		nx[j] = 32u * j + lane < n_whole ? __ldg(src4 + 32u * j + lane) : zero4;
+		nx[j] = unit_piece(lane, j) < n_whole ? __ldg(src4 + unit_piece(lane, j)) : zero4;
 	uint32_t u = 0;
 	for (; u < n_full_units; u++) {
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++)
 			x[j] = nx[j];
-		const uint32_t p1 = (u + 1u) * kUnitPieces + lane;
+		const uint32_t p1 = (u + 1u) * kUnitPieces + unit_piece(lane, 0);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++)
-			nx[j] = p1 + 32u * j < n_whole ? __ldg(src4 + p1 + 32u * j) : zero4;
+			nx[j] = p1 + j < n_whole ? __ldg(src4 + p1 + j) : zero4;
 		o.sbits += encode_unit<MULTI, DIFF, false>(dbg, k, x, front, full_nv, lane, stg_bit + o.sbits);
 		if (o.sbits > kUnitMaxBits)
 			drain(ws, o, lane);
@@ -135,7 +134,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 		uint32_t nv[kRows];
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++) {
-			const uint32_t p = u * kUnitPieces + 32u * j + lane;
+			const uint32_t p = u * kUnitPieces + unit_piece(lane, j);
 			nv[j] = 8u * p >= n ? 0u : min(8u, n - 8u * p);
 			if (nv[j] != 0u && nv[j] != 8u)
 				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j]);

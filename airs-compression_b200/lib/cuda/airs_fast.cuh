@@ -16,7 +16,7 @@
 #define AIRS_FJ_FALLBACK_OK 8u
 
 /* samples of a tile of airs_tile_kernel */
-#define AIRS_TILE_SAMPLES 2048u
+#define AIRS_TILE_SAMPLES 1024u /* two units of 512 samples */
 
 /* largest Golomb parameter of the multiply-high division used by the fast kernels (below) */
 #define AIRS_FAST_MAX_G 32767u

@@ -2,8 +2,11 @@
  * airs_fastcore.cuh - the warp-level encoder shared by airs_fast_kernel (one warp per short job, airs_fast.cu)
  * and airs_tile_kernel (the tiles of long frames spread over CTAs, airs_tile.cu).
  *
- * A "unit" is 512 consecutive samples of one warp: lane l holds pieces l and 32 + l of 8 samples ("rows" 0
- * and 1), so both 128-bit loads of the warp are coalesced.  Per unit:
+ * A "unit" is 512 consecutive samples of one warp: lane l holds the pieces 2 l and 2 l + 1 of 8 samples ("rows"
+ * 0 and 1), 16 consecutive samples.  The strings of one staging instruction then lie a lane's whole bit count
+ * apart (3 to 6 words for most data) instead of one piece's (1.5 words: neighbouring lanes in the same word,
+ * 2.8 wavefronts per shared-memory reduction in ncu) - the price is two 128-bit loads per lane that each
+ * touch only half of every sector (the other half is the other load's: L1 hits).  Per unit:
  *   packed 16x2 residuals (none / diff, VIADD.16x2 + PRMT) -> packed zig-zag -> per sample the Golomb code
  *   word ARITHMETICALLY: quotient by one multiply-high (airs_fast.cuh), code word by one shift, one
  *   multiply-add and one three-input add, escapes by selects (ref cmp_encoder_encode_s16, encoder.c:327-378;
@@ -29,6 +32,12 @@ constexpr uint32_t kRows = 2;               /* pieces per lane and unit */
 constexpr uint32_t kUnitPieces = 32 * kRows;
 constexpr uint32_t kUnit = 8 * kUnitPieces; /* 512 samples */
 constexpr uint32_t kUnitMaxBits = kUnit * 48;
+
+/* the piece of row j of a lane, counted inside the unit */
+__device__ __forceinline__ uint32_t unit_piece(uint32_t lane, uint32_t j)
+{
+	return kRows * lane + j;
+}
 
 /* AIRS_BOUNDS_CHECK builds: the shared-memory window of the warp's staging words, and a counter of the
  * strings that would have left it (airs_fast_bounds_violations() reads and clears it) */
@@ -185,9 +194,14 @@ __device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRo
 		if (DIFF) {
 			/* t = ~r = ~w + predecessor, per 16-bit half; zig-zag of r = ((t << 1) | 1) ^ sign(t)
 			 * (ref map_to_unsigned, encoder.c:274-286) */
-			const uint32_t up = __shfl_sync(kFull, w[3], (lane - 1u) & 31u);
-			uint32_t prev = lane ? up : front;
-			front = up; /* lane 0: lane 31's last word, in front of lane 0's piece of the next row */
+			uint32_t prev;
+			if (j == 0) { /* the last word of the lane in front */
+				const uint32_t up = __shfl_sync(kFull, x[kRows - 1].w, (lane - 1u) & 31u);
+				prev = lane ? up : front;
+				front = up; /* lane 0: lane 31's last word, in front of the next unit */
+			} else {
+				prev = x[j - 1].w;
+			}
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
 				const uint32_t t = __vadd2(~w[i], __byte_perm(prev, w[i], 0x5432));
@@ -233,8 +247,14 @@ __device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRo
 	return row_bits[0] | (row_bits[1] << 16);
 }
 
-/* inclusive warp scan of the packed row bits: stream order is row 0 of all lanes, then row 1 of all lanes.
- * The shuffle's "source lane exists" predicate feeds the adds directly. */
+/* the bits of a lane's rows together */
+__device__ __forceinline__ uint32_t lane_bits(uint32_t packed)
+{
+	return (packed & 0xFFFFu) + (packed >> 16);
+}
+
+/* inclusive warp scan of the lanes' bit counts (stream order is lane by lane).  The shuffle's "source lane
+ * exists" predicate feeds the adds directly. */
 __device__ __forceinline__ uint32_t unit_scan(uint32_t b)
 {
 	uint32_t incl = b;
@@ -276,12 +296,12 @@ __device__ __forceinline__ uint32_t encode_unit(const Dbg &dbg, const FK &k, con
 {
 	UnitStrings<MULTI> s;
 	const uint32_t b = unit_codes<MULTI, DIFF, RAGGED>(k, x, front, nv, lane, s);
-	const uint32_t incl = unit_scan(b);
-	const uint32_t tot = __shfl_sync(kFull, incl, 31), excl = incl - b;
-	const uint32_t tot0 = tot & 0xFFFFu;
-	const uint32_t pos[kRows] = {abs_bit + (excl & 0xFFFFu), abs_bit + tot0 + (excl >> 16)};
+	const uint32_t mine = lane_bits(b);
+	const uint32_t incl = unit_scan(mine);
+	const uint32_t tot = __shfl_sync(kFull, incl, 31), at = abs_bit + incl - mine;
+	const uint32_t pos[kRows] = {at, at + (b & 0xFFFFu)};
 	unit_put<MULTI>(dbg, s, pos);
-	return tot0 + (tot >> 16);
+	return tot;
 }
 
 } /* namespace fastcore */

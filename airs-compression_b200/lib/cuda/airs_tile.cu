@@ -1,26 +1,27 @@
 /*
  * airs_tile.cu - airs_tile_kernel: long single-frame jobs (chunks of more than 32768 samples without model:
- * BASELINE configs 1, 4 and 5 in their 2 MiB cut) spread over ALL resident CTAs, 2048 samples ("tile") at a
+ * BASELINE configs 1, 4 and 5 in their 2 MiB cut) spread over ALL resident warps, 1024 samples ("tile") at a
  * time, whatever the number of jobs - one 1 Mi-sample cmp_compress_u16() call uses the whole GPU.
  *
- * The bit position at which a tile's code words start is the sum of the bit counts of all tiles in front of
- * it in its frame: a single-pass scan with decoupled look-back over 64-bit tile descriptors in global memory
- * (flag | tile id | bits: "aggregate" as soon as the tile's bits are counted, "inclusive prefix" once its own
- * start is known).  Tiles are handed out in stream order by an atomic ticket, so every tile a CTA waits for
- * is held by a CTA that is running.  Software pipeline per CTA (128 threads, 4 warps, one unit of
- * airs_fastcore.cuh per warp), iteration k:
- *   code words of tile k (registers) -> warp scans -> barrier -> thread 0 publishes the aggregate of tile k;
- *   all warps stage tile k at TILE-LOCAL bit positions in staging area k % 2 while warp 0 resolves the
- *   look-back of tile k - 1 (published one tile earlier: its predecessors have had a tile's time to answer)
- *   -> barrier -> tile k - 1 leaves its staging area shifted by its start position: five shared-memory
- *   words and four funnel shifts per 16-byte group, byte-swapped 128-bit stores.
+ * ONE WARP PER TILE, no block barrier anywhere (an earlier version gave a tile to a whole CTA and pipelined
+ * three barriers per tile around a look-back warp: 45 % of the issue slots, barrier stalls on top of the list).
+ * Tiles are numbered in stream order over all tile jobs and dealt out round robin over the warps of the grid
+ * (all resident: every tile a warp waits for is held by a warp that is running and works on it in the same
+ * iteration); a warp then works like airs_fast_kernel on a short job:
+ *   two units of airs_fastcore.cuh (code words in registers, warp scan, strings OR-ed into the warp's own
+ *   staging words) at TILE-LOCAL bit positions -> the tile's bit count and its last seven bits are published ->
+ *   the tile's start in its stream = the bit counts of all tiles in front of it in its frame, summed over
+ *   three levels of descriptors in global memory (look_back()) -> the staging words leave shifted to their
+ *   place: five shared-memory words and four funnel shifts per 16-byte group, byte-swapped 128-bit stores.
+ * The job of a tile is found two tiles ahead, its record and first samples one ahead, so the only thing a warp
+ * ever waits for is the look-back - while the other 23 warps of its SM encode.
  * Seams: tiles meet at bit granularity.  A tile writes the bytes [start / 8, end / 8) of the stream; the
- * start % 8 bits of its first byte that belong to its predecessor come out of a second ring ("tail": the
- * last 7 bits of every tile, published when the tile is staged).  The tile that ends a frame also writes the
- * last, zero-padded byte, the header (ref cmp_hdr_serialize, header.c:24-67) and the result.
+ * start % 8 bits of its first byte that belong to its predecessor come out of the "tails" ring.  The tile that
+ * ends a frame also writes the last, zero-padded byte, the 22 header bytes (ref cmp_hdr_serialize,
+ * header.c:24-67; the first tile starts behind them) and the result.
  *
  * Reference being replaced: the per-sample loop of compress_engine (cmp.c:296-312) with
- * bitstream_add_bits32 (bitstream_writer.h:124-158), for one frame by many CTAs.
+ * bitstream_add_bits32 (bitstream_writer.h:124-158), for one frame by many warps.
  */
 #include <cuda_runtime.h>
 
@@ -31,29 +32,32 @@ namespace {
 
 using namespace fastcore;
 
+#ifndef AIRS_TILE_ABLATE
+#define AIRS_TILE_ABLATE 0
+#endif
+#ifndef AIRS_TILE_NAP
+#define AIRS_TILE_NAP 200 /* ns between two polls of a window that is not complete */
+#endif
 constexpr uint32_t kTWarps = AIRS_TILE_THREADS / 32;
-constexpr uint32_t kTile = kTWarps * kUnit;             /* 2048 samples */
+constexpr uint32_t kTile = AIRS_TILE_SAMPLES;            /* 1024 samples */
+constexpr uint32_t kTileUnits = kTile / kUnit;
 constexpr uint32_t kTileWords = kTile * 48 / 32;         /* a tile at 48 bits per sample */
-constexpr uint32_t kPad = 8;                             /* words in front of an area: word -1 takes the carried bits */
+constexpr uint32_t kPad = 8;                             /* words in front of the area: word -1 takes the carried bits */
 constexpr uint32_t kRing = AIRS_TILE_RING;               /* descriptors of the last kRing tiles (far more than are in flight) */
+constexpr uint32_t kHdrBits = 8u * (CMP_HDR_SIZE + 6u);
+static_assert(kTile % kUnit == 0 && kTileUnits >= 1, "a tile is whole units");
 
-constexpr uint64_t kFlagA = 1ull << 62, kFlagP = 2ull << 62;
-constexpr uint32_t kValBits = 28;                        /* bits of a frame: less than 2^27 + header */
+constexpr uint64_t kFlagA = 1ull << 62;
+constexpr uint32_t kValBits = 28; /* bits of 1024 tiles: less than 2^26 */
 
-struct TileInfo {          /* one tile in flight (current or pending), shared memory */
-	uint32_t rec[16];  /* its job's record (FastJob) */
-	uint32_t T;        /* global tile id */
-	uint32_t tidx;     /* index of the tile in its job */
-	uint32_t bits;     /* code bits of the tile */
-	uint32_t excl;     /* stream bits in front of the tile (header included), from the look-back */
-	uint32_t valid;
+/* the staging words of one warp: MSB-first 32-bit words of the tile under construction at tile-local bit
+ * positions, all zero when idle; strings that end in word 0 or 1 OR zeros below the area (pad) */
+struct TileArea {
+	alignas(16) uint32_t pad[kPad];
+	uint32_t stg[kTileWords + 8];
 };
-
-struct TileShared {
-	alignas(16) uint32_t stg[2][kPad + kTileWords + 8];
-	TileInfo tile[3];  /* [k % 3]: current, pending and next tile */
-	uint32_t wtot[2][kTWarps];
-	uint32_t slot, slot_base, slot_tiles; /* the tile job the last ticket fell into */
+struct TileWarp {
+	TileArea area[2]; /* [k % 2]: the tile being encoded, the tile waiting for its place */
 };
 
 __device__ __forceinline__ uint64_t ld_desc(const uint64_t *p)
@@ -68,158 +72,205 @@ __device__ __forceinline__ void st_desc(uint64_t *p, uint64_t v)
 	asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ uint64_t make_desc(uint64_t flag, uint32_t T, uint32_t value)
+__device__ __forceinline__ uint64_t make_desc(uint32_t tag, uint32_t value)
 {
-	return flag | ((uint64_t)(T + 1u) << kValBits) | value;
+	return kFlagA | ((uint64_t)(tag + 1u) << kValBits) | value;
 }
 
-/* warp 0, one iteration early: the descriptors of the 32 tiles in front of `ti` and the tail of the one right in
- * front of it are requested (no waiting here); look_back() looks at the answers behind the tile's code words */
-__device__ __forceinline__ void look_back_early(const TileInfo &ti, const uint64_t *ring, const uint64_t *tails, uint32_t hdr_bits,
-						uint32_t lane, uint64_t &v0, uint64_t &tail0)
+/* a descriptor that has been published for entry `tag` of its ring? */
+__device__ __forceinline__ bool desc_ready(uint64_t v, uint32_t tag)
 {
-	const uint32_t T = ti.T, tidx = ti.tidx;
-	const int64_t j = (int64_t)T - 1 - lane;
-	v0 = (tidx != 0u && j >= (int64_t)T - tidx) ? ld_desc(ring + ((uint32_t)j & (kRing - 1u))) : (kFlagP | hdr_bits);
-	tail0 = tidx != 0u ? ld_desc(tails + ((T - 1u) & (kRing - 1u))) : 0ull;
+	return (uint32_t)(v >> kValBits) == tag + 1u && (v >> 62) != 0;
 }
 
-/* warp 0: where tile `ti` starts in its stream (decoupled look-back), and the bits it shares its first byte with.
- * v0 / tail0: the answers to look_back_early(); only what they leave open is polled */
-__device__ __forceinline__ void look_back(TileInfo &ti, uint64_t *ring, uint64_t *tails, uint32_t hdr_bits, uint32_t lane,
-					  uint32_t *carry_word, uint64_t v0, uint64_t tail0, uint32_t *stats)
-{
-#ifdef AIRS_TILE_STATS
-	uint32_t st_polls = 0, st_tail = 0, st_windows = 0;
-#endif
-	const uint32_t T = ti.T, tidx = ti.tidx;
-	uint32_t excl = hdr_bits;
-
-	if (tidx != 0u) {
-		const int64_t lowest = (int64_t)T - tidx; /* first tile of the job; in front of it: the header */
-		int64_t idx = (int64_t)T - 1;
-		uint32_t sum = 0;
-		bool early = true;
-		for (;;) {
-			const int64_t j = idx - lane;
-			const bool real = j >= lowest;
-			uint64_t v;
-			bool ready;
-			uint32_t nr, spins = 0;
-			do { /* until every descriptor in front of the nearest prefix has been published */
-				if (++spins > (1u << 24))
-					__trap(); /* a predecessor that never answers: fail the launch instead of hanging the device */
-#ifdef AIRS_TILE_STATS
-				st_polls += early ? 0u : 1u;
-#endif
-				v = early ? v0 : (real ? ld_desc(ring + ((uint32_t)j & (kRing - 1u))) : (kFlagP | hdr_bits));
-				early = false;
-				ready = !real || (((uint32_t)(v >> kValBits) == (uint32_t)j + 1u) && (v >> 62) != 0);
-				nr = __ballot_sync(kFull, !ready);
-				const uint32_t pm = __ballot_sync(kFull, ready && (v >> 62) == 2u);
-				const uint32_t first_nr = nr ? (uint32_t)__ffs((int)nr) - 1u : 32u;
-				const uint32_t p = pm ? (uint32_t)__ffs((int)pm) - 1u : 32u;
-				if (p < first_nr) { /* aggregates of the lanes in front of p, prefix of p */
-					sum += __reduce_add_sync(kFull, lane <= p ? (uint32_t)v & ((1u << kValBits) - 1u) : 0u);
-					nr = 0;
-					idx = -1; /* done */
-					break;
-				}
-			} while (nr);
-			if (idx < 0)
-				break;
-			sum += __reduce_add_sync(kFull, (uint32_t)v & ((1u << kValBits) - 1u)); /* 32 aggregates, no prefix yet */
-			idx -= 32;
-#ifdef AIRS_TILE_STATS
-			st_windows++;
-#endif
+/* one entry of a look-back window: polled until it is there, then kept */
+struct Probe {
+	const uint64_t *p; /* nullptr: this lane has no entry in the window, or has it already */
+	uint64_t v;        /* the answer to the last request */
+	uint32_t tag, val;
+	__device__ __forceinline__ void set(const uint64_t *ring_, uint32_t mask, uint32_t idx, bool wanted)
+	{
+		p = wanted ? ring_ + (idx & mask) : nullptr;
+		tag = idx;
+		val = 0;
+		v = 0;
+	}
+	__device__ __forceinline__ void request() /* (no waiting here: the answer is looked at by check()) */
+	{
+		if (p)
+			v = ld_desc(p);
+	}
+	__device__ __forceinline__ void check()
+	{
+		if (p && desc_ready(v, tag)) {
+			val = (uint32_t)v & ((1u << kValBits) - 1u);
+			p = nullptr;
 		}
-		excl = sum;
 	}
-	/* the predecessor's last bits that share this tile's first byte */
-	uint32_t carry = 0;
-	const uint32_t m = excl & 7u;
-	if (m && tidx != 0u) {
-		uint64_t v = tail0;
-		uint32_t spins = 0;
-		while ((uint32_t)(v >> 8) != T) { /* tag of tile T - 1 is T */
-			v = ld_desc(tails + ((T - 1u) & (kRing - 1u)));
-			if (++spins > (1u << 24))
-				__trap();
-#ifdef AIRS_TILE_STATS
-			st_tail++;
-#endif
-		}
-		carry = (uint32_t)v & ((1u << m) - 1u);
+	__device__ __forceinline__ void poll()
+	{
+		request();
+		check();
 	}
-#ifdef AIRS_TILE_STATS
-	if (lane == 0) {
-		atomicAdd(stats + 0, 1u);
-		atomicAdd(stats + 1, st_polls);
-		atomicAdd(stats + 2, st_tail);
-		atomicAdd(stats + 3, st_windows);
+};
+
+/* the five windows of a tile's look-back (see look_back()) and the tail of the tile in front of it */
+struct LookBack {
+	Probe t_own, t_first, b_own, b_first, q_mid;
+	const uint64_t *tail_p;
+	uint64_t tail_v;
+};
+
+/* The holder of the last tile of a block of 32 (1024) tiles publishes the block's bit count: it polls the 31
+ * entries in front of its own.  They belong to tiles that other warps count at about the same time (tickets
+ * are drawn in order): nothing they wait for depends on this warp. */
+static __device__ __noinline__ void publish_block_sums(uint64_t *ring, uint32_t T, uint32_t my_bits, uint32_t lane)
+{
+	uint64_t *l1 = ring + 2u * kRing, *l2 = l1 + kRing / 32u;
+	const uint32_t B = T >> 5, Q = B >> 5;
+	Probe pr;
+	uint32_t spins = 0;
+	pr.set(ring, kRing - 1u, 32u * B + lane, lane < 31u);
+	for (;;) {
+		pr.poll();
+		if (__all_sync(kFull, pr.p == nullptr))
+			break;
+		__nanosleep(AIRS_TILE_NAP);
+		if (++spins > (1u << 22))
+			__trap();
 	}
-#endif
-	if (lane == 0) {
-		ti.excl = excl;
-		*carry_word = carry; /* word -1 of the tile's staging area: the bits in front of its first bit */
-		st_desc(ring + (T & (kRing - 1u)), make_desc(kFlagP, T, excl + ti.bits));
+	const uint32_t block = __reduce_add_sync(kFull, pr.val) + my_bits;
+	if (lane == 0)
+		st_desc(l1 + (B & (kRing / 32u - 1u)), make_desc(B, block));
+	if ((T & 1023u) != 1023u)
+		return;
+	pr.set(l1, kRing / 32u - 1u, 32u * Q + lane, lane < 31u);
+	for (;;) {
+		pr.poll();
+		if (__all_sync(kFull, pr.p == nullptr))
+			break;
+		__nanosleep(AIRS_TILE_NAP);
+		if (++spins > (1u << 22))
+			__trap();
 	}
+	const uint32_t big = __reduce_add_sync(kFull, pr.val) + block;
+	if (lane == 0)
+		st_desc(l2 + (Q & (kRing / 1024u - 1u)), make_desc(Q, big));
 }
 
-/* Tile k of a job whose encoder / preprocessing are fixed at compile time: code words (registers), warp scan,
- * barrier B1, the tile's aggregate published, strings staged at tile-local bit positions in area `par`.
- * Contains a block barrier: all threads of the CTA call it (they all hold the same tile). */
+/*
+ * Where tile T (number tidx of its frame) starts in its stream, in bits behind the header.
+ *
+ * All warps work on one "row" of consecutive tiles at the same time, so a look-back that walks from count to
+ * count until it meets a finished prefix walks half a row (thousands of tiles, a round trip per window).
+ * Instead the counts are summed over THREE LEVELS: tiles, blocks of 32 tiles (ring l1) and blocks of 1024 tiles
+ * (ring l2); the sums of a block are published by the holder of its last tile right when that tile is counted
+ * (publish_block_sums()).  A tile's start is at most five windows of 32 entries - tiles of its own block,
+ * blocks of its own 1024-block, whole 1024-blocks, and the same again upwards from the frame's first tile -
+ * whose entries do not depend on any look-back: all are requested at once and polled until they are there.
+ */
+__device__ __forceinline__ void look_back_begin(LookBack &lb, const uint64_t *ring, const uint64_t *tails, uint32_t T, uint32_t tidx,
+						uint32_t lane)
+{
+	const uint64_t *l1 = ring + 2u * kRing, *l2 = l1 + kRing / 32u;
+	const uint32_t T0 = T - tidx;
+	const uint32_t B = T >> 5, B0 = T0 >> 5, Q = B >> 5, Q0 = B0 >> 5;
+	const bool any = tidx != 0u;
+
+	/* tiles of my block in front of me, in my frame */
+	lb.t_own.set(ring, kRing - 1u, 32u * B + lane, any && lane < (T & 31u) && 32u * B + lane >= T0);
+	/* the frame's first tiles, up to the end of their block (another block than mine) */
+	lb.t_first.set(ring, kRing - 1u, T0 + lane, any && B > B0 && T0 + lane < 32u * (B0 + 1u));
+	/* blocks of my 1024-block in front of mine, behind the frame's first block */
+	lb.b_own.set(l1, kRing / 32u - 1u, 32u * Q + lane, any && lane < (B & 31u) && 32u * Q + lane > B0);
+	/* the blocks behind the frame's first one, up to the end of their 1024-block (another one than mine) */
+	lb.b_first.set(l1, kRing / 32u - 1u, B0 + 1u + lane, any && Q > Q0 && B0 + 1u + lane < 32u * (Q0 + 1u));
+	/* whole 1024-blocks between the two */
+	lb.q_mid.set(l2, kRing / 1024u - 1u, Q0 + 1u + lane, any && Q0 + 1u + lane < Q);
+	lb.t_own.request();
+	lb.t_first.request();
+	lb.b_own.request();
+	lb.b_first.request();
+	lb.q_mid.request();
+	lb.tail_p = any ? tails + ((T - 1u) & (kRing - 1u)) : nullptr;
+	lb.tail_v = any ? ld_desc(lb.tail_p) : 0ull;
+}
+
+/* ... the answers; what is still missing is polled.  Returns the bits in front of the tile (behind the header) */
+__device__ __forceinline__ uint32_t look_back_finish(LookBack &lb)
+{
+	uint32_t spins = 0;
+	lb.t_own.check();
+	lb.t_first.check();
+	lb.b_own.check();
+	lb.b_first.check();
+	lb.q_mid.check();
+	while (!__all_sync(kFull, lb.t_own.p == nullptr && lb.t_first.p == nullptr && lb.b_own.p == nullptr && lb.b_first.p == nullptr &&
+					  lb.q_mid.p == nullptr)) {
+		__nanosleep(AIRS_TILE_NAP); /* the issue slots of a spinning warp are taken from the warps that encode */
+		lb.t_own.poll();
+		lb.t_first.poll();
+		lb.b_own.poll();
+		lb.b_first.poll();
+		lb.q_mid.poll();
+		if (++spins > (1u << 22))
+			__trap(); /* an entry that never arrives: fail the launch instead of hanging the device */
+	}
+	return __reduce_add_sync(kFull, lb.t_own.val + lb.t_first.val + lb.b_own.val + lb.b_first.val + lb.q_mid.val);
+}
+
+/* the units of one tile: code words, scans, strings staged from tile-local bit 0 on; returns the tile's bits */
 template <bool MULTI, bool DIFF>
-__device__ __forceinline__ void tile_encode(const Dbg &dbg, TileShared &sh, TileInfo &cur, uint64_t *ring, const FK &k,
-					    const uint4 (&x)[kRows], uint32_t front, uint32_t par)
+__device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, TileArea &ws, const uint8_t *src, uint32_t n, uint32_t first,
+					       uint4 (&nx)[kRows], uint32_t front, uint32_t lane)
 {
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	const uint32_t n = cur.rec[6], first = cur.tidx * kTile + warp * kUnit;
-	UnitStrings<MULTI> s;
-	uint32_t b;
+	const uint32_t stg_bit = 8u * (uint32_t)__cvta_generic_to_shared(ws.stg);
+	const uint32_t n_whole = n / 8u;
+	const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
+	const uint4 zero4 = make_uint4(0, 0, 0, 0);
+	uint32_t bits = 0;
 
-	if (first + kUnit <= n) {
-		const uint32_t nv[kRows] = {8u, 8u};
-		b = unit_codes<MULTI, DIFF, false>(k, x, front, nv, lane, s);
-	} else { /* the ragged end of the frame (or nothing at all) */
-		uint32_t nv[kRows];
 #pragma unroll
-		for (uint32_t j = 0; j < kRows; j++) {
-			const uint32_t p = first + 8u * (32u * j + lane);
-			nv[j] = p >= n ? 0u : min(8u, n - p);
+	for (uint32_t u = 0; u < kTileUnits; u++) {
+		const uint32_t ufirst = first + u * kUnit;
+		if (ufirst >= n)
+			break;
+		uint4 x[kRows];
+#pragma unroll
+		for (uint32_t j = 0; j < kRows; j++)
+			x[j] = nx[j];
+		if (u + 1u < kTileUnits) { /* the next unit's samples travel while this one is encoded */
+#pragma unroll
+			for (uint32_t j = 0; j < kRows; j++) {
+				const uint32_t p = (ufirst + kUnit) / 8u + unit_piece(lane, j);
+				nx[j] = p < n_whole ? __ldg(src4 + p) : zero4;
+				if (p == n_whole && (n & 7u))
+					nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u);
+			}
 		}
-		b = unit_codes<MULTI, DIFF, true>(k, x, front, nv, lane, s);
-	}
-	const uint32_t incl = unit_scan(b);
-	if (lane == 31u)
-		sh.wtot[par][warp] = (incl & 0xFFFFu) + (incl >> 16);
-	__syncthreads(); /* B1: warp totals of the tile */
-
-	uint32_t wpre = 0, tile_bits = 0;
+		if (ufirst + kUnit <= n) {
+			const uint32_t nv[kRows] = {8u, 8u};
+			bits += encode_unit<MULTI, DIFF, false>(dbg, k, x, front, nv, lane, stg_bit + bits);
+		} else { /* the ragged end of the frame */
+			uint32_t nv[kRows];
 #pragma unroll
-	for (uint32_t w = 0; w < kTWarps; w++) {
-		const uint32_t t = sh.wtot[par][w];
-		wpre += w < warp ? t : 0u;
-		tile_bits += t;
+			for (uint32_t j = 0; j < kRows; j++) {
+				const uint32_t p = ufirst + 8u * unit_piece(lane, j);
+				nv[j] = p >= n ? 0u : min(8u, n - p);
+			}
+			bits += encode_unit<MULTI, DIFF, true>(dbg, k, x, front, nv, lane, stg_bit + bits);
+		}
 	}
-	if (tid == 0) {
-		cur.bits = tile_bits;
-		st_desc(ring + (cur.T & (kRing - 1u)), make_desc(kFlagA, cur.T, tile_bits));
-	}
-	/* staged at tile-local bit positions: the shift to the stream position happens on the way out */
-	const uint32_t tot0 = __shfl_sync(kFull, incl, 31) & 0xFFFFu, excl = incl - b;
-	const uint32_t base = 8u * (uint32_t)__cvta_generic_to_shared(&sh.stg[par][kPad]) + wpre;
-	const uint32_t pos[kRows] = {base + (excl & 0xFFFFu), base + tot0 + (excl >> 16)};
-	unit_put<MULTI>(dbg, s, pos);
+	return bits;
 }
 
 } /* namespace */
 
 __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs_tile_kernel(AirsLaunch b)
 {
-	__shared__ TileShared sh;
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	__shared__ TileWarp wsh[kTWarps];
+	const uint32_t lane = threadIdx.x & 31u;
+	TileWarp &ws = wsh[threadIdx.x >> 5];
 
 	if (b.ticket[AIRS_TICKET_INVALID] || (b.gate && (*b.gate != 0u) != (b.gate_want != 0u))) /* a bad job table; two-phase CONCAT: not the phase that runs */
 		return;
@@ -230,26 +281,20 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	const FastJob *recs_end = reinterpret_cast<const FastJob *>(b.fast_jobs) + (b.n_jobs - 1u); /* slot s at recs_end - s */
 	uint64_t *ring = b.tile_ring, *tails = b.tile_ring + kRing;
 
-	for (uint32_t w = tid; w < 2u * (kPad + kTileWords + 8u); w += AIRS_TILE_THREADS)
-		(&sh.stg[0][0])[w] = 0;
-	if (tid < 3u)
-		sh.tile[tid].valid = 0;
-	if (tid == 0) {
-		sh.slot = 0xFFFFFFFFu; /* "the slot in front of slot 0": the first search starts at slot 0 */
-		sh.slot_base = 0;
-		sh.slot_tiles = 0;
-	}
-	__syncthreads();
+	for (uint32_t w = lane; w < 2u * (kPad + kTileWords + 8u); w += 32u)
+		ws.area[0].pad[w] = 0;
+	__syncwarp();
+	Dbg dbg;
+#ifdef AIRS_BOUNDS_CHECK
+	dbg.lo = (uint32_t)__cvta_generic_to_shared(&ws);
+	dbg.hi = dbg.lo + (uint32_t)sizeof(TileWarp);
+#endif
 
-	/* Warp 1 finds the job of every tile, in steps spread over three iterations so that no step waits for
-	 * global memory: tickets are drawn three tiles ahead; the tile_base fields of the 32 jobs behind the job of
-	 * the tile before (tile jobs sit at recs_end - slot with ascending tile_base, and a CTA's tickets only grow)
-	 * are requested two tiles ahead; the slot follows from a ballot one tile ahead, when the job's record is
-	 * requested; the record reaches shared memory behind the code words of the tile in front. */
-	uint32_t t1 = 0, t2 = 0, t3 = 0;   /* tickets of tiles k + 1, k + 2, k + 3 (warp 1, lane 0 draws) */
-	uint32_t slot1 = 0xFFFFFFFFu;      /* slot of tile k + 1 once resolved; before: of the tile in front of it */
-	uint32_t fb = 0xFFFFFFFFu;         /* tile_base of slot (slot of tile k) + 1 + lane, requested for tile k + 1 */
-	uint32_t recw = 0;                 /* word `lane` of the record of tile k + 1 */
+	/* The job of a tile is found in steps spread over the tiles in front of it, so that no step waits for global
+	 * memory: tickets are drawn three tiles ahead; the tile_base fields of the 32 jobs behind the job of the tile
+	 * before (tile jobs sit at recs_end - slot with ascending tile_base, and a warp's tickets only grow) are
+	 * requested two tiles ahead; the slot follows from a ballot one tile ahead, when the job's record and the
+	 * tile's first samples are requested. */
 	auto probe = [&](uint32_t slot, uint32_t T) -> uint32_t { /* tile_base of the 32 slots behind `slot` */
 		const uint32_t s = slot + 1u + lane;
 		return (T < n_tiles && s < n_tjobs) ? __ldg(&(recs_end - s)->tile_base) : 0xFFFFFFFFu;
@@ -266,157 +311,159 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			v = probe(slot, T); /* a jump over more than 32 jobs: keep probing */
 		}
 	};
-	auto publish_tile = [&](uint32_t q, uint32_t T, uint32_t word) { /* record word `lane` -> sh.tile[q] */
-		TileInfo &ti = sh.tile[q];
-		if (T < n_tiles) {
-			if (lane < 16u)
-				ti.rec[lane] = word;
-			const uint32_t base = __shfl_sync(kFull, word, 14);
-			if (lane == 0) {
-				ti.T = T;
-				ti.tidx = T - base;
-				ti.valid = 1;
-			}
-		} else if (lane == 0) {
-			ti.valid = 0;
-		}
-		__syncwarp();
+	auto record = [&](uint32_t slot, uint32_t T) -> uint32_t { /* word `lane` of the record of tile T's job */
+		return (T < n_tiles && lane < 16u) ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot) + lane) : 0u;
 	};
-	if (warp == 1) { /* prologue: tile 0 in full, tile 1 probed, tile 2 drawn */
-		/* the first three tiles of every CTA are dealt out round robin: a CTA must never hold consecutive tiles (the
-		 * second one would be counted an iteration after the first, and every tile behind it would wait for that) */
-		const uint32_t t0 = blockIdx.x;
-		t1 = blockIdx.x + gridDim.x;
-		t2 = blockIdx.x + 2u * gridDim.x;
-		resolve(slot1, t0, probe(slot1, t0));
-		const uint32_t w0 = (t0 < n_tiles && lane < 16u) ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot1) + lane) : 0u;
-		publish_tile(0, t0, w0);
-		fb = probe(slot1, t1);
-	}
-	__syncthreads();
-
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
 	uint4 nx[kRows] = {zero4, zero4};
 	uint32_t nfront = 0;
-	/* the samples of this warp's unit of tile sh.tile[q], requested ahead */
-	auto request = [&](uint32_t q) {
-		const TileInfo &ti = sh.tile[q];
-		if (!ti.valid)
+	/* the samples of the first unit of tile T (job record in `rec`), and the sample in front of the tile */
+	auto request = [&](uint32_t rec, uint32_t T) {
+		if (T >= n_tiles)
 			return;
-		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(ti.rec[0] | (uint64_t)ti.rec[1] << 32));
-		const uint32_t n = ti.rec[6], first = ti.tidx * kTile + warp * kUnit, n_whole = n / 8u;
+		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(__shfl_sync(kFull, rec, 0) | (uint64_t)__shfl_sync(kFull, rec, 1) << 32));
+		const uint32_t n = __shfl_sync(kFull, rec, 6), first = (T - __shfl_sync(kFull, rec, 14)) * kTile, n_whole = n / 8u;
 		const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++) {
-			const uint32_t p = first / 8u + 32u * j + lane;
+			const uint32_t p = first / 8u + unit_piece(lane, j);
 			nx[j] = p < n_whole ? __ldg(src4 + p) : zero4;
 			if (p == n_whole && (n & 7u))
 				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u);
 		}
-		/* lane 0: the sample in front of the unit (DIFF), in the upper half of a word */
+		/* lane 0: the sample in front of the tile (DIFF), in the upper half of a word */
 		nfront = (lane == 0 && first != 0u && first < n) ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(src) + first - 1u) << 16 : 0u;
 	};
-	request(0);
 
-	Dbg dbg;
-#ifdef AIRS_BOUNDS_CHECK
-	dbg.lo = (uint32_t)__cvta_generic_to_shared(&sh.stg[0][0]);
-	dbg.hi = dbg.lo + (uint32_t)sizeof(sh.stg);
-#endif
+	/* Tiles are dealt out round robin over all warps of the grid (all resident): tile T belongs to warp T mod
+	 * n_warps in its iteration T / n_warps.  A counter would hand tiles to whoever asks first - but a tile has to be
+	 * asked for a few tiles ahead to hide the way to its samples, and a tile that sits reserved while its warp
+	 * is still busy with earlier ones keeps EVERY tile behind it in the frame waiting (measured: 7 x slower).
+	 * prologue: tile 0 in full, tile 1 probed */
+	const uint32_t n_warps = gridDim.x * kTWarps, gw = blockIdx.x * kTWarps + (threadIdx.x >> 5);
+	uint32_t t0 = gw, t1 = gw + n_warps, t2 = gw + 2u * n_warps, t3 = 0;
+	uint32_t slot0 = 0xFFFFFFFFu; /* "the slot in front of slot 0" */
+	resolve(slot0, t0, probe(slot0, t0));
+	uint32_t rec = record(slot0, t0);
+	uint32_t slot1 = slot0;
+	uint32_t fb = probe(slot1, t1); /* candidates for tile 1 */
+	request(rec, t0);
 
-	for (uint32_t k = 0;; k++) {
-		const uint32_t q = k % 3u, qp = (k + 2u) % 3u, qn = (k + 1u) % 3u, par = k & 1u;
-		TileInfo &cur = sh.tile[q], &pend = sh.tile[qp];
-		const bool have_cur = cur.valid != 0u, have_pend = k > 0u && pend.valid != 0u;
+	/* Software pipeline, iteration k: tile k is encoded into staging area k % 2 and counted; then tile k - 1, counted
+	 * one iteration ago - the tiles in front of it have had a tile's time to be counted as well - gets its place and
+	 * leaves area (k - 1) % 2.  A warp that waited for its place right behind its own code words would wait for the
+	 * slowest warp of the device in every iteration, together with all other warps of its SM. */
+	uint32_t prec = 0, pT = 0xFFFFFFFFu, pbits = 0; /* the pending tile: its job's record, its number, its bits */
+	for (uint32_t par = 0;; par ^= 1u) {
+		const bool have_cur = t0 < n_tiles, have_pend = pT != 0xFFFFFFFFu;
 		if (!have_cur && !have_pend)
 			break;
-
-		/* ---- requests whose answers are looked at behind this tile's code words */
-		uint64_t lb_v0 = 0, lb_tail0 = 0;
-		if (warp == 0 && have_pend)
-			look_back_early(pend, ring, tails, 8u * (CMP_HDR_SIZE + 6u), lane, lb_v0, lb_tail0);
-		if (warp == 1) {
-			resolve(slot1, t1, fb);                                /* job of tile k + 1 */
-			recw = (t1 < n_tiles && lane < 16u) ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot1) + lane) : 0u;
-			t2 = __shfl_sync(kFull, t2, 0);                        /* (drawn one iteration ago) */
-			fb = probe(slot1, t2);                                 /* candidates for tile k + 2 */
-			if (lane == 0)
-				t3 = 3u * gridDim.x + atomicAdd(&b.ticket[12], 1u); /* ticket of tile k + 3 */
-		}
-
-		/* ---- tile k: code words, aggregate, staging (tile_encode holds barrier B1) */
+		uint32_t bits = 0;
+		uint32_t nrec = 0;
 		if (have_cur) {
-			const uint32_t flags = cur.rec[8];
+			/* ---- requests whose answers are looked at behind this tile's code words */
+			resolve(slot1, t1, fb);                   /* job of the next tile */
+			nrec = record(slot1, t1);
+			fb = probe(slot1, t2);                    /* candidates for the tile behind it */
+			t3 = t2 + n_warps;
+
+#define AIRS_REC(i) __shfl_sync(kFull, rec, (i))
+			const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(AIRS_REC(0) | (uint64_t)AIRS_REC(1) << 32));
+			const uint32_t n = AIRS_REC(6), flags = AIRS_REC(8);
+			const uint32_t g = AIRS_REC(10), outlier = AIRS_REC(11), magic = AIRS_REC(12);
+			const uint32_t T = t0, tidx = T - AIRS_REC(14);
+#undef AIRS_REC
 			const bool multi = (flags & AIRS_FJ_MULTI) != 0u;
-			const FK kk = make_fk(multi, cur.rec[10], (flags >> 8) & 15u, cur.rec[11], cur.rec[12]);
-			uint4 x[kRows];
-#pragma unroll
-			for (uint32_t j = 0; j < kRows; j++)
-				x[j] = nx[j];
+			const FK kk = make_fk(multi, g, (flags >> 8) & 15u, outlier, magic);
+			const uint32_t first = tidx * kTile;
+			const bool last = first + kTile >= n;
+			TileArea &ar = ws.area[par];
+
+			/* ---- the tile's code words, staged at tile-local bit positions */
 			if (multi) {
 				if (flags & AIRS_FJ_PRE_DIFF)
-					tile_encode<true, true>(dbg, sh, cur, ring, kk, x, nfront, par);
+					bits = tile_units<true, true>(dbg, kk, ar, src, n, first, nx, nfront, lane);
 				else
-					tile_encode<true, false>(dbg, sh, cur, ring, kk, x, nfront, par);
+					bits = tile_units<true, false>(dbg, kk, ar, src, n, first, nx, nfront, lane);
 			} else {
 				if (flags & AIRS_FJ_PRE_DIFF)
-					tile_encode<false, true>(dbg, sh, cur, ring, kk, x, nfront, par);
+					bits = tile_units<false, true>(dbg, kk, ar, src, n, first, nx, nfront, lane);
 				else
-					tile_encode<false, false>(dbg, sh, cur, ring, kk, x, nfront, par);
+					bits = tile_units<false, false>(dbg, kk, ar, src, n, first, nx, nfront, lane);
 			}
-		} else {
-			__syncthreads(); /* B1 of a CTA that only has a tile left to send off */
+			__syncwarp();
+			if (lane == 0) {
+				st_desc(ring + (T & (kRing - 1u)), make_desc(T, bits));
+				if (!last) { /* the last 7 bits of the tile, for the tile behind it (bits >= 1024 > 7) */
+					const uint32_t wi = bits >> 5, sft = bits & 31u;
+					const uint32_t before = wi ? ar.stg[wi - 1u] : 0u;
+					const uint32_t last32 = sft ? __funnelshift_l(ar.stg[wi], before, sft) : before; /* the 32 bits that end at bit `bits` */
+					st_desc(tails + (T & (kRing - 1u)), ((uint64_t)(T + 1u) << 8) | (last32 & 0x7Fu));
+				}
+			}
+			if ((T & 31u) == 31u && AIRS_TILE_ABLATE < 1)
+				publish_block_sums(ring, T, bits, lane);
+			/* ---- the next tile's first samples travel while the tile before this one leaves */
+			request(nrec, t1);
 		}
-		if (warp == 0 && have_pend) /* (thread 0 wrote pend.bits two barriers ago) */
-			look_back(pend, ring, tails, 8u * (CMP_HDR_SIZE + 6u), lane, &sh.stg[par ^ 1u][kPad - 1u], lb_v0, lb_tail0, b.ticket + 16);
-		if (warp == 1) { /* the record of tile k + 1 has arrived */
-			publish_tile(qn, t1, recw);
-			t1 = t2;
-			t2 = t3; /* lane 0; broadcast when it is needed */
-		}
-		__syncthreads(); /* B2: tile k staged, tile k - 1 placed, tile k + 1 known */
 
-		if (have_cur && tid == 0) { /* the last 7 bits of tile k, for the tile behind it */
-			const uint32_t e = cur.bits; /* >= 2048 > 7 unless the frame ends here (then nobody asks) */
-			const uint32_t *stg = &sh.stg[par][kPad];
-			const uint32_t wi = e >> 5, sft = e & 31u;
-			const uint32_t before = wi ? stg[wi - 1u] : 0u;
-			const uint32_t last32 = sft ? __funnelshift_l(stg[wi], before, sft) : before; /* the 32 bits that end at bit e */
-			st_desc(tails + (cur.T & (kRing - 1u)), ((uint64_t)(cur.T + 1u) << 8) | (last32 & 0x7Fu));
-		}
-		request(qn); /* samples of tile k + 1 travel while tile k - 1 leaves */
-
-		/* ---- tile k - 1 leaves its staging area, shifted to its place in the stream */
 		if (have_pend) {
-			const uint32_t parp = par ^ 1u;
-			uint32_t *stg = &sh.stg[parp][kPad];
-			uint8_t *dst = reinterpret_cast<uint8_t *>((uintptr_t)(pend.rec[2] | (uint64_t)pend.rec[3] << 32));
-			const uint32_t n = pend.rec[6], cap_eff = pend.rec[7], flags = pend.rec[8];
+#define AIRS_REC(i) __shfl_sync(kFull, prec, (i))
+			uint8_t *dst = reinterpret_cast<uint8_t *>((uintptr_t)(AIRS_REC(2) | (uint64_t)AIRS_REC(3) << 32));
+			const uint32_t n = AIRS_REC(6), cap_eff = AIRS_REC(7), flags = AIRS_REC(8);
+			const uint32_t T = pT, tidx = T - AIRS_REC(14);
+			const bool last = tidx * kTile + kTile >= n;
+			uint32_t *stg = ws.area[par ^ 1u].stg;
+
+			/* ---- where the tile starts; the bits of its first byte that belong to the tile in front */
+#if AIRS_TILE_ABLATE >= 1 /* development: timing without the look-back (wrong streams) */
+			const uint32_t excl = kHdrBits + tidx * 4096u;
+#else
+			/* (requesting the windows in front of the tile's code words and looking at them behind was measured: the 17
+			 * registers the answers sit in spill the encoder: 1.33 -> 1.82 ms on 256 x 4 MiB) */
+			LookBack lb;
+			look_back_begin(lb, ring, tails, T, tidx, lane);
+			const uint32_t excl = kHdrBits + look_back_finish(lb);
+#endif
+			const uint32_t m = excl & 7u;
+			if (m && tidx != 0u) {
+				uint64_t v = lb.tail_v;
+				uint32_t spins = 0;
+				while ((uint32_t)(v >> 8) != T) { /* tag of tile T - 1 is T */
+					v = ld_desc(lb.tail_p);
+					if (++spins > (1u << 22))
+						__trap();
+				}
+				if (lane == 0)
+					stg[-1] = (uint32_t)v & ((1u << m) - 1u); /* word -1: the bits in front of the tile's first bit */
+			}
+			__syncwarp();
+
+			/* ---- the tile leaves its staging words, shifted to its place in the stream */
 			const uint32_t a = (uint32_t)((uintptr_t)dst & 15u);
 			uint8_t *base = dst - a;
-			const uint32_t g0 = 8u * a + pend.excl, g1 = g0 + pend.bits;
-			const bool last = (pend.tidx + 1u) * kTile >= n;
+			const uint32_t g0 = 8u * a + excl, g1 = g0 + pbits;
 			const uint32_t B0 = g0 >> 3;
 			uint32_t B1 = last ? (g1 + 7u) >> 3 : g1 >> 3;
 			B1 = min(B1, a + cap_eff);
 			const uint32_t s = g0 & 31u, W0 = g0 >> 5;
-			/* whole 16-byte groups: five staging words, four funnel shifts, one byte-swapped 128-bit store */
-			const uint32_t Gfull0 = (B0 + 15u) >> 4, Gfull1 = B1 >> 4;
-			for (uint32_t G = Gfull0 + tid; G < Gfull1; G += AIRS_TILE_THREADS) {
-				const int32_t i0 = (int32_t)(4u * G) - (int32_t)W0; /* local word of the group's first word */
-				uint32_t wv[5];
+			if (B1 > B0 && AIRS_TILE_ABLATE < 2) {
+				/* whole 16-byte groups: five staging words, four funnel shifts, one byte-swapped 128-bit store */
+				const uint32_t Gfull0 = (B0 + 15u) >> 4, Gfull1 = B1 >> 4;
+				for (uint32_t G = Gfull0 + lane; G < Gfull1; G += 32u) {
+					const int32_t i0 = (int32_t)(4u * G) - (int32_t)W0; /* local word of the group's first word */
+					uint32_t wv[5];
 #pragma unroll
-				for (int i = 0; i < 5; i++)
-					wv[i] = stg[i0 - 1 + i];
-				*reinterpret_cast<uint4 *>(base + 16u * G) =
-					make_uint4(airs_bswap32(__funnelshift_r(wv[1], wv[0], s)), airs_bswap32(__funnelshift_r(wv[2], wv[1], s)),
-						   airs_bswap32(__funnelshift_r(wv[3], wv[2], s)), airs_bswap32(__funnelshift_r(wv[4], wv[3], s)));
-			}
-			/* the bytes in front of the first and behind the last whole group (fewer than 16 each; all bytes of a
-			 * tile without a whole group): one byte per lane of the last warp */
-			if (warp == kTWarps - 1u) {
+					for (int i = 0; i < 5; i++)
+						wv[i] = stg[i0 - 1 + i];
+					*reinterpret_cast<uint4 *>(base + 16u * G) =
+						make_uint4(airs_bswap32(__funnelshift_r(wv[1], wv[0], s)), airs_bswap32(__funnelshift_r(wv[2], wv[1], s)),
+							   airs_bswap32(__funnelshift_r(wv[3], wv[2], s)), airs_bswap32(__funnelshift_r(wv[4], wv[3], s)));
+				}
+				/* the bytes in front of the first and behind the last whole group (fewer than 16 each; all bytes of a
+				 * tile without a whole group): one byte per lane */
 				const uint32_t head_end = min(16u * Gfull0, B1);
-				uint32_t byte = lane < 16u ? B0 + lane : max(16u * Gfull1, head_end) + (lane - 16u);
+				const uint32_t byte = lane < 16u ? B0 + lane : max(16u * Gfull1, head_end) + (lane - 16u);
 				const bool mine = lane < 16u ? byte < head_end : (Gfull1 >= Gfull0 && byte < B1);
 				if (mine) {
 					const int32_t L = (int32_t)(8u * byte) - (int32_t)g0; /* tile-local bit of the byte's first bit: >= -7 */
@@ -425,25 +472,26 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 					base[byte] = (uint8_t)(v >> 24);
 				}
 			}
-			__syncthreads(); /* B3: everybody has read what it needs */
+			__syncwarp();
 			{ /* the area goes back to all zero: word -1 (the carried bits), then whole 16-byte groups */
-				const uint32_t nv4 = ((pend.bits + 31u) / 32u + 1u + 3u) / 4u;
+				const uint32_t nv4 = ((pbits + 31u) / 32u + 1u + 3u) / 4u;
 				uint4 *stg4 = reinterpret_cast<uint4 *>(stg);
-				for (uint32_t v = tid; v < nv4; v += AIRS_TILE_THREADS)
+				for (uint32_t v = lane; v < nv4; v += 32u)
 					stg4[v] = make_uint4(0, 0, 0, 0);
-				if (tid == 0)
+				if (lane == 0)
 					stg[-1] = 0;
 			}
 			if (last) { /* the frame is complete: header, result (ref cmp.c:321-337) */
 				const uint32_t checksum = (flags & AIRS_FJ_CHECKSUM) ? 1u : 0u;
-				const uint32_t size = ((pend.excl + pend.bits + 7u) >> 3) + 4u * checksum;
+				const uint32_t size = ((excl + pbits + 7u) >> 3) + 4u * checksum;
+				const uint32_t id_lo = AIRS_REC(4), id_hi = AIRS_REC(5), first_result = AIRS_REC(9), job = AIRS_REC(13);
+				const uint32_t g = AIRS_REC(10), outlier = AIRS_REC(11);
 				if (size <= cap_eff) {
-					if (tid < CMP_HDR_SIZE + 6u) {
-						const uint32_t id_lo = pend.rec[4], id_hi = pend.rec[5], g = pend.rec[10], outlier = pend.rec[11];
+					if (lane < CMP_HDR_SIZE + 6u) {
 						const uint32_t pre = (flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE;
 						const uint32_t enc = (flags & AIRS_FJ_MULTI) ? CMP_ENCODER_GOLOMB_MULTI : CMP_ENCODER_GOLOMB_ZERO;
 						uint32_t v;
-						switch (tid) {
+						switch (lane) {
 						case 0: v = 0x80u | (CMP_VERSION_NUMBER >> 8); break;
 						case 1: v = CMP_VERSION_NUMBER & 0xFFu; break;
 						case 2: v = size >> 16; break;
@@ -467,20 +515,31 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 						case 20: v = outlier >> 8; break;
 						default: v = outlier; break;
 						}
-						dst[tid] = (uint8_t)v;
+						dst[lane] = (uint8_t)v;
 					}
-					if (tid == 0)
-						b.results[pend.rec[9]] = size;
-				} else if (tid == 0) {
+					if (lane == 0)
+						b.results[first_result] = size;
+				} else if (lane == 0) {
 					if (flags & AIRS_FJ_FALLBACK_OK) /* stored raw instead: airs_encode_kernel, which runs behind this kernel, redoes the job */
-						b.big_list[atomicAdd(&b.ticket[2], 1u)] = pend.rec[13];
+						b.big_list[atomicAdd(&b.ticket[2], 1u)] = job;
 					else
-						b.results[pend.rec[9]] = AIRS_ERR(DST_TOO_SMALL);
+						b.results[first_result] = AIRS_ERR(DST_TOO_SMALL);
 				}
 			}
+			__syncwarp();
+#undef AIRS_REC
 		}
-		/* (no barrier: what iteration k + 1 writes before its barrier B1 - registers, requests - touches nothing that
-		 * is read here; the tile structs and staging areas change hands behind B1) */
+
+		/* tile k becomes the pending one */
+		prec = rec;
+		pT = have_cur ? t0 : 0xFFFFFFFFu;
+		pbits = bits;
+		if (have_cur) {
+			t0 = t1;
+			rec = nrec;
+			t1 = t2;
+			t2 = t3;
+		}
 	}
 }
 
@@ -490,7 +549,7 @@ extern "C" cudaError_t airs_launch_tile(const AirsLaunch *b, unsigned int grid, 
 	return cudaGetLastError();
 }
 
-/* AIRS_BOUNDS_CHECK builds: strings that would have been staged outside the CTA's staging areas since the last
+/* AIRS_BOUNDS_CHECK builds: strings that would have been staged outside the warp's staging words since the last
  * call (-1: not such a build) */
 extern "C" int airs_tile_bounds_violations(void)
 {
@@ -512,7 +571,7 @@ extern "C" cudaError_t airs_tile_resident_ctas(int *out)
 	if (e == cudaSuccess)
 		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	if (e == cudaSuccess) {
-		const size_t need = (size_t)AIRS_TILE_CTAS_PER_SM * (sizeof(TileShared) + 1024);
+		const size_t need = (size_t)AIRS_TILE_CTAS_PER_SM * (sizeof(TileWarp) * kTWarps + 1024);
 		const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
 		e = cudaFuncSetAttribute(airs_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 	}
