@@ -210,7 +210,7 @@ extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_resul
 	 * the job table on temporary slots (two-phase CONCAT) */
 	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs +
 	       4 * (size_t)n_results + 64 + sizeof(struct airs_job) * (size_t)n_jobs + 64 +
-	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 64 * (size_t)n_jobs + 64 + (size_t)AIRS_TILE_RING_BYTES;
+	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 128 * (size_t)n_jobs + 128 + (size_t)AIRS_TILE_RING_BYTES;
 }
 
 extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results)
@@ -265,11 +265,13 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.big_list = (uint32_t *)((uint8_t *)l.plans + 128 * (size_t)b->n_jobs);
 	l.small_list = l.big_list + b->n_jobs;
 	l.result_job = l.small_list + b->n_jobs;
-	{ /* from the end of the scratch memory: tile rings, then the fast-job records in front of them */
+	{ /* from the end of the scratch memory: tile rings, in front of them the tile extensions, then the fast-job records */
 		const size_t end = airs_cuda_batch_scratch_size(b->n_jobs, b->n_results);
 		const size_t ring = (end - (size_t)AIRS_TILE_RING_BYTES) & ~(size_t)63;
 		l.tile_ring = (uint64_t *)((uint8_t *)b->scratch + ring);
-		l.fast_jobs = (uint8_t *)b->scratch + ((ring - 64 * (size_t)b->n_jobs) & ~(size_t)63);
+		const size_t ext = (ring - 64 * (size_t)b->n_jobs) & ~(size_t)63;
+		l.tile_ext = (uint8_t *)b->scratch + ext;
+		l.fast_jobs = (uint8_t *)b->scratch + ((ext - 64 * (size_t)b->n_jobs) & ~(size_t)63);
 	}
 	l.ctx_io = ctx_io;
 	l.dst_size = b->dst_size;

@@ -38,6 +38,29 @@ struct alignas(16) FastJob {
 };
 static_assert(sizeof(FastJob) == 64, "FastJob is read as 16 words");
 
+/* flags2 of a TileExt: the secondary passes of a context whose frames go through airs_tile_kernel */
+#define AIRS_TX_PRE2_DIFF  1u
+#define AIRS_TX_MULTI2     2u
+#define AIRS_TX_PRE2_MODEL 4u
+#define AIRS_TX_MODEL      8u  /* the context keeps a model (AIRS_PF_MODEL): primary passes store the samples as model */
+#define AIRS_TX_SIGNED    16u  /* i16 container: the model update sign-extends */
+/* ... | floor(log2 g2) << 8 | model_rate << 16 */
+
+/* What a tile job has beyond its FastJob: the 16 words behind it in a tile's record (lanes 16-31).  A context
+ * of n_frames frames has n_frames * tiles_per_frame tiles, frame by frame. */
+struct alignas(16) TileExt {
+	uint64_t src_frame_stride;
+	uint64_t dst_frame_stride;
+	uint64_t model;          /* device address of the context's model (16-byte aligned), 0: none */
+	uint32_t n_frames;
+	uint32_t tiles_per_frame;
+	uint32_t g2, outlier2, magic2; /* secondary encoder */
+	uint32_t flags2;         /* AIRS_TX_* */
+	uint32_t sec_iter;       /* secondary passes behind every primary one */
+	uint32_t pad[3];
+};
+static_assert(sizeof(TileExt) == 64, "TileExt is read as 16 words");
+
 /*
  * floor(x / g) for 0 <= x <= 65536 + g and 1 <= g <= AIRS_FAST_MAX_G as one multiply-high:
  *   g >= 2: M = ceil(2^32 / g), q = umulhi(x, M).  With e = M g - 2^32 (0 <= e < g) the result is
@@ -70,6 +93,25 @@ __device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const
 	f.job = job_index;
 	f.tile_base = tile_base;
 	f.n_tiles = n_tiles;
+}
+
+__device__ inline void airs_fill_tile_ext(TileExt &t, const airs_job &job, const JobPlan &pl, uint8_t *work_base, uint32_t frame_tiles)
+{
+	const bool model = (pl.flags & AIRS_PF_MODEL) != 0u;
+	t.src_frame_stride = job.src_frame_stride;
+	t.dst_frame_stride = job.dst_frame_stride;
+	t.model = model ? (uint64_t)(uintptr_t)(work_base + job.work_offset) : 0u;
+	t.n_frames = job.n_frames;
+	t.tiles_per_frame = frame_tiles;
+	t.g2 = pl.enc[1].g;
+	t.outlier2 = pl.enc[1].outlier;
+	t.magic2 = airs_fast_magic(pl.enc[1].g);
+	t.flags2 = (pl.pre[1] == CMP_PREPROCESS_DIFF ? AIRS_TX_PRE2_DIFF : 0u) |
+		   (pl.enc[1].type == CMP_ENCODER_GOLOMB_MULTI ? AIRS_TX_MULTI2 : 0u) |
+		   (pl.pre[1] == CMP_PREPROCESS_MODEL ? AIRS_TX_PRE2_MODEL : 0u) | (model ? AIRS_TX_MODEL : 0u) |
+		   ((pl.flags & AIRS_PF_SIGNED) ? AIRS_TX_SIGNED : 0u) | (pl.enc[1].L << 8) | (pl.rate << 16);
+	t.sec_iter = pl.sec_iter;
+	t.pad[0] = t.pad[1] = t.pad[2] = 0;
 }
 #endif
 

@@ -174,16 +174,53 @@ struct UnitStrings {
 	uint32_t a[kRows][MULTI ? 8 : 4], lo[kRows][MULTI ? 8 : 4], n[kRows][MULTI ? 1 : 4];
 };
 
+/* preprocessing of a unit: what the residual of a sample is taken against */
+constexpr int kPreNone = 0, kPreDiff = 1, kPreModel = 2;
+
+/* model of a secondary pass (ref cmp.c:120-142,304-311): rate 16 keeps the model, rate 0 replaces it by the samples,
+ * anything between is (rate * model + (16 - rate) * sample) / 16 on two lanes at once (IDP.2A: 16-bit x 8-bit
+ * products, weights 16 rate and 16 (16 - rate), the quotient in bytes 1-2 of each sum) */
+struct ModelK {
+	uint32_t rate, wdp;
+	bool is_signed; /* i16 containers: the average is taken of sign-extended values */
+};
+
+__device__ __forceinline__ ModelK make_model_k(uint32_t rate, bool is_signed)
+{
+	ModelK mk;
+	mk.rate = rate;
+	mk.wdp = (rate << 4) | ((16u - rate) << 12);
+	mk.is_signed = is_signed;
+	return mk;
+}
+
+template <bool SIGNED>
+__device__ __forceinline__ uint32_t model_update_pair(uint32_t x, uint32_t m, uint32_t wdp)
+{
+	const uint32_t lo = __byte_perm(m, x, 0x5410), hi = __byte_perm(m, x, 0x7632); /* (m, x) of the low / high lane */
+	uint32_t tl, th;
+	if (SIGNED) {
+		asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(tl) : "r"(lo), "r"(wdp), "r"(0u));
+		asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(th) : "r"(hi), "r"(wdp), "r"(0u));
+	} else {
+		asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(tl) : "r"(lo), "r"(wdp), "r"(0u));
+		asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(th) : "r"(hi), "r"(wdp), "r"(0u));
+	}
+	return __byte_perm(tl, th, 0x6521);
+}
+
 /*
  * One unit, first half: the two pieces x[0], x[1] of this lane (rows 0 and 1) -> strings.
- * front: lane 0's word in front of its row-0 piece (upper half = the sample before the unit, 0 at the
- * start of a frame: the first "difference" is the sample itself, ref preprocess.c:284-290); updated for
- * the next unit of the same warp.  nv[j]: valid samples of the lane's piece in row j (RAGGED units only).
+ * PRE = kPreDiff: front is lane 0's word in front of its row-0 piece (upper half = the sample before the unit,
+ * 0 at the start of a frame: the first "difference" is the sample itself, ref preprocess.c:284-290); updated
+ * for the next unit of the same warp.  PRE = kPreModel: m[0], m[1] are the model words of the two pieces; the
+ * residual is taken against them and they are replaced by the updated model (ref cmp.c:304-311).
+ * nv[j]: valid samples of the lane's piece in row j (RAGGED units only).
  * Returns the bits of the lane's rows: row 0 | row 1 << 16.
  */
-template <bool MULTI, bool DIFF, bool RAGGED>
-__device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRows], uint32_t &front, const uint32_t (&nv)[kRows],
-					       uint32_t lane, UnitStrings<MULTI> &s)
+template <bool MULTI, int PRE, bool RAGGED>
+__device__ __forceinline__ uint32_t unit_codes_pre(const FK &k, const uint4 (&x)[kRows], uint4 (&m)[kRows], const ModelK &mk, uint32_t &front,
+						   const uint32_t (&nv)[kRows], uint32_t lane, UnitStrings<MULTI> &s)
 {
 	uint32_t row_bits[kRows];
 
@@ -191,7 +228,7 @@ __device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRo
 	for (uint32_t j = 0; j < kRows; j++) {
 		const uint32_t w[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
 		uint32_t z[4];
-		if (DIFF) {
+		if (PRE == kPreDiff) {
 			/* t = ~r = ~w + predecessor, per 16-bit half; zig-zag of r = ((t << 1) | 1) ^ sign(t)
 			 * (ref map_to_unsigned, encoder.c:274-286) */
 			uint32_t prev;
@@ -210,6 +247,20 @@ __device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRo
 				z[i] = ((t << 1) | 0x00010001u) ^ sign;
 				prev = w[i];
 			}
+		} else if (PRE == kPreModel) {
+			uint32_t mw[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const uint32_t t = __vadd2(~w[i], mw[i]); /* ~(sample - model) */
+				uint32_t sign;
+				asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sign) : "r"(t), "r"(0u), "r"(0xBB99u));
+				z[i] = ((t << 1) | 0x00010001u) ^ sign;
+				if (mk.rate == 0u)
+					mw[i] = w[i];
+				else if (mk.rate < 16u)
+					mw[i] = mk.is_signed ? model_update_pair<true>(w[i], mw[i], mk.wdp) : model_update_pair<false>(w[i], mw[i], mk.wdp);
+			}
+			m[j] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
 		} else {
 #pragma unroll
 			for (int i = 0; i < 4; i++) {
@@ -245,6 +296,16 @@ __device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRo
 		row_bits[j] = bits;
 	}
 	return row_bits[0] | (row_bits[1] << 16);
+}
+
+/* ... without a model */
+template <bool MULTI, bool DIFF, bool RAGGED>
+__device__ __forceinline__ uint32_t unit_codes(const FK &k, const uint4 (&x)[kRows], uint32_t &front, const uint32_t (&nv)[kRows],
+					       uint32_t lane, UnitStrings<MULTI> &s)
+{
+	uint4 none[kRows];
+	const ModelK mk = {0u, 0u, false};
+	return unit_codes_pre<MULTI, DIFF ? kPreDiff : kPreNone, RAGGED>(k, x, none, mk, front, nv, lane, s);
 }
 
 /* the bits of a lane's rows together */
@@ -290,6 +351,20 @@ __device__ __forceinline__ void unit_put(const Dbg &dbg, const UnitStrings<MULTI
 }
 
 /* a whole unit of a warp that owns its staging words: strings, scan, staging at abs_bit; returns the unit's bits */
+template <bool MULTI, int PRE, bool RAGGED>
+__device__ __forceinline__ uint32_t encode_unit_pre(const Dbg &dbg, const FK &k, const uint4 (&x)[kRows], uint4 (&m)[kRows], const ModelK &mk,
+						    uint32_t &front, const uint32_t (&nv)[kRows], uint32_t lane, uint32_t abs_bit)
+{
+	UnitStrings<MULTI> s;
+	const uint32_t b = unit_codes_pre<MULTI, PRE, RAGGED>(k, x, m, mk, front, nv, lane, s);
+	const uint32_t mine = lane_bits(b);
+	const uint32_t incl = unit_scan(mine);
+	const uint32_t tot = __shfl_sync(kFull, incl, 31), at = abs_bit + incl - mine;
+	const uint32_t pos[kRows] = {at, at + (b & 0xFFFFu)};
+	unit_put<MULTI>(dbg, s, pos);
+	return tot;
+}
+
 template <bool MULTI, bool DIFF, bool RAGGED>
 __device__ __forceinline__ uint32_t encode_unit(const Dbg &dbg, const FK &k, const uint4 (&x)[kRows], uint32_t &front,
 						const uint32_t (&nv)[kRows], uint32_t lane, uint32_t abs_bit)

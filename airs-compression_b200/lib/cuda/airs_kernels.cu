@@ -1694,19 +1694,35 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	 * in the CONCAT layout and on the host-shim path, where every job is "big" and the list is the
 	 * identity (the look-back scan needs the frames to start in result order). */
 	const bool listed = b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io;
-	/* what both fast kernels ask of a job */
-	const bool quick = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
-			   !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 &&
-			   (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
-			   pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
-			   ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
-			   pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
+	/* what the fast kernels ask of a job */
+	const bool common = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
+			    (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
+			    pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
+			    ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
+			    pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
+	const bool quick = common && !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1;
 	const bool small = quick && pl.n <= kSmallMaxSamples; /* one warp per job: airs_fast_kernel */
-	/* Tiles over all CTAs (airs_tile_kernel, arithmetic code words) for long frames when the batch has too few jobs to
+	/* Contexts of several frames (with or without model) in a batch of few jobs: their frames go through
+	 * airs_tile_kernel tile by tile, frame by frame (a CTA per context would leave most of the device idle).
+	 * Only contexts in which no frame can fail or fall back - slots of cmp_compress_bound() bytes (48 bits a
+	 * sample, ref cmp.c:59-74), no uncompressed fallback: a frame that fails changes the passes of all frames
+	 * behind it (ref cmp.c:228-262), whose tiles are already on their way */
+	const bool secondary_ok = pl.sec_iter == 0u ||
+				  (!pl.pre_err[1] && pl.enc[1].type != CMP_ENCODER_UNCOMPRESSED && pl.enc[1].g <= AIRS_FAST_MAX_G &&
+				   (pl.pre[1] == CMP_PREPROCESS_NONE || pl.pre[1] == CMP_PREPROCESS_DIFF || pl.pre[1] == CMP_PREPROCESS_MODEL));
+	const bool never_fails = !(pl.flags & AIRS_PF_FALLBACK_OK) && !job.params.uncompressed_fallback_enabled &&
+				 (uint64_t)job.dst_capacity >= CMP_HDR_SIZE + 6u + 4u + 6ull * pl.n;
+	const bool frames_tiled = common && job.n_frames > 1u && b.n_jobs < b.tile_below_jobs && secondary_ok && !pl.model_err && never_fails &&
+				  pl.n >= 2u * AIRS_TILE_SAMPLES && (pl.n & 7u) == 0 && (job.src_frame_stride & 15u) == 0 &&
+				  (job.dst_frame_stride & 7u) == 0 &&
+				  (!(pl.flags & AIRS_PF_MODEL) || (b.work && ((uintptr_t)(b.work + job.work_offset) & 15u) == 0));
+	/* Tiles over all warps (airs_tile_kernel, arithmetic code words) for long frames when the batch has too few jobs to
 	 * give every resident CTA of airs_encode_kernel one, or when that kernel's code word table cannot cover the
 	 * residuals anyway (no preprocessing: the samples themselves are coded; tiny g: long code words) */
-	const bool tiled = quick && !small && (b.n_jobs < b.tile_below_jobs || pl.pre[0] == CMP_PREPROCESS_NONE || pl.enc[0].g < 4u);
-	const uint32_t my_tiles = tiled ? (pl.n + AIRS_TILE_SAMPLES - 1u) / AIRS_TILE_SAMPLES : 0u;
+	const bool tiled = frames_tiled ||
+			   (quick && !small && (b.n_jobs < b.tile_below_jobs || pl.pre[0] == CMP_PREPROCESS_NONE || pl.enc[0].g < 4u));
+	const uint32_t frame_tiles = (pl.n + AIRS_TILE_SAMPLES - 1u) / AIRS_TILE_SAMPLES;
+	const uint32_t my_tiles = tiled ? frame_tiles * job.n_frames : 0u;
 	if (small)
 		pl.flags |= AIRS_PF_SMALL;
 	if (have && b.init_results && !b.ctx_io)
@@ -1726,6 +1742,17 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	}
 	const uint32_t warp_tiles = __shfl_sync(kFull, tiles_incl, 31);
 	uint32_t base_small = 0, base_big = 0, base_tslot = 0, base_tile = 0;
+	if (m_tiled) { /* do all tile jobs have the same shape?  (airs_tile_kernel deals their tiles frame by frame then) */
+		const uint32_t fr = tiled ? job.n_frames : 0u;
+		const uint32_t tmin = __reduce_min_sync(kFull, tiled ? frame_tiles : 0xFFFFFFFFu), tmax = __reduce_max_sync(kFull, tiled ? frame_tiles : 0u);
+		const uint32_t fmin = __reduce_min_sync(kFull, tiled ? fr : 0xFFFFFFFFu), fmax = __reduce_max_sync(kFull, fr);
+		if (lane == 0) {
+			atomicMax(&b.ticket[AIRS_TICKET_TILE_SHAPE], ~tmin);
+			atomicMax(&b.ticket[AIRS_TICKET_TILE_SHAPE + 1], tmax);
+			atomicMax(&b.ticket[AIRS_TICKET_TILE_SHAPE + 2], ~fmin);
+			atomicMax(&b.ticket[AIRS_TICKET_TILE_SHAPE + 3], fmax);
+		}
+	}
 	if (lane == 0) {
 		if (m_cs)
 			atomicAdd(&b.ticket[4], (uint32_t)__popc(m_cs));
@@ -1761,6 +1788,9 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			FastJob fj;
 			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, base_tile + tiles_incl - my_tiles, my_tiles);
 			recs[b.n_jobs - 1u - slot] = fj;
+			TileExt tx;
+			airs_fill_tile_ext(tx, job, pl, b.work, frame_tiles);
+			reinterpret_cast<TileExt *>(b.tile_ext)[b.n_jobs - 1u - slot] = tx;
 		} else {
 			b.big_list[base_big + (uint32_t)__popc(m_big & below)] = j;
 		}

@@ -28,9 +28,10 @@ struct JobPlan;
 #define AIRS_TILE_THREADS 96 /* three warps with two staging areas of a whole tile each: 37 KB a CTA */
 #endif
 #ifndef AIRS_TILE_CTAS_PER_SM
-#define AIRS_TILE_CTAS_PER_SM 6
+#define AIRS_TILE_CTAS_PER_SM 5 /* 128 registers: six instantiations of the warp encoder are inlined; 96 spill */
 #endif
 #define AIRS_TICKET_INVALID 6u
+#define AIRS_TICKET_TILE_SHAPE 20u /* four words: ~min and max of the tile jobs' tiles per frame, ~min and max of their frames */
 #define AIRS_TILE_RING 65536u /* tile descriptors kept (a power of two, far more than tiles are in flight) */
 /* 64-bit words of the rings: tile descriptors, tile tails, blocks of 32 tiles, blocks of 1024 tiles */
 #define AIRS_TILE_RING_BYTES (8u * (2u * AIRS_TILE_RING + AIRS_TILE_RING / 32u + AIRS_TILE_RING / 1024u))
@@ -52,6 +53,7 @@ struct AirsLaunch {
 	uint32_t *small_list;  /* job indices of airs_fast_kernel's records, in their order (SLOTS layout only) */
 	void *fast_jobs;       /* n_jobs 64-byte records (FastJob, airs_fast.cuh): the short jobs of airs_fast_kernel from
 				  the front in the order of small_list, the long jobs of airs_tile_kernel from the back */
+	void *tile_ext;        /* n_jobs 64-byte records (TileExt) of the tile jobs, from the back like their FastJob records */
 	uint64_t *tile_ring;   /* AIRS_TILE_RING_BYTES, zeroed before the launch: tile descriptors, tile tails, block sums */
 	uint32_t *result_job;  /* n_results entries: the job a frame belongs to (airs_checksum_kernel) */
 	struct JobPlan *plans; /* n_jobs plans written by airs_plan_kernel */

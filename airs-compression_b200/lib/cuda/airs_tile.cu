@@ -159,7 +159,9 @@ static __device__ __noinline__ void publish_block_sums(uint64_t *ring, uint32_t 
 }
 
 /*
- * Where tile T (number tidx of its frame) starts in its stream, in bits behind the header.
+ * Where the tile dealt at position T (number tidx of its frame) starts in its stream, in bits behind the header.
+ * All rings are indexed by DEALING POSITION: the tiles of a frame are consecutive in it, every tile a tile waits
+ * for has a lower one, and the positions in flight lie within a few rows of each other (the rings wrap).
  *
  * All warps work on one "row" of consecutive tiles at the same time, so a look-back that walks from count to
  * count until it meets a finished prefix walks half a row (thousands of tiles, a round trip per window).
@@ -219,10 +221,19 @@ __device__ __forceinline__ uint32_t look_back_finish(LookBack &lb)
 	return __reduce_add_sync(kFull, lb.t_own.val + lb.t_first.val + lb.b_own.val + lb.b_first.val + lb.q_mid.val);
 }
 
-/* the units of one tile: code words, scans, strings staged from tile-local bit 0 on; returns the tile's bits */
-template <bool MULTI, bool DIFF>
+__device__ __forceinline__ uint4 ld_cg4(const uint4 *p) /* from the L2: the line may have been written by another SM */
+{
+	uint4 v;
+	asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+	return v;
+}
+
+/* the units of one tile: code words, scans, strings staged from tile-local bit 0 on; returns the tile's bits.
+ * model: the context's model (nullptr: none) - PRE = kPreModel takes the residuals against it and leaves the
+ * updated model behind, init_model (primary pass of a context with model) leaves the samples behind */
+template <bool MULTI, int PRE>
 __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, TileArea &ws, const uint8_t *src, uint32_t n, uint32_t first,
-					       uint4 (&nx)[kRows], uint32_t front, uint32_t lane)
+					       uint4 (&nx)[kRows], uint32_t front, uint32_t lane, uint4 *model, bool init_model, const ModelK &mk)
 {
 	const uint32_t stg_bit = 8u * (uint32_t)__cvta_generic_to_shared(ws.stg);
 	const uint32_t n_whole = n / 8u;
@@ -230,15 +241,20 @@ __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, Tile
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
 	uint32_t bits = 0;
 
-#pragma unroll
+#pragma unroll 1 /* (one copy of the unit per instantiation: six instantiations are inlined into the kernel) */
 	for (uint32_t u = 0; u < kTileUnits; u++) {
 		const uint32_t ufirst = first + u * kUnit;
 		if (ufirst >= n)
 			break;
-		uint4 x[kRows];
+		uint4 x[kRows], m[kRows];
 #pragma unroll
-		for (uint32_t j = 0; j < kRows; j++)
+		for (uint32_t j = 0; j < kRows; j++) {
 			x[j] = nx[j];
+			if (PRE == kPreModel) { /* (frames with a model are whole pieces) */
+				const uint32_t p = ufirst / 8u + unit_piece(lane, j);
+				m[j] = p < n_whole ? ld_cg4(model + p) : zero4;
+			}
+		}
 		if (u + 1u < kTileUnits) { /* the next unit's samples travel while this one is encoded */
 #pragma unroll
 			for (uint32_t j = 0; j < kRows; j++) {
@@ -250,7 +266,7 @@ __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, Tile
 		}
 		if (ufirst + kUnit <= n) {
 			const uint32_t nv[kRows] = {8u, 8u};
-			bits += encode_unit<MULTI, DIFF, false>(dbg, k, x, front, nv, lane, stg_bit + bits);
+			bits += encode_unit_pre<MULTI, PRE, false>(dbg, k, x, m, mk, front, nv, lane, stg_bit + bits);
 		} else { /* the ragged end of the frame */
 			uint32_t nv[kRows];
 #pragma unroll
@@ -258,10 +274,41 @@ __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, Tile
 				const uint32_t p = ufirst + 8u * unit_piece(lane, j);
 				nv[j] = p >= n ? 0u : min(8u, n - p);
 			}
-			bits += encode_unit<MULTI, DIFF, true>(dbg, k, x, front, nv, lane, stg_bit + bits);
+			bits += encode_unit_pre<MULTI, PRE, true>(dbg, k, x, m, mk, front, nv, lane, stg_bit + bits);
+		}
+		if (PRE == kPreModel || init_model) {
+#pragma unroll
+			for (uint32_t j = 0; j < kRows; j++) {
+				const uint32_t p = ufirst / 8u + unit_piece(lane, j);
+				if (p < n_whole)
+					model[p] = PRE == kPreModel ? m[j] : x[j];
+			}
 		}
 	}
 	return bits;
+}
+
+/* what tile T of a job is: its frame and its place in it, the pass the frame takes (ref cmp.c:228-262: a primary
+ * pass, then sec_iter secondary ones, again and again - nothing fails on this path, a frame that does not fit sends
+ * its whole job to airs_encode_kernel) */
+struct TileWhat {
+	uint32_t f, tidx, phase, cyc;
+};
+__device__ __forceinline__ TileWhat tile_what(uint32_t T, uint32_t rec, uint32_t lane)
+{
+	TileWhat w;
+	const uint32_t jt = T - __shfl_sync(kFull, rec, 14);
+	if (__shfl_sync(kFull, rec, 22) <= 1u) { /* a single frame: no divisions */
+		w.f = w.phase = w.cyc = 0;
+		w.tidx = jt;
+		return w;
+	}
+	const uint32_t tpf = __shfl_sync(kFull, rec, 23), s1 = __shfl_sync(kFull, rec, 28) + 1u;
+	w.f = jt / tpf;
+	w.tidx = jt - w.f * tpf;
+	w.cyc = w.f / s1;
+	w.phase = w.f - w.cyc * s1;
+	return w;
 }
 
 } /* namespace */
@@ -311,8 +358,12 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			v = probe(slot, T); /* a jump over more than 32 jobs: keep probing */
 		}
 	};
-	auto record = [&](uint32_t slot, uint32_t T) -> uint32_t { /* word `lane` of the record of tile T's job */
-		return (T < n_tiles && lane < 16u) ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot) + lane) : 0u;
+	const TileExt *ext_end = reinterpret_cast<const TileExt *>(b.tile_ext) + (b.n_jobs - 1u);
+	auto record = [&](uint32_t slot, uint32_t T) -> uint32_t { /* word `lane` of the record of tile T's job: FastJob, TileExt */
+		if (T >= n_tiles)
+			return 0u;
+		return lane < 16u ? __ldg(reinterpret_cast<const uint32_t *>(recs_end - slot) + lane)
+				  : __ldg(reinterpret_cast<const uint32_t *>(ext_end - slot) + (lane - 16u));
 	};
 	const uint4 zero4 = make_uint4(0, 0, 0, 0);
 	uint4 nx[kRows] = {zero4, zero4};
@@ -321,8 +372,10 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	auto request = [&](uint32_t rec, uint32_t T) {
 		if (T >= n_tiles)
 			return;
-		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(__shfl_sync(kFull, rec, 0) | (uint64_t)__shfl_sync(kFull, rec, 1) << 32));
-		const uint32_t n = __shfl_sync(kFull, rec, 6), first = (T - __shfl_sync(kFull, rec, 14)) * kTile, n_whole = n / 8u;
+		const TileWhat tw = tile_what(T, rec, lane);
+		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(__shfl_sync(kFull, rec, 0) | (uint64_t)__shfl_sync(kFull, rec, 1) << 32)) +
+				     (uint64_t)tw.f * (__shfl_sync(kFull, rec, 16) | (uint64_t)__shfl_sync(kFull, rec, 17) << 32);
+		const uint32_t n = __shfl_sync(kFull, rec, 6), first = tw.tidx * kTile, n_whole = n / 8u;
 		const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++) {
@@ -339,79 +392,138 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	 * n_warps in its iteration T / n_warps.  A counter would hand tiles to whoever asks first - but a tile has to be
 	 * asked for a few tiles ahead to hide the way to its samples, and a tile that sits reserved while its warp
 	 * is still busy with earlier ones keeps EVERY tile behind it in the frame waiting (measured: 7 x slower).
+	 *
+	 * The order in which tiles are dealt is the order of their numbers - unless all tile jobs have the same number of
+	 * frames and of tiles per frame (airs_plan_kernel leaves minima and maxima behind).  Then the tiles are dealt
+	 * FRAME BY FRAME over all contexts (frame 0 of every context, then frame 1 of every context, ...): a tile of a
+	 * frame with model waits for the same tile of the frame before, so of one context only a frame or two are in
+	 * work at a time, and a batch of contexts dealt context by context would be encoded one context after the other.
+	 * Either way every tile a tile waits for - the tiles in front of it in its frame, the same tile of the frame
+	 * before - is dealt before it.  In the uniform order the job of a tile follows from its number by arithmetic.
 	 * prologue: tile 0 in full, tile 1 probed */
 	const uint32_t n_warps = gridDim.x * kTWarps, gw = blockIdx.x * kTWarps + (threadIdx.x >> 5);
-	uint32_t t0 = gw, t1 = gw + n_warps, t2 = gw + 2u * n_warps, t3 = 0;
+	const uint32_t u_tpf = b.ticket[AIRS_TICKET_TILE_SHAPE + 1], u_frames = b.ticket[AIRS_TICKET_TILE_SHAPE + 3];
+	const uint32_t u_row = n_tjobs * u_tpf, u_job = u_frames * u_tpf;
+	/* (a frame with model waits for the count a row before it: the row has to fit the ring several times) */
+	const bool uniform = ~b.ticket[AIRS_TICKET_TILE_SHAPE] == u_tpf && ~b.ticket[AIRS_TICKET_TILE_SHAPE + 2] == u_frames &&
+			     (uint64_t)n_tjobs * u_tpf <= kRing / 4u;
+	/* the d-th tile that is dealt: its number and (uniform order) the slot of its job */
+	auto dealt = [&](uint32_t d, uint32_t &slot) -> uint32_t {
+		if (!uniform || d >= n_tiles)
+			return d;
+		const uint32_t f = d / u_row, rem = d - f * u_row, sl = rem / u_tpf;
+		slot = sl;
+		return sl * u_job + f * u_tpf + (rem - sl * u_tpf);
+	};
+	uint32_t d0 = gw, d1 = gw + n_warps, d2 = gw + 2u * n_warps; /* dealing positions of this warp's next tiles */
 	uint32_t slot0 = 0xFFFFFFFFu; /* "the slot in front of slot 0" */
-	resolve(slot0, t0, probe(slot0, t0));
+	uint32_t t0 = dealt(d0, slot0);
+	if (!uniform)
+		resolve(slot0, t0, probe(slot0, t0));
 	uint32_t rec = record(slot0, t0);
 	uint32_t slot1 = slot0;
-	uint32_t fb = probe(slot1, t1); /* candidates for tile 1 */
+	uint32_t t1 = dealt(d1, slot1);
+	uint32_t fb = uniform ? 0u : probe(slot1, t1); /* candidates for tile 1 */
 	request(rec, t0);
 
 	/* Software pipeline, iteration k: tile k is encoded into staging area k % 2 and counted; then tile k - 1, counted
 	 * one iteration ago - the tiles in front of it have had a tile's time to be counted as well - gets its place and
 	 * leaves area (k - 1) % 2.  A warp that waited for its place right behind its own code words would wait for the
 	 * slowest warp of the device in every iteration, together with all other warps of its SM. */
-	uint32_t prec = 0, pT = 0xFFFFFFFFu, pbits = 0; /* the pending tile: its job's record, its number, its bits */
+	uint32_t prec = 0, pT = 0xFFFFFFFFu, pD = 0, pbits = 0; /* the pending tile: its job's record, its number, its dealing position, its bits */
 	for (uint32_t par = 0;; par ^= 1u) {
-		const bool have_cur = t0 < n_tiles, have_pend = pT != 0xFFFFFFFFu;
+		const bool have_cur = d0 < n_tiles, have_pend = pT != 0xFFFFFFFFu;
 		if (!have_cur && !have_pend)
 			break;
 		uint32_t bits = 0;
 		uint32_t nrec = 0;
 		if (have_cur) {
 			/* ---- requests whose answers are looked at behind this tile's code words */
-			resolve(slot1, t1, fb);                   /* job of the next tile */
+			if (!uniform)
+				resolve(slot1, t1, fb);           /* job of the next tile */
 			nrec = record(slot1, t1);
-			fb = probe(slot1, t2);                    /* candidates for the tile behind it */
-			t3 = t2 + n_warps;
+			if (!uniform)
+				fb = probe(slot1, d2);            /* candidates for the tile behind it */
 
 #define AIRS_REC(i) __shfl_sync(kFull, rec, (i))
-			const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(AIRS_REC(0) | (uint64_t)AIRS_REC(1) << 32));
-			const uint32_t n = AIRS_REC(6), flags = AIRS_REC(8);
-			const uint32_t g = AIRS_REC(10), outlier = AIRS_REC(11), magic = AIRS_REC(12);
-			const uint32_t T = t0, tidx = T - AIRS_REC(14);
+			const uint32_t T = t0;
+			const TileWhat tw = tile_what(T, rec, lane);
+			const uint32_t tidx = tw.tidx;
+			const bool sec = tw.phase != 0u; /* a secondary pass */
+			const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(AIRS_REC(0) | (uint64_t)AIRS_REC(1) << 32)) +
+					     (uint64_t)tw.f * (AIRS_REC(16) | (uint64_t)AIRS_REC(17) << 32);
+			const uint32_t n = AIRS_REC(6), flags = AIRS_REC(8), flags2 = AIRS_REC(27), tpf = AIRS_REC(23);
+			const uint32_t g = sec ? AIRS_REC(24) : AIRS_REC(10), outlier = sec ? AIRS_REC(25) : AIRS_REC(11);
+			const uint32_t magic = sec ? AIRS_REC(26) : AIRS_REC(12), L = ((sec ? flags2 : flags) >> 8) & 15u;
+			uint4 *model = reinterpret_cast<uint4 *>((uintptr_t)(AIRS_REC(20) | (uint64_t)AIRS_REC(21) << 32));
 #undef AIRS_REC
-			const bool multi = (flags & AIRS_FJ_MULTI) != 0u;
-			const FK kk = make_fk(multi, g, (flags >> 8) & 15u, outlier, magic);
+			const bool multi = sec ? (flags2 & AIRS_TX_MULTI2) != 0u : (flags & AIRS_FJ_MULTI) != 0u;
+			const int pre = sec ? ((flags2 & AIRS_TX_PRE2_MODEL) ? kPreModel : (flags2 & AIRS_TX_PRE2_DIFF) ? kPreDiff : kPreNone)
+					    : ((flags & AIRS_FJ_PRE_DIFF) ? kPreDiff : kPreNone);
+			const bool has_model = (flags2 & AIRS_TX_MODEL) != 0u;
+			const FK kk = make_fk(multi, g, L, outlier, magic);
+			const ModelK mk = make_model_k((flags2 >> 16) & 31u, (flags2 & AIRS_TX_SIGNED) != 0u);
 			const uint32_t first = tidx * kTile;
 			const bool last = first + kTile >= n;
 			TileArea &ar = ws.area[par];
 
-			/* ---- the tile's code words, staged at tile-local bit positions */
-			if (multi) {
-				if (flags & AIRS_FJ_PRE_DIFF)
-					bits = tile_units<true, true>(dbg, kk, ar, src, n, first, nx, nfront, lane);
-				else
-					bits = tile_units<true, false>(dbg, kk, ar, src, n, first, nx, nfront, lane);
-			} else {
-				if (flags & AIRS_FJ_PRE_DIFF)
-					bits = tile_units<false, true>(dbg, kk, ar, src, n, first, nx, nfront, lane);
-				else
-					bits = tile_units<false, false>(dbg, kk, ar, src, n, first, nx, nfront, lane);
+			/* ---- a context with model: the tile's slice of the model is what the same tile of the frame before left
+			 * (its count is published behind its model stores) */
+			if (has_model && tw.f != 0u) {
+				const uint32_t Tp = d0 - (uniform ? u_row : tpf); /* (its dealing position) */
+				const uint64_t *p = ring + (Tp & (kRing - 1u));
+				uint32_t spins = 0;
+				while (!desc_ready(ld_desc(p), Tp)) {
+					__nanosleep(AIRS_TILE_NAP);
+					if (++spins > (1u << 22))
+						__trap();
+				}
 			}
+
+			/* ---- the tile's code words, staged at tile-local bit positions */
+			const bool init_model = has_model && !sec;
+			if (multi) {
+				if (pre == kPreModel)
+					bits = tile_units<true, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk);
+				else if (pre == kPreDiff)
+					bits = tile_units<true, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+				else
+					bits = tile_units<true, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+			} else {
+				if (pre == kPreModel)
+					bits = tile_units<false, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk);
+				else if (pre == kPreDiff)
+					bits = tile_units<false, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+				else
+					bits = tile_units<false, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+			}
+			if (has_model)
+				__threadfence(); /* the model stores of all lanes in front of the count */
 			__syncwarp();
 			if (lane == 0) {
-				st_desc(ring + (T & (kRing - 1u)), make_desc(T, bits));
+				st_desc(ring + (d0 & (kRing - 1u)), make_desc(d0, bits));
 				if (!last) { /* the last 7 bits of the tile, for the tile behind it (bits >= 1024 > 7) */
 					const uint32_t wi = bits >> 5, sft = bits & 31u;
 					const uint32_t before = wi ? ar.stg[wi - 1u] : 0u;
 					const uint32_t last32 = sft ? __funnelshift_l(ar.stg[wi], before, sft) : before; /* the 32 bits that end at bit `bits` */
-					st_desc(tails + (T & (kRing - 1u)), ((uint64_t)(T + 1u) << 8) | (last32 & 0x7Fu));
+					st_desc(tails + (d0 & (kRing - 1u)), ((uint64_t)(d0 + 1u) << 8) | (last32 & 0x7Fu));
 				}
 			}
-			if ((T & 31u) == 31u && AIRS_TILE_ABLATE < 1)
-				publish_block_sums(ring, T, bits, lane);
+			if ((d0 & 31u) == 31u && AIRS_TILE_ABLATE < 1)
+				publish_block_sums(ring, d0, bits, lane);
 			/* ---- the next tile's first samples travel while the tile before this one leaves */
 			request(nrec, t1);
 		}
 
 		if (have_pend) {
 #define AIRS_REC(i) __shfl_sync(kFull, prec, (i))
-			uint8_t *dst = reinterpret_cast<uint8_t *>((uintptr_t)(AIRS_REC(2) | (uint64_t)AIRS_REC(3) << 32));
-			const uint32_t n = AIRS_REC(6), cap_eff = AIRS_REC(7), flags = AIRS_REC(8);
-			const uint32_t T = pT, tidx = T - AIRS_REC(14);
+			const uint32_t T = pT;
+			const TileWhat tw = tile_what(T, prec, lane);
+			const uint32_t tidx = tw.tidx;
+			const bool sec = tw.phase != 0u;
+			uint8_t *dst = reinterpret_cast<uint8_t *>((uintptr_t)(AIRS_REC(2) | (uint64_t)AIRS_REC(3) << 32)) +
+				       (uint64_t)tw.f * (AIRS_REC(18) | (uint64_t)AIRS_REC(19) << 32);
+			const uint32_t n = AIRS_REC(6), cap_eff = AIRS_REC(7), flags = AIRS_REC(8), flags2 = AIRS_REC(27);
 			const bool last = tidx * kTile + kTile >= n;
 			uint32_t *stg = ws.area[par ^ 1u].stg;
 
@@ -422,14 +534,14 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			/* (requesting the windows in front of the tile's code words and looking at them behind was measured: the 17
 			 * registers the answers sit in spill the encoder: 1.33 -> 1.82 ms on 256 x 4 MiB) */
 			LookBack lb;
-			look_back_begin(lb, ring, tails, T, tidx, lane);
+			look_back_begin(lb, ring, tails, pD, tidx, lane);
 			const uint32_t excl = kHdrBits + look_back_finish(lb);
 #endif
 			const uint32_t m = excl & 7u;
 			if (m && tidx != 0u) {
 				uint64_t v = lb.tail_v;
 				uint32_t spins = 0;
-				while ((uint32_t)(v >> 8) != T) { /* tag of tile T - 1 is T */
+				while ((uint32_t)(v >> 8) != pD) { /* the tag of the tile in front is its position + 1 */
 					v = ld_desc(lb.tail_p);
 					if (++spins > (1u << 22))
 						__trap();
@@ -484,12 +596,18 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			if (last) { /* the frame is complete: header, result (ref cmp.c:321-337) */
 				const uint32_t checksum = (flags & AIRS_FJ_CHECKSUM) ? 1u : 0u;
 				const uint32_t size = ((excl + pbits + 7u) >> 3) + 4u * checksum;
-				const uint32_t id_lo = AIRS_REC(4), id_hi = AIRS_REC(5), first_result = AIRS_REC(9), job = AIRS_REC(13);
-				const uint32_t g = AIRS_REC(10), outlier = AIRS_REC(11);
+				const uint64_t id = (((uint64_t)AIRS_REC(5) << 32 | AIRS_REC(4)) + tw.cyc) & 0xFFFFFFFFFFFFull; /* a reset per primary pass */
+				const uint32_t id_lo = (uint32_t)id, id_hi = (uint32_t)(id >> 32);
+				const uint32_t first_result = AIRS_REC(9) + tw.f, job = AIRS_REC(13);
+				const uint32_t g = sec ? AIRS_REC(24) : AIRS_REC(10), outlier = sec ? AIRS_REC(25) : AIRS_REC(11);
+				const bool multi = sec ? (flags2 & AIRS_TX_MULTI2) != 0u : (flags & AIRS_FJ_MULTI) != 0u;
+				const uint32_t pre = sec ? ((flags2 & AIRS_TX_PRE2_MODEL) ? CMP_PREPROCESS_MODEL : (flags2 & AIRS_TX_PRE2_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE)
+							 : ((flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE);
+				const uint32_t rate = pre == CMP_PREPROCESS_MODEL ? (flags2 >> 16) & 31u : 0u;
+				const bool frames = AIRS_REC(22) > 1u; /* a context of several frames */
 				if (size <= cap_eff) {
 					if (lane < CMP_HDR_SIZE + 6u) {
-						const uint32_t pre = (flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE;
-						const uint32_t enc = (flags & AIRS_FJ_MULTI) ? CMP_ENCODER_GOLOMB_MULTI : CMP_ENCODER_GOLOMB_ZERO;
+						const uint32_t enc = multi ? CMP_ENCODER_GOLOMB_MULTI : CMP_ENCODER_GOLOMB_ZERO;
 						uint32_t v;
 						switch (lane) {
 						case 0: v = 0x80u | (CMP_VERSION_NUMBER >> 8); break;
@@ -506,9 +624,9 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 						case 11: v = id_lo >> 16; break;
 						case 12: v = id_lo >> 8; break;
 						case 13: v = id_lo; break;
-						case 14: v = 0; break;
+						case 14: v = tw.phase; break; /* sequence number */
 						case 15: v = (pre << 4) | (checksum << 3) | enc; break;
-						case 16: v = 0; break;
+						case 16: v = rate; break;
 						case 17: v = g >> 8; break;
 						case 18: v = g; break;
 						case 19: v = outlier >> 16; break;
@@ -520,10 +638,15 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 					if (lane == 0)
 						b.results[first_result] = size;
 				} else if (lane == 0) {
-					if (flags & AIRS_FJ_FALLBACK_OK) /* stored raw instead: airs_encode_kernel, which runs behind this kernel, redoes the job */
-						b.big_list[atomicAdd(&b.ticket[2], 1u)] = job;
-					else
+					/* A frame that does not fit.  Stored raw instead, or - in a context of several frames - a failure after
+					 * which the context goes on differently: airs_encode_kernel, which runs behind this kernel, redoes the
+					 * whole job (once, whatever the number of its frames that do not fit) */
+					if ((flags & AIRS_FJ_FALLBACK_OK) || frames) {
+						if (atomicExch(&b.plans[job].pad[0], 1u) == 0u)
+							b.big_list[atomicAdd(&b.ticket[2], 1u)] = job;
+					} else {
 						b.results[first_result] = AIRS_ERR(DST_TOO_SMALL);
+					}
 				}
 			}
 			__syncwarp();
@@ -533,12 +656,15 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		/* tile k becomes the pending one */
 		prec = rec;
 		pT = have_cur ? t0 : 0xFFFFFFFFu;
+		pD = d0;
 		pbits = bits;
 		if (have_cur) {
 			t0 = t1;
 			rec = nrec;
-			t1 = t2;
-			t2 = t3;
+			d0 = d1;
+			d1 = d2;
+			d2 += n_warps;
+			t1 = dealt(d1, slot1);
 		}
 	}
 }

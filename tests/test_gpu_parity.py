@@ -223,6 +223,43 @@ def test_config1_one_mebisample_buffer(gpu, oracle, pkg):
 
 
 @pytest.mark.parametrize("dtype", [2, 0])
+def test_contexts_through_the_tile_kernel(gpu, oracle, pkg, dtype):
+    """A batch of few contexts of several frames: the frames go through airs_tile_kernel tile by tile (a tile of a
+    frame waits for the same tile of the frame before to leave its slice of the model).  Primary passes come back
+    every sec_iter + 1 frames with a new identifier; secondary passes with model (rates 0, 5, 16), with differences,
+    with nothing; GOLOMB_MULTI; ragged frame ends; checksums; a frame that does not fit sends its context to
+    airs_encode_kernel, with and without the uncompressed fallback."""
+    abi = pkg.abi
+    rng = np.random.default_rng(50 + dtype)
+    cases = [  # (n, frames, sec_iter, secondary preprocessing, secondary encoder, g2, rate, checksum, capacity, fallback)
+        (32768, 9, 3, abi.PRE_MODEL, 1, 8, 5, 0, None, 0),
+        (5000 * 8, 7, 2, abi.PRE_MODEL, 2, 6, 0, 1, None, 0),
+        (2048 + 512, 6, 255, abi.PRE_MODEL, 1, 9, 16, 0, None, 0),
+        (40000, 5, 1, abi.PRE_DIFF, 2, 12, 0, 1, None, 0),
+        (4096, 5, 4, abi.PRE_NONE, 1, 4000, 0, 0, None, 0),
+        (16384, 4, 0, abi.PRE_MODEL, 1, 8, 8, 0, None, 0),
+        (32768, 6, 5, abi.PRE_MODEL, 1, 8, 8, 0, 30000, 0),     # some frames do not fit
+        (32768, 6, 5, abi.PRE_MODEL, 1, 8, 8, 1, 65536 + 20, 1),  # ... and are stored raw
+    ]
+    for n, nf, it, pre2, enc2, g2, rate, cs, cap, fb in cases:
+        p = abi.make_params(primary_preprocessing=abi.PRE_DIFF if n != 4096 else abi.PRE_NONE, primary_encoder_type=1,
+                            primary_encoder_param=16 if n != 4096 else 3000, secondary_iterations=it, secondary_preprocessing=pre2,
+                            secondary_encoder_type=enc2, secondary_encoder_param=g2, secondary_encoder_outlier=60,
+                            model_rate=rate, checksum_enabled=cs, uncompressed_fallback_enabled=fb)
+        js = _uniform_jobs(pkg, 3, n, nf, p, dtype=dtype, cap=cap)
+        walk = rng.integers(-25, 26, size=(3, 1, n)).cumsum(axis=2) + 20000
+        x = walk + rng.integers(-12, 13, size=(3, nf, n)) + np.arange(nf)[None, :, None] * 3
+        if cap == 30000:
+            x[:, 2] = rng.integers(0, 65536, size=(3, n))        # a frame of noise: larger than the slot
+        if fb:
+            x[:, 3] = rng.integers(0, 65536, size=(3, n))
+        js["src"] = (x & 0xFFFF).astype(np.uint16).reshape(-1).view(np.uint8)
+        want = jobgen.run_cpu(oracle, js, threads=3)
+        got = gpu.run_jobs_device(js)
+        jobgen.compare(want, got, js, "tile-contexts n=%d frames=%d iter=%d" % (n, nf, it))
+
+
+@pytest.mark.parametrize("dtype", [2, 0])
 def test_config2_model_frames(gpu, oracle, pkg, dtype):
     """BASELINE config 2: model-based preprocessing with model update over 256 consecutive 64 KiB frames."""
     abi, synth = pkg.abi, pkg.synth

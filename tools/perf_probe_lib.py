@@ -142,6 +142,11 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     def p_model_cs(p, idx):
         p_model(p, idx); p["checksum_enabled"] = 1
+    if case in ("c2lit", "c2lit8"):   # config 2 as stated: ONE context (c2lit8: eight), slots of cmp_compress_bound() bytes
+        R, F, n = (8 if case == "c2lit8" else 1), 256, 32768
+        data = synth.frames_torch(1, 0, R, F, n, device=dev)
+        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, model=True)
+        return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
     if case in ("c2", "c2one", "c2cs"):
         R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "0")) or pkg.load_library().airs_cuda_concurrent_jobs()) if case in ("c2", "c2cs") else 1, 256, 32768
         print("c2 contexts:", R)
