@@ -101,6 +101,9 @@ struct DevBuf {
 };
 
 constexpr int kMaxGroups = 64; /* pipeline stages of one host batch */
+#ifndef AIRS_HOST_GROUP_BYTES
+#define AIRS_HOST_GROUP_BYTES (32u << 20) /* source bytes of a stage of the pipelined CONCAT path */
+#endif
 
 /* Everything a thread keeps between calls lives on ONE device (stream_dev): when the thread's current device
  * has changed, cache_stream() gives all of it back under the old device before anything is created on the new one. */
@@ -529,11 +532,15 @@ static int host_batch_concat_pipelined(const struct airs_host_batch *hb, cudaStr
 	}
 	if (frames != hb->n_results)
 		return AIRS_OK;
-	int n_groups = (int)(bytes_total / (32u << 20)) + 1; /* ~32 MiB a group: the first copy in and the last copy out are not overlapped */
+	int n_groups = (int)(bytes_total / (size_t)AIRS_HOST_GROUP_BYTES) + 1; /* the first copy in and the last copy out are not overlapped */
 	if (n_groups < 4)
 		n_groups = 4;
 	if (n_groups > kMaxGroups)
 		n_groups = kMaxGroups;
+	/* a group has to keep the device busy: contexts of many frames take a CTA each for as long as their frames last,
+	 * however few of them a group holds */
+	if ((uint32_t)n_groups > hb->n_jobs / 32u)
+		n_groups = hb->n_jobs / 32u > 4u ? (int)(hb->n_jobs / 32u) : 4;
 	if ((uint32_t)n_groups > hb->n_jobs)
 		n_groups = (int)hb->n_jobs;
 	const uint64_t per_group = bytes_total / (uint64_t)n_groups + 1;
@@ -576,10 +583,9 @@ static int host_batch_concat_pipelined(const struct airs_host_batch *hb, cudaStr
 		r0 = r1;
 		ng++;
 	}
-	{
+	if (tmp_need > c.tmp.cap) { /* (cudaMemGetInfo costs milliseconds: only when the slots have to grow) */
 		size_t free_b = 0, total_b = 0;
-		if (!(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (tmp_need <= c.tmp.cap || tmp_need < free_b / 2) &&
-		      c.tmp.reserve(tmp_need) == AIRS_OK)) {
+		if (!(cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && tmp_need < free_b / 2 && c.tmp.reserve(tmp_need) == AIRS_OK)) {
 			cudaGetLastError();
 			return AIRS_OK;
 		}

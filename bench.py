@@ -185,6 +185,59 @@ def run_workload(pkg, w, device, steps, warmup, barrier, peak, sampler=None, par
     return out, db, data
 
 
+def e2e_run(pkg, lib, workload, units, rank, world, device, barrier, e_steps):
+    """The metric end to end: airs_cuda_compress_batch_host on pinned HOST buffers (samples and job table in, streams,
+    sizes and offsets out), host wall clock around e_steps calls, max over ranks."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    abi = pkg.abi
+    e_units = {"c2": max(8, units // 4), "c3": 1 << 18, "c5": 512}[workload]
+    e_units = max(1, min(units, e_units))
+    we = build_workload(pkg, workload, e_units, rank * units, device=device)
+    src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
+    src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
+    # every workload goes through the CONCAT layout: only the compressed bytes travel back
+    dst_h = torch.empty(int(we["n_samples_total"] * 2 * 1.1) + (1 << 20), dtype=torch.uint8).pin_memory()
+
+    def pinned(nbytes, dtype):                   # job table and result arrays in pinned memory as well
+        return torch.zeros(nbytes, dtype=torch.uint8).pin_memory().numpy().view(dtype)
+    jobs_h = pinned(we["jobs"].nbytes, we["jobs"].dtype)
+    jobs_h[:] = we["jobs"]
+    results_h = pinned(4 * we["n_results"], np.uint32)
+    init_h = pinned(4 * e_units, np.uint32)
+    offs_h = pinned(8 * (we["n_results"] + 1), np.uint64)
+    hb = abi.AirsHostBatch()
+    hb.src, hb.src_size = src_h.data_ptr(), src_h.numel()
+    hb.dst, hb.dst_size = dst_h.data_ptr(), dst_h.numel()
+    hb.work, hb.work_size = None, we["work_size"]
+    hb.jobs, hb.results, hb.init_results = jobs_h.ctypes.data, results_h.ctypes.data, init_h.ctypes.data
+    hb.out_offsets = offs_h.ctypes.data
+    hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], abi.LAYOUT_CONCAT
+    for _ in range(2):
+        assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
+    barrier()
+    times = []
+    for _ in range(e_steps):
+        t0 = time.perf_counter()
+        assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
+        times.append(time.perf_counter() - t0)
+    torch.cuda.synchronize(device)
+    td = torch.tensor([sum(times)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    e_in = we["n_samples_total"] * 2
+    out = {"value": e_in * world * e_steps / float(td[0]) / 1e9, "unit": "GB/s",
+           "h2d_bytes_per_step": int(src_h.numel() + jobs_h.nbytes),
+           "d2h_bytes_per_step": int(offs_h[-1]) + offs_h.nbytes + results_h.nbytes + init_h.nbytes,
+           "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, CONCAT layout)",
+           "timing": "host wall clock, max over ranks, %d steps" % e_steps,
+           "ms_per_step_min_max": [round(min(times) * 1e3, 2), round(max(times) * 1e3, 2)],
+           "ms_steps": [round(t * 1e3, 1) for t in times]}
+    lib.airs_cuda_release_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,48 +399,7 @@ def main():
     e2e = None
     if not args.no_e2e and args.workload != "c4":
         try:
-            e_units = {"c2": max(8, units // 4), "c3": 1 << 18, "c5": 512}[args.workload]
-            e_units = max(1, min(units, e_units))
-            we = build_workload(pkg, args.workload, e_units, rank * units, device=device)
-            src_h = torch.empty(we["data"].numel() * 2, dtype=torch.uint8).pin_memory()
-            src_h.copy_(we["data"].view(torch.uint8).reshape(-1).cpu())
-            # every workload goes through the CONCAT layout: only the compressed bytes travel back
-            dst_h = torch.empty(int(we["n_samples_total"] * 2 * 1.1) + (1 << 20), dtype=torch.uint8).pin_memory()
-            def pinned(nbytes, dtype):                   # job table and result arrays in pinned memory as well
-                return torch.zeros(nbytes, dtype=torch.uint8).pin_memory().numpy().view(dtype)
-            jobs_h = pinned(we["jobs"].nbytes, we["jobs"].dtype)
-            jobs_h[:] = we["jobs"]
-            results_h = pinned(4 * we["n_results"], np.uint32)
-            init_h = pinned(4 * e_units, np.uint32)
-            offs_h = pinned(8 * (we["n_results"] + 1), np.uint64)
-            import ctypes as C
-            hb = abi.AirsHostBatch()
-            hb.src, hb.src_size = src_h.data_ptr(), src_h.numel()
-            hb.dst, hb.dst_size = dst_h.data_ptr(), dst_h.numel()
-            hb.work, hb.work_size = None, we["work_size"]
-            hb.jobs, hb.results, hb.init_results = jobs_h.ctypes.data, results_h.ctypes.data, init_h.ctypes.data
-            hb.out_offsets = offs_h.ctypes.data
-            hb.n_jobs, hb.n_results, hb.layout = e_units, we["n_results"], abi.LAYOUT_CONCAT
-            e_steps = max(3, min(args.steps, 10))
-            for _ in range(2):
-                assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e_steps):
-                assert lib.airs_cuda_compress_batch_host(C.byref(hb)) == 0, lib.airs_cuda_last_error()
-            torch.cuda.synchronize(device)
-            dt = time.perf_counter() - t0
-            td = torch.tensor([dt], dtype=torch.float64, device=device)
-            if world > 1:
-                dist.all_reduce(td, op=dist.ReduceOp.MAX)
-            e_in = we["n_samples_total"] * 2
-            e2e = {"value": e_in * world * e_steps / float(td[0]) / 1e9, "unit": "GB/s",
-                   "h2d_bytes_per_step": int(src_h.numel() + jobs_h.nbytes),
-                   "d2h_bytes_per_step": int(offs_h[-1]) + offs_h.nbytes + results_h.nbytes + init_h.nbytes,
-                   "workload": we["desc"], "api": "airs_cuda_compress_batch_host (pinned host buffers, CONCAT layout)",
-                   "timing": "host wall clock, max over ranks, %d steps" % e_steps}
-            lib.airs_cuda_release_cache()
-            del we, src_h, dst_h
+            e2e = e2e_run(pkg, lib, args.workload, units, rank, world, device, barrier, max(3, min(args.steps, 10)))
         except Exception as exc:  # the metric line must survive (host memory, pinning)
             e2e = {"error": repr(exc)[:300]}
 
