@@ -232,18 +232,17 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 	CU(airs_launch_plan(&l, stream));
 	g_launches++;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) {
-		static thread_local int fast_dev = -1, fast_ctas = 0, tile_ctas = 0;
+		static thread_local int fast_dev = -1, fast_ctas = 0;
 		int dev;
 		CU(cudaGetDevice(&dev));
 		if (dev != fast_dev) {
 			CU(airs_fast_resident_ctas(&fast_ctas));
-			CU(airs_tile_resident_ctas(&tile_ctas));
 			fast_dev = dev;
 		}
 		const unsigned int want = (l.n_jobs + AIRS_FAST_THREADS / 32 - 1) / (AIRS_FAST_THREADS / 32);
 		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
-		CU(airs_launch_tile(&l, (unsigned int)tile_ctas, stream));
-		g_launches += 2;
+		CU(airs_launch_tile(&l, stream));
+		g_launches += 3;
 	}
 	CU(airs_launch_encode(&l, grid, stream));
 	CU(airs_launch_checksum(&l, stream));

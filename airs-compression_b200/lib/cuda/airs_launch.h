@@ -28,7 +28,7 @@ struct JobPlan;
 #define AIRS_TILE_THREADS 96 /* three warps with two staging areas of a whole tile each: 37 KB a CTA */
 #endif
 #ifndef AIRS_TILE_CTAS_PER_SM
-#define AIRS_TILE_CTAS_PER_SM 5 /* 128 registers: six instantiations of the warp encoder are inlined; 96 spill */
+#define AIRS_TILE_CTAS_PER_SM 5 /* 128 registers; with six (96 registers) the inlined warp encoders spill: measured slower */
 #endif
 #define AIRS_TICKET_INVALID 6u
 #define AIRS_TICKET_TILE_SHAPE 20u /* four words: ~min and max of the tile jobs' tiles per frame, ~min and max of their frames */
@@ -104,8 +104,7 @@ cudaError_t airs_launch_encode(const struct AirsLaunch *b, unsigned int grid, cu
 cudaError_t airs_encode_ctas_per_sm(int *out);
 cudaError_t airs_launch_fast(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_fast_resident_ctas(int *out);
-cudaError_t airs_launch_tile(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
-cudaError_t airs_tile_resident_ctas(int *out);
+cudaError_t airs_launch_tile(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_hash(const struct AirsLaunch *b, uint64_t *hashes, cudaStream_t stream);
 cudaError_t airs_launch_hash_ranges(const uint8_t *base, const uint64_t *offsets, const uint32_t *sizes, uint32_t n,

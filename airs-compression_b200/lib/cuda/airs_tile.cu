@@ -294,11 +294,12 @@ __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, Tile
 struct TileWhat {
 	uint32_t f, tidx, phase, cyc;
 };
+template <bool FRAMES>
 __device__ __forceinline__ TileWhat tile_what(uint32_t T, uint32_t rec, uint32_t lane)
 {
 	TileWhat w;
 	const uint32_t jt = T - __shfl_sync(kFull, rec, 14);
-	if (__shfl_sync(kFull, rec, 22) <= 1u) { /* a single frame: no divisions */
+	if (!FRAMES || __shfl_sync(kFull, rec, 22) <= 1u) { /* a single frame: no divisions */
 		w.f = w.phase = w.cyc = 0;
 		w.tidx = jt;
 		return w;
@@ -313,6 +314,10 @@ __device__ __forceinline__ TileWhat tile_what(uint32_t T, uint32_t rec, uint32_t
 
 } /* namespace */
 
+/* FRAMES = false: a batch whose tile jobs are single frames (no model, no secondary passes: four instantiations of
+ * the warp encoder, 96 registers, six CTAs per SM); FRAMES = true: contexts of several frames among them (six
+ * instantiations, 128 registers, five CTAs per SM).  Both are launched; airs_plan_kernel leaves behind which one works. */
+template <bool FRAMES>
 __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs_tile_kernel(AirsLaunch b)
 {
 	__shared__ TileWarp wsh[kTWarps];
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		return;
 	const uint64_t counts = *reinterpret_cast<const uint64_t *>(b.ticket + 10); /* airs_plan_kernel: tile jobs << 40 | tiles */
 	const uint32_t n_tiles = (uint32_t)(counts & ((1ull << 40) - 1u)), n_tjobs = (uint32_t)(counts >> 40);
-	if (n_tiles == 0u)
+	if (n_tiles == 0u || (b.ticket[AIRS_TICKET_TILE_SHAPE + 3] > 1u) != FRAMES) /* (the largest number of frames of a tile job) */
 		return;
 	const FastJob *recs_end = reinterpret_cast<const FastJob *>(b.fast_jobs) + (b.n_jobs - 1u); /* slot s at recs_end - s */
 	uint64_t *ring = b.tile_ring, *tails = b.tile_ring + kRing;
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	auto request = [&](uint32_t rec, uint32_t T) {
 		if (T >= n_tiles)
 			return;
-		const TileWhat tw = tile_what(T, rec, lane);
+		const TileWhat tw = tile_what<FRAMES>(T, rec, lane);
 		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(__shfl_sync(kFull, rec, 0) | (uint64_t)__shfl_sync(kFull, rec, 1) << 32)) +
 				     (uint64_t)tw.f * (__shfl_sync(kFull, rec, 16) | (uint64_t)__shfl_sync(kFull, rec, 17) << 32);
 		const uint32_t n = __shfl_sync(kFull, rec, 6), first = tw.tidx * kTile, n_whole = n / 8u;
@@ -447,9 +452,9 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 
 #define AIRS_REC(i) __shfl_sync(kFull, rec, (i))
 			const uint32_t T = t0;
-			const TileWhat tw = tile_what(T, rec, lane);
+			const TileWhat tw = tile_what<FRAMES>(T, rec, lane);
 			const uint32_t tidx = tw.tidx;
-			const bool sec = tw.phase != 0u; /* a secondary pass */
+			const bool sec = FRAMES && tw.phase != 0u; /* a secondary pass */
 			const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(AIRS_REC(0) | (uint64_t)AIRS_REC(1) << 32)) +
 					     (uint64_t)tw.f * (AIRS_REC(16) | (uint64_t)AIRS_REC(17) << 32);
 			const uint32_t n = AIRS_REC(6), flags = AIRS_REC(8), flags2 = AIRS_REC(27), tpf = AIRS_REC(23);
@@ -460,7 +465,7 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			const bool multi = sec ? (flags2 & AIRS_TX_MULTI2) != 0u : (flags & AIRS_FJ_MULTI) != 0u;
 			const int pre = sec ? ((flags2 & AIRS_TX_PRE2_MODEL) ? kPreModel : (flags2 & AIRS_TX_PRE2_DIFF) ? kPreDiff : kPreNone)
 					    : ((flags & AIRS_FJ_PRE_DIFF) ? kPreDiff : kPreNone);
-			const bool has_model = (flags2 & AIRS_TX_MODEL) != 0u;
+			const bool has_model = FRAMES && (flags2 & AIRS_TX_MODEL) != 0u;
 			const FK kk = make_fk(multi, g, L, outlier, magic);
 			const ModelK mk = make_model_k((flags2 >> 16) & 31u, (flags2 & AIRS_TX_SIGNED) != 0u);
 			const uint32_t first = tidx * kTile;
@@ -483,14 +488,14 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 			/* ---- the tile's code words, staged at tile-local bit positions */
 			const bool init_model = has_model && !sec;
 			if (multi) {
-				if (pre == kPreModel)
+				if (FRAMES && pre == kPreModel)
 					bits = tile_units<true, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk);
 				else if (pre == kPreDiff)
 					bits = tile_units<true, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
 				else
 					bits = tile_units<true, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
 			} else {
-				if (pre == kPreModel)
+				if (FRAMES && pre == kPreModel)
 					bits = tile_units<false, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk);
 				else if (pre == kPreDiff)
 					bits = tile_units<false, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
@@ -518,9 +523,9 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		if (have_pend) {
 #define AIRS_REC(i) __shfl_sync(kFull, prec, (i))
 			const uint32_t T = pT;
-			const TileWhat tw = tile_what(T, prec, lane);
+			const TileWhat tw = tile_what<FRAMES>(T, prec, lane);
 			const uint32_t tidx = tw.tidx;
-			const bool sec = tw.phase != 0u;
+			const bool sec = FRAMES && tw.phase != 0u;
 			uint8_t *dst = reinterpret_cast<uint8_t *>((uintptr_t)(AIRS_REC(2) | (uint64_t)AIRS_REC(3) << 32)) +
 				       (uint64_t)tw.f * (AIRS_REC(18) | (uint64_t)AIRS_REC(19) << 32);
 			const uint32_t n = AIRS_REC(6), cap_eff = AIRS_REC(7), flags = AIRS_REC(8), flags2 = AIRS_REC(27);
@@ -669,9 +674,44 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 	}
 }
 
-extern "C" cudaError_t airs_launch_tile(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
+/* resident CTAs of one variant of the kernel on the current device */
+template <bool FRAMES>
+static cudaError_t tile_resident(int *out)
 {
-	airs_tile_kernel<<<grid, AIRS_TILE_THREADS, 0, stream>>>(*b);
+	int dev = 0, sms = 0, per_sm = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e == cudaSuccess)
+		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (e == cudaSuccess) {
+		const size_t need = (size_t)AIRS_TILE_CTAS_PER_SM * (sizeof(TileWarp) * kTWarps + 1024);
+		const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+		e = cudaFuncSetAttribute(airs_tile_kernel<FRAMES>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+	}
+	if (e == cudaSuccess)
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_tile_kernel<FRAMES>, AIRS_TILE_THREADS, 0);
+	*out = sms * per_sm;
+	return e;
+}
+
+/* Both variants are launched, each over the CTAs that are resident at the same time (tiles are dealt round robin
+ * over the grid and wait for each other: a CTA that is not resident would never be waited for in vain); the variant
+ * the batch does not need returns at once. */
+extern "C" cudaError_t airs_launch_tile(const AirsLaunch *b, cudaStream_t stream)
+{
+	static thread_local int cached_dev = -1, grid[2] = {0, 0};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (dev != cached_dev) {
+		if ((e = tile_resident<false>(&grid[0])) != cudaSuccess || (e = tile_resident<true>(&grid[1])) != cudaSuccess)
+			return e;
+		if (grid[0] < 1 || grid[1] < 1)
+			return cudaErrorLaunchOutOfResources;
+		cached_dev = dev;
+	}
+	airs_tile_kernel<false><<<grid[0], AIRS_TILE_THREADS, 0, stream>>>(*b);
+	airs_tile_kernel<true><<<grid[1], AIRS_TILE_THREADS, 0, stream>>>(*b);
 	return cudaGetLastError();
 }
 
@@ -687,22 +727,4 @@ extern "C" int airs_tile_bounds_violations(void)
 #else
 	return -1;
 #endif
-}
-
-/* resident CTAs of airs_tile_kernel on the current device */
-extern "C" cudaError_t airs_tile_resident_ctas(int *out)
-{
-	int dev = 0, sms = 0, per_sm = 0;
-	cudaError_t e = cudaGetDevice(&dev);
-	if (e == cudaSuccess)
-		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	if (e == cudaSuccess) {
-		const size_t need = (size_t)AIRS_TILE_CTAS_PER_SM * (sizeof(TileWarp) * kTWarps + 1024);
-		const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-		e = cudaFuncSetAttribute(airs_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-	}
-	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_tile_kernel, AIRS_TILE_THREADS, 0);
-	*out = sms * per_sm;
-	return e;
 }

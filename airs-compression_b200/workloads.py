@@ -38,11 +38,13 @@ def _pack(data, jobs, dsz, wsz, n, nf, desc, model=False):
                 n_samples_total=units * nf * n, model_bytes=(2 * 2 * n * units if model else 0))
 
 
-def config2(units, first_unit=0, device=None, rate=8, g2=8, checksum=0):
+def config2(units, first_unit=0, device=None, rate=8, g2=8, checksum=0, bound_slots=False):
     """Config 2 batched: `units` independent contexts x 256 frames x 64 KiB, DIFF+GOLOMB_ZERO g16 primary pass,
-    MODEL+GOLOMB_ZERO secondary passes with model update."""
+    MODEL+GOLOMB_ZERO secondary passes with model update.  Slots of 2 n + 64 bytes, or (bound_slots) of
+    cmp_compress_bound() bytes, in which no frame can fail - what lets a batch of few contexts go through the
+    tile kernel."""
     n, nf = FRAME_SAMPLES, FRAMES
-    jobs, dsz, wsz = uniform_jobs(units, n, nf, 2 * n + 64, first_unit, model=True)
+    jobs, dsz, wsz = uniform_jobs(units, n, nf, abi.compress_bound(2 * n) if bound_slots else 2 * n + 64, first_unit, model=True)
     jobs["params"] = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=abi.ENC_GOLOMB_ZERO,
                                      primary_encoder_param=16, secondary_iterations=255,
                                      secondary_preprocessing=abi.PRE_MODEL, secondary_encoder_type=abi.ENC_GOLOMB_ZERO,
@@ -51,8 +53,9 @@ def config2(units, first_unit=0, device=None, rate=8, g2=8, checksum=0):
         data = np.stack([synth.frames(1, first_unit + c, nf, n) for c in range(units)])
     else:
         data = synth.frames_torch(1, first_unit, units, nf, n, device=device)
-    desc = "config2 batched: %d contexts x %d frames x 64 KiB u16, DIFF+GOLOMB_ZERO g16 -> MODEL+GOLOMB_ZERO g%d, " \
-           "255 secondary iterations, model_rate %d%s" % (units, nf, g2, rate, ", checksum" if checksum else "")
+    desc = "config2%s: %d context%s x %d frames x 64 KiB u16, DIFF+GOLOMB_ZERO g16 -> MODEL+GOLOMB_ZERO g%d, " \
+           "255 secondary iterations, model_rate %d%s" % (" batched" if units > 1 else " as stated", units, "s" if units > 1 else "",
+                                                           nf, g2, rate, ", checksum" if checksum else "")
     return _pack(data, jobs, dsz, wsz, n, nf, desc, model=True)
 
 
@@ -127,6 +130,17 @@ def config4_row(row, total_samples=1 << 29, chunk_samples=BIG_CHUNK_SAMPLES, dev
                 synth.chunks(1, first_unit, units, n))
     desc = "config4 %s: %d x %d frames x %d KiB" % (name, units, nf, 2 * n // 1024)
     return _pack(data, jobs, dsz, wsz, n, nf, desc, model=sec is not None)
+
+
+def config1(device=None):
+    """Config 1: ONE chunk of 1 Mi u16 samples (2 MiB), DIFF+GOLOMB_ZERO g16 - what a single cmp_compress_u16() call
+    on a large buffer is."""
+    n = BIG_CHUNK_SAMPLES
+    jobs, dsz, wsz = uniform_jobs(1, n, 1, abi.compress_bound(2 * n))
+    P = jobs["params"]
+    P["primary_preprocessing"], P["primary_encoder_type"], P["primary_encoder_param"] = abi.PRE_DIFF, 1, 16
+    data = synth.chunks_torch(1, 0, 1, n, device=device) if device is not None else synth.chunks(1, 0, 1, n)
+    return _pack(data, jobs, dsz, wsz, n, 1, "config1: one chunk of 1 Mi u16 samples, DIFF+GOLOMB_ZERO g16")
 
 
 def config5(units, first_unit=0, device=None):

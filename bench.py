@@ -418,6 +418,16 @@ def main():
                              "parity_frames": r2.get("parity", {}).get("frames")}
             del w2, db2, d2
             torch.cuda.empty_cache()
+            # configs 1 and 2 AS STATED (one chunk, one context): latency of a single call's worth of work, every stream
+            # compared with the CPU reference
+            po1 = None if args.no_parity else {"threads": cores, "sample_every": 1, "max_jobs": None}
+            for key, w1 in (("c1", wl.config1(device)), ("c2", wl.config2(1, 0, device, bound_slots=True))):
+                r1, db1, d1 = run_workload(pkg, w1, device, 10, 3, barrier, peak, None, po1)
+                extras[key] = {"workload": w1["desc"], "ms": round(r1["launch_ms"], 4), "input_gbs": round(r1["input_gbs"], 1),
+                               "frac": round(r1["frac"], 4), "parity": r1.get("parity", {}).get("identical"),
+                               "frames": r1.get("parity", {}).get("frames")}
+                del w1, db1, d1
+            torch.cuda.empty_cache()
             extras["c4"] = []
             po = None if args.no_parity else {"threads": cores, "sample_every": 100, "max_jobs": None}
             for row in wl.CONFIG4_ROWS:
@@ -455,6 +465,8 @@ def main():
                    "compression_ratio": all_in / max(all_out, 1), "frames_with_errors": all_err},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "traffic_note": "dram__bytes_read + dram__bytes_write of one launch from a stored ncu --set full capture of "
+                                     "this workload (profiles/roofline_traffic.json names the commit); not measured in this run",
                      "kernel": "airs_fast_kernel" if args.workload == "c3" else "airs_encode_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                      "bytes_per_sample": alg_bytes / (in_bytes / 2)},
