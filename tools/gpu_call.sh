@@ -35,6 +35,21 @@ launches:*)
   timeout 300 python tools/ncu_case.py $case > gpurun_out/ncu_plain_$name.log 2>&1 &&
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:airs\|concat\|Memset -c 40 --csv --log-file gpurun_out/$name.csv python tools/ncu_case.py $case > gpurun_out/ncu_$name.log 2>&1
   tail -n 3 gpurun_out/ncu_$name.log ;;
+launchbench:*)   # launch list of the default bench command: launchbench:<name>:<bench args>
+  IFS=: read -r _ name bargs <<< "$step"
+  timeout 900 python bench.py ${bargs//,/ } > gpurun_out/ncu_plain_$name.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:airs\|concat -c 400 --csv --log-file gpurun_out/$name.csv python bench.py ${bargs//,/ } > gpurun_out/ncu_$name.log 2>&1
+  tail -n 2 gpurun_out/ncu_$name.log | cut -c1-300 ;;
+ncubench:*)      # full capture of one kernel of a bench command: ncubench:<kernel regex>:<skip>:<name>:<bench args>
+  IFS=: read -r _ kern skip name bargs <<< "$step"
+  timeout 900 python bench.py ${bargs//,/ } > gpurun_out/ncu_plain_$name.log 2>&1 &&
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c 1 -f -o gpurun_out/$name python bench.py ${bargs//,/ } > gpurun_out/ncu_$name.log 2>&1
+  tail -n 2 gpurun_out/ncu_$name.log | cut -c1-300 ;;
+ncucase:*)       # full capture of one kernel of a probe case: ncucase:<case>:<kernel regex>:<skip>:<name>
+  IFS=: read -r _ case kern skip name <<< "$step"
+  timeout 300 python tools/ncu_case.py $case > gpurun_out/ncu_plain_$name.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kern -s $skip -c 1 -f -o gpurun_out/$name python tools/ncu_case.py $case > gpurun_out/ncu_$name.log 2>&1
+  tail -n 3 gpurun_out/ncu_$name.log ;;
 *) echo "unknown step $step" ;;
 esac
 done
