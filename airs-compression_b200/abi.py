@@ -12,6 +12,7 @@ import numpy as np
 PRE_NONE, PRE_DIFF, PRE_IWT, PRE_MODEL = 0, 1, 2, 3
 ENC_UNCOMPRESSED, ENC_GOLOMB_ZERO, ENC_GOLOMB_MULTI = 0, 1, 2
 DT_I16, DT_I16_IN_I32, DT_U16 = 0, 1, 2
+DT_BE = 4                                  # flag: 16-bit samples big-endian in memory (AIRS_DTYPE_BE)
 LAYOUT_SLOTS, LAYOUT_CONCAT = 0, 1
 
 ERRORS = {
@@ -113,6 +114,8 @@ class AirsDecBatch(C.Structure):
 STATS_DTYPE = np.dtype([("sum_mapped", "<u8"), ("n_samples", "<u4"), ("max_mapped", "<u4"),
                         ("log2_hist", "<u4", (17,)), ("reserved", "<u4")])
 assert STATS_DTYPE.itemsize == 88
+CANDIDATE_DTYPE = np.dtype([("encoder_type", "<u4"), ("g", "<u4"), ("outlier", "<u4"), ("reserved", "<u4")])
+MAX_CANDIDATES = 32
 
 
 def dec_err(name):

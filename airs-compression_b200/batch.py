@@ -245,3 +245,32 @@ def residual_stats(src, jobs, device="cuda:0"):
         raise RuntimeError("airs_cuda_residual_stats failed (%d): %s" % (rc, lib.airs_cuda_last_error().decode()))
     torch.cuda.synchronize(dev)
     return out.cpu().numpy().view(abi.STATS_DTYPE)[:n_jobs]
+
+
+def param_candidates(stats_row, encoder_type):
+    """airs_cuda_param_candidates: candidate encoders around what the statistics of one job suggest."""
+    lib = load_library()
+    out = np.zeros(abi.MAX_CANDIDATES, dtype=abi.CANDIDATE_DTYPE)
+    st = np.ascontiguousarray(stats_row).reshape(1)
+    n = lib.airs_cuda_param_candidates(C.c_void_p(st.ctypes.data), int(encoder_type), C.c_void_p(out.ctypes.data), len(out))
+    return out[:n].copy()
+
+
+def candidate_bits(src, jobs, cand, device="cuda:0"):
+    """airs_cuda_candidate_bits: exact code bits of every job's first frame under every candidate encoder.
+    Returns a uint64 array [n_jobs, n_cand] (2^64 - 1: a candidate cmp_initialise would refuse)."""
+    lib = load_library()
+    dev = torch.device(device)
+    s = src if isinstance(src, torch.Tensor) else _dev_u8(src, dev)
+    j = jobs if isinstance(jobs, torch.Tensor) else _dev_u8(jobs, dev)
+    c = _dev_u8(np.ascontiguousarray(cand), dev)
+    n_jobs, n_cand = len(jobs), len(cand)
+    out = torch.zeros(max(n_jobs * n_cand, 1) * 8, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.airs_cuda_candidate_bits(C.c_void_p(s.data_ptr()), C.c_void_p(j.data_ptr()), n_jobs, C.c_void_p(c.data_ptr()),
+                                          n_cand, C.c_void_p(out.data_ptr()),
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError("airs_cuda_candidate_bits failed (%d): %s" % (rc, lib.airs_cuda_last_error().decode()))
+    torch.cuda.synchronize(dev)
+    return out.cpu().numpy().view(np.uint64)[:n_jobs * n_cand].reshape(n_jobs, n_cand)

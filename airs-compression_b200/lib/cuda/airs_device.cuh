@@ -172,6 +172,17 @@ __device__ __forceinline__ void airs_encode(const EncConst &e, uint32_t r16, uin
 	}
 }
 
+/* both samples of a word from big-endian to host order (AIRS_DTYPE_BE) */
+__device__ __forceinline__ uint32_t airs_swap16x2(uint32_t w)
+{
+	return __byte_perm(w, 0, 0x2301);
+}
+
+__device__ __forceinline__ uint4 airs_swap16x8(uint4 v)
+{
+	return make_uint4(airs_swap16x2(v.x), airs_swap16x2(v.y), airs_swap16x2(v.z), airs_swap16x2(v.w));
+}
+
 /* one model update (ref update_model, cmp.c:120-142); SIGNED for i16 containers */
 __device__ __forceinline__ uint32_t airs_model_update(uint32_t x, uint32_t m, uint32_t rate, bool is_signed)
 {

@@ -102,7 +102,8 @@ __device__ __forceinline__ void drain(FastWarp &ws, Out &o, uint32_t lane)
 
 /* the pass of one job through its units */
 template <bool MULTI, bool DIFF>
-__device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWarp &ws, Out &o, const uint8_t *src, uint32_t n, uint32_t lane)
+__device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWarp &ws, Out &o, const uint8_t *src, uint32_t n, uint32_t lane,
+					     bool be)
 {
 	const uint32_t n_whole = n / 8u;         /* complete pieces */
 	const uint32_t n_full_units = n / kUnit; /* units whose 64 pieces are all complete */
@@ -116,7 +117,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 	/* the complete pieces of the next unit are requested while one unit is encoded */
 #pragma unroll
 	for (uint32_t j = 0; j < kRows; j++)
-		nx[j] = unit_piece(lane, j) < n_whole ? __ldg(src4 + unit_piece(lane, j)) : zero4;
+		nx[j] = unit_piece(lane, j) < n_whole ? load_piece(src4, unit_piece(lane, j), be) : zero4;
 	uint32_t u = 0;
 	for (; u < n_full_units; u++) {
 #pragma unroll
@@ -125,7 +126,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 		const uint32_t p1 = (u + 1u) * kUnitPieces + unit_piece(lane, 0);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++)
-			nx[j] = p1 + j < n_whole ? __ldg(src4 + p1 + j) : zero4;
+			nx[j] = p1 + j < n_whole ? load_piece(src4, p1 + j, be) : zero4;
 		o.sbits += encode_unit<MULTI, DIFF, false>(dbg, k, x, front, full_nv, lane, stg_bit + o.sbits);
 		if (o.sbits > kUnitMaxBits)
 			drain(ws, o, lane);
@@ -137,7 +138,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 			const uint32_t p = u * kUnitPieces + unit_piece(lane, j);
 			nv[j] = 8u * p >= n ? 0u : min(8u, n - 8u * p);
 			if (nv[j] != 0u && nv[j] != 8u)
-				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j]);
+				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j], be);
 		}
 		o.sbits += encode_unit<MULTI, DIFF, true>(dbg, k, nx, front, nv, lane, stg_bit + o.sbits);
 	}
@@ -220,16 +221,17 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 		__syncwarp();
 		o.sbits += 8u * (CMP_HDR_SIZE + 6u);
 
+		const bool be = (flags & AIRS_FJ_BE) != 0u;
 		if (multi) {
 			if (flags & AIRS_FJ_PRE_DIFF)
-				encode_units<true, true>(dbg, k, ws, o, src, n, lane);
+				encode_units<true, true>(dbg, k, ws, o, src, n, lane, be);
 			else
-				encode_units<true, false>(dbg, k, ws, o, src, n, lane);
+				encode_units<true, false>(dbg, k, ws, o, src, n, lane, be);
 		} else {
 			if (flags & AIRS_FJ_PRE_DIFF)
-				encode_units<false, true>(dbg, k, ws, o, src, n, lane);
+				encode_units<false, true>(dbg, k, ws, o, src, n, lane, be);
 			else
-				encode_units<false, false>(dbg, k, ws, o, src, n, lane);
+				encode_units<false, false>(dbg, k, ws, o, src, n, lane, be);
 		}
 
 		const uint32_t frame_bits = o.gw0 * 32u + o.sbits - 8u * a;
@@ -257,9 +259,11 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 			uint32_t *out = reinterpret_cast<uint32_t *>(dst + CMP_HDR_SIZE);
 			const uint32_t *in = reinterpret_cast<const uint32_t *>(src);
 			for (uint32_t i = lane; i < n / 2u; i += 32u)
-				out[i] = airs_be_pair(__ldg(in + i));
+				out[i] = be ? __ldg(in + i) : airs_be_pair(__ldg(in + i));
 			if (lane == 0 && (n & 1u)) {
-				const uint32_t xs = __ldg(reinterpret_cast<const uint16_t *>(src) + n - 1u);
+				uint32_t xs = __ldg(reinterpret_cast<const uint16_t *>(src) + n - 1u);
+				if (be)
+					xs = ((xs << 8) | (xs >> 8)) & 0xFFFFu;
 				dst[CMP_HDR_SIZE + 2u * (n - 1u)] = (uint8_t)(xs >> 8);
 				dst[CMP_HDR_SIZE + 2u * (n - 1u) + 1u] = (uint8_t)xs;
 			}

@@ -14,6 +14,7 @@
 #define AIRS_FJ_MULTI       2u  /* GOLOMB_MULTI (else GOLOMB_ZERO) */
 #define AIRS_FJ_CHECKSUM    4u
 #define AIRS_FJ_FALLBACK_OK 8u
+#define AIRS_FJ_BE          16u /* samples big-endian in memory (AIRS_DTYPE_BE) */
 
 /* samples of a tile of airs_tile_kernel */
 #define AIRS_TILE_SAMPLES 1024u /* two units of 512 samples */
@@ -85,7 +86,8 @@ __device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const
 	f.flags = (pl.pre[0] == CMP_PREPROCESS_DIFF ? AIRS_FJ_PRE_DIFF : 0u) |
 		  (pl.enc[0].type == CMP_ENCODER_GOLOMB_MULTI ? AIRS_FJ_MULTI : 0u) |
 		  ((pl.flags & AIRS_PF_CHECKSUM) ? AIRS_FJ_CHECKSUM : 0u) |
-		  ((pl.flags & AIRS_PF_FALLBACK_OK) ? AIRS_FJ_FALLBACK_OK : 0u) | (pl.enc[0].L << 8);
+		  ((pl.flags & AIRS_PF_FALLBACK_OK) ? AIRS_FJ_FALLBACK_OK : 0u) | ((pl.flags & AIRS_PF_BE) ? AIRS_FJ_BE : 0u) |
+		  (pl.enc[0].L << 8);
 	f.first_result = job.first_result;
 	f.g = pl.enc[0].g;
 	f.outlier = pl.enc[0].outlier;

@@ -148,12 +148,15 @@ __device__ __forceinline__ FK make_fk(bool multi, uint32_t g, uint32_t L, uint32
 
 /* the incomplete last piece of a frame: cnt (1..7) samples from sample `first` on, the rest 0.  Called by
  * one lane once per job: kept out of line */
-static __device__ __noinline__ uint4 load_partial_piece(const uint16_t *s16, uint32_t first, uint32_t cnt)
+static __device__ __noinline__ uint4 load_partial_piece(const uint16_t *s16, uint32_t first, uint32_t cnt, bool be = false)
 {
 	uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
 #pragma unroll 1
 	for (uint32_t i = 0; i < cnt; i++) {
-		const uint32_t v = (uint32_t)__ldg(s16 + first + i) << (16u * (i & 1u));
+		uint32_t x = __ldg(s16 + first + i);
+		if (be)
+			x = ((x << 8) | (x >> 8)) & 0xFFFFu;
+		const uint32_t v = x << (16u * (i & 1u));
 		if (i < 2u)
 			w0 |= v;
 		else if (i < 4u)
@@ -164,6 +167,13 @@ static __device__ __noinline__ uint4 load_partial_piece(const uint16_t *s16, uin
 			w3 |= v;
 	}
 	return make_uint4(w0, w1, w2, w3);
+}
+
+/* the whole piece p of a frame (16-byte aligned 16-bit samples, `be`: big-endian in memory: AIRS_DTYPE_BE) */
+__device__ __forceinline__ uint4 load_piece(const uint4 *src4, uint32_t p, bool be)
+{
+	const uint4 v = __ldg(src4 + p);
+	return be ? airs_swap16x8(v) : v;
 }
 
 /* the strings of one unit, in registers: GOLOMB_ZERO one string per pair of samples (hi, lo, bits);

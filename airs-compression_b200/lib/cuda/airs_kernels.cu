@@ -277,7 +277,8 @@ __device__ __forceinline__ uint32_t sample_at(const uint8_t *src, uint32_t dtype
 	/* ref sample_read_i16, sample_reader.h:63-72 */
 	if (dtype == AIRS_DTYPE_I16_IN_I32)
 		return __ldg((const uint32_t *)src + i) & 0xFFFFu;
-	return __ldg((const uint16_t *)src + i);
+	const uint32_t v = __ldg((const uint16_t *)src + i);
+	return (dtype & AIRS_DTYPE_BE) ? ((v << 8) | (v >> 8)) & 0xFFFFu : v;
 }
 
 /* -------------------------------------------------------------------------
@@ -340,7 +341,7 @@ __device__ __noinline__ void iwt_global(const Pass &P, uint32_t *buf32)
 	const uint32_t n = P.n;
 	const uint32_t tid = threadIdx.x;
 	/* 16-byte accesses for stage 0: tiles and halos start at multiples of 32 samples */
-	const bool vec = P.dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)P.src & 15u) == 0 && ((uintptr_t)w & 15u) == 0;
+	const bool vec = P.dtype != AIRS_DTYPE_I16_IN_I32 && !(P.dtype & AIRS_DTYPE_BE) && ((uintptr_t)P.src & 15u) == 0 && ((uintptr_t)w & 15u) == 0;
 
 	for (uint32_t S = 1, stage = 0; stage == 0 || S < n; S <<= kIwtStageLevels, stage++) {
 		const uint32_t m = (n + S - 1u) / S; /* elements of this stage */
@@ -408,10 +409,14 @@ __device__ __forceinline__ uint32_t sample_pair_at(const uint8_t *src, uint32_t 
 		const uint32_t *p = (const uint32_t *)src;
 		return (__ldg(p + i) & 0xFFFFu) | (__ldg(p + i + 1) << 16);
 	}
-	if (al4)
-		return __ldg((const uint32_t *)((const uint16_t *)src + i));
-	const uint16_t *p = (const uint16_t *)src;
-	return (uint32_t)__ldg(p + i) | ((uint32_t)__ldg(p + i + 1) << 16);
+	uint32_t w;
+	if (al4) {
+		w = __ldg((const uint32_t *)((const uint16_t *)src + i));
+	} else {
+		const uint16_t *p = (const uint16_t *)src;
+		w = (uint32_t)__ldg(p + i) | ((uint32_t)__ldg(p + i + 1) << 16);
+	}
+	return (dtype & AIRS_DTYPE_BE) ? airs_swap16x2(w) : w;
 }
 
 __device__ uint32_t stream_checksum(const uint8_t *src, uint32_t dtype, uint32_t n)
@@ -420,6 +425,7 @@ __device__ uint32_t stream_checksum(const uint8_t *src, uint32_t dtype, uint32_t
 	const uint32_t seed = AIRS_CHECKSUM_SEED;
 	uint32_t v0 = seed + AIRS_XP1 + AIRS_XP2, v1 = seed + AIRS_XP2, v2 = seed, v3 = seed - AIRS_XP1;
 	uint32_t s = 0;
+	const bool be = (dtype & AIRS_DTYPE_BE) != 0u;
 
 	if (dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)src & 15u) == 0) {
 		/* whole 128-byte lines: 8 x LDG.128 in flight, then 8 stripes of rounds */
@@ -430,11 +436,12 @@ __device__ uint32_t stream_checksum(const uint8_t *src, uint32_t dtype, uint32_t
 			for (int k = 0; k < 8; k++)
 				q[k] = __ldg(p + s + k);
 #pragma unroll
-			for (int k = 0; k < 8; k++) {
-				v0 = airs_xxh_round(v0, airs_be_pair(q[k].x));
-				v1 = airs_xxh_round(v1, airs_be_pair(q[k].y));
-				v2 = airs_xxh_round(v2, airs_be_pair(q[k].z));
-				v3 = airs_xxh_round(v3, airs_be_pair(q[k].w));
+			for (int k = 0; k < 8; k++) { /* (big-endian samples are the image the hash is taken of) */
+				const uint4 e = be ? q[k] : make_uint4(airs_be_pair(q[k].x), airs_be_pair(q[k].y), airs_be_pair(q[k].z), airs_be_pair(q[k].w));
+				v0 = airs_xxh_round(v0, e.x);
+				v1 = airs_xxh_round(v1, e.y);
+				v2 = airs_xxh_round(v2, e.z);
+				v3 = airs_xxh_round(v3, e.w);
 			}
 		}
 	}
@@ -1047,6 +1054,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	const bool unc = UNC >= 0 ? UNC != 0 : P.enc.type == CMP_ENCODER_UNCOMPRESSED;
 	/* samples in the low halves of 32-bit words (catch-all instantiations only) */
 	const bool c32 = PRE < 0 && P.dtype == AIRS_DTYPE_I16_IN_I32;
+	/* samples big-endian in memory (catch-all instantiations only) */
+	const bool be = PRE < 0 && (P.dtype & AIRS_DTYPE_BE) != 0u;
 	/* table of this pass: built for this encoder (encode_pass) */
 	const bool have_lut = !unc && sh.plut_key[0] == P.enc.type && sh.plut_key[1] == P.enc.g &&
 			      sh.plut_key[2] == P.enc.outlier;
@@ -1081,11 +1090,12 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 	/* samples / work words of segment j_ of the tile whose warp starts at piece pw_ (none beyond the frame) */
 #define AIRS_SEG_VALID(pw_, j_) (!PARTIAL || ((j_) < nseg && (pw_) + 32u * (j_) + lane < n_pieces))
 #define AIRS_LOAD_X(pw_, j_) ((need_x && AIRS_SEG_VALID(pw_, j_)) ? (c32 ? ld_stream32(src4 + 2u * ((pw_) + 32u * (j_) + lane), pol_stream) \
-									       : ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream)) : zero4)
+									 : be ? airs_swap16x8(ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream)) \
+									      : ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream)) : zero4)
 #define AIRS_LOAD_M(pw_, j_) ((need_m && AIRS_SEG_VALID(pw_, j_)) ? ld_keep(work4 + (pw_) + 32u * (j_) + lane, pol_keep) : zero4)
 	/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */
 #define AIRS_LOAD_PS(pw_) ((diff && lane == 0 && (pw_) != 0 && AIRS_SEG_VALID(pw_, 0)) ? \
-	(c32 ? __ldg(reinterpret_cast<const uint32_t *>(src16) + 8u * (pw_) - 1u) & 0xFFFFu : (uint32_t)__ldg(src16 + 8u * (pw_) - 1u)) : 0u)
+	(c32 ? __ldg(reinterpret_cast<const uint32_t *>(src16) + 8u * (pw_) - 1u) & 0xFFFFu : sample_at(P.src, P.dtype, 8u * (pw_) - 1u)) : 0u)
 
 	/* the whole next tile is loaded one tile ahead (the scheduler pulls the first consumers of
 	 * all four segments to the top of the loop body, so a later load would be waited for) */
@@ -1463,7 +1473,7 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 	uint32_t key = P.pre * 4u + P.model_mode;
 	if (P.model_mode == 2u)
 		key = (P.rate >= 1u && P.rate <= 15u) ? key + P.is_signed : 99u;
-	if (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only || P.dtype == AIRS_DTYPE_I16_IN_I32)
+	if (P.enc.type == CMP_ENCODER_UNCOMPRESSED || size_only || P.dtype == AIRS_DTYPE_I16_IN_I32 || (P.dtype & AIRS_DTYPE_BE))
 		key = 99u;
 	const bool model_pass = key == CMP_PREPROCESS_MODEL * 4u + 2u || key == CMP_PREPROCESS_MODEL * 4u + 3u;
 	const bool half = model_pass || P.enc.type == CMP_ENCODER_UNCOMPRESSED;
@@ -2036,6 +2046,7 @@ __global__ void __launch_bounds__(32) airs_checksum_warp_kernel(AirsLaunch b)
 			}
 		}
 		const bool staged = todo && dtype != AIRS_DTYPE_I16_IN_I32 && ((uintptr_t)src & 15u) == 0;
+		const bool be = (dtype & AIRS_DTYPE_BE) != 0u; /* the samples are the big-endian image already */
 		const uint32_t nbytes = 2u * n, full = staged ? nbytes & ~15u : 0u; /* whole stripes */
 		const uint32_t n_blocks = (full + kCsBlock - 1u) / kCsBlock;
 		const uint32_t max_blocks = __reduce_max_sync(kFull, n_blocks);
@@ -2068,10 +2079,10 @@ __global__ void __launch_bounds__(32) airs_checksum_warp_kernel(AirsLaunch b)
 						q[i] = w[4u * (st + i)];
 #pragma unroll
 					for (int i = 0; i < 16; i++)
-						v = airs_xxh_round(v, airs_be_pair(q[i]));
+						v = airs_xxh_round(v, be ? q[i] : airs_be_pair(q[i]));
 				}
 				for (; st < nst; st++)
-					v = airs_xxh_round(v, airs_be_pair(w[4u * st]));
+					v = airs_xxh_round(v, be ? w[4u * st] : airs_be_pair(w[4u * st]));
 			}
 			__syncwarp(); /* the slot has been read: it may be filled again */
 		}
@@ -2089,9 +2100,9 @@ __global__ void __launch_bounds__(32) airs_checksum_warp_kernel(AirsLaunch b)
 			h += nbytes;
 			uint32_t i = full / 2u; /* what is left of the frame behind its last whole stripe */
 			for (; i + 2 <= n; i += 2)
-				h = airs_rotl(h + airs_be_pair(sample_pair_at(src, AIRS_DTYPE_U16, true, i)) * AIRS_XP3, 17) * AIRS_XP4;
+				h = airs_rotl(h + airs_be_pair(sample_pair_at(src, dtype, true, i)) * AIRS_XP3, 17) * AIRS_XP4;
 			if (i < n) {
-				const uint32_t sv = sample_at(src, AIRS_DTYPE_U16, i);
+				const uint32_t sv = sample_at(src, dtype, i);
 				h = airs_rotl(h + (sv >> 8) * AIRS_XP5, 11) * AIRS_XP1;
 				h = airs_rotl(h + (sv & 0xFFu) * AIRS_XP5, 11) * AIRS_XP1;
 			}

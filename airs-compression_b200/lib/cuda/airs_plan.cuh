@@ -16,6 +16,7 @@
 #define AIRS_PF_FALLBACK_OK  8u  /* fallback enabled and capacity >= raw size (cmp.c:363) */
 #define AIRS_PF_SIGNED      16u  /* i16 containers: model update sign-extends (cmp.c:132-142) */
 #define AIRS_PF_SMALL       32u  /* one short frame without model: a warp of airs_small_kernel encodes it */
+#define AIRS_PF_BE          64u  /* AIRS_DTYPE_BE: samples big-endian in memory */
 
 /* 128 bytes, read by the encode kernel with one coalesced 32-lane load */
 struct alignas(16) JobPlan {
@@ -125,6 +126,7 @@ __device__ inline void airs_make_plan(JobPlan &pl, const airs_job &j, const uint
 	const cmp_params &p = j.params;
 	const uint8_t *work = (work_base && j.work_size) ? work_base + j.work_offset : nullptr;
 	const uint32_t stride = j.dtype == AIRS_DTYPE_I16_IN_I32 ? 4u : 2u;
+	const bool dtype_ok = j.dtype <= AIRS_DTYPE_U16 || j.dtype == AIRS_DTYPE_I16_BE || j.dtype == AIRS_DTYPE_U16_BE;
 
 	memset(&pl, 0, sizeof(pl));
 	pl.init_result = airs_validate(j, work);
@@ -134,7 +136,7 @@ __device__ inline void airs_make_plan(JobPlan &pl, const airs_job &j, const uint
 	 * (ref sample_reader.h:19-51, cmp.c:350-357), in their order */
 	if (!src_base)
 		pl.frame_err = AIRS_ERR(SRC_NULL);
-	else if (j.src_size == 0 || j.dtype > AIRS_DTYPE_U16 || j.src_size % stride)
+	else if (j.src_size == 0 || !dtype_ok || j.src_size % stride)
 		pl.frame_err = AIRS_ERR(SRC_SIZE_WRONG);
 	else if (!(pl.flags & AIRS_PF_VALID))
 		pl.frame_err = AIRS_ERR(CONTEXT_INVALID);
@@ -161,8 +163,10 @@ __device__ inline void airs_make_plan(JobPlan &pl, const airs_job &j, const uint
 	}
 	if (p.checksum_enabled)
 		pl.flags |= AIRS_PF_CHECKSUM;
-	if (j.dtype != AIRS_DTYPE_U16)
+	if ((j.dtype & 3u) != AIRS_DTYPE_U16)
 		pl.flags |= AIRS_PF_SIGNED;
+	if (j.dtype & AIRS_DTYPE_BE)
+		pl.flags |= AIRS_PF_BE;
 	pl.raw_size = CMP_HDR_SIZE + packed + (p.checksum_enabled ? 4u : 0u);
 	if (p.uncompressed_fallback_enabled && j.dst_capacity >= pl.raw_size)
 		pl.flags |= AIRS_PF_FALLBACK_OK;

@@ -233,7 +233,7 @@ __device__ __forceinline__ uint4 ld_cg4(const uint4 *p) /* from the L2: the line
  * updated model behind, init_model (primary pass of a context with model) leaves the samples behind */
 template <bool MULTI, int PRE>
 __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, TileArea &ws, const uint8_t *src, uint32_t n, uint32_t first,
-					       uint4 (&nx)[kRows], uint32_t front, uint32_t lane, uint4 *model, bool init_model, const ModelK &mk)
+					       uint4 (&nx)[kRows], uint32_t front, uint32_t lane, uint4 *model, bool init_model, const ModelK &mk, bool be)
 {
 	const uint32_t stg_bit = 8u * (uint32_t)__cvta_generic_to_shared(ws.stg);
 	const uint32_t n_whole = n / 8u;
@@ -259,9 +259,9 @@ __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, Tile
 #pragma unroll
 			for (uint32_t j = 0; j < kRows; j++) {
 				const uint32_t p = (ufirst + kUnit) / 8u + unit_piece(lane, j);
-				nx[j] = p < n_whole ? __ldg(src4 + p) : zero4;
+				nx[j] = p < n_whole ? load_piece(src4, p, be) : zero4;
 				if (p == n_whole && (n & 7u))
-					nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u);
+					nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u, be);
 			}
 		}
 		if (ufirst + kUnit <= n) {
@@ -381,16 +381,21 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(__shfl_sync(kFull, rec, 0) | (uint64_t)__shfl_sync(kFull, rec, 1) << 32)) +
 				     (uint64_t)tw.f * (__shfl_sync(kFull, rec, 16) | (uint64_t)__shfl_sync(kFull, rec, 17) << 32);
 		const uint32_t n = __shfl_sync(kFull, rec, 6), first = tw.tidx * kTile, n_whole = n / 8u;
+		const bool be = (__shfl_sync(kFull, rec, 8) & AIRS_FJ_BE) != 0u;
 		const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++) {
 			const uint32_t p = first / 8u + unit_piece(lane, j);
-			nx[j] = p < n_whole ? __ldg(src4 + p) : zero4;
+			nx[j] = p < n_whole ? load_piece(src4, p, be) : zero4;
 			if (p == n_whole && (n & 7u))
-				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u);
+				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u, be);
 		}
 		/* lane 0: the sample in front of the tile (DIFF), in the upper half of a word */
-		nfront = (lane == 0 && first != 0u && first < n) ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(src) + first - 1u) << 16 : 0u;
+		nfront = 0;
+		if (lane == 0 && first != 0u && first < n) {
+			const uint32_t v = __ldg(reinterpret_cast<const uint16_t *>(src) + first - 1u);
+			nfront = (be ? ((v << 8) | (v >> 8)) & 0xFFFFu : v) << 16;
+		}
 	};
 
 	/* Tiles are dealt out round robin over all warps of the grid (all resident): tile T belongs to warp T mod
@@ -487,20 +492,21 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 
 			/* ---- the tile's code words, staged at tile-local bit positions */
 			const bool init_model = has_model && !sec;
+			const bool be = (flags & AIRS_FJ_BE) != 0u;
 			if (multi) {
 				if (FRAMES && pre == kPreModel)
-					bits = tile_units<true, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk);
+					bits = tile_units<true, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk, be);
 				else if (pre == kPreDiff)
-					bits = tile_units<true, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+					bits = tile_units<true, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 				else
-					bits = tile_units<true, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+					bits = tile_units<true, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 			} else {
 				if (FRAMES && pre == kPreModel)
-					bits = tile_units<false, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk);
+					bits = tile_units<false, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk, be);
 				else if (pre == kPreDiff)
-					bits = tile_units<false, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+					bits = tile_units<false, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 				else
-					bits = tile_units<false, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk);
+					bits = tile_units<false, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 			}
 			if (has_model)
 				__threadfence(); /* the model stores of all lanes in front of the count */

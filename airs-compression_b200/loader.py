@@ -19,6 +19,7 @@ EXPORTS = [
     "airs_cuda_concat_tmp_size", "airs_cuda_residual_stats", "airs_cuda_golomb_param_for_mean",
     "airs_cuda_compress_batch", "airs_cuda_last_launch_count", "airs_cuda_compress_batch_host",
     "airs_cuda_release_cache", "airs_cuda_hash_streams", "airs_cuda_hash_ranges",
+    "airs_cuda_candidate_bits", "airs_cuda_param_candidates",
     # include/airs_cuda_decode.h
     "airs_cuda_decode_scratch_size", "airs_cuda_decompress_batch",
 ]
@@ -74,6 +75,10 @@ def load_library():
     lib.airs_cuda_concat_tmp_size.restype = C.c_size_t
     lib.airs_cuda_residual_stats.argtypes = [vp, vp, u32, vp, vp]
     lib.airs_cuda_residual_stats.restype = C.c_int
+    lib.airs_cuda_candidate_bits.argtypes = [vp, vp, u32, vp, u32, vp, vp]
+    lib.airs_cuda_candidate_bits.restype = C.c_int
+    lib.airs_cuda_param_candidates.argtypes = [vp, u32, vp, u32]
+    lib.airs_cuda_param_candidates.restype = u32
     lib.airs_cuda_golomb_param_for_mean.argtypes = [C.c_uint64, u32]
     lib.airs_cuda_golomb_param_for_mean.restype = u32
     lib.airs_cuda_compress_batch.argtypes = [C.POINTER(abi.AirsBatch), vp]

@@ -53,6 +53,13 @@ extern "C" {
 #define AIRS_DTYPE_I16        0u
 #define AIRS_DTYPE_I16_IN_I32 1u
 #define AIRS_DTYPE_U16        2u
+/* ... | AIRS_DTYPE_BE: the 16-bit samples lie BIG-ENDIAN in memory - a sample file as the reference's front end
+ * reads it (programs/file.c:337-358 loads it and swaps every sample to host order before it compresses).  The
+ * kernels swap while they load; the streams are those of the swapped samples in the plain container.  Not with
+ * AIRS_DTYPE_I16_IN_I32. */
+#define AIRS_DTYPE_BE         4u
+#define AIRS_DTYPE_I16_BE     (AIRS_DTYPE_I16 | AIRS_DTYPE_BE)
+#define AIRS_DTYPE_U16_BE     (AIRS_DTYPE_U16 | AIRS_DTYPE_BE)
 
 #define AIRS_LAYOUT_SLOTS  0u /* every frame has its own dst slot */
 #define AIRS_LAYOUT_CONCAT 1u /* streams laid out back to back by a device-wide scan */
@@ -210,6 +217,32 @@ int airs_cuda_residual_stats(const void *src, const struct airs_job *jobs, uint3
 /* Golomb parameter g for a mean mapped residual sum / n: the code is shortest near g = mean * ln 2.
  * Plain integer arithmetic (ln 2 = 45426 / 65536), 1 <= g <= 65535.  Host function. */
 uint32_t airs_cuda_golomb_param_for_mean(uint64_t sum_mapped, uint32_t n_samples);
+
+/*
+ * Parameter search.  The reference leaves primary_encoder_param / primary_encoder_outlier to the user (what it
+ * derives itself is the zero-escape outlier and the upper bound of the multi-escape one, lib/compress/encoder.c:
+ * 154-182, 205-216).  airs_cuda_candidate_bits() computes, for the first frame of every job under the job's primary
+ * preprocessing (NONE: the samples; anything else: first differences - exact for NONE and DIFF), the EXACT number of
+ * code bits the frame takes with each of n_cand candidate encoders (at most AIRS_MAX_CANDIDATES), in one pass over the
+ * samples: bits[j * n_cand + c].  Compressed with candidate c the frame is CMP_HDR_SIZE + 6 + ceil(bits / 8) (+ 4 with
+ * checksum) bytes long.  A candidate cmp_initialise() would refuse has bits = UINT64_MAX; GOLOMB_ZERO ignores
+ * `outlier`.  src, jobs, cand and bits are device pointers; asynchronous on `stream`.
+ */
+#define AIRS_MAX_CANDIDATES 32u
+struct airs_candidate {
+	uint32_t encoder_type; /* enum cmp_encoder_type */
+	uint32_t g;            /* encoder_param */
+	uint32_t outlier;      /* encoder_outlier */
+	uint32_t reserved;
+};
+int airs_cuda_candidate_bits(const void *src, const struct airs_job *jobs, uint32_t n_jobs,
+			     const struct airs_candidate *cand, uint32_t n_cand, uint64_t *bits, void *stream);
+
+/* Candidates around what the statistics of a job suggest, for airs_cuda_candidate_bits(): Golomb parameters from
+ * half to twice g = mean * ln 2, and for GOLOMB_MULTI outliers of 4, 8 and 16 g (where valid).  Fills at most
+ * `max` entries of `out` and returns their number.  Host function. */
+uint32_t airs_cuda_param_candidates(const struct airs_stats *stats, uint32_t encoder_type, struct airs_candidate *out,
+				    uint32_t max);
 
 /* Release cached device staging buffers of this thread (optional). */
 void airs_cuda_release_cache(void);

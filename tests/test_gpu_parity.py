@@ -99,6 +99,55 @@ def test_bad_job_table_is_refused(gpu, pkg):
             assert all(int(r) == generic for r in got[1]), (layout, breakage, tmp)
 
 
+def _to_big_endian(js):
+    """The same job set with the samples of every 16-bit job stored big-endian (AIRS_DTYPE_BE): what a sample file of
+    the reference's front end holds before programs/file.c:337-358 swaps it to host order."""
+    src = js["src"].copy()
+    jobs = js["jobs"].copy()
+    for job in jobs:
+        if int(job["dtype"]) == 1:
+            continue
+        for f in range(int(job["n_frames"])):
+            o, sz = int(job["src_offset"]) + f * int(job["src_frame_stride"]), int(job["src_size"]) & ~1
+            if o + sz <= len(src):
+                src[o:o + sz] = src[o:o + sz].reshape(-1, 2)[:, ::-1].reshape(-1)
+        job["dtype"] = int(job["dtype"]) | 4
+    return dict(js, src=src, jobs=jobs)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_big_endian_samples_random(gpu, oracle, seed):
+    """the byte swap of a big-endian sample file fused into the loads.  Random jobs (every
+    preprocessing, encoder, capacity mode, checksum, fallback, model contexts): the streams, results and models of the
+    big-endian job set on the GPU are those of the host-order job set on the CPU."""
+    rng = np.random.default_rng(600 + seed)
+    js = jobgen.build_jobs(rng, 200, sizes=SMALL + MEDIUM + [40000], max_frames=4, allow_invalid=True)
+    want = jobgen.run_cpu(oracle, js)
+    got = gpu.run_jobs_device(_to_big_endian(js))
+    jobgen.compare(want, got, js, "big-endian")
+
+
+def test_big_endian_samples_every_kernel(gpu, oracle, pkg):
+    """... and through every kernel: short chunks (warp per job), a few long frames and a few contexts with model (tiles),
+    many long frames (CTA per job), each with checksums (the hash is taken of the big-endian image: of the memory as
+    it is)."""
+    abi = pkg.abi
+    rng = np.random.default_rng(77)
+    plain = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=2, primary_encoder_param=11,
+                            primary_encoder_outlier=90, checksum_enabled=1)
+    model = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16,
+                            secondary_iterations=3, secondary_preprocessing=abi.PRE_MODEL, secondary_encoder_type=1,
+                            secondary_encoder_param=8, model_rate=7, checksum_enabled=1)
+    for n_jobs, n, nf, p, dtype in ((600, 2048 + 5, 1, plain, 2), (3, 70001, 1, plain, 0), (3, 32768, 5, model, 0),
+                                    (460, 36000, 1, plain, 2), (40000, 24, 1, plain, 2)):
+        js = _uniform_jobs(pkg, n_jobs, n, nf, p, dtype=dtype)
+        x = (20000 + rng.integers(-30, 31, size=n_jobs * nf * n).cumsum()) & 0xFFFF
+        js["src"] = x.astype(np.uint16).view(np.uint8)
+        want = jobgen.run_cpu(oracle, js, threads=8)
+        got = gpu.run_jobs_device(_to_big_endian(js))
+        jobgen.compare(want, got, js, "big-endian n_jobs=%d n=%d" % (n_jobs, n))
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 def test_host_batch(gpu, oracle, layout):
     """airs_cuda_compress_batch_host: host buffers in, host buffers out."""

@@ -54,3 +54,43 @@ def test_suggested_parameter_is_near_the_best(gpu, pkg):
             sizes[g] = int(res.astype(np.int64).sum())
         best = min(sizes.values())
         assert sizes[g_sug] <= 1.02 * best, (amp, g_sug, sizes)
+
+
+@pytest.mark.parametrize("dtype", [2, 0, 1])
+def test_candidate_bits_are_exact_and_the_search_pays(gpu, oracle, pkg, dtype):
+    """airs_cuda_candidate_bits (the parameter search the reference leaves to the user): for candidates around the
+    statistics' suggestion - GOLOMB_ZERO and GOLOMB_MULTI, NONE and DIFF preprocessing, smooth / rough / escape-heavy
+    data - the bit count per candidate is EXACT: compressing the frame with that candidate (oracle = reference) gives
+    CMP_HDR_SIZE + 6 + ceil(bits / 8) bytes.  Invalid candidates report 2^64 - 1.  The best candidate beats the
+    plain suggestion g = mean * ln 2 where escapes matter."""
+    from test_gpu_parity import _uniform_jobs
+    abi = pkg.abi
+    rng = np.random.default_rng(31 + dtype)
+    n = 12000
+    gained = []
+    for pre in (abi.PRE_DIFF, abi.PRE_NONE):
+        for step, esc in ((3, 0), (60, 0), (900, 0), (12, 40)):
+            x = (20000 + rng.integers(-step, step + 1, size=n).cumsum()) & 0xFFFF
+            if pre == abi.PRE_NONE:
+                x = (rng.integers(-step, step + 1, size=n) * 3) & 0xFFFF
+            if esc:
+                x[rng.integers(0, n, size=n // esc)] ^= rng.integers(0, 65536, size=n // esc)
+            for enc in (1, 2):
+                p = abi.make_params(primary_preprocessing=pre, primary_encoder_type=enc, primary_encoder_param=1, primary_encoder_outlier=16)
+                js = _uniform_jobs(pkg, 1, n, 1, p, dtype=dtype)
+                js["src"] = (x.astype("<i4") if dtype == 1 else x.astype(np.uint16)).view(np.uint8)
+                st = gpu.residual_stats(js["src"], js["jobs"])
+                cand = gpu.param_candidates(st[0], enc)
+                assert 3 <= len(cand) <= abi.MAX_CANDIDATES and cand[0]["g"] == pkg.load_library().airs_cuda_golomb_param_for_mean(
+                    int(st[0]["sum_mapped"]), int(st[0]["n_samples"]))
+                bad = np.zeros(1, dtype=abi.CANDIDATE_DTYPE)
+                bad[0] = (enc, 0, 5, 0)                                   # g = 0: cmp_initialise refuses it
+                bits = gpu.candidate_bits(js["src"], js["jobs"], np.concatenate([cand, bad]))[0]
+                assert int(bits[-1]) == 2**64 - 1
+                for c, b in zip(cand, bits[:-1]):
+                    js["jobs"]["params"]["primary_encoder_param"] = c["g"]
+                    js["jobs"]["params"]["primary_encoder_outlier"] = c["outlier"]
+                    _, res, init, _, _ = jobgen.run_cpu(oracle, js)
+                    assert not abi.is_error(int(init[0])) and int(res[0]) == 22 + (int(b) + 7) // 8, (pre, step, esc, enc, c)
+                gained.append(int(bits[0]) / int(bits[:-1].min()))
+    assert min(gained) >= 1.0 and max(gained) > 1.02, gained
