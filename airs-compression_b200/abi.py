@@ -12,6 +12,7 @@ import numpy as np
 PRE_NONE, PRE_DIFF, PRE_IWT, PRE_MODEL = 0, 1, 2, 3
 ENC_UNCOMPRESSED, ENC_GOLOMB_ZERO, ENC_GOLOMB_MULTI = 0, 1, 2
 DT_I16, DT_I16_IN_I32, DT_U16 = 0, 1, 2
+BATCH_BIG_ENDIAN = 1                       # airs_batch.flags: the batch may hold DT_BE containers
 DT_BE = 4                                  # flag: 16-bit samples big-endian in memory (AIRS_DTYPE_BE)
 LAYOUT_SLOTS, LAYOUT_CONCAT = 0, 1
 
@@ -75,7 +76,7 @@ class AirsBatch(C.Structure):
                 ("jobs", C.c_void_p), ("results", C.c_void_p), ("init_results", C.c_void_p),
                 ("out_offsets", C.c_void_p), ("scratch", C.c_void_p), ("dst_size", C.c_uint64),
                 ("n_jobs", C.c_uint32), ("n_results", C.c_uint32), ("layout", C.c_uint32),
-                ("reserved", C.c_uint32), ("tmp", C.c_void_p), ("tmp_size", C.c_uint64)]
+                ("flags", C.c_uint32), ("tmp", C.c_void_p), ("tmp_size", C.c_uint64)]
 
 
 class AirsHostBatch(C.Structure):
@@ -83,7 +84,7 @@ class AirsHostBatch(C.Structure):
                 ("dst_size", C.c_uint64), ("work", C.c_void_p), ("work_size", C.c_uint64),
                 ("jobs", C.c_void_p), ("results", C.c_void_p), ("init_results", C.c_void_p),
                 ("out_offsets", C.c_void_p), ("n_jobs", C.c_uint32), ("n_results", C.c_uint32),
-                ("layout", C.c_uint32), ("reserved", C.c_uint32)]
+                ("layout", C.c_uint32), ("flags", C.c_uint32)]
 
 
 # include/airs_cuda_decode.h

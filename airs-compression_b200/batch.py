@@ -53,6 +53,7 @@ class DeviceBatch:
         b.n_jobs = self.n_jobs
         b.n_results = self.n_results
         b.layout = layout
+        b.flags = abi.BATCH_BIG_ENDIAN if bool((np.asarray(jobs)["dtype"] & abi.DT_BE).any()) else 0
         self.tmp = None
         if layout == abi.LAYOUT_CONCAT and concat_tmp:
             self.tmp = torch.empty(int(concat_tmp), dtype=torch.uint8, device=self.device)
@@ -142,6 +143,7 @@ def run_jobs_host(js, fill=0xA5, work_fill=0x5A):
     hb.jobs, hb.results, hb.init_results = jobs.ctypes.data, results.ctypes.data, init.ctypes.data
     hb.out_offsets = offs.ctypes.data if js["layout"] == abi.LAYOUT_CONCAT else None
     hb.n_jobs, hb.n_results, hb.layout = n_jobs, n_results, js["layout"]
+    hb.flags = abi.BATCH_BIG_ENDIAN if bool((jobs["dtype"] & abi.DT_BE).any()) else 0
     rc = lib.airs_cuda_compress_batch_host(C.byref(hb))
     if rc != 0:
         raise RuntimeError("airs_cuda_compress_batch_host failed (%d): %s"

@@ -281,6 +281,7 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.n_results = b->n_results;
 	l.layout = b->layout;
 	l.ordered = b->layout == AIRS_LAYOUT_CONCAT;
+	l.be_batch = (b->flags & AIRS_BATCH_BIG_ENDIAN) != 0u;
 }
 
 /* slice: the batch is a run of consecutive jobs of a larger CONCAT batch whose first frame is number
@@ -480,6 +481,7 @@ static int host_batch_pipelined(const struct airs_host_batch *hb, cudaStream_t s
 		b.n_jobs = j1 - j0;
 		b.n_results = hb->n_results;
 		b.layout = AIRS_LAYOUT_SLOTS;
+		b.flags = hb->flags;
 		int rc = launch_batch(&b, nullptr, s_comp);
 		if (rc)
 			return rc;
@@ -619,6 +621,7 @@ static int host_batch_concat_pipelined(const struct airs_host_batch *hb, cudaStr
 		b.n_jobs = G.j1 - G.j0;
 		b.n_results = G.r1 - G.r0;
 		b.layout = AIRS_LAYOUT_CONCAT;
+		b.flags = hb->flags;
 		b.tmp = c.tmp.p;
 		b.tmp_size = tmp_need;
 		ConcatSlice sl = {G.r0, g ? (const uint64_t *)c.offs.p + G.r0 : nullptr};
@@ -709,6 +712,7 @@ extern "C" int airs_cuda_compress_batch_host(const struct airs_host_batch *hb)
 	b.n_jobs = hb->n_jobs;
 	b.n_results = hb->n_results;
 	b.layout = hb->layout;
+	b.flags = hb->flags;
 	if (hb->layout == AIRS_LAYOUT_CONCAT) {
 		/* temporary slots for the two-phase path, if the device has room for them */
 		uint64_t caps = 0;

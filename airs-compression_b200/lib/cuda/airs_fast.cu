@@ -101,7 +101,7 @@ __device__ __forceinline__ void drain(FastWarp &ws, Out &o, uint32_t lane)
 }
 
 /* the pass of one job through its units */
-template <bool MULTI, bool DIFF>
+template <bool MULTI, bool DIFF, bool BE>
 __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWarp &ws, Out &o, const uint8_t *src, uint32_t n, uint32_t lane,
 					     bool be)
 {
@@ -117,7 +117,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 	/* the complete pieces of the next unit are requested while one unit is encoded */
 #pragma unroll
 	for (uint32_t j = 0; j < kRows; j++)
-		nx[j] = unit_piece(lane, j) < n_whole ? load_piece(src4, unit_piece(lane, j), be) : zero4;
+		nx[j] = unit_piece(lane, j) < n_whole ? load_piece<BE>(src4, unit_piece(lane, j), be) : zero4;
 	uint32_t u = 0;
 	for (; u < n_full_units; u++) {
 #pragma unroll
@@ -126,7 +126,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 		const uint32_t p1 = (u + 1u) * kUnitPieces + unit_piece(lane, 0);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++)
-			nx[j] = p1 + j < n_whole ? load_piece(src4, p1 + j, be) : zero4;
+			nx[j] = p1 + j < n_whole ? load_piece<BE>(src4, p1 + j, be) : zero4;
 		o.sbits += encode_unit<MULTI, DIFF, false>(dbg, k, x, front, full_nv, lane, stg_bit + o.sbits);
 		if (o.sbits > kUnitMaxBits)
 			drain(ws, o, lane);
@@ -138,7 +138,7 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 			const uint32_t p = u * kUnitPieces + unit_piece(lane, j);
 			nv[j] = 8u * p >= n ? 0u : min(8u, n - 8u * p);
 			if (nv[j] != 0u && nv[j] != 8u)
-				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j], be);
+				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, nv[j], BE && be);
 		}
 		o.sbits += encode_unit<MULTI, DIFF, true>(dbg, k, nx, front, nv, lane, stg_bit + o.sbits);
 	}
@@ -147,6 +147,9 @@ __device__ __forceinline__ void encode_units(const Dbg &dbg, const FK &k, FastWa
 
 } /* namespace */
 
+/* BE: the variant for batches that may hold big-endian containers (AIRS_BATCH_BIG_ENDIAN); the other one has no trace
+ * of them */
+template <bool BE>
 __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs_fast_kernel(AirsLaunch b)
 {
 	__shared__ FastWarp wsh[kFWarps];
@@ -221,17 +224,17 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 		__syncwarp();
 		o.sbits += 8u * (CMP_HDR_SIZE + 6u);
 
-		const bool be = (flags & AIRS_FJ_BE) != 0u;
+		const bool be = BE && (flags & AIRS_FJ_BE) != 0u;
 		if (multi) {
 			if (flags & AIRS_FJ_PRE_DIFF)
-				encode_units<true, true>(dbg, k, ws, o, src, n, lane, be);
+				encode_units<true, true, BE>(dbg, k, ws, o, src, n, lane, be);
 			else
-				encode_units<true, false>(dbg, k, ws, o, src, n, lane, be);
+				encode_units<true, false, BE>(dbg, k, ws, o, src, n, lane, be);
 		} else {
 			if (flags & AIRS_FJ_PRE_DIFF)
-				encode_units<false, true>(dbg, k, ws, o, src, n, lane, be);
+				encode_units<false, true, BE>(dbg, k, ws, o, src, n, lane, be);
 			else
-				encode_units<false, false>(dbg, k, ws, o, src, n, lane, be);
+				encode_units<false, false, BE>(dbg, k, ws, o, src, n, lane, be);
 		}
 
 		const uint32_t frame_bits = o.gw0 * 32u + o.sbits - 8u * a;
@@ -297,7 +300,10 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 
 extern "C" cudaError_t airs_launch_fast(const AirsLaunch *b, unsigned int grid, cudaStream_t stream)
 {
-	airs_fast_kernel<<<grid, AIRS_FAST_THREADS, 0, stream>>>(*b);
+	if (b->be_batch)
+		airs_fast_kernel<true><<<grid, AIRS_FAST_THREADS, 0, stream>>>(*b);
+	else
+		airs_fast_kernel<false><<<grid, AIRS_FAST_THREADS, 0, stream>>>(*b);
 	return cudaGetLastError();
 }
 
@@ -327,10 +333,17 @@ extern "C" cudaError_t airs_fast_resident_ctas(int *out)
 		 * rest of the 228 KiB stays L1 */
 		const size_t need = (size_t)AIRS_FAST_CTAS_PER_SM * (sizeof(FastWarp) * kFWarps + 1024);
 		const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-		e = cudaFuncSetAttribute(airs_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+		e = cudaFuncSetAttribute(airs_fast_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(airs_fast_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 	}
-	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_fast_kernel, AIRS_FAST_THREADS, 0);
+	if (e == cudaSuccess) { /* (a job per warp by ticket: the grid need not be resident at once; the smaller of both counts) */
+		int per_sm_be = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_fast_kernel<false>, AIRS_FAST_THREADS, 0);
+		if (e == cudaSuccess)
+			e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_be, airs_fast_kernel<true>, AIRS_FAST_THREADS, 0);
+		per_sm = per_sm_be < per_sm ? per_sm_be : per_sm;
+	}
 	*out = sms * per_sm;
 	return e;
 }

@@ -170,10 +170,11 @@ static __device__ __noinline__ uint4 load_partial_piece(const uint16_t *s16, uin
 }
 
 /* the whole piece p of a frame (16-byte aligned 16-bit samples, `be`: big-endian in memory: AIRS_DTYPE_BE) */
+template <bool BE>
 __device__ __forceinline__ uint4 load_piece(const uint4 *src4, uint32_t p, bool be)
 {
 	const uint4 v = __ldg(src4 + p);
-	return be ? airs_swap16x8(v) : v;
+	return (BE && be) ? airs_swap16x8(v) : v;
 }
 
 /* the strings of one unit, in registers: GOLOMB_ZERO one string per pair of samples (hi, lo, bits);

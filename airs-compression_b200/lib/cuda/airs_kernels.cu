@@ -1095,7 +1095,8 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 #define AIRS_LOAD_M(pw_, j_) ((need_m && AIRS_SEG_VALID(pw_, j_)) ? ld_keep(work4 + (pw_) + 32u * (j_) + lane, pol_keep) : zero4)
 	/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */
 #define AIRS_LOAD_PS(pw_) ((diff && lane == 0 && (pw_) != 0 && AIRS_SEG_VALID(pw_, 0)) ? \
-	(c32 ? __ldg(reinterpret_cast<const uint32_t *>(src16) + 8u * (pw_) - 1u) & 0xFFFFu : sample_at(P.src, P.dtype, 8u * (pw_) - 1u)) : 0u)
+	(c32 ? __ldg(reinterpret_cast<const uint32_t *>(src16) + 8u * (pw_) - 1u) & 0xFFFFu \
+	     : be ? sample_at(P.src, P.dtype, 8u * (pw_) - 1u) : (uint32_t)__ldg(src16 + 8u * (pw_) - 1u)) : 0u)
 
 	/* the whole next tile is loaded one tile ahead (the scheduler pulls the first consumers of
 	 * all four segments to the top of the loop body, so a later load would be waited for) */
@@ -1696,7 +1697,7 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	if (in_warp == 0u)
 		return;
 	JobPlan pl;
-	airs_make_plan(pl, job, b.src, b.work);
+	airs_make_plan(pl, job, b.src, b.work, b.be_batch != 0u);
 	/* Short single-frame jobs without model, with a Golomb encoder, none / diff preprocessing,
 	 * an aligned 16-bit source and nothing that could fail before the encoding go to
 	 * airs_fast_kernel (one warp per job); everything else to airs_encode_kernel.  Jobs keep their

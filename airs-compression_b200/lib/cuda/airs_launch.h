@@ -68,6 +68,7 @@ struct AirsLaunch {
 	const uint32_t *gate;
 	uint32_t gate_want;
 	uint32_t tile_below_jobs; /* batches with fewer jobs send every long single-frame job to airs_tile_kernel */
+	uint32_t be_batch;        /* AIRS_BATCH_BIG_ENDIAN: jobs may have AIRS_DTYPE_BE containers */
 	uint32_t ordered;         /* the caller's layout is CONCAT: the jobs must list the frames 0 .. n_results - 1 in order */
 };
 

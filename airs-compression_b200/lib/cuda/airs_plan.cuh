@@ -121,12 +121,12 @@ __device__ inline uint32_t airs_pre_err(uint32_t pre, const uint8_t *work, uint3
 	return 0;
 }
 
-__device__ inline void airs_make_plan(JobPlan &pl, const airs_job &j, const uint8_t *src_base, uint8_t *work_base)
+__device__ inline void airs_make_plan(JobPlan &pl, const airs_job &j, const uint8_t *src_base, uint8_t *work_base, bool be_batch)
 {
 	const cmp_params &p = j.params;
 	const uint8_t *work = (work_base && j.work_size) ? work_base + j.work_offset : nullptr;
 	const uint32_t stride = j.dtype == AIRS_DTYPE_I16_IN_I32 ? 4u : 2u;
-	const bool dtype_ok = j.dtype <= AIRS_DTYPE_U16 || j.dtype == AIRS_DTYPE_I16_BE || j.dtype == AIRS_DTYPE_U16_BE;
+	const bool dtype_ok = j.dtype <= AIRS_DTYPE_U16 || (be_batch && (j.dtype == AIRS_DTYPE_I16_BE || j.dtype == AIRS_DTYPE_U16_BE));
 
 	memset(&pl, 0, sizeof(pl));
 	pl.init_result = airs_validate(j, work);

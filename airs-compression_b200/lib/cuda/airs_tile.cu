@@ -231,7 +231,7 @@ __device__ __forceinline__ uint4 ld_cg4(const uint4 *p) /* from the L2: the line
 /* the units of one tile: code words, scans, strings staged from tile-local bit 0 on; returns the tile's bits.
  * model: the context's model (nullptr: none) - PRE = kPreModel takes the residuals against it and leaves the
  * updated model behind, init_model (primary pass of a context with model) leaves the samples behind */
-template <bool MULTI, int PRE>
+template <bool MULTI, int PRE, bool BE>
 __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, TileArea &ws, const uint8_t *src, uint32_t n, uint32_t first,
 					       uint4 (&nx)[kRows], uint32_t front, uint32_t lane, uint4 *model, bool init_model, const ModelK &mk, bool be)
 {
@@ -259,9 +259,9 @@ __device__ __forceinline__ uint32_t tile_units(const Dbg &dbg, const FK &k, Tile
 #pragma unroll
 			for (uint32_t j = 0; j < kRows; j++) {
 				const uint32_t p = (ufirst + kUnit) / 8u + unit_piece(lane, j);
-				nx[j] = p < n_whole ? load_piece(src4, p, be) : zero4;
+				nx[j] = p < n_whole ? load_piece<BE>(src4, p, be) : zero4;
 				if (p == n_whole && (n & 7u))
-					nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u, be);
+					nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u, BE && be);
 			}
 		}
 		if (ufirst + kUnit <= n) {
@@ -317,7 +317,7 @@ __device__ __forceinline__ TileWhat tile_what(uint32_t T, uint32_t rec, uint32_t
 /* FRAMES = false: a batch whose tile jobs are single frames (no model, no secondary passes: four instantiations of
  * the warp encoder, 96 registers, six CTAs per SM); FRAMES = true: contexts of several frames among them (six
  * instantiations, 128 registers, five CTAs per SM).  Both are launched; airs_plan_kernel leaves behind which one works. */
-template <bool FRAMES>
+template <bool FRAMES, bool BE>
 __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs_tile_kernel(AirsLaunch b)
 {
 	__shared__ TileWarp wsh[kTWarps];
@@ -381,14 +381,14 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 		const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)(__shfl_sync(kFull, rec, 0) | (uint64_t)__shfl_sync(kFull, rec, 1) << 32)) +
 				     (uint64_t)tw.f * (__shfl_sync(kFull, rec, 16) | (uint64_t)__shfl_sync(kFull, rec, 17) << 32);
 		const uint32_t n = __shfl_sync(kFull, rec, 6), first = tw.tidx * kTile, n_whole = n / 8u;
-		const bool be = (__shfl_sync(kFull, rec, 8) & AIRS_FJ_BE) != 0u;
+		const bool be = BE && (__shfl_sync(kFull, rec, 8) & AIRS_FJ_BE) != 0u;
 		const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
 		for (uint32_t j = 0; j < kRows; j++) {
 			const uint32_t p = first / 8u + unit_piece(lane, j);
-			nx[j] = p < n_whole ? load_piece(src4, p, be) : zero4;
+			nx[j] = p < n_whole ? load_piece<BE>(src4, p, be) : zero4;
 			if (p == n_whole && (n & 7u))
-				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u, be);
+				nx[j] = load_partial_piece(reinterpret_cast<const uint16_t *>(src), 8u * p, n & 7u, BE && be);
 		}
 		/* lane 0: the sample in front of the tile (DIFF), in the upper half of a word */
 		nfront = 0;
@@ -492,21 +492,21 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 
 			/* ---- the tile's code words, staged at tile-local bit positions */
 			const bool init_model = has_model && !sec;
-			const bool be = (flags & AIRS_FJ_BE) != 0u;
+			const bool be = BE && (flags & AIRS_FJ_BE) != 0u;
 			if (multi) {
 				if (FRAMES && pre == kPreModel)
-					bits = tile_units<true, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk, be);
+					bits = tile_units<true, kPreModel, BE>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk, be);
 				else if (pre == kPreDiff)
-					bits = tile_units<true, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
+					bits = tile_units<true, kPreDiff, BE>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 				else
-					bits = tile_units<true, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
+					bits = tile_units<true, kPreNone, BE>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 			} else {
 				if (FRAMES && pre == kPreModel)
-					bits = tile_units<false, kPreModel>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk, be);
+					bits = tile_units<false, kPreModel, BE>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, false, mk, be);
 				else if (pre == kPreDiff)
-					bits = tile_units<false, kPreDiff>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
+					bits = tile_units<false, kPreDiff, BE>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 				else
-					bits = tile_units<false, kPreNone>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
+					bits = tile_units<false, kPreNone, BE>(dbg, kk, ar, src, n, first, nx, nfront, lane, model, init_model, mk, be);
 			}
 			if (has_model)
 				__threadfence(); /* the model stores of all lanes in front of the count */
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 }
 
 /* resident CTAs of one variant of the kernel on the current device */
-template <bool FRAMES>
+template <bool FRAMES, bool BE>
 static cudaError_t tile_resident(int *out)
 {
 	int dev = 0, sms = 0, per_sm = 0;
@@ -691,10 +691,10 @@ static cudaError_t tile_resident(int *out)
 	if (e == cudaSuccess) {
 		const size_t need = (size_t)AIRS_TILE_CTAS_PER_SM * (sizeof(TileWarp) * kTWarps + 1024);
 		const int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-		e = cudaFuncSetAttribute(airs_tile_kernel<FRAMES>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+		e = cudaFuncSetAttribute(airs_tile_kernel<FRAMES, BE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
 	}
 	if (e == cudaSuccess)
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_tile_kernel<FRAMES>, AIRS_TILE_THREADS, 0);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, airs_tile_kernel<FRAMES, BE>, AIRS_TILE_THREADS, 0);
 	*out = sms * per_sm;
 	return e;
 }
@@ -704,20 +704,26 @@ static cudaError_t tile_resident(int *out)
  * the batch does not need returns at once. */
 extern "C" cudaError_t airs_launch_tile(const AirsLaunch *b, cudaStream_t stream)
 {
-	static thread_local int cached_dev = -1, grid[2] = {0, 0};
+	static thread_local int cached_dev = -1, grid[4] = {0, 0, 0, 0};
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess)
 		return e;
 	if (dev != cached_dev) {
-		if ((e = tile_resident<false>(&grid[0])) != cudaSuccess || (e = tile_resident<true>(&grid[1])) != cudaSuccess)
+		if ((e = tile_resident<false, false>(&grid[0])) != cudaSuccess || (e = tile_resident<true, false>(&grid[1])) != cudaSuccess ||
+		    (e = tile_resident<false, true>(&grid[2])) != cudaSuccess || (e = tile_resident<true, true>(&grid[3])) != cudaSuccess)
 			return e;
-		if (grid[0] < 1 || grid[1] < 1)
+		if (grid[0] < 1 || grid[1] < 1 || grid[2] < 1 || grid[3] < 1)
 			return cudaErrorLaunchOutOfResources;
 		cached_dev = dev;
 	}
-	airs_tile_kernel<false><<<grid[0], AIRS_TILE_THREADS, 0, stream>>>(*b);
-	airs_tile_kernel<true><<<grid[1], AIRS_TILE_THREADS, 0, stream>>>(*b);
+	if (b->be_batch) { /* the variants that know big-endian containers (AIRS_BATCH_BIG_ENDIAN) */
+		airs_tile_kernel<false, true><<<grid[2], AIRS_TILE_THREADS, 0, stream>>>(*b);
+		airs_tile_kernel<true, true><<<grid[3], AIRS_TILE_THREADS, 0, stream>>>(*b);
+	} else {
+		airs_tile_kernel<false, false><<<grid[0], AIRS_TILE_THREADS, 0, stream>>>(*b);
+		airs_tile_kernel<true, false><<<grid[1], AIRS_TILE_THREADS, 0, stream>>>(*b);
+	}
 	return cudaGetLastError();
 }
 

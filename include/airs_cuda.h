@@ -64,6 +64,10 @@ extern "C" {
 #define AIRS_LAYOUT_SLOTS  0u /* every frame has its own dst slot */
 #define AIRS_LAYOUT_CONCAT 1u /* streams laid out back to back by a device-wide scan */
 
+/* flags of a batch */
+#define AIRS_BATCH_BIG_ENDIAN 1u /* the batch may hold jobs with AIRS_DTYPE_BE containers (the kernel variants that
+				    know them run; without the flag such a job fails like an unknown container) */
+
 /* result value of a frame that was not attempted because its job failed to
  * initialise: the reference returns CMP_ERR_CONTEXT_INVALID there (cmp.c:353) */
 
@@ -102,7 +106,7 @@ struct airs_batch {
 	uint32_t n_jobs;
 	uint32_t n_results;          /* total number of frames */
 	uint32_t layout;             /* AIRS_LAYOUT_* */
-	uint32_t reserved;
+	uint32_t flags;              /* AIRS_BATCH_* */
 	void *tmp;                   /* CONCAT: temporary device memory, 16-byte aligned, or NULL (see below) */
 	uint64_t tmp_size;           /* bytes behind tmp */
 };
@@ -192,7 +196,7 @@ struct airs_host_batch {
 	uint32_t n_jobs;
 	uint32_t n_results;
 	uint32_t layout;
-	uint32_t reserved;
+	uint32_t flags;              /* AIRS_BATCH_* */
 };
 int airs_cuda_compress_batch_host(const struct airs_host_batch *batch);
 

@@ -123,8 +123,16 @@ def test_big_endian_samples_random(gpu, oracle, seed):
     rng = np.random.default_rng(600 + seed)
     js = jobgen.build_jobs(rng, 200, sizes=SMALL + MEDIUM + [40000], max_frames=4, allow_invalid=True)
     want = jobgen.run_cpu(oracle, js)
-    got = gpu.run_jobs_device(_to_big_endian(js))
+    be = _to_big_endian(js)
+    got = gpu.run_jobs_device(be)
     jobgen.compare(want, got, js, "big-endian")
+    if seed == 0:      # a batch that does not declare them (AIRS_BATCH_BIG_ENDIAN): an unknown container, as dtype 3 is
+        db = gpu.DeviceBatch(be["src"], be["jobs"], be["dst_size"], be["work_size"], be["n_results"])
+        db.desc.flags = 0
+        res = db.run().fetch()[1]
+        for job in be["jobs"]:
+            if int(job["dtype"]) & 4 and int(job["n_frames"]):
+                assert int(res[int(job["first_result"])]) == jobgen.abi.err("SRC_SIZE_WRONG")
 
 
 def test_big_endian_samples_every_kernel(gpu, oracle, pkg):
