@@ -822,7 +822,10 @@ extern "C" int airs_cuda_compress_resume(const struct airs_job *job, struct airs
 		b.src = src;
 	}
 	if (dst && !dst_dev) {
-		if ((rc = c.dst.reserve((size_t)j.dst_capacity + 64)))
+		/* (a stream never exceeds cmp_compress_bound(): callers pass the size of whatever buffer they have) */
+		const uint32_t stride = j.dtype == AIRS_DTYPE_I16_IN_I32 ? 4u : 2u;
+		const uint64_t bound = 64u + 6ull * (j.src_size / stride), need = j.dst_capacity < bound ? j.dst_capacity : bound;
+		if ((rc = c.dst.reserve((size_t)need + 64)))
 			return rc;
 		b.dst = c.dst.p; /* cudaMalloc memory is 256-byte aligned: reproduce the caller's alignment */
 		j.dst_offset = mis;

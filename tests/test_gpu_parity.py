@@ -442,3 +442,100 @@ def test_random_jobs_long_frames(gpu, oracle, seed):
     want = jobgen.run_cpu(oracle, js, threads=4)
     got = gpu.run_jobs_device(js)
     jobgen.compare(want, got, js, "gpu-vs-oracle-long")
+
+
+def test_capacity_sweep_around_the_exact_size(gpu, oracle, pkg):
+    """dst_capacity from four bytes below to two bytes above what the stream needs, with and without checksum and
+    uncompressed fallback, through the warp-per-job kernel (2048 samples), the tile kernel (70001 samples, three jobs)
+    and the CTA-per-job kernel (model context): success, DST_TOO_SMALL and the raw fallback switch at exactly the
+    capacity where the reference switches."""
+    abi = pkg.abi
+    rng = np.random.default_rng(808)
+    for n, nf, n_jobs in ((2048, 1, 20), (70001, 1, 3), (5000, 3, 4)):
+        for cs, fb in ((0, 0), (1, 0), (0, 1), (1, 1)):
+            p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16,
+                                secondary_iterations=2 if nf > 1 else 0, secondary_preprocessing=abi.PRE_MODEL,
+                                secondary_encoder_type=1, secondary_encoder_param=8, model_rate=8, checksum_enabled=cs,
+                                uncompressed_fallback_enabled=fb)
+            x = (20000 + rng.integers(-40, 41, size=n_jobs * nf * n).cumsum()) & 0xFFFF
+            if fb:                                       # noise: the compressed stream is longer than the raw one
+                x = rng.integers(0, 65536, size=n_jobs * nf * n)
+            src = x.astype(np.uint16).view(np.uint8)
+            js = _uniform_jobs(pkg, n_jobs, n, nf, p)
+            js["src"] = src
+            exact = int(jobgen.run_cpu(oracle, js)[1][0])        # size of the first stream with room to spare
+            assert not abi.is_error(exact)
+            target = 16 + 2 * n + 4 * cs if fb else exact       # where the decision falls: raw size / stream size
+            for delta in (-4, -2, -1, 0, 1, 2):
+                js = _uniform_jobs(pkg, n_jobs, n, nf, p, cap=target + delta)
+                js["src"] = src
+                want = jobgen.run_cpu(oracle, js, threads=4)
+                got = gpu.run_jobs_device(js)
+                jobgen.compare(want, got, js, "capacity n=%d cs=%d fb=%d delta=%d" % (n, cs, fb, delta))
+
+
+def test_frames_beyond_the_header_limits(gpu, oracle, pkg):
+    """A frame of more than 2^24 - 1 bytes cannot be described by the header (HDR_ORIGINAL_TOO_LARGE, header.c:34),
+    the largest one that can is compressed; both as the reference answers, through the tile kernel and (CONCAT) the
+    CTA-per-job kernel."""
+    abi = pkg.abi
+    rng = np.random.default_rng(99)
+    p = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=1, primary_encoder_param=16)
+    for n in ((1 << 23) - 1, 1 << 23):                  # 16 MiB - 2 bytes, 16 MiB
+        cap = min(abi.CMP_MAX_SIZE // 8 * 8, 22 + 6 * n)
+        for layout in (0, 1):
+            js = _uniform_jobs(pkg, 1, n, 1, p, cap=cap)
+            js["layout"] = layout
+            js["src"] = ((20000 + rng.integers(-20, 21, size=n).cumsum()) & 0xFFFF).astype(np.uint16).view(np.uint8)
+            want = jobgen.run_cpu(oracle, js)
+            got = gpu.run_jobs_device(js)
+            jobgen.compare(want, got, js, "header-limit n=%d layout=%d" % (n, layout))
+            assert abi.is_error(int(want[1][0])) == (n == 1 << 23)
+
+
+def test_shards_give_the_bytes_of_the_whole(gpu, pkg):
+    """the output does not depend on how the jobs are cut over GPUs.  Config 3 and config 2 workloads as
+    ONE batch and as the two / three contiguous shards `parallel.shard_range` gives the ranks (each shard a batch of its
+    own, as on its own GPU): the same stream hashes and sizes, frame by frame."""
+    import torch
+    abi = pkg.abi
+    for w in (pkg.workloads.config3(3 * 4096 + 17, 7, "cuda"), pkg.workloads.config2(10, 3, "cuda")):
+        data = w["data"].view(torch.uint8).reshape(-1)
+        whole = gpu.DeviceBatch(data, w["jobs"], w["dst_size"], w["work_size"], w["n_results"])
+        whole.run()
+        h_all, r_all = whole.hash_streams().cpu().numpy(), whole.results.cpu().numpy()
+        nf = int(w["jobs"][0]["n_frames"])
+        for world in (2, 3):
+            hs, rs = [], []
+            for rank in range(world):
+                lo, hi = pkg.parallel.shard_range(len(w["jobs"]), rank, world)
+                jobs = w["jobs"][lo:hi].copy()
+                jobs["first_result"] -= np.uint32(lo * nf)
+                jobs["dst_offset"] -= jobs["dst_offset"][0]
+                jobs["work_offset"] -= jobs["work_offset"][0]
+                dsz = int(jobs["dst_offset"][-1] + jobs["dst_frame_stride"][-1] * nf) + 64
+                db = gpu.DeviceBatch(data, jobs, dsz, w["work_size"], (hi - lo) * nf)
+                db.run()
+                hs.append(db.hash_streams().cpu().numpy())
+                rs.append(db.results.cpu().numpy())
+            assert np.array_equal(np.concatenate(hs), h_all) and np.array_equal(np.concatenate(rs), r_all), world
+
+
+def test_thread_changes_device(gpu, oracle, pkg):
+    """One host thread, two GPUs: the per-thread cache of the host-buffer entry points (staging buffers, streams,
+    events) belongs to ONE device; after cudaSetDevice(other) it is given back under the old device and rebuilt, instead
+    of handing the new device pointers into the old one's memory.  Needs two devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    rng = np.random.default_rng(12)
+    js = jobgen.build_jobs(rng, 80, sizes=[64, 2048, 4099], max_frames=3)
+    want = jobgen.run_cpu(oracle, js)
+    cur = torch.cuda.current_device()
+    try:
+        for dev in (0, 1, 0, 1):
+            torch.cuda.set_device(dev)
+            got = gpu.run_jobs_host(js)
+            jobgen.compare(want, got, js, "host batch on device %d" % dev, check_tail=False)
+    finally:
+        torch.cuda.set_device(cur)
