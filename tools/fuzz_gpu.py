@@ -13,7 +13,7 @@ gpu = pkg.batch
 oracle = oracle_py.load_oracle()
 first, count = int(sys.argv[1]), int(sys.argv[2])
 SMALL = [1, 2, 3, 5, 7, 8, 9, 15, 16, 17, 63, 64, 65, 255, 256, 257, 511, 1023]
-MED = [1000, 2047, 2048, 2049, 4095, 4096, 4097, 4099, 6000, 8191, 8192, 10000, 16384, 20001, 33000]
+MED = [1000, 2047, 2048, 2049, 4095, 4096, 4097, 4099, 6000, 8191, 8192, 10000, 16384, 20001, 33000, 40000, 70001, 131072]
 n_frames = 0
 for seed in range(first, first + count):
     rng = np.random.default_rng(seed)
@@ -24,6 +24,9 @@ for seed in range(first, first + count):
     want = jobgen.run_cpu(oracle, js)
     got = gpu.run_jobs_device(js)
     jobgen.compare(want, got, js, f"seed {seed} layout {layout}")
+    if seed % 3 == 0:  # the same job set with big-endian sample containers (AIRS_DTYPE_BE)
+        from test_gpu_parity import _to_big_endian
+        jobgen.compare(want, gpu.run_jobs_device(_to_big_endian(js)), js, f"seed {seed} big-endian")
     if layout == 1:
         got2 = gpu.run_jobs_device(js, concat_tmp=gpu.concat_tmp_size(js["jobs"], js["n_results"]))
         jobgen.compare(want, got2, js, f"seed {seed} two-phase")
