@@ -242,7 +242,10 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 		const unsigned int want = (l.n_jobs + AIRS_FAST_THREADS / 32 - 1) / (AIRS_FAST_THREADS / 32);
 		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
 		CU(airs_launch_tile(&l, stream));
-		g_launches += 3;
+#ifndef AIRS_SKIP_RAW /* (development: the cost of the launch) */
+		CU(airs_launch_raw(&l, (unsigned int)resident / 2u, stream)); /* (a few CTAs of 256 threads per SM) */
+#endif
+		g_launches += 4;
 	}
 	CU(airs_launch_encode(&l, grid, stream));
 	CU(airs_launch_checksum(&l, stream));
@@ -347,7 +350,10 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 			c.base = slice->base;
 		}
 		CU(airs_launch_concat_slots(&c, stream));
-		g_launches += 3;
+#ifndef AIRS_SKIP_RAW /* (development: the cost of the launch) */
+		CU(airs_launch_raw(&l, (unsigned int)resident / 2u, stream)); /* (a few CTAs of 256 threads per SM) */
+#endif
+		g_launches += 4;
 
 		AirsLaunch l1 = l;
 		l1.jobs = c.slot_jobs;

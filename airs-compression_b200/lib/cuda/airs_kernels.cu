@@ -1732,6 +1732,14 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	 * residuals anyway (no preprocessing: the samples themselves are coded; tiny g: long code words) */
 	const bool tiled = frames_tiled ||
 			   (quick && !small && (b.n_jobs < b.tile_below_jobs || pl.pre[0] == CMP_PREPROCESS_NONE || pl.enc[0].g < 4u));
+	/* Single frames under the UNCOMPRESSED encoder whose slot holds the stream: a copy with a byte swap, airs_raw_kernel */
+	const bool raw = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
+			 !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 && pl.enc[0].type == CMP_ENCODER_UNCOMPRESSED &&
+			 (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
+			 (job.dtype == AIRS_DTYPE_I16 || job.dtype == AIRS_DTYPE_U16) && b.dst &&
+			 ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
+			 (uint64_t)pl.cap_eff >= (pl.pre[0] == CMP_PREPROCESS_DIFF ? CMP_HDR_SIZE + 6u : CMP_HDR_SIZE) + 2ull * pl.n +
+							 ((pl.flags & AIRS_PF_CHECKSUM) ? 4u : 0u);
 	const uint32_t frame_tiles = (pl.n + AIRS_TILE_SAMPLES - 1u) / AIRS_TILE_SAMPLES;
 	const uint32_t my_tiles = tiled ? frame_tiles * job.n_frames : 0u;
 	if (small)
@@ -1743,7 +1751,8 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	const uint32_t m_cs = __ballot_sync(kFull, have && (pl.flags & AIRS_PF_CHECKSUM));
 	const uint32_t m_small = __ballot_sync(kFull, small);
 	const uint32_t m_tiled = __ballot_sync(kFull, tiled);
-	const uint32_t m_big = __ballot_sync(kFull, have && listed && !small && !tiled);
+	const uint32_t m_raw = __ballot_sync(kFull, raw);
+	const uint32_t m_big = __ballot_sync(kFull, have && listed && !small && !tiled && !raw);
 	uint32_t tiles_incl = my_tiles; /* tiles of the lanes up to this one */
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
@@ -1752,7 +1761,18 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			tiles_incl += t;
 	}
 	const uint32_t warp_tiles = __shfl_sync(kFull, tiles_incl, 31);
-	uint32_t base_small = 0, base_big = 0, base_tslot = 0, base_tile = 0;
+	uint32_t base_small = 0, base_big = 0, base_tslot = 0, base_tile = 0, base_raw = 0, base_raw_chunk = 0;
+	/* chunks of the raw jobs of the lanes up to this one */
+	const uint32_t raw_hdr = pl.pre[0] == CMP_PREPROCESS_DIFF ? CMP_HDR_SIZE + 6u : CMP_HDR_SIZE;
+	const uint32_t my_raw_chunks = raw ? ((raw_hdr + 2u * pl.n) / 8u + AIRS_RAW_CHUNK - 1u) / AIRS_RAW_CHUNK : 0u;
+	uint32_t raw_incl = raw ? max(my_raw_chunks, 1u) : 0u;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(kFull, raw_incl, d);
+		if (lane >= (uint32_t)d)
+			raw_incl += t;
+	}
+	const uint32_t warp_raw_chunks = __shfl_sync(kFull, raw_incl, 31);
 	if (m_tiled) { /* do all tile jobs have the same shape?  (airs_tile_kernel deals their tiles frame by frame then) */
 		const uint32_t fr = tiled ? job.n_frames : 0u;
 		const uint32_t tmin = __reduce_min_sync(kFull, tiled ? frame_tiles : 0xFFFFFFFFu), tmax = __reduce_max_sync(kFull, tiled ? frame_tiles : 0u);
@@ -1771,6 +1791,12 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			base_small = atomicAdd(&b.ticket[3], (uint32_t)__popc(m_small));
 		if (m_big)
 			base_big = atomicAdd(&b.ticket[2], (uint32_t)__popc(m_big));
+		if (m_raw) { /* slots and chunks from ONE counter: the order of the records is the order of their chunks */
+			const unsigned long long got = atomicAdd(reinterpret_cast<unsigned long long *>(b.ticket + AIRS_TICKET_RAW),
+								 ((unsigned long long)__popc(m_raw) << 40) | warp_raw_chunks);
+			base_raw = (uint32_t)(got >> 40);
+			base_raw_chunk = (uint32_t)(got & ((1ull << 40) - 1u));
+		}
 		if (m_tiled) { /* slots and tiles from ONE counter: the order of the slots is the order of their tiles */
 			const unsigned long long got = atomicAdd(reinterpret_cast<unsigned long long *>(b.ticket + 10),
 								 ((unsigned long long)__popc(m_tiled) << 40) | warp_tiles);
@@ -1782,6 +1808,8 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	base_big = __shfl_sync(kFull, base_big, 0);
 	base_tslot = __shfl_sync(kFull, base_tslot, 0);
 	base_tile = __shfl_sync(kFull, base_tile, 0);
+	base_raw = __shfl_sync(kFull, base_raw, 0);
+	base_raw_chunk = __shfl_sync(kFull, base_raw_chunk, 0);
 	if (have) {
 		FastJob *recs = reinterpret_cast<FastJob *>(b.fast_jobs);
 		if (!listed) {
@@ -1794,6 +1822,11 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			FastJob fj;
 			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, 0u, 0u);
 			recs[slot] = fj;
+		} else if (raw) { /* (FastJob records in the front of the tile extensions) */
+			FastJob fj;
+			const uint32_t chunks = max(my_raw_chunks, 1u);
+			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, base_raw_chunk + raw_incl - chunks, chunks);
+			reinterpret_cast<FastJob *>(b.tile_ext)[base_raw + (uint32_t)__popc(m_raw & below)] = fj;
 		} else if (tiled) { /* the records of the long jobs fill the array from its end */
 			const uint32_t slot = base_tslot + (uint32_t)__popc(m_tiled & below);
 			FastJob fj;
