@@ -243,7 +243,7 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
 		CU(airs_launch_tile(&l, stream));
 #ifndef AIRS_SKIP_RAW /* (development: the cost of the launch) */
-		CU(airs_launch_raw(&l, (unsigned int)resident / 2u, stream)); /* (a few CTAs of 256 threads per SM) */
+		CU(airs_launch_raw(&l, (unsigned int)resident / AIRS_CTAS_PER_SM * 8u, stream)); /* (eight CTAs of 256 threads per SM: enough loads in flight) */
 #endif
 		g_launches += 4;
 	}
@@ -350,10 +350,7 @@ static int launch_batch(const struct airs_batch *b, struct airs_ctx_state *ctx_i
 			c.base = slice->base;
 		}
 		CU(airs_launch_concat_slots(&c, stream));
-#ifndef AIRS_SKIP_RAW /* (development: the cost of the launch) */
-		CU(airs_launch_raw(&l, (unsigned int)resident / 2u, stream)); /* (a few CTAs of 256 threads per SM) */
-#endif
-		g_launches += 4;
+		g_launches += 3;
 
 		AirsLaunch l1 = l;
 		l1.jobs = c.slot_jobs;
