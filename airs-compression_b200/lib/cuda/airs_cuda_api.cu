@@ -853,6 +853,29 @@ extern "C" int airs_cuda_compress_resume(const struct airs_job *job, struct airs
 	b.n_jobs = 1;
 	b.n_results = 1;
 	b.layout = AIRS_LAYOUT_SLOTS;
+	/* A context without secondary passes and without fallback: every call is a primary pass of a fresh context
+	 * (ref cmp.c:228-262) - the frame goes through the batched path, where a long frame is spread over the whole
+	 * device (airs_tile_kernel) instead of being encoded by the one CTA that continues a caller's context.  One
+	 * identifier is drawn (the caller puts the real one into the stream); sequence number 0 -> 1.  A frame that
+	 * fails here is done again below, where the context's state is followed step by step. */
+	if (job->params.secondary_iterations == 0 && !job->params.uncompressed_fallback_enabled && state->valid) {
+		rc = launch_batch(&b, nullptr, s);
+		if (rc)
+			return rc;
+		CU(cudaMemcpyAsync(result, c.results.p, 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));
+		if (!airs_failed(*result)) {
+			const uint32_t stride = j.dtype == AIRS_DTYPE_I16_IN_I32 ? 4u : 2u;
+			state->counter = 1;
+			state->seq = 1;
+			state->model_size = j.src_size / stride * 2u;
+			if (dst && !dst_dev) {
+				CU(cudaMemcpyAsync(dst, (uint8_t *)c.dst.p + mis, *result, cudaMemcpyDeviceToHost, s));
+				CU(cudaStreamSynchronize(s));
+			}
+			return AIRS_OK;
+		}
+	}
 	rc = launch_batch(&b, (struct airs_ctx_state *)c.state.p, s);
 	if (rc)
 		return rc;
