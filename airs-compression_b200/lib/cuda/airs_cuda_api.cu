@@ -213,7 +213,8 @@ extern "C" size_t airs_cuda_batch_scratch_size(uint32_t n_jobs, uint32_t n_resul
 	 * the job table on temporary slots (two-phase CONCAT) */
 	return kScratchHeader + lookback_bytes(n_results) + 128 * (size_t)n_jobs + 8 * (size_t)n_jobs +
 	       4 * (size_t)n_results + 64 + sizeof(struct airs_job) * (size_t)n_jobs + 64 +
-	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 128 * (size_t)n_jobs + 128 + (size_t)AIRS_TILE_RING_BYTES;
+	       airs_concat_scratch_bytes(n_jobs, n_results) + 64 + 128 * (size_t)n_jobs + 128 + (size_t)AIRS_TILE_RING_BYTES +
+	       32 * (size_t)n_jobs + 64; /* (the frames of airs_iwt_kernel) */
 }
 
 extern "C" size_t airs_cuda_concat_tmp_size(uint64_t sum_of_capacities, uint32_t n_results)
@@ -239,6 +240,8 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 			CU(airs_fast_resident_ctas(&fast_ctas));
 			fast_dev = dev;
 		}
+		CU(airs_launch_iwt(&l, stream)); /* (the coefficients the two kernels below code; returns at once without such frames) */
+		g_launches += 2;
 		const unsigned int want = (l.n_jobs + AIRS_FAST_THREADS / 32 - 1) / (AIRS_FAST_THREADS / 32);
 		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
 		CU(airs_launch_tile(&l, stream));
@@ -272,7 +275,9 @@ static void fill_launch(AirsLaunch &l, const struct airs_batch *b, struct airs_c
 	l.result_job = l.small_list + b->n_jobs;
 	{ /* from the end of the scratch memory: tile rings, in front of them the tile extensions, then the fast-job records */
 		const size_t end = airs_cuda_batch_scratch_size(b->n_jobs, b->n_results);
-		const size_t ring = (end - (size_t)AIRS_TILE_RING_BYTES) & ~(size_t)63;
+		const size_t iwt = (end - 32 * (size_t)b->n_jobs) & ~(size_t)63;
+		l.iwt_recs = (uint8_t *)b->scratch + iwt;
+		const size_t ring = (iwt - (size_t)AIRS_TILE_RING_BYTES) & ~(size_t)63;
 		l.tile_ring = (uint64_t *)((uint8_t *)b->scratch + ring);
 		const size_t ext = (ring - 64 * (size_t)b->n_jobs) & ~(size_t)63;
 		l.tile_ext = (uint8_t *)b->scratch + ext;

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(AIRS_FAST_THREADS, AIRS_FAST_CTAS_PER_SM) airs
 		 * fields cmp.c:265-279.  The area is all zero here, a is 0 or 8: plain stores */
 		if (lane == 0) {
 			uint32_t *h = ws.stg + a / 4u;
-			const uint32_t pre = (flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE;
+			const uint32_t pre = (flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : (flags & AIRS_FJ_IWT) ? CMP_PREPROCESS_IWT : CMP_PREPROCESS_NONE;
 			const uint32_t enc = multi ? CMP_ENCODER_GOLOMB_MULTI : CMP_ENCODER_GOLOMB_ZERO;
 			h[0] = (0x8000u | CMP_VERSION_NUMBER) << 16;
 			h[1] = (2u * n) & 0xFFFFFFu;

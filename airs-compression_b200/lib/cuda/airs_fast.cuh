@@ -15,6 +15,8 @@
 #define AIRS_FJ_CHECKSUM    4u
 #define AIRS_FJ_FALLBACK_OK 8u
 #define AIRS_FJ_BE          16u /* samples big-endian in memory (AIRS_DTYPE_BE) */
+#define AIRS_FJ_IWT         32u /* src is the job's work buffer, holding the IWT coefficients airs_iwt_kernel left there;
+				   they are coded like samples without preprocessing, the header says IWT */
 
 /* samples of a tile of airs_tile_kernel */
 #define AIRS_TILE_SAMPLES 1024u /* two units of 512 samples */
@@ -38,6 +40,18 @@ struct alignas(16) FastJob {
 	uint32_t n_tiles;      /* ... and the number of its tiles */
 };
 static_assert(sizeof(FastJob) == 64, "FastJob is read as 16 words");
+
+/* a frame whose wavelet transform (ref preprocess.c:140-221) airs_iwt_kernel computes: tiles of AIRS_IWT_TILE samples,
+ * numbered over all such frames of the batch */
+struct alignas(16) IwtRec {
+	uint64_t src;       /* device address of the samples (16-bit container, host order, 4-byte aligned) */
+	uint64_t work;      /* device address of the work buffer the coefficients go to */
+	uint32_t n;         /* samples */
+	uint32_t tile_base; /* global id of the frame's first tile ... */
+	uint32_t n_tiles;   /* ... and the number of its tiles */
+	uint32_t job;
+};
+static_assert(sizeof(IwtRec) == 32, "IwtRec is read as two 16-byte words");
 
 /* flags2 of a TileExt: the secondary passes of a context whose frames go through airs_tile_kernel */
 #define AIRS_TX_PRE2_DIFF  1u
@@ -76,9 +90,11 @@ __host__ __device__ inline uint32_t airs_fast_magic(uint32_t g)
 
 #ifdef __CUDACC__
 __device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const JobPlan &pl, const uint8_t *src_base,
-					  uint8_t *dst_base, uint32_t job_index, uint32_t tile_base, uint32_t n_tiles)
+					  uint8_t *dst_base, uint32_t job_index, uint32_t tile_base, uint32_t n_tiles,
+					  const uint8_t *iwt_work = nullptr)
 {
-	f.src = (uint64_t)(uintptr_t)(src_base + job.src_offset);
+	/* (iwt_work: the coefficients in the job's work buffer take the place of the samples) */
+	f.src = iwt_work ? (uint64_t)(uintptr_t)iwt_work : (uint64_t)(uintptr_t)(src_base + job.src_offset);
 	f.dst = (uint64_t)(uintptr_t)(dst_base + job.dst_offset);
 	f.identifier = (job.identifier_base + 1u) & 0xFFFFFFFFFFFFull;
 	f.n = pl.n;
@@ -87,7 +103,7 @@ __device__ inline void airs_fill_fast_job(FastJob &f, const airs_job &job, const
 		  (pl.enc[0].type == CMP_ENCODER_GOLOMB_MULTI ? AIRS_FJ_MULTI : 0u) |
 		  ((pl.flags & AIRS_PF_CHECKSUM) ? AIRS_FJ_CHECKSUM : 0u) |
 		  ((pl.flags & AIRS_PF_FALLBACK_OK) ? AIRS_FJ_FALLBACK_OK : 0u) | ((pl.flags & AIRS_PF_BE) ? AIRS_FJ_BE : 0u) |
-		  (pl.enc[0].L << 8);
+		  (iwt_work ? AIRS_FJ_IWT : 0u) | (pl.enc[0].L << 8);
 	f.first_result = job.first_result;
 	f.g = pl.enc[0].g;
 	f.outlier = pl.enc[0].outlier;

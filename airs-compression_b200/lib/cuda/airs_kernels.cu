@@ -1706,8 +1706,15 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	 * identity (the look-back scan needs the frames to start in result order). */
 	const bool listed = b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io;
 	/* what the fast kernels ask of a job */
+	/* Single frames under the wavelet transform: airs_iwt_kernel (all CTAs over the tiles of all such frames) leaves the
+	 * coefficients in the job's work buffer, exactly where the reference keeps them (preprocess.c:337-353), and the warp
+	 * encoders code them like samples without preprocessing - the coarse coefficients are far outside any code word
+	 * table, which the arithmetic code words do not mind.  Not with the uncompressed fallback (the fast kernel would
+	 * store the coefficients raw) and not beyond the frame length whose last levels fit one CTA. */
+	const bool iwt = have && pl.pre[0] == CMP_PREPROCESS_IWT && b.work && job.n_frames == 1 && !(pl.flags & (AIRS_PF_FALLBACK_OK | AIRS_PF_BE)) &&
+			 pl.n <= AIRS_IWT_MAX_SAMPLES && ((uintptr_t)(b.work + job.work_offset) & 15u) == 0;
 	const bool common = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
-			    (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF) &&
+			    (pl.pre[0] == CMP_PREPROCESS_NONE || pl.pre[0] == CMP_PREPROCESS_DIFF || iwt) &&
 			    pl.enc[0].type != CMP_ENCODER_UNCOMPRESSED && job.dtype != AIRS_DTYPE_I16_IN_I32 && b.dst &&
 			    ((uintptr_t)(b.dst + job.dst_offset) & 7u) == 0 && ((uintptr_t)(b.src + job.src_offset) & 15u) == 0 &&
 			    pl.cap_eff >= (CMP_HDR_SIZE + 6u) && pl.enc[0].g <= AIRS_FAST_MAX_G;
@@ -1723,7 +1730,7 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 				   (pl.pre[1] == CMP_PREPROCESS_NONE || pl.pre[1] == CMP_PREPROCESS_DIFF || pl.pre[1] == CMP_PREPROCESS_MODEL));
 	const bool never_fails = !(pl.flags & AIRS_PF_FALLBACK_OK) && !job.params.uncompressed_fallback_enabled &&
 				 (uint64_t)job.dst_capacity >= CMP_HDR_SIZE + 6u + 4u + 6ull * pl.n;
-	const bool frames_tiled = common && job.n_frames > 1u && b.n_jobs < b.tile_below_jobs && secondary_ok && !pl.model_err && never_fails &&
+	const bool frames_tiled = common && !iwt && job.n_frames > 1u && b.n_jobs < b.tile_below_jobs && secondary_ok && !pl.model_err && never_fails &&
 				  pl.n >= 2u * AIRS_TILE_SAMPLES && (pl.n & 7u) == 0 && (job.src_frame_stride & 15u) == 0 &&
 				  (job.dst_frame_stride & 7u) == 0 &&
 				  (!(pl.flags & AIRS_PF_MODEL) || (b.work && ((uintptr_t)(b.work + job.work_offset) & 15u) == 0));
@@ -1731,7 +1738,9 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 	 * give every resident CTA of airs_encode_kernel one, or when that kernel's code word table cannot cover the
 	 * residuals anyway (no preprocessing: the samples themselves are coded; tiny g: long code words) */
 	const bool tiled = frames_tiled ||
-			   (quick && !small && (b.n_jobs < b.tile_below_jobs || pl.pre[0] == CMP_PREPROCESS_NONE || pl.enc[0].g < 4u));
+			   (quick && !small && (b.n_jobs < b.tile_below_jobs || pl.pre[0] == CMP_PREPROCESS_NONE || pl.enc[0].g < 4u || iwt));
+	const bool iwt_job = iwt && (small || tiled);
+	const uint32_t my_iwt_tiles = iwt_job ? (pl.n + AIRS_IWT_TILE - 1u) / AIRS_IWT_TILE : 0u;
 	/* Single frames under the UNCOMPRESSED encoder whose slot holds the stream: a copy with a byte swap, airs_raw_kernel */
 	const bool raw = have && listed && (pl.flags & AIRS_PF_VALID) && !pl.frame_err && !pl.orig_err && !pl.pre_err[0] &&
 			 !(pl.flags & AIRS_PF_MODEL) && job.n_frames == 1 && pl.enc[0].type == CMP_ENCODER_UNCOMPRESSED &&
@@ -1773,6 +1782,24 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			raw_incl += t;
 	}
 	const uint32_t warp_raw_chunks = __shfl_sync(kFull, raw_incl, 31);
+	const uint32_t m_iwt = __ballot_sync(kFull, iwt_job);
+	uint32_t iwt_incl = my_iwt_tiles, base_iwt = 0, base_iwt_tile = 0;
+	if (m_iwt) {
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(kFull, iwt_incl, d);
+			if (lane >= (uint32_t)d)
+				iwt_incl += t;
+		}
+		if (lane == 31) { /* records and tiles from ONE counter: the order of the records is the order of their tiles */
+			const unsigned long long got = atomicAdd(reinterpret_cast<unsigned long long *>(b.ticket + AIRS_TICKET_IWT),
+								 ((unsigned long long)__popc(m_iwt) << 40) | iwt_incl);
+			base_iwt = (uint32_t)(got >> 40);
+			base_iwt_tile = (uint32_t)(got & ((1ull << 40) - 1u));
+		}
+		base_iwt = __shfl_sync(kFull, base_iwt, 31);
+		base_iwt_tile = __shfl_sync(kFull, base_iwt_tile, 31);
+	}
 	if (m_tiled) { /* do all tile jobs have the same shape?  (airs_tile_kernel deals their tiles frame by frame then) */
 		const uint32_t fr = tiled ? job.n_frames : 0u;
 		const uint32_t tmin = __reduce_min_sync(kFull, tiled ? frame_tiles : 0xFFFFFFFFu), tmax = __reduce_max_sync(kFull, tiled ? frame_tiles : 0u);
@@ -1820,7 +1847,7 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 			const uint32_t slot = base_small + (uint32_t)__popc(m_small & below);
 			b.small_list[slot] = j;
 			FastJob fj;
-			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, 0u, 0u);
+			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, 0u, 0u, iwt ? b.work + job.work_offset : nullptr);
 			recs[slot] = fj;
 		} else if (raw) { /* (FastJob records in the front of the tile extensions) */
 			FastJob fj;
@@ -1830,13 +1857,24 @@ __global__ void __launch_bounds__(128) airs_plan_kernel(AirsLaunch b)
 		} else if (tiled) { /* the records of the long jobs fill the array from its end */
 			const uint32_t slot = base_tslot + (uint32_t)__popc(m_tiled & below);
 			FastJob fj;
-			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, base_tile + tiles_incl - my_tiles, my_tiles);
+			airs_fill_fast_job(fj, job, pl, b.src, b.dst, j, base_tile + tiles_incl - my_tiles, my_tiles,
+					   iwt ? b.work + job.work_offset : nullptr);
 			recs[b.n_jobs - 1u - slot] = fj;
 			TileExt tx;
 			airs_fill_tile_ext(tx, job, pl, b.work, frame_tiles);
 			reinterpret_cast<TileExt *>(b.tile_ext)[b.n_jobs - 1u - slot] = tx;
 		} else {
 			b.big_list[base_big + (uint32_t)__popc(m_big & below)] = j;
+		}
+		if (iwt_job) {
+			IwtRec ir;
+			ir.src = (uint64_t)(uintptr_t)(b.src + job.src_offset);
+			ir.work = (uint64_t)(uintptr_t)(b.work + job.work_offset);
+			ir.n = pl.n;
+			ir.tile_base = base_iwt_tile + iwt_incl - my_iwt_tiles;
+			ir.n_tiles = my_iwt_tiles;
+			ir.job = j;
+			reinterpret_cast<IwtRec *>(b.iwt_recs)[base_iwt + (uint32_t)__popc(m_iwt & below)] = ir;
 		}
 		/* the plan of a short job is read again only by the checksum kernels and by airs_encode_kernel when the job is
 		 * handed back to it: a million 4 KiB chunks without either save a third of this kernel's memory traffic */

@@ -33,6 +33,9 @@ struct JobPlan;
 #define AIRS_TICKET_INVALID 6u
 #define AIRS_TICKET_RAW 8u /* 64-bit: jobs of airs_raw_kernel << 40 | their chunks */
 #define AIRS_RAW_CHUNK 4096u /* 8-byte groups of stream per chunk */
+#define AIRS_TICKET_IWT 14u /* 64-bit: jobs whose transform airs_iwt_kernel computes << 40 | their tiles */
+#define AIRS_IWT_TILE 8192u /* samples of a tile of airs_iwt_kernel */
+#define AIRS_IWT_MAX_SAMPLES (1u << 21) /* longest frame of that kernel: what is left behind its eight levels fits one CTA */
 #define AIRS_TICKET_TILE_SHAPE 20u /* four words: ~min and max of the tile jobs' tiles per frame, ~min and max of their frames */
 #define AIRS_TILE_RING 65536u /* tile descriptors kept (a power of two, far more than tiles are in flight) */
 /* 64-bit words of the rings: tile descriptors, tile tails, blocks of 32 tiles, blocks of 1024 tiles */
@@ -57,6 +60,8 @@ struct AirsLaunch {
 				  the front in the order of small_list, the long jobs of airs_tile_kernel from the back */
 	void *tile_ext;        /* n_jobs 64-byte records: TileExt of the tile jobs from the back (like their FastJob records), FastJob
 				  records of the jobs of airs_raw_kernel from the front */
+	void *iwt_recs;        /* n_jobs 32-byte records (IwtRec, airs_fast.cuh): the frames airs_iwt_kernel transforms into their
+				  work buffers in front of the warp encoders */
 	uint64_t *tile_ring;   /* AIRS_TILE_RING_BYTES, zeroed before the launch: tile descriptors, tile tails, block sums */
 	uint32_t *result_job;  /* n_results entries: the job a frame belongs to (airs_checksum_kernel) */
 	struct JobPlan *plans; /* n_jobs plans written by airs_plan_kernel */
@@ -109,6 +114,7 @@ cudaError_t airs_encode_ctas_per_sm(int *out);
 cudaError_t airs_launch_fast(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_fast_resident_ctas(int *out);
 cudaError_t airs_launch_tile(const struct AirsLaunch *b, cudaStream_t stream);
+cudaError_t airs_launch_iwt(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_raw(const struct AirsLaunch *b, unsigned int grid, cudaStream_t stream);
 cudaError_t airs_launch_checksum(const struct AirsLaunch *b, cudaStream_t stream);
 cudaError_t airs_launch_hash(const struct AirsLaunch *b, uint64_t *hashes, cudaStream_t stream);

@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(AIRS_TILE_THREADS, AIRS_TILE_CTAS_PER_SM) airs
 				const uint32_t g = sec ? AIRS_REC(24) : AIRS_REC(10), outlier = sec ? AIRS_REC(25) : AIRS_REC(11);
 				const bool multi = sec ? (flags2 & AIRS_TX_MULTI2) != 0u : (flags & AIRS_FJ_MULTI) != 0u;
 				const uint32_t pre = sec ? ((flags2 & AIRS_TX_PRE2_MODEL) ? CMP_PREPROCESS_MODEL : (flags2 & AIRS_TX_PRE2_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE)
-							 : ((flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : CMP_PREPROCESS_NONE);
+							 : ((flags & AIRS_FJ_PRE_DIFF) ? CMP_PREPROCESS_DIFF : (flags & AIRS_FJ_IWT) ? CMP_PREPROCESS_IWT : CMP_PREPROCESS_NONE);
 				const uint32_t rate = pre == CMP_PREPROCESS_MODEL ? (flags2 >> 16) & 31u : 0u;
 				const bool frames = AIRS_REC(22) > 1u; /* a context of several frames */
 				if (size <= cap_eff) {

@@ -539,3 +539,52 @@ def test_thread_changes_device(gpu, oracle, pkg):
             jobgen.compare(want, got, js, "host batch on device %d" % dev, check_tail=False)
     finally:
         torch.cuda.set_device(cur)
+
+
+IWT_SIZES = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 255, 256, 257, 511, 513, 1000, 4095, 7679, 7680, 7681, 8191, 8192, 8193,
+             8703, 8704, 8705, 9216, 16384, 16389, 24576 + 3, 32768, 32769, 65536 + 255, 100003]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_iwt_transform_kernel(gpu, oracle, pkg, seed):
+    """Single IWT frames take airs_iwt_kernel (tiles of 8192 samples with halos over all CTAs, levels 1-3 in registers,
+    4-8 in shared memory, the rest by one CTA per frame) in front of the warp encoders: sizes around the tile, halo and
+    level boundaries, both 16-bit containers, every data style (full-range samples wrap in every level), slots that
+    are too small.  Streams, results AND the coefficients left in the work buffers (ref preprocess.c:337-353) equal
+    the oracle's."""
+    abi = pkg.abi
+    rng = np.random.default_rng(900 + seed)
+
+    def params(r):
+        enc = int(r.integers(1, 3))
+        return abi.make_params(primary_preprocessing=abi.PRE_IWT, primary_encoder_type=enc,
+                               primary_encoder_param=int(r.choice([1, 3, 16, 60, 1000])),
+                               primary_encoder_outlier=int(r.choice([5, 60, 300])) if enc == 2 else 0,
+                               checksum_enabled=int(r.integers(0, 2)))
+    js = jobgen.build_jobs(rng, 90, sizes=IWT_SIZES, max_frames=1, dtypes=(0, 2), params_fn=params,
+                           capacity_modes=["bound", "bound", "bound", "big", "tight"])
+    jobs = js["jobs"]
+    jobs["work_size"] = 2 * (jobs["src_size"] // 2)   # (build_jobs also hands out work buffers that are too small)
+    jobs["work_offset"] = np.concatenate(([0], np.cumsum((jobs["work_size"].astype(np.int64) + 15) // 16 * 16)[:-1]))
+    js["work_size"] = int(jobs["work_offset"][-1]) + int(jobs["work_size"][-1]) + 64
+    want = jobgen.run_cpu(oracle, js, threads=4)
+    got = gpu.run_jobs_device(js)
+    jobgen.compare(want, got, js, "iwt-kernel")
+    for j in range(len(jobs)):
+        o, n2 = int(jobs[j]["work_offset"]), int(jobs[j]["src_size"])
+        assert np.array_equal(want[4][o:o + n2], got[4][o:o + n2]), f"job {j}: coefficients differ (n={n2 // 2})"
+
+
+def test_iwt_longest_frames_of_the_transform_kernel(gpu, oracle, pkg):
+    """2 Mi samples is the longest frame airs_iwt_kernel takes (8192 coefficients left for its last levels); a longer one
+    stays with the CTA-per-job kernel."""
+    abi = pkg.abi
+    for n in (1 << 21, (1 << 21) + 8):
+        p = abi.make_params(primary_preprocessing=abi.PRE_IWT, primary_encoder_type=1, primary_encoder_param=16)
+        jobs, dsz, wsz = pkg.workloads.uniform_jobs(2, n, 1, abi.compress_bound(2 * n), model=True)
+        jobs["params"] = p
+        x = pkg.synth.chunks(11, 0, 2, n)
+        js = dict(src=x.view(np.uint8).reshape(-1), jobs=jobs, dst_size=dsz, work_size=wsz, n_results=2, layout=0)
+        want, got = jobgen.run_cpu(oracle, js, threads=2), gpu.run_jobs_device(js)
+        jobgen.compare(want, got, js, "iwt-longest")
+        assert np.array_equal(want[4][:4 * n], got[4][:4 * n])

@@ -127,10 +127,11 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         return rows
     def p_iwtunc(p, idx):
         p_plain(p, idx); p["primary_preprocessing"] = abi.PRE_IWT; p["primary_encoder_type"] = 0
-    if case in ("iwt", "none", "unc", "iwtunc"):
-        n_chunks, n = 4096, 1 << 16
+    if case in ("iwt", "none", "unc", "iwtunc", "iwt4", "iwt32k", "none4"):
+        n_chunks, n = {"iwt4": (512, 1 << 20), "none4": (512, 1 << 20), "iwt32k": (1 << 14, 1 << 15)}.get(case, (4096, 1 << 16))
         data = synth.chunks_torch(1, 0, n_chunks, n, device=dev)
-        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc, "iwtunc": p_iwtunc}[case], model=(case in ("iwt", "iwtunc")))
+        jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc, "iwtunc": p_iwtunc, "iwt4": p_iwt, "iwt32k": p_iwt, "none4": p_none}[case],
+                                           model=(case in ("iwt", "iwtunc", "iwt4", "iwt32k")))
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
     if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k", "c4b_esc1", "c4b_esc8", "c256", "c4cs", "c4bcs", "c32kcs"):
         n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
