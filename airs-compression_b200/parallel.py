@@ -24,22 +24,34 @@ def _counts(n, device, group):
     return [int(c) for c in out.tolist()]
 
 
-def _gather_ragged(part, group):
-    """Every rank's 1-D tensor laid out back to back in rank order in ONE preallocated buffer: each part is
-    broadcast from its owner straight into its final place (no padding to the longest part, no list of
-    temporaries, no concatenation afterwards).  Over NCCL a broadcast runs at NVLink / NVSwitch speed."""
+def _gather_ragged(part, group, out=None):
+    """Every rank's 1-D tensor laid out back to back in rank order in ONE preallocated buffer: every rank sends its
+    part to every peer and receives every peer's part straight into its final place, all transfers of a rank in one
+    group (ncclSend / ncclRecv between ncclGroupStart / End: they run at the same time, so a rank's NVLink ports
+    are busy in both directions - no padding to the longest part, no list of temporaries, no concatenation
+    afterwards, no serial chain of broadcasts).  `out`: a buffer to reuse (at least the gathered size)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     counts = _counts(part.numel(), part.device, group)
     offsets = [0]
     for c in counts[:-1]:
         offsets.append(offsets[-1] + c)
-    out = torch.empty(sum(counts), dtype=part.dtype, device=part.device)
+    total = sum(counts)
+    if out is None or out.numel() < total or out.dtype != part.dtype:
+        out = torch.empty(total, dtype=part.dtype, device=part.device)
+    out = out[:total]
     out[offsets[rank]:offsets[rank] + counts[rank]].copy_(part)
-    for r in range(world):
-        if counts[r]:
-            src = dist.get_global_rank(group, r) if group is not None else r
-            dist.broadcast(out[offsets[r]:offsets[r] + counts[r]], src=src, group=group)
+    ops = []
+    for step in range(1, world):  # (peers in a rotated order: no rank is everybody's first target)
+        to, frm = (rank + step) % world, (rank - step) % world
+        if counts[rank]:
+            ops.append(dist.P2POp(dist.isend, part, dist.get_global_rank(group, to) if group is not None else to, group))
+        if counts[frm]:
+            ops.append(dist.P2POp(dist.irecv, out[offsets[frm]:offsets[frm] + counts[frm]],
+                                  dist.get_global_rank(group, frm) if group is not None else frm, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     return out, counts, offsets
 
 
@@ -49,10 +61,10 @@ def allgather_sizes(sizes, group=None):
     return out, counts
 
 
-def allgather_streams(stream, group=None):
+def allgather_streams(stream, group=None, out=None):
     """Variable-length byte streams of all ranks laid out back to back in rank order.
 
     Returns (gathered uint8 tensor, byte offset of every rank's part).  NCCL moves the bytes over
     NVLink; with gloo (CPU tensors) the same code is what the world_size-2 tests run."""
-    out, _, offsets = _gather_ragged(stream, group)
+    out, _, offsets = _gather_ragged(stream, group, out)
     return out, offsets

@@ -367,12 +367,16 @@ def main():
             own_hashes = cb.hash_streams()
             torch.cuda.synchronize(device)
             total = int(cb.out_offsets[-1].item())
+            # (an untimed first gather: NCCL sets up its point-to-point channels on first use; the buffer is reused)
+            _, _ = pkg.parallel.allgather_sizes(cb.results)
+            streams_all, _ = pkg.parallel.allgather_streams(cb.dst[:total])
+            torch.cuda.synchronize(device)
             barrier()
             stream = torch.cuda.current_stream(device)
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(stream)
             sizes_all, counts = pkg.parallel.allgather_sizes(cb.results)
-            streams_all, offs = pkg.parallel.allgather_streams(cb.dst[:total])
+            streams_all, offs = pkg.parallel.allgather_streams(cb.dst[:total], out=streams_all)
             g1.record(stream)
             barrier()
             tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
@@ -389,7 +393,8 @@ def main():
             gather = {"contexts_or_chunks_per_rank": g_units, "frames": int(sizes_all.numel()),
                       "gathered_bytes": int(streams_all.numel()), "ms": float(tg[0]),
                       "gbs": streams_all.numel() / (float(tg[0]) * 1e-3) / 1e9, "gathered_bytes_match_rank_hashes": gathered_ok,
-                      "what": "CONCAT layout per rank, then sizes and streams broadcast into one buffer in rank order (NCCL), "
+                      "what": "CONCAT layout per rank, then sizes and streams sent by every rank to every peer into one buffer in rank order "
+                              "(grouped ncclSend / ncclRecv), second of two gathers timed, "
                               "max over ranks; every gathered stream re-hashed and compared with its rank's hash"}
             del cb, streams_all
         except Exception as exc:  # the metric line must survive a failing epilogue
