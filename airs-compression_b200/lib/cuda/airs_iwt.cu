@@ -11,8 +11,9 @@
  *   airs_iwt_kernel:      every CTA takes a run of consecutive tiles, each with a halo of 512 samples on either side
  *                         (recomputed, never exchanged: 510 positions is as far as eight levels look).  Levels 1-3
  *                         run in registers - a lane holds 8 consecutive samples, neighbours by shuffle - and give seven
- *                         of eight coefficients; levels 4-8 act on the approximations at every 8th position, in shared
- *                         memory; the tile's coefficients leave as 16-byte stores to the work buffer.
+ *                         of eight coefficients; levels 4-6 run the same way on the approximations at every 8th
+ *                         position (shared memory), levels 7-8 as sweeps over every 64th; the tile's coefficients
+ *                         leave as 16-byte stores to the work buffer.
  *   airs_iwt_tail_kernel: what is left - levels 9 and up act on every 256th coefficient only, at most 8192 of them for the
  *                         frames this path takes (AIRS_IWT_MAX_SAMPLES) - by one CTA per frame, in shared memory at once.
  * The sweeps in shared memory work on 16-bit elements with one pad word behind every 32 words, so that the lanes of
@@ -143,7 +144,7 @@ __device__ __forceinline__ int32_t pack_levels(const uint4 v, int32_t i0, int32_
 
 constexpr uint32_t kPackLanes = 28; /* packs a warp finishes per step: lanes 2 .. 29 */
 constexpr uint32_t kRegLevels = 3;  /* levels in registers; the others act on every 8th coefficient, in shared memory */
-constexpr uint32_t kApxWords = kBuf / 16u + kBuf / 512u + 2u;
+constexpr uint32_t kApxWords = kBuf / 16u + kBuf / 512u + 8u; /* (a whole pack behind an incomplete last one) */
 
 __global__ void __launch_bounds__(kThreads) airs_iwt_kernel(AirsLaunch b)
 {
@@ -191,14 +192,22 @@ __global__ void __launch_bounds__(kThreads) airs_iwt_kernel(AirsLaunch b)
 		const int32_t P_t0 = (int32_t)(t0 / 8u), P_t1 = (int32_t)((t1 + 7u) / 8u);
 		const uint4 *src4 = reinterpret_cast<const uint4 *>((uintptr_t)rec.src);
 
-		/* levels 1-3: warps over runs of 28 packs of [P_lo, P_hi), two more packs in front and two behind */
-		for (int32_t c = P_lo + (int32_t)(kPackLanes * warp); c < P_hi; c += (int32_t)(kPackLanes * (kThreads / 32u))) {
+		/* levels 1-3: warps over runs of 28 packs of [P_lo, P_hi), two more packs in front and two behind; the
+		 * samples of a warp's next run travel while it works on one */
+#define AIRS_LOAD_PACK(p_)                                                                                     \
+	(((p_) >= 0 && 8 * (p_) + 8 <= (int32_t)n) ? __ldg(src4 + (p_))                                         \
+	 : ((p_) >= 0 && 8 * (p_) < (int32_t)n)   ? load_partial_pack(reinterpret_cast<const uint16_t *>((uintptr_t)rec.src), 8u * (uint32_t)(p_), n - 8u * (uint32_t)(p_)) \
+						    : make_uint4(0, 0, 0, 0))
+		constexpr int32_t kStep = (int32_t)(kPackLanes * (kThreads / 32u));
+		int32_t c = P_lo + (int32_t)(kPackLanes * warp);
+		uint4 v = make_uint4(0, 0, 0, 0);
+		if (c < P_hi)
+			v = AIRS_LOAD_PACK(c - 2 + (int32_t)lane);
+		for (; c < P_hi; c += kStep) {
 			const int32_t p = c - 2 + (int32_t)lane;
-			uint4 v = make_uint4(0, 0, 0, 0);
-			if (p >= 0 && 8 * p + 8 <= (int32_t)n)
-				v = __ldg(src4 + p);
-			else if (p >= 0 && 8 * p < (int32_t)n)
-				v = load_partial_pack(reinterpret_cast<const uint16_t *>((uintptr_t)rec.src), 8u * (uint32_t)p, n - 8u * (uint32_t)p);
+			uint4 vn = make_uint4(0, 0, 0, 0);
+			if (c + kStep < P_hi)
+				vn = AIRS_LOAD_PACK(p + kStep);
 			const bool edge = c - 2 <= 0 || 8 * (c + 30) + 8 > (int32_t)n; /* (for the whole warp) */
 			uint4 o;
 			const int32_t a3 = edge ? pack_levels<true>(v, 8 * p, (int32_t)n, o) : pack_levels<false>(v, 8 * p, (int32_t)n, o);
@@ -207,10 +216,38 @@ __global__ void __launch_bounds__(kThreads) airs_iwt_kernel(AirsLaunch b)
 				if (p >= P_t0 && p < P_t1)
 					outb[p - P_t0] = o;
 			}
+			v = vn;
 		}
+#undef AIRS_LOAD_PACK
 		__syncthreads();
-		/* levels 4-8 on the approximations: to y[k] = w[8 k] they are the levels 1-5 */
-		for (uint32_t l = kRegLevels, s = 1; l < kLevels && 8u * s < n; l++, s <<= 1)
+		/* levels 4-6 the same way on the approximations: to y[k] = w[8 k] they are the levels 1-3.  At most 144 packs
+		 * of 8: one run per warp, all of them read before any is written back in place */
+		{
+			const int32_t Q_lo = P_lo / 8, Q_hi = (P_hi + 7) / 8;
+			const int32_t c2 = Q_lo + (int32_t)(kPackLanes * warp), q = c2 - 2 + (int32_t)lane;
+			static_assert(kBuf / 64u <= kPackLanes * (kThreads / 32u), "one run of packs per warp");
+			uint4 y = make_uint4(0, 0, 0, 0), o = y;
+			int32_t a6 = 0;
+			const bool have = c2 < Q_hi; /* (for the whole warp) */
+			uint32_t *yw = apx + (phys((uint32_t)(8 * q - P_lo)) >> 1);
+			const bool inside = have && q >= Q_lo && q < Q_hi;
+			if (inside) /* (elements behind the region or the frame: never read by a coefficient that counts) */
+				y = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+			if (have) {
+				const bool edge = c2 - 2 <= 0 || 8 * (c2 + 30) + 8 > P_n;
+				a6 = edge ? pack_levels<true>(y, 8 * q, P_n, o) : pack_levels<false>(y, 8 * q, P_n, o);
+			}
+			__syncthreads();
+			if (inside && lane >= 2u && lane < 2u + kPackLanes) {
+				yw[0] = o.x | ((uint32_t)a6 & 0xFFFFu);
+				yw[1] = o.y;
+				yw[2] = o.z;
+				yw[3] = o.w;
+			}
+			__syncthreads();
+		}
+		/* levels 7-8 on every 64th position: sweeps in shared memory */
+		for (uint32_t l = 2u * kRegLevels, s = 8; l < kLevels && 8u * s < n; l++, s <<= 1)
 			level_sweep(hb, s, (uint32_t)P_lo, (uint32_t)P_hi, (uint32_t)P_n);
 		for (uint32_t k = tid; k < (uint32_t)(P_t1 - P_t0); k += kThreads)
 			reinterpret_cast<uint16_t *>(outb)[8u * k] = (uint16_t)hb[phys((uint32_t)(P_t0 - P_lo) + k)];
