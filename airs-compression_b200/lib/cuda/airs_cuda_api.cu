@@ -229,7 +229,9 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 {
 	AirsLaunch l = l_in;
 	unsigned int grid = l.n_jobs < (uint32_t)resident ? l.n_jobs : (unsigned int)resident;
-	l.tile_below_jobs = (uint32_t)resident / 2u;
+	/* (crossover of the two kernels on long frames: the CTA-per-job kernel at n_jobs / resident of its 0.69 against
+	 * 0.17 - 0.2 of the tile kernel) */
+	l.tile_below_jobs = (uint32_t)resident / 3u;
 	CU(airs_launch_plan(&l, stream));
 	g_launches++;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) {

@@ -72,8 +72,14 @@ constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair 
 constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
 constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
 constexpr uint32_t kSmallMaxSamples = 32768; /* longest frame a single warp encodes (airs_small_kernel); measured crossover */
+constexpr uint32_t kCtxFrames = 64;         /* most frames of a run of model_run_fast(): their state must leave the SM a 196 KB carve-out and some L1 */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+#ifdef AIRS_EXP_NO_MODEL_IO
+constexpr bool kExpNoModelIo = true;
+#else
+constexpr bool kExpNoModelIo = false;
+#endif
 
 /* one pass over one frame, written by thread 0 (cheap: copies from the plan) */
 struct Pass {
@@ -121,6 +127,11 @@ struct Shared {
 	CtxState ctx;
 	uint64_t offset;
 	uint32_t ticket;
+	/* context_fast(): where the stream of every frame of the context stands (bits from the start of its 16-byte aligned
+	 * space) and its last, incomplete 16-byte group */
+	uint32_t cx_bit[kCtxFrames];
+	uint32_t cx_abort;
+	alignas(16) uint4 cx_carry[kCtxFrames];
 };
 
 /* byte window of the destination a pass may write, in the 16-byte aligned
@@ -541,7 +552,7 @@ __device__ __forceinline__ uint32_t block_scan(Shared &sh, uint32_t tb, uint32_t
  * same time.  No barrier afterwards: the next staging into a drained area
  * happens behind the next scan barrier. */
 __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, uint32_t buf, uint32_t gw0, uint32_t staged,
-					 uint32_t carry_to)
+					 uint32_t carry_to, uint4 *carry_slot = nullptr)
 {
 	const uint32_t tid = threadIdx.x;
 	const uint32_t nvec = staged >> 7;
@@ -572,7 +583,10 @@ __device__ __forceinline__ void copy_out(Shared &sh, const OutWin &o, uint32_t b
 			stg4[v] = make_uint4(0, 0, 0, 0);
 		}
 	}
-	if (tid == 0 && (nvec || carry_to != buf)) { /* thread 0 drained group 0 itself; group nvec is nobody else's */
+	if (tid == 0 && carry_slot) { /* (context_fast: the group waits in the frame's slot, the area is left all zero) */
+		*carry_slot = stg4[nvec];
+		stg4[nvec] = make_uint4(0, 0, 0, 0);
+	} else if (tid == 0 && (nvec || carry_to != buf)) { /* thread 0 drained group 0 itself; group nvec is nobody else's */
 		const uint4 carry = stg4[nvec];
 		stg4[nvec] = make_uint4(0, 0, 0, 0);
 		uint32_t *dst = stg_of(sh, carry_to);
@@ -1092,7 +1106,11 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 #define AIRS_LOAD_X(pw_, j_) ((need_x && AIRS_SEG_VALID(pw_, j_)) ? (c32 ? ld_stream32(src4 + 2u * ((pw_) + 32u * (j_) + lane), pol_stream) \
 									 : be ? airs_swap16x8(ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream)) \
 									      : ld_stream(src4 + (pw_) + 32u * (j_) + lane, pol_stream)) : zero4)
+#ifdef AIRS_EXP_NO_MODEL_IO /* (timing experiment, wrong streams: the model never travels) */
+#define AIRS_LOAD_M(pw_, j_) zero4
+#else
 #define AIRS_LOAD_M(pw_, j_) ((need_m && AIRS_SEG_VALID(pw_, j_)) ? ld_keep(work4 + (pw_) + 32u * (j_) + lane, pol_keep) : zero4)
+#endif
 	/* lane 0: the sample in front of the warp's first piece (previous warp or tile) */
 #define AIRS_LOAD_PS(pw_) ((diff && lane == 0 && (pw_) != 0 && AIRS_SEG_VALID(pw_, 0)) ? \
 	(c32 ? __ldg(reinterpret_cast<const uint32_t *>(src16) + 8u * (pw_) - 1u) & 0xFFFFu \
@@ -1127,6 +1145,10 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			const uint4 mj = kAheadM ? nm[j] : AIRS_LOAD_M(pw, j);
 			w[j][0] = nx[j].x; w[j][1] = nx[j].y; w[j][2] = nx[j].z; w[j][3] = nx[j].w;
 			m[j][0] = mj.x; m[j][1] = mj.y; m[j][2] = mj.z; m[j][3] = mj.w;
+			if (kExpNoModelIo && use_m) { /* (small residuals of about the real length) */
+				m[j][0] = __vsub2(w[j][0], 0x00050002u); m[j][1] = __vsub2(w[j][1], 0x0001000Bu);
+				m[j][2] = __vsub2(w[j][2], 0x00070003u); m[j][3] = __vsub2(w[j][3], 0x00020009u);
+			}
 		}
 		const uint32_t ps = nps;
 		/* the model words of the next tile come from the L2: requested a whole tile ahead */
@@ -1219,7 +1241,7 @@ __device__ __forceinline__ uint32_t frame_fast(Shared &sh, const OutWin &o, uint
 			/* the scan barrier is behind us: the tile before is completely staged */   \
 			if (pend)                                                                    \
 				copy_out(sh, o, c.buf ^ 1u, pend_gw0, pend_bits, c.buf);             \
-			if (mm) {                                                                    \
+			if (mm && !kExpNoModelIo) {                                                  \
 				_Pragma("unroll") for (int j = 0; j < SEG; j++)                \
 					if (v[j])                                                    \
 						st_keep(work4 + pw + 32u * j + lane, make_uint4(m[j][0], m[j][1], m[j][2], m[j][3]), pol_keep); \
@@ -1507,6 +1529,294 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 		if (!frame_fast_tail_rt(sh, o, a, c, n_full * tp, n_pieces, size_only))
 			c = generic_span(sh, o, a, c, n_full * tp * 8u, n_pieces * 8u, size_only);
 	}
+}
+
+/*
+ * A run of consecutive secondary MODEL passes of a context (ref cmp.c:228-262, 296-312) with the FRAMES IN THE INNER
+ * LOOP: for every tile position (2048 samples) the CTA walks through all frames of the run, so that the model of the
+ * position lives in registers from the first frame to the last (16 samples a thread; read from the work buffer once
+ * and written back once per run) - the frame-by-frame order reads and rewrites the whole model through the L2 once
+ * per frame, and with a context per CTA those are 58 MB in flight that the L2 does not hold (1.54 x the algorithmic
+ * DRAM traffic).  The tiles of a frame are still visited in stream order, `run` visits apart: where its stream stands
+ * and its last incomplete 16-byte group wait in shared memory (cx_bit, cx_carry).  One barrier per visit as in
+ * frame_fast(); the samples of the next visit are in flight while one is encoded.
+ * Frames f0 .. f0 + run - 1 of the job; the first one has sequence number seq0; all carry the context's identifier.
+ * Warps whose residuals are not all in the pair table compute their code words arithmetically.  A stream that leaves
+ * its slot (or comes near the point where the reference's writer gives up) - returns false: streams and model are
+ * half done, the caller starts the context over frame by frame.
+ */
+/* the arithmetic arm of model_run_fast(), behind calls: the code words of the two segments of a thread from their
+ * biased residuals d[0..7] into cw[0..31] (returns the segments' bit counts, packed), and from there into the staging
+ * area */
+__device__ __noinline__ uint32_t run_slow_codes(const EncConst &e, uint32_t *d, uint32_t R, uint32_t *cw)
+{
+	const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
+	uint32_t b01, b23;
+#pragma unroll 1
+	for (uint32_t k = 0; k < 4u * kSegModel; k++)
+		d[k] = __vadd2(d[k], negRb);
+	slow_codes(e, d, 4u * kSegModel, (1u << kSegModel) - 1u, cw, b01, b23);
+	return b01;
+}
+
+__device__ __noinline__ void run_slow_put(const uint32_t *cw, uint32_t *stg, uint32_t pos0, uint32_t pos1)
+{
+	slow_put_codes(cw, stg, pos0);
+	slow_put_codes(cw + 16, stg, pos1);
+}
+
+template <bool SIGNED>
+__device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uint32_t f0, uint32_t run, uint32_t seq0)
+{
+	const JobPlan &pl = sh.plan;
+	const airs_job &jb = sh.job;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	constexpr uint32_t SEG = kSegModel, kTP = kThreads * SEG;
+	const uint32_t n_pos = pl.n / (8u * kTP);
+	const uint8_t *src0 = b.src + jb.src_offset + (uint64_t)f0 * jb.src_frame_stride;
+	uint8_t *dst0 = b.dst + jb.dst_offset + (uint64_t)f0 * jb.dst_frame_stride;
+	uint4 *work4 = reinterpret_cast<uint4 *>(b.work + jb.work_offset);
+	const uint64_t sstride = jb.src_frame_stride, dstride = jb.dst_frame_stride;
+	const uint32_t hdr_len = CMP_HDR_SIZE + 6u, cap = pl.cap_eff;
+	const uint32_t rate = pl.rate, wdp = (rate << 4) | ((16u - rate) << 12);
+	const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(sh.plut);
+	const uint64_t pol_stream = l2_policy_evict_first();
+	const uint4 zero4 = make_uint4(0, 0, 0, 0);
+	const EncConst &e = pl.enc[1];
+
+	for (uint32_t i = tid; i < run; i += kThreads) {
+		const uint32_t a = (uint32_t)((uintptr_t)(dst0 + i * dstride) & 15u);
+		sh.cx_bit[i] = 8u * (a + hdr_len);
+		sh.cx_carry[i] = zero4;
+	}
+	if (tid == 0)
+		sh.cx_abort = 0;
+	if (sh.plut_key[0] != e.type || sh.plut_key[1] != e.g || sh.plut_key[2] != e.outlier)
+		build_pair_lut(sh, e);
+	__syncthreads();
+	const uint32_t R = sh.plut_R;
+	if (R == 0u)
+		return false; /* (nothing touched yet - but the caller does not tell) */
+	const uint32_t Rb = R * 0x00010001u, B1 = (R + 1u) * 0x00010001u, notmask = ~((2u * R - 1u) * 0x00010001u);
+
+	bool ok = true, pend = false;
+	uint32_t it = 0, buf = 0, pend_i = 0, pend_gw0 = 0, pend_bits = 0;
+
+	/* samples of segment j_ of the visit (frame i_ of the run, first piece of the warp pw_) */
+#define AIRS_CX_X(i_, pw_, j_) ld_stream(reinterpret_cast<const uint4 *>(src0 + (i_) * sstride) + (pw_) + 32u * (j_) + lane, pol_stream)
+	uint4 nx[SEG];
+#pragma unroll
+	for (int j = 0; j < SEG; j++)
+		nx[j] = AIRS_CX_X(0u, warp * 32u * SEG, j);
+
+	for (uint32_t t = 0; t < n_pos && ok; t++) {
+		const uint32_t pw = t * kTP + warp * 32u * SEG;
+		uint32_t m[SEG][4];
+#pragma unroll
+		for (int j = 0; j < SEG; j++) {
+			const uint4 mj = work4[pw + 32u * j + lane];
+			m[j][0] = mj.x; m[j][1] = mj.y; m[j][2] = mj.z; m[j][3] = mj.w;
+		}
+		for (uint32_t i = 0; i < run; i++, it++) {
+			uint32_t w[SEG][4];
+#pragma unroll
+			for (int j = 0; j < SEG; j++) {
+				w[j][0] = nx[j].x; w[j][1] = nx[j].y; w[j][2] = nx[j].z; w[j][3] = nx[j].w;
+			}
+			{ /* the next visit: the next frame at this position, or the first frame at the next one */
+				const bool wrap = i + 1u == run;
+				if (!wrap || t + 1u < n_pos) {
+#pragma unroll
+					for (int j = 0; j < SEG; j++)
+						nx[j] = AIRS_CX_X(wrap ? 0u : i + 1u, wrap ? pw + kTP : pw, j);
+				}
+			}
+			uint32_t u[SEG][4], chk = 0;
+#pragma unroll
+			for (int j = 0; j < SEG; j++) {
+				seg_residuals(CMP_PREPROCESS_MODEL, w[j], m[j], 0u, Rb, B1, u[j]);
+				if (rate == 0u) { /* rate 16 keeps the model as it is, rate 0 replaces it by the samples */
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						m[j][k] = w[j][k];
+				} else if (rate < 16u) {
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						m[j][k] = model_update2<SIGNED>(w[j][k], m[j][k], wdp);
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					chk |= u[j][k];
+			}
+			/* the table arm of frame_fast(), or nothing */
+			uint32_t sh_[SEG], sl_[SEG], sn_[SEG], qchk = 0;
+			const bool hit = __all_sync(kFull, (chk & notmask) == 0u);
+#pragma unroll
+			for (int j = 0; j < SEG; j++) {
+				uint32_t pc[4], pl_[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const uint32_t ent = lut_pair(lut_s, hit ? u[j][k] : 0u);
+					pc[k] = ent & ((1u << kLutLenShift) - 1u);
+					pl_[k] = ent >> kLutLenShift;
+				}
+				uint32_t lo = pc[0], hi = 0u, nb = pl_[0];
+#pragma unroll
+				for (int k = 1; k < 4; k++) {
+					hi = __funnelshift_l(lo, hi, pl_[k]);
+					lo = (lo << pl_[k]) | pc[k];
+					nb += pl_[k];
+				}
+				qchk |= nb + 63u; /* bit 7 set: a segment longer than 64 bits */
+				sl_[j] = lo; sh_[j] = hi; sn_[j] = nb;
+			}
+			/* a warp with a residual outside the table or a segment longer than 64 bits: all its code words
+			 * arithmetically, from plain residuals (the arithmetic arm of frame_fast(), for the whole warp) */
+			const bool slow = !(hit && __all_sync(kFull, (qchk & 128u) == 0u));
+			uint32_t cwords[SEG * 16]; /* (local memory, touched by the two calls below only) */
+			uint32_t b01 = sn_[0] | (sn_[1] << 16);
+			if (slow) {
+				uint32_t d[SEG * 4];
+#pragma unroll
+				for (int j = 0; j < SEG; j++)
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						d[4 * j + k] = u[j][k];
+				b01 = run_slow_codes(e, d, R, cwords);
+			}
+			const uint32_t bit = sh.cx_bit[i];
+			const uint32_t gw0 = (bit >> 7) << 2, sbits = bit & 127u;
+			uint32_t pos[4];
+			const uint32_t tile_bits = tile_scan<SEG>(sh, it & 1u, lane, warp, b01, 0u, sbits, pos);
+			/* behind the scan barrier: everything of the visit before is staged; every thread takes the same turns */
+			const uint32_t a = (uint32_t)((uintptr_t)(dst0 + i * dstride) & 15u);
+			if (pend) {
+				uint8_t *pd = dst0 + pend_i * dstride;
+				const uint32_t pa = (uint32_t)((uintptr_t)pd & 15u);
+				OutWin po;
+				po.base = pd - pa;
+				po.lo = pa + hdr_len;
+				po.hi = pa + cap;
+				copy_out(sh, po, buf ^ 1u, pend_gw0, pend_bits, buf ^ 1u, &sh.cx_carry[pend_i]);
+				pend = false;
+			}
+			if (sbits + tile_bits > kStgBits || bit + tile_bits > 8u * (a + cap) || (uint64_t)bit - 8u * a + tile_bits >= pl.trip) {
+				ok = false; /* a tile beyond the staging area, a stream that leaves its slot: the frame-by-frame path */
+#ifdef AIRS_CTX_DEBUG
+				if (tid == 0 && atomicAdd(&b.ticket[41], 1u) == 0u) {
+					b.ticket[42] = t; b.ticket[43] = i; b.ticket[44] = 2u; b.ticket[45] = R; b.ticket[46] = bit; b.ticket[47] = tile_bits;
+				}
+#endif
+				break;
+			}
+			uint32_t *stg = stg_of(sh, buf);
+			if (tid == 0) { /* the frame's incomplete group from its tile before */
+				const uint4 cg = sh.cx_carry[i];
+				atomicOr(stg, cg.x);
+				atomicOr(stg + 1, cg.y);
+				atomicOr(stg + 2, cg.z);
+				atomicOr(stg + 3, cg.w);
+				sh.cx_bit[i] = bit + tile_bits;
+			}
+			if (slow) {
+				run_slow_put(cwords, stg, pos[0], pos[1]);
+			} else {
+#pragma unroll
+				for (int j = 0; j < SEG; j++) {
+					int32_t ne = -(int32_t)pos[j];
+					put_unit(stg, ne, sh_[j], sl_[j], sn_[j]);
+				}
+			}
+			pend = true;
+			pend_i = i;
+			pend_gw0 = gw0;
+			pend_bits = sbits + tile_bits;
+			buf ^= 1u;
+		}
+		if (ok) { /* the model of this position behind the run's last frame (ref cmp.c:304-311) */
+#pragma unroll
+			for (int j = 0; j < SEG; j++)
+				work4[pw + 32u * j + lane] = make_uint4(m[j][0], m[j][1], m[j][2], m[j][3]);
+		}
+	}
+#undef AIRS_CX_X
+	__syncthreads();
+	if (ok && pend) {
+		uint8_t *pd = dst0 + pend_i * dstride;
+		const uint32_t pa = (uint32_t)((uintptr_t)pd & 15u);
+		OutWin po;
+		po.base = pd - pa;
+		po.lo = pa + hdr_len;
+		po.hi = pa + cap;
+		copy_out(sh, po, buf ^ 1u, pend_gw0, pend_bits, buf ^ 1u, &sh.cx_carry[pend_i]);
+	}
+	__syncthreads();
+	/* sizes; a stream that does not fit sends the context to the frame-by-frame path */
+	const uint32_t checksum = (pl.flags & AIRS_PF_CHECKSUM) ? 1u : 0u;
+	if (ok) {
+		for (uint32_t i = tid; i < run; i += kThreads) {
+			const uint32_t a = (uint32_t)((uintptr_t)(dst0 + i * dstride) & 15u);
+			const uint32_t size = ((sh.cx_bit[i] - 8u * a + 7u) >> 3) + 4u * checksum;
+			if (size > cap || size > CMP_HDR_MAX_COMPRESSED_SIZE)
+				sh.cx_abort = 1;
+		}
+	}
+	__syncthreads();
+#ifdef AIRS_CTX_DEBUG
+	if (tid == 0)
+		atomicAdd(&b.ticket[(!ok || sh.cx_abort) ? 48 : 40], 1u);
+#endif
+	if (!ok || sh.cx_abort) {
+		for (uint32_t wd = tid; wd < 2u * (4u + kStgWords); wd += kThreads)
+			(&sh.stg_mem[0][0])[wd] = 0;
+		__syncthreads();
+		return false;
+	}
+	/* last bytes (zero padded, ref bitstream_writer.h:205-227), headers (ref cmp.c:265-279, 329-334), results */
+	for (uint32_t i = tid; i < run; i += kThreads) {
+		uint8_t *fd = dst0 + i * dstride;
+		const uint32_t a = (uint32_t)((uintptr_t)fd & 15u);
+		const uint32_t bit = sh.cx_bit[i], size = ((bit - 8u * a + 7u) >> 3) + 4u * checksum;
+		const uint32_t cg[4] = {sh.cx_carry[i].x, sh.cx_carry[i].y, sh.cx_carry[i].z, sh.cx_carry[i].w};
+		uint8_t *gp = fd - a + (size_t)(bit >> 7) * 16u;
+		const uint32_t nb = ((bit & 127u) + 7u) >> 3;
+#pragma unroll 1
+		for (uint32_t k = 0; k < nb; k++)
+			gp[k] = (uint8_t)((k < 4u ? cg[0] : k < 8u ? cg[1] : k < 12u ? cg[2] : cg[3]) >> (24u - 8u * (k & 3u)));
+		Pass P;
+		P.enc = e;
+		P.pre = CMP_PREPROCESS_MODEL;
+		P.n = pl.n;
+		P.identifier = sh.ctx.identifier;
+		P.seq = seq0 + i;
+		P.checksum = checksum;
+		P.rate = rate;
+#pragma unroll 1
+		for (uint32_t k = 0; k < hdr_len; k++)
+			fd[k] = (uint8_t)header_byte(P, k, size);
+		b.results[jb.first_result + f0 + i] = size;
+	}
+	return true;
+}
+
+/* what model_run_fast() asks of a job (uniform over the CTA) */
+__device__ __forceinline__ bool model_run_ok(const Shared &sh, const AirsLaunch &b)
+{
+	const JobPlan &pl = sh.plan;
+	const airs_job &jb = sh.job;
+	return b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io && b.dst && b.work && b.src && (pl.flags & AIRS_PF_VALID) &&
+	       (pl.flags & AIRS_PF_MODEL) && !(pl.flags & AIRS_PF_BE) && !pl.frame_err && !pl.orig_err && !pl.pre_err[1] &&
+	       !pl.model_err && pl.pre[1] == CMP_PREPROCESS_MODEL && pl.enc[1].type != CMP_ENCODER_UNCOMPRESSED &&
+	       pl.sec_iter >= 2u && jb.dtype != AIRS_DTYPE_I16_IN_I32 && jb.n_frames >= 3u &&
+	       pl.n >= 8u * kThreads * kSegModel && pl.n % (8u * kThreads * kSegModel) == 0 && pl.cap_eff >= CMP_HDR_SIZE + 6u &&
+	       ((uintptr_t)(b.src + jb.src_offset) & 15u) == 0 && (jb.src_frame_stride & 15u) == 0 &&
+	       ((uintptr_t)(b.work + jb.work_offset) & 15u) == 0 && ((uintptr_t)(b.dst + jb.dst_offset) & 7u) == 0 &&
+	       (jb.dst_frame_stride & 7u) == 0 &&
+	       /* no frame can fail or fall back (slots of cmp_compress_bound() bytes: 48 bits a sample, ref cmp.c:59-74): a run
+		* writes the streams of all its frames side by side, and a frame that fails changes the passes - and the streams -
+		* of every frame behind it (ref cmp.c:228-262), in whose slots bytes behind the final stream would then stay */
+	       !(pl.flags & AIRS_PF_FALLBACK_OK) && !jb.params.uncompressed_fallback_enabled &&
+	       (uint64_t)jb.dst_capacity >= CMP_HDR_SIZE + 6u + 4u + 6ull * pl.n;
 }
 
 /* one pass over one frame; returns the stream size or an error (uniform over the CTA).
@@ -1931,6 +2241,9 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 		const bool concat = b.layout == AIRS_LAYOUT_CONCAT;
 		if (tid == 0 && n_frames == 0)
 			sh.ticket = atomicAdd(b.ticket, 1u);
+		/* runs of secondary MODEL passes: all their frames tile position by tile position, the model in registers */
+		const bool runs_ok = model_run_ok(sh, b);
+		bool runs_off = false; /* a run gave up: the context is redone frame by frame */
 		for (uint32_t f = 0; f < n_frames; f++) {
 			if (tid == 0) {
 				/* the next job is drawn while the last frame of this one is encoded: early
@@ -1994,6 +2307,31 @@ __global__ void __launch_bounds__(AIRS_THREADS, AIRS_CTAS_PER_SM) airs_encode_ke
 				if (!airs_failed(r))
 					sh.ctx.seq = (sh.ctx.seq + 1u) & 0xFFu;
 				b.results[first + f] = r;
+			}
+			if (runs_ok && !runs_off && !airs_failed(r) && f + 1u < n_frames) {
+				__syncthreads();
+				const uint32_t seq = sh.ctx.seq;
+				const uint32_t run = (seq >= 1u && seq <= sh.plan.sec_iter) ? min(min(n_frames - (f + 1u), sh.plan.sec_iter - seq + 1u), kCtxFrames) : 0u;
+				if (run >= 2u) {
+					const bool done = (sh.plan.flags & AIRS_PF_SIGNED) ? model_run_fast<true>(sh, b, f + 1u, run, seq)
+											    : model_run_fast<false>(sh, b, f + 1u, run, seq);
+					__syncthreads();
+					if (done) {
+						f += run;
+						if (tid == 0) {
+							sh.ctx.seq = (seq + run) & 0xFFu;
+							if (f + 1u == n_frames) /* (the run ended the job: its last frame did not draw the next one) */
+								sh.ticket = atomicAdd(b.ticket, 1u);
+						}
+					} else { /* from the first frame again: its primary pass sets the model anew */
+						runs_off = true;
+						if (tid == 0) {
+							sh.ctx.counter = sh.job.identifier_base;
+							ctx_reset(sh.ctx);
+						}
+						f = 0xFFFFFFFFu;
+					}
+				}
 			}
 		}
 		if (tid == 0 && b.ctx_io) {

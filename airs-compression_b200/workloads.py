@@ -38,11 +38,12 @@ def _pack(data, jobs, dsz, wsz, n, nf, desc, model=False):
                 n_samples_total=units * nf * n, model_bytes=(2 * 2 * n * units if model else 0))
 
 
-def config2(units, first_unit=0, device=None, rate=8, g2=8, checksum=0, bound_slots=False):
+def config2(units, first_unit=0, device=None, rate=8, g2=8, checksum=0, bound_slots=True):
     """Config 2 batched: `units` independent contexts x 256 frames x 64 KiB, DIFF+GOLOMB_ZERO g16 primary pass,
-    MODEL+GOLOMB_ZERO secondary passes with model update.  Slots of 2 n + 64 bytes, or (bound_slots) of
-    cmp_compress_bound() bytes, in which no frame can fail - what lets a batch of few contexts go through the
-    tile kernel."""
+    MODEL+GOLOMB_ZERO secondary passes with model update.  Slots of cmp_compress_bound() bytes - the destination size
+    the reference's API names (cmp.h: cmp_compress_bound), in which no frame can fail: what lets the runs of
+    secondary passes go through model_run_fast() and a batch of few contexts through the tile kernel - or
+    (bound_slots=False) of 2 n + 64 bytes (round 1's layout: frame by frame)."""
     n, nf = FRAME_SAMPLES, FRAMES
     jobs, dsz, wsz = uniform_jobs(units, n, nf, abi.compress_bound(2 * n) if bound_slots else 2 * n + 64, first_unit, model=True)
     jobs["params"] = abi.make_params(primary_preprocessing=abi.PRE_DIFF, primary_encoder_type=abi.ENC_GOLOMB_ZERO,
@@ -54,8 +55,9 @@ def config2(units, first_unit=0, device=None, rate=8, g2=8, checksum=0, bound_sl
     else:
         data = synth.frames_torch(1, first_unit, units, nf, n, device=device)
     desc = "config2%s: %d context%s x %d frames x 64 KiB u16, DIFF+GOLOMB_ZERO g16 -> MODEL+GOLOMB_ZERO g%d, " \
-           "255 secondary iterations, model_rate %d%s" % (" batched" if units > 1 else " as stated", units, "s" if units > 1 else "",
-                                                           nf, g2, rate, ", checksum" if checksum else "")
+           "255 secondary iterations, model_rate %d%s, slots of %s bytes" % (
+               " batched" if units > 1 else " as stated", units, "s" if units > 1 else "", nf, g2, rate,
+               ", checksum" if checksum else "", "cmp_compress_bound()" if bound_slots else "2 n + 64")
     return _pack(data, jobs, dsz, wsz, n, nf, desc, model=True)
 
 

@@ -42,6 +42,8 @@ def time_batch(name, data, jobs, dst_size, work_size, n_results, steps=5, warmup
         a.record(); db.run(); b.record()
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in evs)
+    if os.environ.get("AIRS_PROBE_DEBUG"):  # development builds leave counters in the header of the scratch memory
+        print("scratch words 40-48:", db.scratch[:512].cpu().numpy().view(np.uint32)[40:49].tolist())
     res = db.results.cpu().numpy().view(np.uint32)
     bad = int((res > 0xFFFFFF80).sum())
     out_bytes = int(res[res <= 0xFFFFFF80].astype(np.int64).sum())
@@ -148,10 +150,10 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         data = synth.frames_torch(1, 0, R, F, n, device=dev)
         jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model, model=True)
         return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
-    if case in ("c2", "c2one", "c2cs"):
-        R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "0")) or pkg.load_library().airs_cuda_concurrent_jobs()) if case in ("c2", "c2cs") else 1, 256, 32768
+    if case in ("c2", "c2one", "c2cs", "c2small"):   # c2small: slots of 2 n + 64 bytes (frame by frame), else cmp_compress_bound()
+        R, F, n = (int(os.environ.get("AIRS_C2_CONTEXTS", "0")) or pkg.load_library().airs_cuda_concurrent_jobs()) if case != "c2one" else 1, 256, 32768
         print("c2 contexts:", R)
         data = synth.frames_torch(1, 0, R, F, n, device=dev)
-        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model_cs if case == "c2cs" else p_model, cap=2 * n + 64, model=True)
+        jobs, dsz, wsz = make_uniform_jobs(R, n, F, p_model_cs if case == "c2cs" else p_model, cap=(2 * n + 64) if case == "c2small" else None, model=True)
         return time_batch(case, data, jobs, dsz, wsz, R * F, steps, warmup)
     raise SystemExit("unknown case " + case)
