@@ -1601,6 +1601,7 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 
 	bool ok = true, pend = false;
 	uint32_t it = 0, buf = 0, pend_i = 0, pend_gw0 = 0, pend_bits = 0;
+	uint8_t *pend_d = dst0;
 
 	/* samples of segment j_ of the visit (frame i_ of the run, first piece of the warp pw_) */
 #define AIRS_CX_X(i_, pw_, j_) ld_stream(reinterpret_cast<const uint4 *>(src0 + (i_) * sstride) + (pw_) + 32u * (j_) + lane, pol_stream)
@@ -1617,6 +1618,8 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 			const uint4 mj = work4[pw + 32u * j + lane];
 			m[j][0] = mj.x; m[j][1] = mj.y; m[j][2] = mj.z; m[j][3] = mj.w;
 		}
+		uint8_t *fd = dst0;        /* slot of the visit's frame */
+		const uint8_t *xs = src0;  /* ... and its samples */
 		for (uint32_t i = 0; i < run; i++, it++) {
 			uint32_t w[SEG][4];
 #pragma unroll
@@ -1626,49 +1629,51 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 			{ /* the next visit: the next frame at this position, or the first frame at the next one */
 				const bool wrap = i + 1u == run;
 				if (!wrap || t + 1u < n_pos) {
+					const uint4 *nx4 = reinterpret_cast<const uint4 *>(wrap ? src0 : xs + sstride) + (wrap ? pw + kTP : pw) + lane;
 #pragma unroll
 					for (int j = 0; j < SEG; j++)
-						nx[j] = AIRS_CX_X(wrap ? 0u : i + 1u, wrap ? pw + kTP : pw, j);
+						nx[j] = ld_stream(nx4 + 32u * j, pol_stream);
 				}
 			}
 			uint32_t u[SEG][4], chk = 0;
 #pragma unroll
 			for (int j = 0; j < SEG; j++) {
 				seg_residuals(CMP_PREPROCESS_MODEL, w[j], m[j], 0u, Rb, B1, u[j]);
-				if (rate == 0u) { /* rate 16 keeps the model as it is, rate 0 replaces it by the samples */
 #pragma unroll
-					for (int k = 0; k < 4; k++)
-						m[j][k] = w[j][k];
-				} else if (rate < 16u) {
-#pragma unroll
-					for (int k = 0; k < 4; k++)
-						m[j][k] = model_update2<SIGNED>(w[j][k], m[j][k], wdp);
-				}
+				for (int k = 0; k < 4; k++) /* (rates 1 .. 15: model_run_ok()) */
+					m[j][k] = model_update2<SIGNED>(w[j][k], m[j][k], wdp);
 #pragma unroll
 				for (int k = 0; k < 4; k++)
 					chk |= u[j][k];
 			}
 			/* the table arm of frame_fast(), or nothing */
-			uint32_t sh_[SEG], sl_[SEG], sn_[SEG], qchk = 0;
+			uint32_t sh_[SEG], sl_[SEG], sn_[SEG], qchk = 128u;
 			const bool hit = __all_sync(kFull, (chk & notmask) == 0u);
+			if (hit) {
+				qchk = 0;
 #pragma unroll
-			for (int j = 0; j < SEG; j++) {
-				uint32_t pc[4], pl_[4];
+				for (int j = 0; j < SEG; j++) {
+					uint32_t pc[4], pl_[4];
 #pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const uint32_t ent = lut_pair(lut_s, hit ? u[j][k] : 0u);
-					pc[k] = ent & ((1u << kLutLenShift) - 1u);
-					pl_[k] = ent >> kLutLenShift;
+					for (int k = 0; k < 4; k++) {
+						const uint32_t ent = lut_pair(lut_s, u[j][k]);
+						pc[k] = ent & ((1u << kLutLenShift) - 1u);
+						pl_[k] = ent >> kLutLenShift;
+					}
+					uint32_t lo = pc[0], hi = 0u, nb = pl_[0];
+#pragma unroll
+					for (int k = 1; k < 4; k++) {
+						hi = __funnelshift_l(lo, hi, pl_[k]);
+						lo = (lo << pl_[k]) | pc[k];
+						nb += pl_[k];
+					}
+					qchk |= nb + 63u; /* bit 7 set: a segment longer than 64 bits */
+					sl_[j] = lo; sh_[j] = hi; sn_[j] = nb;
 				}
-				uint32_t lo = pc[0], hi = 0u, nb = pl_[0];
+			} else {
 #pragma unroll
-				for (int k = 1; k < 4; k++) {
-					hi = __funnelshift_l(lo, hi, pl_[k]);
-					lo = (lo << pl_[k]) | pc[k];
-					nb += pl_[k];
-				}
-				qchk |= nb + 63u; /* bit 7 set: a segment longer than 64 bits */
-				sl_[j] = lo; sh_[j] = hi; sn_[j] = nb;
+				for (int j = 0; j < SEG; j++)
+					sl_[j] = sh_[j] = sn_[j] = 0;
 			}
 			/* a warp with a residual outside the table or a segment longer than 64 bits: all its code words
 			 * arithmetically, from plain residuals (the arithmetic arm of frame_fast(), for the whole warp) */
@@ -1689,19 +1694,17 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 			uint32_t pos[4];
 			const uint32_t tile_bits = tile_scan<SEG>(sh, it & 1u, lane, warp, b01, 0u, sbits, pos);
 			/* behind the scan barrier: everything of the visit before is staged; every thread takes the same turns */
-			const uint32_t a = (uint32_t)((uintptr_t)(dst0 + i * dstride) & 15u);
 			if (pend) {
-				uint8_t *pd = dst0 + pend_i * dstride;
-				const uint32_t pa = (uint32_t)((uintptr_t)pd & 15u);
+				const uint32_t pa = (uint32_t)((uintptr_t)pend_d & 15u);
 				OutWin po;
-				po.base = pd - pa;
+				po.base = pend_d - pa;
 				po.lo = pa + hdr_len;
 				po.hi = pa + cap;
 				copy_out(sh, po, buf ^ 1u, pend_gw0, pend_bits, buf ^ 1u, &sh.cx_carry[pend_i]);
 				pend = false;
 			}
-			if (sbits + tile_bits > kStgBits || bit + tile_bits > 8u * (a + cap) || (uint64_t)bit - 8u * a + tile_bits >= pl.trip) {
-				ok = false; /* a tile beyond the staging area, a stream that leaves its slot: the frame-by-frame path */
+			if (sbits + tile_bits > kStgBits) { /* (no stream can leave its slot: model_run_ok()) */
+				ok = false; /* a tile beyond the staging area (most of its samples escape): the frame-by-frame path */
 #ifdef AIRS_CTX_DEBUG
 				if (tid == 0 && atomicAdd(&b.ticket[41], 1u) == 0u) {
 					b.ticket[42] = t; b.ticket[43] = i; b.ticket[44] = 2u; b.ticket[45] = R; b.ticket[46] = bit; b.ticket[47] = tile_bits;
@@ -1729,9 +1732,12 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 			}
 			pend = true;
 			pend_i = i;
+			pend_d = fd;
 			pend_gw0 = gw0;
 			pend_bits = sbits + tile_bits;
 			buf ^= 1u;
+			fd += dstride;
+			xs += sstride;
 		}
 		if (ok) { /* the model of this position behind the run's last frame (ref cmp.c:304-311) */
 #pragma unroll
@@ -1742,10 +1748,9 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 #undef AIRS_CX_X
 	__syncthreads();
 	if (ok && pend) {
-		uint8_t *pd = dst0 + pend_i * dstride;
-		const uint32_t pa = (uint32_t)((uintptr_t)pd & 15u);
+		const uint32_t pa = (uint32_t)((uintptr_t)pend_d & 15u);
 		OutWin po;
-		po.base = pd - pa;
+		po.base = pend_d - pa;
 		po.lo = pa + hdr_len;
 		po.hi = pa + cap;
 		copy_out(sh, po, buf ^ 1u, pend_gw0, pend_bits, buf ^ 1u, &sh.cx_carry[pend_i]);
@@ -1807,7 +1812,7 @@ __device__ __forceinline__ bool model_run_ok(const Shared &sh, const AirsLaunch 
 	return b.layout == AIRS_LAYOUT_SLOTS && !b.ctx_io && b.dst && b.work && b.src && (pl.flags & AIRS_PF_VALID) &&
 	       (pl.flags & AIRS_PF_MODEL) && !(pl.flags & AIRS_PF_BE) && !pl.frame_err && !pl.orig_err && !pl.pre_err[1] &&
 	       !pl.model_err && pl.pre[1] == CMP_PREPROCESS_MODEL && pl.enc[1].type != CMP_ENCODER_UNCOMPRESSED &&
-	       pl.sec_iter >= 2u && jb.dtype != AIRS_DTYPE_I16_IN_I32 && jb.n_frames >= 3u &&
+	       pl.sec_iter >= 2u && jb.dtype != AIRS_DTYPE_I16_IN_I32 && jb.n_frames >= 3u && pl.rate >= 1u && pl.rate <= 15u &&
 	       pl.n >= 8u * kThreads * kSegModel && pl.n % (8u * kThreads * kSegModel) == 0 && pl.cap_eff >= CMP_HDR_SIZE + 6u &&
 	       ((uintptr_t)(b.src + jb.src_offset) & 15u) == 0 && (jb.src_frame_stride & 15u) == 0 &&
 	       ((uintptr_t)(b.work + jb.work_offset) & 15u) == 0 && ((uintptr_t)(b.dst + jb.dst_offset) & 7u) == 0 &&
