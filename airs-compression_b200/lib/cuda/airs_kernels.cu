@@ -72,6 +72,10 @@ constexpr uint32_t kLutLenShift = 26;       /* entry = pair length << 26 | pair 
 constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's codeword fits 26 bits */
 constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
 constexpr uint32_t kSmallMaxSamples = 32768; /* longest frame a single warp encodes (airs_small_kernel); measured crossover */
+#ifndef AIRS_SEG_RUN
+#define AIRS_SEG_RUN 2
+#endif
+constexpr uint32_t kSegRun = AIRS_SEG_RUN;  /* segments per thread and visit of model_run_fast() */
 constexpr uint32_t kCtxFrames = 64;         /* most frames of a run of model_run_fast(): their state must leave the SM a 196 KB carve-out and some L1 */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -1548,21 +1552,22 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 /* the arithmetic arm of model_run_fast(), behind calls: the code words of the two segments of a thread from their
  * biased residuals d[0..7] into cw[0..31] (returns the segments' bit counts, packed), and from there into the staging
  * area */
-__device__ __noinline__ uint32_t run_slow_codes(const EncConst &e, uint32_t *d, uint32_t R, uint32_t *cw)
+__device__ __noinline__ uint32_t run_slow_codes(const EncConst &e, uint32_t *d, uint32_t R, uint32_t *cw, uint32_t &b23)
 {
 	const uint32_t negRb = ((0x10000u - R) & 0xFFFFu) * 0x00010001u;
-	uint32_t b01, b23;
+	uint32_t b01;
 #pragma unroll 1
-	for (uint32_t k = 0; k < 4u * kSegModel; k++)
+	for (uint32_t k = 0; k < 4u * kSegRun; k++)
 		d[k] = __vadd2(d[k], negRb);
-	slow_codes(e, d, 4u * kSegModel, (1u << kSegModel) - 1u, cw, b01, b23);
+	slow_codes(e, d, 4u * kSegRun, (1u << kSegRun) - 1u, cw, b01, b23);
 	return b01;
 }
 
-__device__ __noinline__ void run_slow_put(const uint32_t *cw, uint32_t *stg, uint32_t pos0, uint32_t pos1)
+__device__ __noinline__ void run_slow_put(const uint32_t *cw, uint32_t *stg, const uint32_t *pos)
 {
-	slow_put_codes(cw, stg, pos0);
-	slow_put_codes(cw + 16, stg, pos1);
+#pragma unroll 1
+	for (uint32_t j = 0; j < kSegRun; j++)
+		slow_put_codes(cw + 16u * j, stg, pos[j]);
 }
 
 template <bool SIGNED>
@@ -1571,7 +1576,7 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 	const JobPlan &pl = sh.plan;
 	const airs_job &jb = sh.job;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-	constexpr uint32_t SEG = kSegModel, kTP = kThreads * SEG;
+	constexpr uint32_t SEG = kSegRun, kTP = kThreads * SEG;
 	const uint32_t n_pos = pl.n / (8u * kTP);
 	const uint8_t *src0 = b.src + jb.src_offset + (uint64_t)f0 * jb.src_frame_stride;
 	uint8_t *dst0 = b.dst + jb.dst_offset + (uint64_t)f0 * jb.dst_frame_stride;
@@ -1690,7 +1695,7 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 			 * arithmetically, from plain residuals (the arithmetic arm of frame_fast(), for the whole warp) */
 			const bool slow = !(hit && __all_sync(kFull, (qchk & 128u) == 0u));
 			uint32_t cwords[SEG * 16]; /* (local memory, touched by the two calls below only) */
-			uint32_t b01 = sn_[0] | (sn_[1] << 16);
+			uint32_t b01 = sn_[0] | (sn_[1] << 16), b23 = SEG > 2 ? sn_[SEG - 2] | (sn_[SEG - 1] << 16) : 0u;
 			if (slow) {
 				uint32_t d[SEG * 4];
 #pragma unroll
@@ -1698,12 +1703,12 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 #pragma unroll
 					for (int k = 0; k < 4; k++)
 						d[4 * j + k] = u[j][k];
-				b01 = run_slow_codes(e, d, R, cwords);
+				b01 = run_slow_codes(e, d, R, cwords, b23);
 			}
 			const uint32_t bit = sh.cx_bit[i];
 			const uint32_t gw0 = (bit >> 7) << 2, sbits = bit & 127u;
 			uint32_t pos[4];
-			const uint32_t tile_bits = tile_scan<SEG>(sh, it & 1u, lane, warp, b01, 0u, sbits, pos);
+			const uint32_t tile_bits = tile_scan<SEG>(sh, it & 1u, lane, warp, b01, b23, sbits, pos);
 			/* behind the scan barrier: everything of the visit before is staged; every thread takes the same turns */
 			if (pend) {
 				const uint32_t pa = (uint32_t)((uintptr_t)pend_d & 15u);
@@ -1733,7 +1738,7 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 				sh.cx_bit[i] = bit + tile_bits;
 			}
 			if (slow) {
-				run_slow_put(cwords, stg, pos[0], pos[1]);
+				run_slow_put(cwords, stg, pos);
 			} else {
 #pragma unroll
 				for (int j = 0; j < SEG; j++) {
@@ -1824,7 +1829,7 @@ __device__ __forceinline__ bool model_run_ok(const Shared &sh, const AirsLaunch 
 	       (pl.flags & AIRS_PF_MODEL) && !(pl.flags & AIRS_PF_BE) && !pl.frame_err && !pl.orig_err && !pl.pre_err[1] &&
 	       !pl.model_err && pl.pre[1] == CMP_PREPROCESS_MODEL && pl.enc[1].type != CMP_ENCODER_UNCOMPRESSED &&
 	       pl.sec_iter >= 2u && jb.dtype != AIRS_DTYPE_I16_IN_I32 && jb.n_frames >= 3u && pl.rate >= 1u && pl.rate <= 15u &&
-	       pl.n >= 8u * kThreads * kSegModel && pl.n % (8u * kThreads * kSegModel) == 0 && pl.cap_eff >= CMP_HDR_SIZE + 6u &&
+	       pl.n >= 8u * kThreads * kSegRun && pl.n % (8u * kThreads * kSegRun) == 0 && pl.cap_eff >= CMP_HDR_SIZE + 6u &&
 	       ((uintptr_t)(b.src + jb.src_offset) & 15u) == 0 && (jb.src_frame_stride & 15u) == 0 &&
 	       ((uintptr_t)(b.work + jb.work_offset) & 15u) == 0 && ((uintptr_t)(b.dst + jb.dst_offset) & 7u) == 0 &&
 	       (jb.dst_frame_stride & 7u) == 0 &&
