@@ -242,8 +242,10 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 			CU(airs_fast_resident_ctas(&fast_ctas));
 			fast_dev = dev;
 		}
-		CU(airs_launch_iwt(&l, stream)); /* (the coefficients the two kernels below code; returns at once without such frames) */
-		g_launches += 2;
+		if (l.work) { /* (the coefficients the two kernels below code go to work buffers: without any, no such frames) */
+			CU(airs_launch_iwt(&l, stream));
+			g_launches += 2;
+		}
 		const unsigned int want = (l.n_jobs + AIRS_FAST_THREADS / 32 - 1) / (AIRS_FAST_THREADS / 32);
 		CU(airs_launch_fast(&l, want < (unsigned int)fast_ctas ? want : (unsigned int)fast_ctas, stream));
 		CU(airs_launch_tile(&l, stream));
