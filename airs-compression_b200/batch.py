@@ -43,7 +43,7 @@ class DeviceBatch:
         b = abi.AirsBatch()
         b.src = self.src.data_ptr()
         b.dst = self.dst.data_ptr()
-        b.work = self.work.data_ptr()
+        b.work = self.work.data_ptr() if int(work_size) > 0 else None   # (no work buffers: no transform kernels launched)
         b.jobs = self.jobs.data_ptr()
         b.results = self.results.data_ptr()
         b.init_results = self.init_results.data_ptr()

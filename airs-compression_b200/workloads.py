@@ -29,7 +29,7 @@ def uniform_jobs(n_jobs, n, n_frames, cap, first_job=0, model=False, dtype=abi.D
     jobs["n_frames"] = n_frames
     jobs["dtype"] = dtype
     jobs["first_result"] = (idx * np.uint64(n_frames)).astype(np.uint32)
-    return jobs, int(slot) * n_frames * n_jobs, (2 * n * n_jobs if model else 16)
+    return jobs, int(slot) * n_frames * n_jobs, (2 * n * n_jobs if model else 0)
 
 
 def _pack(data, jobs, dsz, wsz, n, nf, desc, model=False):
