@@ -69,6 +69,16 @@ def test_config2_batched_1gib(gpu, pkg):
     assert rep["frames"] == 64 * 256
 
 
+def test_config2_batched_runs_of_model_passes(gpu, pkg):
+    """Config 2 with enough contexts (320: more than a third of the resident CTAs) that they take the CTA-per-context
+    kernel and, their slots holding cmp_compress_bound() bytes, the runs of model passes with the frames in the inner
+    loop (model_run_fast): 5 GiB, every one of the 81920 frames hashed against the compiled reference - and the same
+    contexts with slots of 2 n + 64 bytes (frame by frame)."""
+    for bound in (True, False):
+        rep = _check(pkg, pkg.workloads.config2(320, 5, "cuda", bound_slots=bound), sample_every=40)
+        assert rep["frames"] == 320 * 256 and rep["frames_ok_on_cpu"] == 320 * 256
+
+
 @pytest.mark.parametrize("row", range(15))
 def test_config4_rows_1gib(gpu, pkg, row):
     """The named subset of config 4, 1 GiB per row in the default cut of 512 x 2 MiB chunks."""
