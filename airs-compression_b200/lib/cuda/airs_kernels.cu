@@ -1640,31 +1640,22 @@ __device__ __noinline__ bool model_run_fast(Shared &sh, const AirsLaunch &b, uin
 						nx[j] = ld_stream(nx4 + 32u * j, pol_stream);
 				}
 			}
-			/* Biased residuals of two samples by ONE 32-bit subtraction, u = w - m + (R, R): when the low residual lies in
-			 * [-R, R), the borrow of a negative low difference and the carry of its bias cancel and both halves are
-			 * exact; when it does not, the low half (always exact modulo 2^16) fails the range check - and the warp
-			 * takes the residuals again, half by half, from the model as it still is */
 			uint32_t u[SEG][4], chk = 0;
 #pragma unroll
-			for (int j = 0; j < SEG; j++)
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					u[j][k] = w[j][k] - m[j][k] + Rb;
-					chk |= u[j][k];
-				}
-			/* the table arm of frame_fast(), or nothing */
-			uint32_t sh_[SEG], sl_[SEG], sn_[SEG], qchk = 128u;
-			const bool hit = __all_sync(kFull, (chk & notmask) == 0u);
-			if (!hit) {
-#pragma unroll
-				for (int j = 0; j < SEG; j++)
-					seg_residuals(CMP_PREPROCESS_MODEL, w[j], m[j], 0u, Rb, B1, u[j]);
-			}
-#pragma unroll
-			for (int j = 0; j < SEG; j++)
+			for (int j = 0; j < SEG; j++) {
+				/* (per 16-bit half and modulo 2^16: one 32-bit subtraction per word is NOT the same - samples on either
+				 * side of the 0 / 65535 boundary give a small residual with a borrow that nothing takes back) */
+				seg_residuals(CMP_PREPROCESS_MODEL, w[j], m[j], 0u, Rb, B1, u[j]);
 #pragma unroll
 				for (int k = 0; k < 4; k++) /* (rates 1 .. 15: model_run_ok()) */
 					m[j][k] = model_update2<SIGNED>(w[j][k], m[j][k], wdp);
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					chk |= u[j][k];
+			}
+			/* the table arm of frame_fast(), or nothing */
+			uint32_t sh_[SEG], sl_[SEG], sn_[SEG], qchk = 128u;
+			const bool hit = __all_sync(kFull, (chk & notmask) == 0u);
 			if (hit) {
 				qchk = 0;
 #pragma unroll

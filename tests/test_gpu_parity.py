@@ -593,24 +593,28 @@ def test_iwt_longest_frames_of_the_transform_kernel(gpu, oracle, pkg):
 @pytest.mark.parametrize("dtype", [2, 0])
 def test_contexts_with_frames_in_the_inner_loop(gpu, oracle, pkg, dtype):
     """Runs of secondary MODEL passes take model_run_fast() in airs_encode_kernel: all frames of the run tile position by
-    tile position, the model in registers, the streams of all frames growing side by side (contexts whose slots hold
-    cmp_compress_bound() bytes: no frame can fail).  Frame counts and secondary iterations that put several primary
-    passes and several runs into a context (runs are at most 64 frames long), every model rate class (0, update, 16),
-    both encoders, checksums, primary passes other than DIFF, rough frames in the middle of a run (code words
-    computed arithmetically) - and contexts with smaller slots, which stay on the frame-by-frame path, one of them
-    with a frame that does not fit.  Streams, results, model bytes and the bytes behind the streams against the oracle."""
+    tile position, the model in registers, the streams of all frames growing side by side - contexts whose slots hold
+    cmp_compress_bound() bytes (no frame can fail), in batches of 300 contexts (fewer would take the tile kernel).
+    Frame counts and secondary iterations that put several primary passes and several runs into a context (runs are
+    at most 64 frames long), both encoders, checksums, primary passes other than DIFF, rough frames in the middle of
+    a run (code words computed arithmetically), a context whose samples walk across 0 / 65535 (small residuals between
+    a sample and a model on either side of the boundary) - and what stays on the frame-by-frame path: rates 0 and 16,
+    smaller slots, one of them with a frame that does not fit.  Streams, results, model bytes and the bytes behind the
+    streams against the oracle."""
     abi, synth = pkg.abi, pkg.synth
-    cases = [  # n, frames, sec_iter, rate, pre1, enc1, g1, enc2, g2, outlier, checksum, cap, rough frame
-        (2048, 3, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),
-        (4096, 7, 2, 11, abi.PRE_DIFF, 1, 16, 2, 8, 40, 1, None, None),
-        (32768, 256, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),
-        (6144, 140, 99, 0, abi.PRE_NONE, 2, 16, 1, 4, 60, 0, None, None),
-        (8192, 33, 255, 16, abi.PRE_IWT, 1, 16, 1, 8, 0, 1, None, None),
-        (8192, 21, 5, 5, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, 13),         # one frame of noise: residuals outside the table
-        (32768, 256, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 2 * 32768 + 64, None),  # smaller slots: frame by frame
-        (4096, 12, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 3000, None),     # the DIFF frame (about 3.3 KB) does not fit its slot
+    cases = [  # contexts, n, frames, sec_iter, rate, pre1, enc1, g1, enc2, g2, outlier, checksum, cap, rough frame
+        (300, 2048, 3, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),
+        (300, 4096, 8, 3, 11, abi.PRE_DIFF, 1, 16, 2, 8, 40, 1, None, None),
+        (300, 2048, 70, 255, 8, abi.PRE_NONE, 1, 16, 1, 8, 0, 0, None, None),     # two runs: 64 and 5 frames
+        (300, 8192, 21, 5, 5, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, 13),         # one frame of noise: residuals outside the table
+        (300, 2048, 9, 255, 8, abi.PRE_IWT, 1, 16, 1, 8, 0, 1, None, None),
+        (3, 32768, 256, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),     # few contexts: the tile kernel
+        (300, 2048, 6, 255, 0, abi.PRE_DIFF, 2, 16, 1, 4, 60, 0, None, None),     # rates 0 and 16: frame by frame
+        (300, 2048, 6, 255, 16, abi.PRE_DIFF, 1, 16, 1, 8, 0, 1, None, None),
+        (300, 2048, 12, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 2 * 2048 + 64, None),  # smaller slots: frame by frame
+        (3, 4096, 12, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 3000, None),       # the DIFF frame (about 3.3 KB) does not fit its slot
     ]
-    for n, nf, sec, rate, pre1, e1, g1, e2, g2, outl, cs, cap, rough in cases:
+    for nctx, n, nf, sec, rate, pre1, e1, g1, e2, g2, outl, cs, cap, rough in cases:
         p = abi.make_params(primary_preprocessing=pre1, primary_encoder_type=e1, primary_encoder_param=g1,
                             primary_encoder_outlier=outl if e1 == 2 else 0, secondary_iterations=sec,
                             secondary_preprocessing=abi.PRE_MODEL, secondary_encoder_type=e2, secondary_encoder_param=g2,
@@ -618,6 +622,16 @@ def test_contexts_with_frames_in_the_inner_loop(gpu, oracle, pkg, dtype):
         x = np.stack([synth.frames(3, c, nf, n) for c in range(3)])
         if rough is not None:
             x[1, rough] = np.random.default_rng(5).integers(0, 65536, n).astype(np.uint16)
-        js = _uniform_jobs(pkg, 3, n, nf, p, dtype=dtype, cap=cap)
+        # the third context: flat positions with a little noise - and every 64th one walks across the 0 / 65535 boundary
+        # half way through the context (even positions upwards, odd ones downwards): small residuals between a sample
+        # and a model on either side of it, next to residuals that all sit in the code word table
+        rng2 = np.random.default_rng(77)
+        y = rng2.integers(2000, 60000, n)[None, :] + rng2.integers(-3, 4, (nf, n))
+        step = np.where(np.arange(nf) >= nf // 2, 8, 0)[:, None]
+        y[:, 0::64] = 65530 + rng2.integers(-3, 4, (nf, len(range(0, n, 64)))) + step
+        y[:, 33::64] = 5 + rng2.integers(-3, 4, (nf, len(range(33, n, 64)))) - step
+        x[2] = (y & 0xFFFF).astype(np.uint16)
+        x = np.tile(x, (nctx // 3, 1, 1))
+        js = _uniform_jobs(pkg, nctx, n, nf, p, dtype=dtype, cap=cap)
         js["src"] = x.view(np.uint8).reshape(-1)
-        jobgen.compare(jobgen.run_cpu(oracle, js, threads=3), gpu.run_jobs_device(js), js, f"frames-inner n={n} nf={nf}")
+        jobgen.compare(jobgen.run_cpu(oracle, js, threads=8), gpu.run_jobs_device(js), js, f"frames-inner n={n} nf={nf} rate={rate}")
