@@ -635,3 +635,7 @@ def test_contexts_with_frames_in_the_inner_loop(gpu, oracle, pkg, dtype):
         js = _uniform_jobs(pkg, nctx, n, nf, p, dtype=dtype, cap=cap)
         js["src"] = x.view(np.uint8).reshape(-1)
         jobgen.compare(jobgen.run_cpu(oracle, js, threads=8), gpu.run_jobs_device(js), js, f"frames-inner n={n} nf={nf} rate={rate}")
+        if nf == 8:  # ... and through the CONCAT layout with temporary slots (the same kernels on the temporary job table)
+            js["layout"] = 1
+            got = gpu.run_jobs_device(js, concat_tmp=gpu.concat_tmp_size(js["jobs"], js["n_results"]))
+            jobgen.compare(jobgen.run_cpu(oracle, js, threads=8), got, js, f"frames-inner concat n={n} nf={nf}")
