@@ -5,6 +5,8 @@ The hot path has no collective: every job (context) is independent (ref cmp.c:22
 so rank r simply owns jobs [r*J/W, (r+1)*J/W).  Only sizes and, if asked for, the
 streams travel at the end.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -40,6 +42,20 @@ def _gather_ragged(part, group, out=None):
     if out is None or out.numel() < total or out.dtype != part.dtype:
         out = torch.empty(total, dtype=part.dtype, device=part.device)
     out = out[:total]
+    if os.environ.get("AIRS_GATHER", "sendrecv") == "allgather":
+        # The alternative, kept for measurements: ONE all-gather of parts padded to the longest, then every part moves
+        # to its place behind the part in front of it (device copies).  On 4 B200s 3.4 GB took 11.8 ms this way and
+        # 10.8 ms with the grouped transfers below (290 against 316 GB/s): the default stays the grouped transfers
+        longest = max(counts)
+        mine = part
+        if counts[rank] != longest:
+            mine = torch.empty(longest, dtype=part.dtype, device=part.device)
+            mine[:counts[rank]].copy_(part)
+        padded = torch.empty(world * longest, dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(padded, mine, group=group)
+        for r in range(world):
+            out[offsets[r]:offsets[r] + counts[r]].copy_(padded[r * longest:r * longest + counts[r]])
+        return out, counts, offsets
     out[offsets[rank]:offsets[rank] + counts[rank]].copy_(part)
     ops = []
     for step in range(1, world):  # (peers in a rotated order: no rank is everybody's first target)
