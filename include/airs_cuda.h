@@ -35,6 +35,15 @@
  * n_results) - the order of the concatenation is the order of the table.  A
  * table that breaks this is refused on the device: nothing is encoded and
  * every results[k] is (uint32_t)-CMP_ERR_GENERIC.
+ *
+ * Speed, not results, depends on two things a caller chooses.  dst_capacity:
+ * with cmp_compress_bound(src_size) bytes per stream (lib/cmp.h) and no
+ * uncompressed fallback no frame of a context can fail, and only then are the
+ * frames of a context encoded out of order (runs of secondary MODEL passes with
+ * the model in registers; contexts of few-job batches tile by tile).  work:
+ * a batch whose jobs need no work buffer passes NULL and skips the launches of
+ * the wavelet transform kernels.  Work buffers hold afterwards what the
+ * reference leaves in work_buf: the model, or the IWT coefficients.
  */
 #ifndef AIRS_CUDA_H
 #define AIRS_CUDA_H
