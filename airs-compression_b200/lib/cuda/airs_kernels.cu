@@ -79,6 +79,11 @@ constexpr uint32_t kSegRun = AIRS_SEG_RUN;  /* segments per thread and visit of 
 constexpr uint32_t kCtxFrames = 64;         /* most frames of a run of model_run_fast(): their state must leave the SM a 196 KB carve-out and some L1 */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+/* Development switches (make EXTRA=-D..., never in the shipped library):
+ *   AIRS_EXP_NO_MODEL_IO  timing experiment of DESIGN.md section 4 - the frame-by-frame model pass without its model
+ *                         loads and stores (wrong streams): the bound of any "model on chip" design with that loop order
+ *   AIRS_CTX_DEBUG        counters of finished / abandoned runs of model_run_fast() in words 40-48 of the scratch header
+ *                         (tools/perf_probe.py prints them with AIRS_PROBE_DEBUG=1) */
 #ifdef AIRS_EXP_NO_MODEL_IO
 constexpr bool kExpNoModelIo = true;
 #else
