@@ -6,6 +6,7 @@
  * device is usable every entry point fails with AIRS_E_NO_DEVICE.
  */
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -229,9 +230,12 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 {
 	AirsLaunch l = l_in;
 	unsigned int grid = l.n_jobs < (uint32_t)resident ? l.n_jobs : (unsigned int)resident;
-	/* (crossover of the two kernels on long frames: the CTA-per-job kernel at n_jobs / resident of its 0.69 against
-	 * 0.17 - 0.2 of the tile kernel) */
-	l.tile_below_jobs = (uint32_t)resident / 3u;
+	/* Crossover of the two kernels on long frames, measured on 4 MiB chunks: the CTA-per-job kernel takes 0.56 ms for
+	 * up to one chunk per SM (0.098 / 0.195 / 0.256 / 0.338 of the roofline at 64 / 128 / 192 / 256 jobs), the tile kernel
+	 * 0.154 - 0.171 whatever the count: about 110 jobs */
+	l.tile_below_jobs = (uint32_t)resident * 3u / 20u;
+	if (const char *e = getenv("AIRS_TILE_BELOW")) /* (development: measure the crossover) */
+		l.tile_below_jobs = (uint32_t)atoi(e);
 	CU(airs_launch_plan(&l, stream));
 	g_launches++;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) {

@@ -73,10 +73,13 @@ constexpr uint32_t kLutMaxLen = 13;         /* per sample, so that a pair's code
 constexpr uint32_t kLutMinSamples = 1024;   /* frames shorter than this do not pay for a table build */
 constexpr uint32_t kSmallMaxSamples = 32768; /* longest frame a single warp encodes (airs_small_kernel); measured crossover */
 #ifndef AIRS_SEG_RUN
-#define AIRS_SEG_RUN 2
+#define AIRS_SEG_RUN 4
 #endif
 constexpr uint32_t kSegRun = AIRS_SEG_RUN;  /* segments per thread and visit of model_run_fast() */
-constexpr uint32_t kCtxFrames = 64;         /* most frames of a run of model_run_fast(): their state must leave the SM a 196 KB carve-out and some L1 */
+#ifndef AIRS_CTX_FRAMES
+#define AIRS_CTX_FRAMES 64
+#endif
+constexpr uint32_t kCtxFrames = AIRS_CTX_FRAMES;         /* most frames of a run of model_run_fast(): their state must leave the SM a 196 KB carve-out and some L1 */
 constexpr uint64_t kMask48 = 0xFFFFFFFFFFFFull;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 /* Development switches (make EXTRA=-D..., never in the shipped library):
@@ -1542,8 +1545,8 @@ __device__ __forceinline__ void frame_fast_any(Shared &sh, const OutWin &o, uint
 
 /*
  * A run of consecutive secondary MODEL passes of a context (ref cmp.c:228-262, 296-312) with the FRAMES IN THE INNER
- * LOOP: for every tile position (2048 samples) the CTA walks through all frames of the run, so that the model of the
- * position lives in registers from the first frame to the last (16 samples a thread; read from the work buffer once
+ * LOOP: for every tile position (4096 samples) the CTA walks through all frames of the run, so that the model of the
+ * position lives in registers from the first frame to the last (32 samples a thread; read from the work buffer once
  * and written back once per run) - the frame-by-frame order reads and rewrites the whole model through the L2 once
  * per frame, and with a context per CTA those are 58 MB in flight that the L2 does not hold (1.54 x the algorithmic
  * DRAM traffic).  The tiles of a frame are still visited in stream order, `run` visits apart: where its stream stands

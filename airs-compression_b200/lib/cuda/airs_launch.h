@@ -14,7 +14,10 @@ struct JobPlan;
 #define AIRS_THREADS 128
 #endif
 #ifndef AIRS_CTAS_PER_SM
-#define AIRS_CTAS_PER_SM 6 /* resident CTAs per SM the encode kernel is compiled for */
+#define AIRS_CTAS_PER_SM 5 /* resident CTAs per SM the encode kernel is compiled for: 96 registers a thread.  (Six CTAs of 80
+			    * registers were the choice until the runs of model passes came: with four segments per thread and
+			    * visit they need the registers - config 2 batched 0.464 -> 0.504 - and the other workloads of this
+			    * kernel stay within 1 - 4 % either way: measured) */
 #endif
 
 #ifndef AIRS_FAST_THREADS

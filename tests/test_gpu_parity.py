@@ -603,15 +603,16 @@ def test_contexts_with_frames_in_the_inner_loop(gpu, oracle, pkg, dtype):
     streams against the oracle."""
     abi, synth = pkg.abi, pkg.synth
     cases = [  # contexts, n, frames, sec_iter, rate, pre1, enc1, g1, enc2, g2, outlier, checksum, cap, rough frame
-        (300, 2048, 3, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),
-        (300, 4096, 8, 3, 11, abi.PRE_DIFF, 1, 16, 2, 8, 40, 1, None, None),
-        (300, 2048, 70, 255, 8, abi.PRE_NONE, 1, 16, 1, 8, 0, 0, None, None),     # two runs: 64 and 5 frames
+        (300, 4096, 3, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),
+        (300, 8192, 8, 3, 11, abi.PRE_DIFF, 1, 16, 2, 8, 40, 1, None, None),
+        (300, 4096, 70, 255, 8, abi.PRE_NONE, 1, 16, 1, 8, 0, 0, None, None),     # two runs: 64 and 5 frames
         (300, 8192, 21, 5, 5, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, 13),         # one frame of noise: residuals outside the table
-        (300, 2048, 9, 255, 8, abi.PRE_IWT, 1, 16, 1, 8, 0, 1, None, None),
+        (300, 4096, 9, 255, 8, abi.PRE_IWT, 1, 16, 1, 8, 0, 1, None, None),
+        (300, 6144, 5, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),      # not whole tiles of 4096 samples: frame by frame
         (3, 32768, 256, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, None, None),     # few contexts: the tile kernel
-        (300, 2048, 6, 255, 0, abi.PRE_DIFF, 2, 16, 1, 4, 60, 0, None, None),     # rates 0 and 16: frame by frame
-        (300, 2048, 6, 255, 16, abi.PRE_DIFF, 1, 16, 1, 8, 0, 1, None, None),
-        (300, 2048, 12, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 2 * 2048 + 64, None),  # smaller slots: frame by frame
+        (300, 4096, 6, 255, 0, abi.PRE_DIFF, 2, 16, 1, 4, 60, 0, None, None),     # rates 0 and 16: frame by frame
+        (300, 4096, 6, 255, 16, abi.PRE_DIFF, 1, 16, 1, 8, 0, 1, None, None),
+        (300, 4096, 12, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 2 * 4096 + 64, None),  # smaller slots: frame by frame
         (3, 4096, 12, 255, 8, abi.PRE_DIFF, 1, 16, 1, 8, 0, 0, 3000, None),       # the DIFF frame (about 3.3 KB) does not fit its slot
     ]
     for nctx, n, nf, sec, rate, pre1, e1, g1, e2, g2, outl, cs, cap, rough in cases:

@@ -21,7 +21,7 @@ for seed in range(first, first + count):
     sizes = SMALL if kind < 2 else MED
     layout = kind & 1
     if seed % 5 == 4:  # many contexts of whole tiles, mostly in slots of the bound: the runs of model passes (model_run_fast)
-        js = jobgen.build_jobs(rng, 320, sizes=[2048, 4096, 6144, 2049, 1000], max_frames=6, layout=layout,
+        js = jobgen.build_jobs(rng, 320, sizes=[4096, 8192, 12288, 2048, 4097, 1000], max_frames=6, layout=layout,
                                capacity_modes=["bound", "bound", "bound", "big", "raw", "tight"])
     else:
         js = jobgen.build_jobs(rng, 200 if kind < 2 else 60, sizes=sizes, max_frames=6, allow_invalid=(kind == 0), layout=layout)

@@ -103,6 +103,6 @@ if os.path.exists("gpurun_out/r02_ncu_iwt.ncu-rep"):
     md += s
 open("profiles/r02_ncu_summary.md", "w").write(md)
 json.dump({"c3": {"units": 1 << 20, "dram_bytes_per_launch": t3, "source": "profiles/r02_ncu_summary.md (ncu --set full of airs_fast_kernel, bench.py default workload), code of commit " + head},
-           "c2": {"units": 888, "dram_bytes_per_launch": t2, "source": "profiles/r02_ncu_summary.md (ncu --set full of airs_encode_kernel, bench.py --workload c2), code of commit " + head}},
+           "c2": {"units": int(b2["config"]["per_gpu_input_bytes"] // (256 * 65536)), "dram_bytes_per_launch": t2, "source": "profiles/r02_ncu_summary.md (ncu --set full of airs_encode_kernel, bench.py --workload c2), code of commit " + head}},
           open("profiles/roofline_traffic.json", "w"))
 print("written")

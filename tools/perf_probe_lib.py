@@ -135,8 +135,8 @@ def run_case(case, steps=5, warmup=2, dev="cuda"):
         jobs, dsz, wsz = make_uniform_jobs(n_chunks, n, 1, {"iwt": p_iwt, "none": p_none, "unc": p_unc, "iwtunc": p_iwtunc, "iwt4": p_iwt, "iwt32k": p_iwt, "none4": p_none}[case],
                                            model=(case in ("iwt", "iwtunc", "iwt4", "iwt32k")))
         return time_batch(case, data, jobs, dsz, wsz, n_chunks, steps, warmup)
-    if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k", "c4b_esc1", "c4b_esc8", "c256", "c4cs", "c4bcs", "c32kcs"):
-        n_chunks, n = {"c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
+    if case in ("c4", "c1", "c4b", "c16k", "c32k", "c8k", "c4b_esc1", "c4b_esc8", "c256", "c4cs", "c4bcs", "c32kcs", "c128", "c64", "c192", "c32"):
+        n_chunks, n = {"c128": (128, 1 << 21), "c64": (64, 1 << 21), "c192": (192, 1 << 21), "c32": (32, 1 << 21), "c4": (512, 1 << 20), "c1": (1, 1 << 20), "c4b": (4096, 1 << 17), "c16k": (1 << 15, 1 << 14),
                        "c32k": (1 << 14, 1 << 15), "c8k": (1 << 16, 1 << 13), "c4b_esc1": (4096, 1 << 17),
                        "c4b_esc8": (4096, 1 << 17), "c256": (256, 1 << 21), "c4cs": (512, 1 << 20), "c4bcs": (4096, 1 << 17),
                        "c32kcs": (1 << 14, 1 << 15)}[case]
