@@ -234,8 +234,10 @@ static int launch_kernels(const AirsLaunch &l_in, int resident, cudaStream_t str
 	 * up to one chunk per SM (0.098 / 0.195 / 0.256 / 0.338 of the roofline at 64 / 128 / 192 / 256 jobs), the tile kernel
 	 * 0.154 - 0.171 whatever the count: about 110 jobs */
 	l.tile_below_jobs = (uint32_t)resident * 3u / 20u;
-	if (const char *e = getenv("AIRS_TILE_BELOW")) /* (development: measure the crossover) */
+#ifdef AIRS_DEV_ENV /* (development builds: measure the crossover with AIRS_TILE_BELOW=<jobs>) */
+	if (const char *e = getenv("AIRS_TILE_BELOW"))
 		l.tile_below_jobs = (uint32_t)atoi(e);
+#endif
 	CU(airs_launch_plan(&l, stream));
 	g_launches++;
 	if (l.layout == AIRS_LAYOUT_SLOTS && !l.ctx_io) {
