@@ -42,7 +42,13 @@ def _worker(rank, world, port, js_bytes, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_and_gather(oracle):
+import pytest
+
+
+@pytest.mark.parametrize("method", ["sendrecv", "allgather"])
+def test_two_rank_shard_and_gather(oracle, method, monkeypatch):
+    """Both gathers of parallel.py: grouped send / receive into place (the default) and the padded all-gather."""
+    monkeypatch.setenv("AIRS_GATHER", method)   # (inherited by the spawned ranks)
     rng = np.random.default_rng(77)
     js = jobgen.build_jobs(rng, 41, sizes=[5, 64, 257, 2048], max_frames=3, layout=1)
     want_dst, want_res, _, want_offs, _ = jobgen.run_cpu(oracle, js)
